@@ -1,0 +1,14 @@
+"""ffm_b200 -- B200-native (sm_100a) implementation of the Floor-Field-Model hot path.
+
+Layout
+  csrc/            hand-written CUDA kernels + the C ABI of include/ffm_b200.h (libffm_b200.so)
+  _abi.py          ctypes mirror of the header
+  sim.py           BatchSim: B independent episodes on one map (the batched rollout API)
+  model/           drop-in classes with the reference's model/ffm_*.py interface
+
+The CUDA library is the only compute path; importing this package never falls back to a CPU
+implementation.
+"""
+from .sim import BatchSim  # noqa: F401
+
+__all__ = ["BatchSim"]

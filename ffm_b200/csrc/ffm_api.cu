@@ -1,0 +1,408 @@
+// C ABI of libffm_b200 (include/ffm_b200.h): handle management, host<->device staging and kernel
+// dispatch.  No torch, no C++ types across the boundary, no CPU fallback: every compute entry point
+// launches a kernel on the configured device or fails with FFM_E_CUDA.
+#include "../../include/ffm_b200.h"
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "ffm_core_kernel.cuh"
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CU(call)                                                                               \
+    do {                                                                                       \
+        cudaError_t e_ = (call);                                                               \
+        if (e_ != cudaSuccess)                                                                 \
+            return fail(FFM_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+constexpr int MAX_SMEM_OPTIN = 232448;  // 227 KB per CTA on sm_100
+
+}  // namespace
+
+struct ffm_sim_s {
+    ffm_config_t cfg;
+    int HW;
+    bool have_fields, have_positions;
+    bool fields_in_smem;
+    int threads;
+    int smem_bytes;
+    int ctas_per_sm;
+    int64_t launches;
+    // device state
+    uint8_t* d_map;
+    uint16_t* d_type_grid;
+    void* d_sff;
+    void* d_score;
+    uint32_t* d_pos;
+    int32_t* d_n;
+    int32_t* d_t;
+    unsigned long long* d_ped_steps;
+    float* d_dff;
+    float* d_dff_tmp;
+    int32_t* d_pos_rc;   // staging for (row, col) pairs
+    int32_t* d_err;      // device-side validation flag
+    const void* kernel;  // selected rollout kernel
+};
+
+// ---------------------------------------------------------------------------------------------
+// small staging kernels
+// ---------------------------------------------------------------------------------------------
+namespace ffm {
+
+// map codes -> type bits (+ guard band), and score = (-k_S) * sff in the SFF's own dtype
+// (the first product of ffm_core.py:77; elementwise, so hoisting it out of the step is exact).
+template <typename S>
+__global__ void prep_fields_kernel(const uint8_t* map, const S* sff, uint16_t* type_grid, S* score, int H, int W,
+                                   S neg_ks, int32_t* err) {
+    const int HW = H * W, G = W + 1;
+    for (int x = blockIdx.x * blockDim.x + threadIdx.x; x < HW + 2 * G; x += gridDim.x * blockDim.x) {
+        const int c = x - G;
+        uint32_t type = TYPE_WALL;
+        if (c >= 0 && c < HW) {
+            const uint8_t m = map[c];
+            type = (m == FFM_CELL_FREE) ? TYPE_FREE : (m == FFM_CELL_WALL) ? TYPE_WALL : (m == FFM_CELL_EXIT) ? TYPE_EXIT : TYPE_OTHER;
+            if (m > 3) atomicOr(err, 1);
+            const int r = c / W, col = c - r * W;
+            // the step never bounds-checks neighbours (nor does ffm_core.py:45-53, which "relies on
+            // border walls"): a free cell on the border would let a pedestrian read outside the map
+            if ((r == 0 || r == H - 1 || col == 0 || col == W - 1) && m == FFM_CELL_FREE) atomicOr(err, 2);
+            score[c] = mul_rn(neg_ks, sff[c]);
+        }
+        type_grid[x] = (uint16_t)(type << TYPE_SHIFT);
+    }
+}
+
+__global__ void pack_positions_kernel(const int32_t* pos_rc, const int32_t* n, const uint16_t* type_grid, uint32_t* pos,
+                                      int B, int n_max, int H, int W, int32_t* err) {
+    const int G = W + 1;
+    const long long total = (long long)B * n_max;
+    for (long long x = (long long)blockIdx.x * blockDim.x + threadIdx.x; x < total; x += (long long)gridDim.x * blockDim.x) {
+        const int e = (int)(x / n_max), i = (int)(x - (long long)e * n_max);
+        const int ne = n[e];
+        if (ne < 0 || ne > n_max) { atomicOr(err, 4); continue; }
+        if (i >= ne) continue;
+        const int2 rc = reinterpret_cast<const int2*>(pos_rc)[x];
+        if (rc.x < 0 || rc.x >= H || rc.y < 0 || rc.y >= W) { atomicOr(err, 8); continue; }
+        const int c = rc.x * W + rc.y;
+        if ((type_grid[c + G] >> TYPE_SHIFT) != TYPE_FREE) atomicOr(err, 16);   // initialize_agents(): map == 0 cells only
+        pos[x] = (uint32_t)c;
+    }
+}
+
+__global__ void unpack_positions_kernel(const uint32_t* pos, const int32_t* n, int32_t* pos_rc, int B, int n_max, int W) {
+    const long long total = (long long)B * n_max;
+    for (long long x = (long long)blockIdx.x * blockDim.x + threadIdx.x; x < total; x += (long long)gridDim.x * blockDim.x) {
+        const int e = (int)(x / n_max), i = (int)(x - (long long)e * n_max);
+        int2 rc = make_int2(-1, -1);
+        if (i < n[e]) {
+            const int c = (int)pos[x];
+            rc.x = c / W;
+            rc.y = c - rc.x * W;
+        }
+        reinterpret_cast<int2*>(pos_rc)[x] = rc;
+    }
+}
+
+}  // namespace ffm
+
+namespace {
+
+template <typename S, typename PosT, int NBR, bool DFF, bool FS>
+const void* pick_threads(int threads) {
+    if (threads == 1024) return (const void*)ffm::ffm_core_rollout_kernel<S, PosT, NBR, DFF, FS, 1024>;
+    if (threads == 512) return (const void*)ffm::ffm_core_rollout_kernel<S, PosT, NBR, DFF, FS, 512>;
+    if (threads == 128) return (const void*)ffm::ffm_core_rollout_kernel<S, PosT, NBR, DFF, FS, 128>;
+    return (const void*)ffm::ffm_core_rollout_kernel<S, PosT, NBR, DFF, FS, 256>;
+}
+template <typename S, typename PosT, int NBR, bool DFF>
+const void* pick_fs(bool fs, int threads) {
+    return fs ? pick_threads<S, PosT, NBR, DFF, true>(threads) : pick_threads<S, PosT, NBR, DFF, false>(threads);
+}
+template <typename S, typename PosT, int NBR>
+const void* pick_dff(bool dff, bool fs, int threads) {
+    return dff ? pick_fs<S, PosT, NBR, true>(fs, threads) : pick_fs<S, PosT, NBR, false>(fs, threads);
+}
+template <typename S, typename PosT>
+const void* pick_nbr(int nbr, bool dff, bool fs, int threads) {
+    return nbr == 4 ? pick_dff<S, PosT, 4>(dff, fs, threads) : pick_dff<S, PosT, 8>(dff, fs, threads);
+}
+template <typename S>
+const void* pick_pos(bool small, int nbr, bool dff, bool fs, int threads) {
+    return small ? pick_nbr<S, uint16_t>(nbr, dff, fs, threads) : pick_nbr<S, uint32_t>(nbr, dff, fs, threads);
+}
+const void* pick_kernel(bool f64, bool small, int nbr, bool dff, bool fs, int threads) {
+    return f64 ? pick_pos<double>(small, nbr, dff, fs, threads) : pick_pos<float>(small, nbr, dff, fs, threads);
+}
+
+int check_device_flag(ffm_sim_t s, cudaStream_t st) {
+    int32_t flag = 0;
+    CU(cudaMemcpyAsync(&flag, s->d_err, sizeof(flag), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if (flag == 0) return FFM_OK;
+    CU(cudaMemsetAsync(s->d_err, 0, sizeof(int32_t), st));
+    if (flag & 1) return fail(FFM_E_INVALID, "map_array holds codes outside {0,1,2,3}");
+    if (flag & 2) return fail(FFM_E_INVALID, "map_array has a free cell on its border (the step relies on border walls)");
+    if (flag & 4) return fail(FFM_E_INVALID, "pedestrian count outside [0, n_max]");
+    if (flag & 8) return fail(FFM_E_INVALID, "pedestrian position outside the map");
+    if (flag & 16) return fail(FFM_E_INVALID, "pedestrian placed on a cell that is not free (map != 0)");
+    return fail(FFM_E_INVALID, "device validation flag %d", flag);
+}
+
+int copy_in(void* dst, const void* src, size_t bytes, int space, cudaStream_t st) {
+    CU(cudaMemcpyAsync(dst, src, bytes, space == FFM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+    return FFM_OK;
+}
+int copy_out(void* dst, const void* src, size_t bytes, int space, cudaStream_t st) {
+    CU(cudaMemcpyAsync(dst, src, bytes, space == FFM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
+    if (space == FFM_HOST) CU(cudaStreamSynchronize(st));
+    return FFM_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ffm_abi_version(void) { return FFM_ABI_VERSION; }
+const char* ffm_last_error(void) { return g_err; }
+
+int ffm_create(const ffm_config_t* cfg, ffm_sim_t* out) {
+    if (!cfg || !out) return fail(FFM_E_INVALID, "null argument");
+    *out = nullptr;
+    if (cfg->abi_version != FFM_ABI_VERSION) return fail(FFM_E_INVALID, "abi_version %d != %d", cfg->abi_version, FFM_ABI_VERSION);
+    if (cfg->height < 3 || cfg->width < 3) return fail(FFM_E_INVALID, "map must be at least 3x3");
+    if ((long long)cfg->height * cfg->width > (1 << 24)) return fail(FFM_E_UNSUPPORTED, "map larger than 4096x4096 cells");
+    if (cfg->neighborhood != FFM_NEUMANN && cfg->neighborhood != FFM_MOORE) return fail(FFM_E_INVALID, "neighborhood must be 4 or 8");
+    if (cfg->sff_dtype != FFM_F32 && cfg->sff_dtype != FFM_F64) return fail(FFM_E_INVALID, "sff_dtype must be FFM_F32 or FFM_F64");
+    if (cfg->n_episodes < 1) return fail(FFM_E_INVALID, "n_episodes must be >= 1");
+    if (cfg->n_max < 1 || cfg->n_max > ffm::MAX_PEDS) return fail(FFM_E_UNSUPPORTED, "n_max must be in [1, %d]", ffm::MAX_PEDS);
+    if (!cfg->track_dff && cfg->k_D != 0.0) return fail(FFM_E_INVALID, "track_dff = 0 requires k_D == 0");
+    int ndev = 0;
+    CU(cudaGetDeviceCount(&ndev));
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(FFM_E_INVALID, "device %d not present (%d visible)", cfg->device, ndev);
+    CU(cudaSetDevice(cfg->device));
+    int cc_major = 0;
+    CU(cudaDeviceGetAttribute(&cc_major, cudaDevAttrComputeCapabilityMajor, cfg->device));
+    if (cc_major != 10) return fail(FFM_E_UNSUPPORTED, "libffm_b200 is built for sm_100a only (device is sm_%d*)", cc_major);
+
+    ffm_sim_s* s = new (std::nothrow) ffm_sim_s();
+    if (!s) return fail(FFM_E_INVALID, "out of host memory");
+    memset(s, 0, sizeof(*s));
+    s->cfg = *cfg;
+    s->HW = cfg->height * cfg->width;
+    const int HW = s->HW, W = cfg->width, B = cfg->n_episodes, N = cfg->n_max;
+    const int ssz = cfg->sff_dtype == FFM_F64 ? 8 : 4;
+    const bool dff = cfg->track_dff != 0;
+
+    // kernel variant: fields in shared memory when they fit, and as many threads as pedestrians
+    // (rounded to a supported CTA size) without starving co-resident CTAs
+    ffm::SmemLayout Lin = ffm::make_layout(HW, W, N, ssz, dff, true);
+    ffm::SmemLayout Lout = ffm::make_layout(HW, W, N, ssz, dff, false);
+    if ((int)Lin.total <= MAX_SMEM_OPTIN) {
+        s->fields_in_smem = true;
+        s->smem_bytes = (int)Lin.total;
+    } else if ((int)Lout.total <= MAX_SMEM_OPTIN) {
+        s->fields_in_smem = false;
+        s->smem_bytes = (int)Lout.total;
+    } else {
+        delete s;
+        return fail(FFM_E_UNSUPPORTED, "episode state (%u B) does not fit the 227 KB of shared memory of one SM", Lout.total);
+    }
+    const int work = N > HW / 8 ? N : HW / 8;
+    s->threads = work <= 128 ? 128 : (work <= 1024 ? 256 : (work <= 4096 ? 512 : 1024));
+    s->kernel = pick_kernel(cfg->sff_dtype == FFM_F64, HW <= 65536, cfg->neighborhood, dff, s->fields_in_smem, s->threads);
+    cudaError_t ce = cudaFuncSetAttribute(s->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, s->smem_bytes);
+    if (ce != cudaSuccess) { delete s; return fail(FFM_E_CUDA, "cudaFuncSetAttribute(smem=%d): %s", s->smem_bytes, cudaGetErrorString(ce)); }
+    int occ = 0;
+    ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, s->kernel, s->threads, s->smem_bytes);
+    if (ce != cudaSuccess || occ < 1) { delete s; return fail(FFM_E_CUDA, "rollout kernel cannot be resident (smem=%d, threads=%d): %s", s->smem_bytes, s->threads, cudaGetErrorString(ce)); }
+    s->ctas_per_sm = occ;
+
+#define ALLOC(ptr, bytes)                                                                     \
+    do {                                                                                      \
+        cudaError_t e_ = cudaMalloc((void**)&(ptr), (bytes));                                 \
+        if (e_ != cudaSuccess) { ffm_destroy(s); return fail(FFM_E_CUDA, "cudaMalloc(%zu) failed: %s", (size_t)(bytes), cudaGetErrorString(e_)); } \
+    } while (0)
+    ALLOC(s->d_map, (size_t)HW);
+    ALLOC(s->d_type_grid, (size_t)(HW + 2 * (W + 1)) * 2);
+    ALLOC(s->d_sff, (size_t)HW * ssz);
+    ALLOC(s->d_score, (size_t)HW * ssz);
+    ALLOC(s->d_pos, (size_t)B * N * 4);
+    ALLOC(s->d_pos_rc, (size_t)B * N * 8);
+    ALLOC(s->d_n, (size_t)B * 4);
+    ALLOC(s->d_t, (size_t)B * 4);
+    ALLOC(s->d_ped_steps, (size_t)B * 8);
+    ALLOC(s->d_err, 4);
+    if (dff) {
+        ALLOC(s->d_dff, (size_t)B * HW * 4);
+        if (!s->fields_in_smem) ALLOC(s->d_dff_tmp, (size_t)B * HW * 4);
+    }
+#undef ALLOC
+    cudaMemset(s->d_err, 0, 4);
+    cudaMemset(s->d_n, 0, (size_t)B * 4);
+    cudaMemset(s->d_t, 0, (size_t)B * 4);
+    cudaMemset(s->d_ped_steps, 0, (size_t)B * 8);
+    *out = s;
+    return FFM_OK;
+}
+
+int ffm_destroy(ffm_sim_t s) {
+    if (!s) return FFM_OK;
+    cudaSetDevice(s->cfg.device);
+    cudaFree(s->d_map); cudaFree(s->d_type_grid); cudaFree(s->d_sff); cudaFree(s->d_score);
+    cudaFree(s->d_pos); cudaFree(s->d_pos_rc); cudaFree(s->d_n); cudaFree(s->d_t);
+    cudaFree(s->d_ped_steps); cudaFree(s->d_err); cudaFree(s->d_dff); cudaFree(s->d_dff_tmp);
+    delete s;
+    return FFM_OK;
+}
+
+int ffm_set_fields(ffm_sim_t s, const uint8_t* map, const void* sff, int space, void* stream) {
+    if (!s || !map || !sff) return fail(FFM_E_INVALID, "null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    CU(cudaSetDevice(s->cfg.device));
+    const int HW = s->HW, H = s->cfg.height, W = s->cfg.width;
+    const int ssz = s->cfg.sff_dtype == FFM_F64 ? 8 : 4;
+    int rc;
+    if ((rc = copy_in(s->d_map, map, (size_t)HW, space, st))) return rc;
+    if ((rc = copy_in(s->d_sff, sff, (size_t)HW * ssz, space, st))) return rc;
+    const int blocks = (HW + 2 * (W + 1) + 255) / 256;
+    if (s->cfg.sff_dtype == FFM_F64)
+        ffm::prep_fields_kernel<double><<<blocks, 256, 0, st>>>(s->d_map, (const double*)s->d_sff, s->d_type_grid, (double*)s->d_score, H, W, -s->cfg.k_S, s->d_err);
+    else
+        ffm::prep_fields_kernel<float><<<blocks, 256, 0, st>>>(s->d_map, (const float*)s->d_sff, s->d_type_grid, (float*)s->d_score, H, W, (float)(-s->cfg.k_S), s->d_err);
+    CU(cudaGetLastError());
+    s->launches++;
+    if ((rc = check_device_flag(s, st))) return rc;
+    s->have_fields = true;
+    return FFM_OK;
+}
+
+int ffm_set_positions(ffm_sim_t s, const int32_t* pos_rc, const int32_t* n, int space, void* stream) {
+    if (!s || !pos_rc || !n) return fail(FFM_E_INVALID, "null argument");
+    if (!s->have_fields) return fail(FFM_E_STATE, "ffm_set_fields must precede ffm_set_positions");
+    cudaStream_t st = (cudaStream_t)stream;
+    CU(cudaSetDevice(s->cfg.device));
+    const int B = s->cfg.n_episodes, N = s->cfg.n_max;
+    int rc;
+    const int32_t* src = pos_rc;
+    if (space == FFM_HOST) {
+        if ((rc = copy_in(s->d_pos_rc, pos_rc, (size_t)B * N * 8, FFM_HOST, st))) return rc;
+        src = s->d_pos_rc;
+    }
+    if ((rc = copy_in(s->d_n, n, (size_t)B * 4, space, st))) return rc;
+    CU(cudaMemsetAsync(s->d_t, 0, (size_t)B * 4, st));
+    CU(cudaMemsetAsync(s->d_ped_steps, 0, (size_t)B * 8, st));
+    if (s->d_dff) CU(cudaMemsetAsync(s->d_dff, 0, (size_t)B * s->HW * 4, st));
+    const long long total = (long long)B * N;
+    const int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+    ffm::pack_positions_kernel<<<blocks, 256, 0, st>>>(src, s->d_n, s->d_type_grid, s->d_pos, B, N, s->cfg.height, s->cfg.width, s->d_err);
+    CU(cudaGetLastError());
+    s->launches++;
+    s->have_positions = true;
+    return FFM_OK;
+}
+
+int ffm_get_positions(ffm_sim_t s, int32_t* pos_rc, int32_t* n, int space, void* stream) {
+    if (!s) return fail(FFM_E_INVALID, "null argument");
+    if (!s->have_positions) return fail(FFM_E_STATE, "no positions set");
+    cudaStream_t st = (cudaStream_t)stream;
+    CU(cudaSetDevice(s->cfg.device));
+    const int B = s->cfg.n_episodes, N = s->cfg.n_max;
+    int rc;
+    if ((rc = check_device_flag(s, st))) return rc;
+    if (pos_rc) {
+        const long long total = (long long)B * N;
+        const int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+        int32_t* dst = space == FFM_DEVICE ? pos_rc : s->d_pos_rc;
+        ffm::unpack_positions_kernel<<<blocks, 256, 0, st>>>(s->d_pos, s->d_n, dst, B, N, s->cfg.width);
+        CU(cudaGetLastError());
+        s->launches++;
+        if (space == FFM_HOST && (rc = copy_out(pos_rc, s->d_pos_rc, (size_t)B * N * 8, FFM_HOST, st))) return rc;
+    }
+    if (n && (rc = copy_out(n, s->d_n, (size_t)B * 4, space, st))) return rc;
+    return FFM_OK;
+}
+
+int ffm_set_dff(ffm_sim_t s, const float* dff, int space, void* stream) {
+    if (!s || !dff) return fail(FFM_E_INVALID, "null argument");
+    if (!s->d_dff) return fail(FFM_E_STATE, "handle was created with track_dff = 0");
+    CU(cudaSetDevice(s->cfg.device));
+    return copy_in(s->d_dff, dff, (size_t)s->cfg.n_episodes * s->HW * 4, space, (cudaStream_t)stream);
+}
+
+int ffm_get_dff(ffm_sim_t s, float* dff, int space, void* stream) {
+    if (!s || !dff) return fail(FFM_E_INVALID, "null argument");
+    if (!s->d_dff) return fail(FFM_E_STATE, "handle was created with track_dff = 0");
+    CU(cudaSetDevice(s->cfg.device));
+    return copy_out(dff, s->d_dff, (size_t)s->cfg.n_episodes * s->HW * 4, space, (cudaStream_t)stream);
+}
+
+int ffm_rollout(ffm_sim_t s, int32_t max_steps, const ffm_draws_t* draws, const ffm_rollout_out_t* out, void* stream) {
+    if (!s) return fail(FFM_E_INVALID, "null argument");
+    if (!s->have_fields || !s->have_positions) return fail(FFM_E_STATE, "fields and positions must be set before ffm_rollout");
+    if (max_steps < 0) return fail(FFM_E_INVALID, "max_steps < 0");
+    if (draws && draws->space != FFM_DEVICE) return fail(FFM_E_INVALID, "recorded draws must live in device memory");
+    cudaStream_t st = (cudaStream_t)stream;
+    CU(cudaSetDevice(s->cfg.device));
+    ffm::RolloutParams P;
+    memset(&P, 0, sizeof(P));
+    P.H = s->cfg.height; P.W = s->cfg.width; P.HW = s->HW; P.n_max = s->cfg.n_max; P.B = s->cfg.n_episodes;
+    P.max_steps = max_steps;
+    P.type_grid = s->d_type_grid;
+    P.score = s->d_score;
+    P.kd = (float)s->cfg.k_D;
+    P.c0 = s->cfg.dff_c0; P.c1 = s->cfg.dff_c1; P.thr = s->cfg.dff_threshold;
+    P.pos = s->d_pos; P.n_alive = s->d_n; P.t_done = s->d_t; P.ped_steps = s->d_ped_steps;
+    P.dff = s->d_dff; P.dff_tmp = s->d_dff_tmp;
+    P.seed = s->cfg.seed; P.episode_base = s->cfg.episode_base;
+    if (draws) {
+        P.move_draws = draws->move; P.conflict_draws = draws->conflict;
+        P.draw_steps = draws->steps; P.draw_first = draws->first_step;
+    }
+    if (out && out->traj_cells) {
+        if (!out->traj_n) return fail(FFM_E_INVALID, "traj_cells without traj_n");
+        P.traj = out->traj_cells; P.traj_n = out->traj_n; P.traj_steps = out->traj_steps;
+    }
+    void* args[] = {&P};
+    CU(cudaLaunchKernel(s->kernel, dim3(s->cfg.n_episodes), dim3(s->threads), args, (size_t)s->smem_bytes, st));
+    s->launches++;
+    return FFM_OK;
+}
+
+int ffm_get_counters(ffm_sim_t s, int32_t* steps, int64_t* ped_steps, int space, void* stream) {
+    if (!s) return fail(FFM_E_INVALID, "null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    CU(cudaSetDevice(s->cfg.device));
+    int rc;
+    if (steps && (rc = copy_out(steps, s->d_t, (size_t)s->cfg.n_episodes * 4, space, st))) return rc;
+    if (ped_steps && (rc = copy_out(ped_steps, s->d_ped_steps, (size_t)s->cfg.n_episodes * 8, space, st))) return rc;
+    if (space == FFM_HOST && (rc = check_device_flag(s, st))) return rc;
+    return FFM_OK;
+}
+
+int64_t ffm_launch_count(ffm_sim_t s) { return s ? s->launches : 0; }
+
+int ffm_kernel_info(ffm_sim_t s, int32_t* smem_bytes, int32_t* threads, int32_t* ctas_per_sm, int32_t* fields_in_smem) {
+    if (!s) return fail(FFM_E_INVALID, "null argument");
+    if (smem_bytes) *smem_bytes = s->smem_bytes;
+    if (threads) *threads = s->threads;
+    if (ctas_per_sm) *ctas_per_sm = s->ctas_per_sm;
+    if (fields_in_smem) *fields_in_smem = s->fields_in_smem ? 1 : 0;
+    return FFM_OK;
+}
+
+}  // extern "C"

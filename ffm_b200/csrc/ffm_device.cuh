@@ -1,0 +1,95 @@
+// Device-side building blocks shared by the FFM kernels (sm_100a).
+//
+//  * Philox4x32-10 counter-based draws (Salmon et al., SC'11) keyed (entity, step, episode, stream)
+//    -- the replacement for the reference's process-global generators (model/ffm_core.py:84,95,96).
+//  * IEEE helpers that pin NumPy's evaluation order: separate multiply and add (no FMA
+//    contraction), NumPy's pairwise float sum for n <= 9 (numpy/_core/src/umath/loops_utils.h.src
+//    pairwise_sum: n < 8 sequential; 8 <= n: 8 accumulators folded ((0+1)+(2+3))+((4+5)+(6+7)),
+//    remainder added sequentially).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace ffm {
+
+enum : uint32_t { STREAM_MOVE = 0, STREAM_CONFLICT = 1, STREAM_EPS = 2, STREAM_PLACE = 3 };
+
+__device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                               uint32_t k0, uint32_t k1) {
+    constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(M0, c0), lo0 = M0 * c0;
+        const uint32_t hi1 = __umulhi(M1, c2), lo1 = M1 * c2;
+        const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+        k0 += W0; k1 += W1;
+    }
+    return make_uint4(c0, c1, c2, c3);
+}
+
+// 53-bit double in [0,1) from two words, the construction of NumPy's random_sample().
+__device__ __forceinline__ double u53(uint32_t a, uint32_t b) {
+    const unsigned long long v = ((unsigned long long)(a >> 5) << 26) | (unsigned long long)(b >> 6);
+    return (double)v * (1.0 / 9007199254740992.0);
+}
+
+struct Draw2 { double u0, u1; };
+
+__device__ __forceinline__ Draw2 draw2(unsigned long long seed, uint32_t episode, uint32_t step,
+                                       uint32_t stream, uint32_t entity) {
+    const uint4 o = philox4x32_10(entity, step, episode, stream, (uint32_t)seed, (uint32_t)(seed >> 32));
+    Draw2 d;
+    d.u0 = u53(o.x, o.y);
+    d.u1 = u53(o.z, o.w);
+    return d;
+}
+
+__device__ __forceinline__ double draw_u0(unsigned long long seed, uint32_t episode, uint32_t step,
+                                          uint32_t stream, uint32_t entity) {
+    const uint4 o = philox4x32_10(entity, step, episode, stream, (uint32_t)seed, (uint32_t)(seed >> 32));
+    return u53(o.x, o.y);
+}
+
+// ---- arithmetic with NumPy's rounding sequence -------------------------------------------------
+__device__ __forceinline__ float  add_rn(float a, float b)   { return __fadd_rn(a, b); }
+__device__ __forceinline__ double add_rn(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ float  mul_rn(float a, float b)   { return __fmul_rn(a, b); }
+__device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ float  div_rn(float a, float b)   { return __fdiv_rn(a, b); }
+__device__ __forceinline__ double div_rn(double a, double b) { return __ddiv_rn(a, b); }
+__device__ __forceinline__ float  exp_t(float x)  { return expf(x); }
+__device__ __forceinline__ double exp_t(double x) { return exp(x); }
+__device__ __forceinline__ float  max_t(float a, float b)   { return fmaxf(a, b); }
+__device__ __forceinline__ double max_t(double a, double b) { return fmax(a, b); }
+template <typename S> __device__ __forceinline__ S neg_inf();
+template <> __device__ __forceinline__ float  neg_inf<float>()  { return -__int_as_float(0x7f800000); }
+template <> __device__ __forceinline__ double neg_inf<double>() { return -__longlong_as_double(0x7ff0000000000000LL); }
+
+// NumPy add.reduce over the COMPACTED candidate list (entries of p whose bit is set in mask, in
+// slot order; slot NS-1 = "stay" is always present).  n = popcount(mask) <= 9.
+template <typename S, int NS>
+__device__ __forceinline__ S np_sum_masked(const S (&p)[NS], uint32_t mask, int n) {
+    if (NS == 9 && n >= 8) {
+        S a[8];
+        if (n == 9) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) a[j] = p[j];
+        } else {
+            const int miss = __ffs(~mask & 0xFFu) - 1;   // the one absent neighbour slot
+#pragma unroll
+            for (int j = 0; j < 8; ++j) a[j] = (j < miss) ? p[j] : p[(j + 1 < NS) ? j + 1 : NS - 1];
+        }
+        S r = add_rn(add_rn(add_rn(a[0], a[1]), add_rn(a[2], a[3])),
+                     add_rn(add_rn(a[4], a[5]), add_rn(a[6], a[7])));
+        if (n == 9) r = add_rn(r, p[NS - 1]);
+        return r;
+    }
+    S r = (S)0;
+#pragma unroll
+    for (int k = 0; k < NS; ++k)
+        if ((mask >> k) & 1u) r = add_rn(r, p[k]);
+    return r;
+}
+
+}  // namespace ffm

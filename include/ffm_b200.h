@@ -1,0 +1,136 @@
+/*
+ * ffm_b200 -- C ABI of the B200-native Floor-Field-Model hot path.
+ *
+ * The reference (SoraKurihara/FFM) has no FFI layer: its drivers import the Python classes of
+ * model/ffm_*.py directly (main.py:6, run_unified_critic_training.py:16).  This header is the
+ * boundary a binding for those classes talks to (ffm_b200/model/*.py binds it with ctypes; see
+ * INTEGRATION.md).  Every entry point cites the reference interface it replaces.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no C++/torch types cross the ABI
+ *   - every function returns FFM_OK (0) or a negative FFM_E_* code and never throws;
+ *     ffm_last_error() gives the message for the calling thread
+ *   - `space` says where a caller buffer lives: FFM_HOST (pageable or pinned) or FFM_DEVICE
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); calls that take a
+ *     stream are asynchronous with respect to the host and ordered on that stream
+ *   - one host thread per handle; handles are independent
+ *   - cells are (row, col) int32 pairs at the ABI, row-major linear ids (row * width + col) inside
+ */
+#ifndef FFM_B200_H
+#define FFM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FFM_ABI_VERSION 1
+
+enum {
+    FFM_OK = 0,
+    FFM_E_INVALID = -1,     /* bad argument / configuration (reference: ValueError) */
+    FFM_E_CUDA = -2,        /* CUDA runtime failure, message in ffm_last_error() */
+    FFM_E_UNSUPPORTED = -3, /* configuration outside what the kernels cover */
+    FFM_E_STATE = -4        /* call sequence error (fields / positions not set) */
+};
+
+enum { FFM_HOST = 0, FFM_DEVICE = 1 };
+enum { FFM_NEUMANN = 4, FFM_MOORE = 8 };       /* get_neighbors(): ffm_core.py:28-34 */
+enum { FFM_F32 = 0, FFM_F64 = 1 };             /* dtype of the SFF file (ffm_core.py:17 keeps it) */
+
+/* map cell codes, Create_Map.py:9-19 / ffm_unified.py:283-286 */
+enum { FFM_CELL_FREE = 0, FFM_CELL_PED = 1, FFM_CELL_WALL = 2, FFM_CELL_EXIT = 3 };
+
+typedef struct ffm_sim_s *ffm_sim_t;
+
+/* Static configuration of a batch of B independent episodes on one map.
+ * Replaces FloorFieldModel.__init__(map_array, sff_path, N, params)  -- ffm_core.py:7-21. */
+typedef struct ffm_config {
+    int32_t abi_version;   /* FFM_ABI_VERSION */
+    int32_t device;        /* CUDA device ordinal */
+    int32_t height, width; /* map shape */
+    int32_t neighborhood;  /* FFM_NEUMANN | FFM_MOORE          params["neighborhood"] */
+    int32_t sff_dtype;     /* FFM_F32 | FFM_F64                dtype move scores are computed in */
+    int32_t n_episodes;    /* B */
+    int32_t n_max;         /* capacity: pedestrians per episode (<= 16382) */
+    int32_t track_dff;     /* 0: k_D == 0 and the caller never reads .dff -> DFF skipped entirely */
+    int32_t reserved0;
+    double k_S;            /* params["k_S"]   score = -k_S*sff + k_D*dff   ffm_core.py:77 */
+    double k_D;            /* params["k_D"] */
+    float dff_c0;          /* float32((1-decay)*(1-diffuse))               ffm_core.py:109 */
+    float dff_c1;          /* float32(decay*(1-diffuse)/len(neighbors))    ffm_core.py:113 */
+    float dff_threshold;   /* float32(1e-4)                                ffm_core.py:116-117 */
+    float reserved1;
+    uint64_t seed;         /* Philox key */
+    uint32_t episode_base; /* global id of episode 0 of this handle (multi-GPU sharding) */
+    uint32_t reserved2;
+} ffm_config_t;
+
+/* Optional recorded uniforms that override the keyed Philox streams (parity tests: "both sides
+ * consume the same recorded draws").  Layouts are per episode; NULL members fall back to Philox.
+ *   move     [B][steps][n_max]          u for np.random.choice of agent idx   ffm_core.py:84
+ *   conflict [B][steps][height*width][2] (coin u, winner u) of a target cell  ffm_core.py:95-96
+ * `first_step` is the CA step number row 0 corresponds to. */
+typedef struct ffm_draws {
+    const double *move;
+    const double *conflict;
+    int32_t steps;
+    int32_t first_step;
+    int32_t space; /* FFM_DEVICE only */
+    int32_t reserved;
+} ffm_draws_t;
+
+/* Optional per-step outputs of a rollout (device buffers supplied by the caller).
+ *   traj_cells [B][traj_steps][n_max] uint32 linear cell of every pedestrian still inside AFTER
+ *              step t, alive-rank order -- what run() appends per step (ffm_core.py:125)
+ *   traj_n     [B][traj_steps] int32 number of valid entries of each row */
+typedef struct ffm_rollout_out {
+    uint32_t *traj_cells;
+    int32_t *traj_n;
+    int32_t traj_steps;
+    int32_t reserved;
+} ffm_rollout_out_t;
+
+int ffm_abi_version(void);
+const char *ffm_last_error(void);
+
+/* ffm_core.py:7-21 (constructor) / object lifetime */
+int ffm_create(const ffm_config_t *cfg, ffm_sim_t *out);
+int ffm_destroy(ffm_sim_t sim);
+
+/* map_array (uint8 [H][W], ffm_core.py:16) and SFF ([H][W] float32 or float64 as cfg.sff_dtype,
+ * ffm_core.py:17).  Shared by all episodes of the handle. */
+int ffm_set_fields(ffm_sim_t sim, const uint8_t *map, const void *sff, int space, void *stream);
+
+/* `.positions = ...` (run_trained_ffm.py:235) / reset() (ffm_unified.py:800-812): (row, col) int32
+ * pairs [B][n_max][2] and counts [B]; zeroes the DFF and the step counters. */
+int ffm_set_positions(ffm_sim_t sim, const int32_t *pos_rc, const int32_t *n, int space, void *stream);
+/* `.positions` read (main.py:44,46) */
+int ffm_get_positions(ffm_sim_t sim, int32_t *pos_rc, int32_t *n, int space, void *stream);
+
+/* `.dff` read / assignment (run_trained_ffm.py:236); float32 [B][H][W] */
+int ffm_set_dff(ffm_sim_t sim, const float *dff, int space, void *stream);
+int ffm_get_dff(ffm_sim_t sim, float *dff, int space, void *stream);
+
+/* step() x max_steps, stopping each episode when nobody is left: the loop of run()
+ * (ffm_core.py:119-126, main.py:44-46).  Continues from the current state and step counter. */
+int ffm_rollout(ffm_sim_t sim, int32_t max_steps, const ffm_draws_t *draws, const ffm_rollout_out_t *out,
+                void *stream);
+
+/* per-episode counters since the last ffm_set_positions: steps executed (what run() returns,
+ * ffm_core.py:126) and pedestrian-steps processed (sum over steps of the alive count).
+ * Either pointer may be NULL. */
+int ffm_get_counters(ffm_sim_t sim, int32_t *steps, int64_t *ped_steps, int space, void *stream);
+
+/* number of kernels this handle has launched so far (bench.py "gpu_launches") */
+int64_t ffm_launch_count(ffm_sim_t sim);
+
+/* dynamic shared memory per CTA and CTAs/SM the rollout kernel of this handle runs with */
+int ffm_kernel_info(ffm_sim_t sim, int32_t *smem_bytes, int32_t *threads, int32_t *ctas_per_sm,
+                    int32_t *fields_in_smem);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FFM_B200_H */

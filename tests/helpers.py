@@ -1,0 +1,38 @@
+"""Shared helpers of the parity tests (the checker side: may import oracle/)."""
+import numpy as np
+
+from oracle import assets, ffm_numpy
+from oracle.inject import PhiloxSource
+
+# A move draw closer than this to a CDF boundary may legitimately resolve differently between
+# NumPy's SIMD exp and CUDA's expf/exp (<= 2 ulp each); episodes whose oracle run saw such a draw
+# are excused from bit-exact comparison (and counted).  SURVEY.md section 7, first hard part.
+MARGIN_GUARD = 2e-6
+
+
+def random_positions(map_array, n, rng):
+    free = np.argwhere(map_array == 0)
+    sel = free[rng.choice(len(free), n, replace=False)]
+    return sel.astype(np.int64)
+
+
+def pack_positions(pos_list, n_max):
+    B = len(pos_list)
+    out = np.full((B, n_max, 2), -1, dtype=np.int32)
+    n = np.zeros((B,), dtype=np.int32)
+    for e, p in enumerate(pos_list):
+        n[e] = len(p)
+        out[e, :len(p)] = p
+    return out, n
+
+
+def oracle_core_episode(map_array, sff, pos0, params, seed, episode, max_steps=None, keep_dff=False):
+    o = ffm_numpy.CoreOracle(map_array, sff, pos0, params, PhiloxSource(seed, episode))
+    r = o.run(max_steps=max_steps, keep_dff=keep_dff)
+    r["final_dff"] = o.dff.copy()
+    r["final_positions"] = o.positions.copy()
+    return r
+
+
+def traj_to_cells(traj, width):
+    return [(p[:, 0] * width + p[:, 1]).astype(np.int64) for p in traj]
