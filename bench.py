@@ -1,0 +1,408 @@
+#!/usr/bin/env python
+"""Benchmark of the FFM hot path: pedestrian-steps/s of batched evacuation episodes (BASELINE.json).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c3|c1] [--impl ours|reference]
+
+A "step" is one pass of the hot path over one batch: B episodes placed, then rolled out by the
+persistent kernel until everybody has left (or the step cap).  Workload `c2` (the configuration the
+metric is quoted on): 64x64 single-exit room, SFF only (k_D = 0, DFF not tracked), Moore,
+1024 pedestrians/episode, 4096 episodes per GPU, cap 4096 CA steps.  Episodes are keyed by global
+episode id, sharded over ranks with no data-path collective (weak scaling).
+
+`value`     ped-steps/s with the initial positions already resident in HBM (CUDA events, max over ranks)
+`e2e`       same metric through the public API with HOST buffers: pinned-host positions -> H2D ->
+            rollout -> D2H of the per-episode counters, all inside the timed region
+`roofline`  dominant kernel (ffm_core_rollout_kernel): algorithmic bytes / CUDA-event duration vs the
+            measured HBM copy peak (MEASURED_PEAKS.json)
+`cpu_baseline` the oracle port timed on this box's host cores on a bounded sample (rank 0, N = 1)
+
+`--impl reference` times the CPU implementation (oracle port; the Python reference cannot travel to
+the GPU box) on all host threads on the same workload and prints the same line with impl=reference.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "pedestrian_steps_per_sec"
+UNIT = "ped-steps/s"
+
+# algorithmic bytes per pedestrian-step, SURVEY.md section 8(d): own position read 4 B + 9 cells x
+# (map/occupancy 1 B + SFF 4 B [+ DFF 4 B]) + position write 4 B + occupancy update 2 B
+BYTES_PER_PED_STEP = {False: 55, True: 91}
+
+WORKLOADS = {
+    # name: (H, W, peds/episode, episodes/GPU, step cap, neighbourhood, k_S, k_D, track_dff)
+    "c2": dict(h=64, w=64, n=1024, episodes=4096, cap=4096, nbh="moore", k_S=3, k_D=0, track_dff=False,
+               desc="C2: 4096 episodes/GPU, 64x64 single-exit room, SFF only, Moore, 1024 peds/episode, to evacuation (cap 4096)"),
+    "c2dff": dict(h=64, w=64, n=1024, episodes=4096, cap=4096, nbh="moore", k_S=3, k_D=1, track_dff=True,
+                  desc="C2 geometry with DFF on (k_D=1, diffuse=decay=0.2)"),
+    "c1": dict(h=12, w=12, n=100, episodes=4096, cap=4096, nbh="neumann", k_S=3, k_D=1, track_dff=True,
+               desc="C1 geometry batched: 12x12 room, neumann, N=100, DFF on"),
+}
+
+
+# ------------------------------------------------------------------------------------------------
+# workload construction (product-side code only; no oracle)
+# ------------------------------------------------------------------------------------------------
+def room_map(h, w):
+    """Walled room with one exit in the middle of the top wall (the layout of Create_Map.py:9-19)."""
+    m = np.zeros((h, w), dtype=np.uint8)
+    m[0, :] = 2; m[-1, :] = 2; m[:, 0] = 2; m[:, -1] = 2
+    m[0, w // 2] = 3
+    return m
+
+
+def sff_room(m, nbh):
+    """Obstacle-blind distance to the exit: Linf for Moore, L1 for von Neumann (Create_SFF.py:24,28);
+    float32, inf on non-walkable cells."""
+    h, w = m.shape
+    er, ec = np.argwhere(m == 3)[0]
+    rr, cc = np.meshgrid(np.arange(h), np.arange(w), indexing="ij")
+    d = np.maximum(abs(rr - er), abs(cc - ec)) if nbh == "moore" else abs(rr - er) + abs(cc - ec)
+    out = np.full((h, w), np.inf, dtype=np.float32)
+    walk = (m == 0) | (m == 3)
+    out[walk] = d[walk]
+    return out
+
+
+def place(m, n, episodes, episode_base, seed):
+    """Uniform placement without replacement on free cells, keyed by GLOBAL episode id (Philox stream
+    PLACE): the n free cells with the smallest keys, in key order.  int32 [episodes, n, 2]."""
+    from ffm_b200 import philox
+    free = np.argwhere(m == 0).astype(np.int32)
+    out = np.empty((episodes, n, 2), dtype=np.int32)
+    ords = np.arange(len(free))
+    chunk = 256
+    for e0 in range(0, episodes, chunk):
+        e1 = min(episodes, e0 + chunk)
+        eps = (episode_base + np.arange(e0, e1))[:, None]
+        keys, _ = philox.draw2(seed, eps, 0, philox.STREAM_PLACE, ords[None, :])
+        sel = np.argsort(keys, axis=1, kind="stable")[:, :n]
+        out[e0:e1] = free[sel]
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thr = threading.Thread(target=self._read, daemon=True)
+            self.thr.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); power.append(float(f[2]))
+            except ValueError:
+                continue
+            for nme, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm (the only place this file touches oracle/)
+# ------------------------------------------------------------------------------------------------
+def _cpu_worker(args):
+    """One episode of the NumPy port (oracle/ffm_numpy.py == model/ffm_core.py semantics) for at most
+    `budget` seconds; returns (ped_steps, seconds, steps)."""
+    wl, pos0, budget, seed = args
+    from oracle import ffm_numpy
+
+    class MT:   # the reference's own draw source: global MT19937 (ffm_core.py:84,95,96)
+        rs = np.random.RandomState(seed)
+        def move(self, t, i, cdf=None): return self.rs.random_sample()
+        def coin(self, t, c): return self.rs.random_sample()
+        def winner(self, t, c, k): return self.rs.random_sample()
+
+    m = room_map(wl["h"], wl["w"])
+    o = ffm_numpy.CoreOracle(m, sff_room(m, wl["nbh"]), pos0,
+                             {"k_S": wl["k_S"], "k_D": wl["k_D"], "neighborhood": wl["nbh"]}, MT())
+    t0 = time.perf_counter()
+    ped = 0
+    while o.positions.shape[0] > 0 and o.t < wl["cap"] and time.perf_counter() - t0 < budget:
+        ped += o.positions.shape[0]
+        o.step()
+    return ped, time.perf_counter() - t0, o.t
+
+
+def cpu_numpy_port(wl, budget_s, seed=1234, cores=None):
+    import multiprocessing as mp
+    cores = cores or os.cpu_count() or 1
+    m = room_map(wl["h"], wl["w"])
+    pos = place(m, wl["n"], cores, 0, seed)
+    with mp.get_context("fork").Pool(cores) as pool:
+        t0 = time.perf_counter()
+        res = pool.map(_cpu_worker, [(wl, pos[i].astype(np.int64), budget_s, seed + i) for i in range(cores)])
+        wall = time.perf_counter() - t0
+    ped = sum(r[0] for r in res)
+    return dict(value=ped / wall, unit=UNIT, cores=cores, kind="port",
+                sample=f"{cores} processes x 1 episode of the NumPy port (oracle/ffm_numpy.py, global-MT19937 draws like "
+                       f"the reference), each cut at {budget_s:.0f} s: {ped} ped-steps, {sum(r[2] for r in res)} CA steps "
+                       f"(dense early phase of the episode, where the port is fastest per ped-step)")
+
+
+def cpu_c_port(wl, episodes, seed=1234, cores=None):
+    """C restatement (oracle/c), one episode per thread; full episodes."""
+    from oracle import c_oracle
+    cores = cores or os.cpu_count() or 1
+    m = room_map(wl["h"], wl["w"])
+    pos = place(m, wl["n"], episodes, 0, seed)
+    t0 = time.perf_counter()
+    steps, ped = c_oracle.run_core_batch(m, sff_room(m, wl["nbh"]), pos, np.full((episodes,), wl["n"], np.int32),
+                                        {"k_S": wl["k_S"], "k_D": wl["k_D"], "neighborhood": wl["nbh"]},
+                                        seed=seed, episode_base=0, max_steps=wl["cap"], threads=cores,
+                                        track_dff=wl["track_dff"])
+    wall = time.perf_counter() - t0
+    return dict(value=float(ped.sum()) / wall, unit=UNIT, cores=cores, kind="port",
+                sample=f"{episodes} full episodes of the C restatement (oracle/c/ffm_oracle.c, keyed Philox draws), "
+                       f"{cores} threads, {int(ped.sum())} ped-steps in {wall:.1f} s")
+
+
+def have_c_oracle():
+    try:
+        from oracle import c_oracle
+        return c_oracle.available()
+    except Exception:
+        return False
+
+
+def run_reference_arm(args, wl):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    times, vals, last = [], [], None
+    for it in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        if have_c_oracle() and not args.numpy_port:
+            last = cpu_c_port(wl, episodes=max(cores, 32), seed=1234 + it, cores=cores)
+        else:
+            last = cpu_numpy_port(wl, budget_s=args.cpu_budget, seed=1234 + it, cores=cores)
+        if it >= args.warmup:
+            times.append(time.perf_counter() - t0)
+            vals.append(last["value"])
+    v = float(np.mean(vals))
+    last["value"] = v
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(times)), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": wl["desc"], "note": "each step = bounded sample of the workload on host cores"},
+            "cpu_baseline": last,
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--episodes", type=int, default=None, help="episodes per GPU (default: workload's)")
+    ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU work for the cpu_baseline sample")
+    ap.add_argument("--numpy-port", action="store_true", help="reference arm: force the NumPy port")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--seed", type=lambda s: int(s, 0), default=0x5EED0002)
+    args = ap.parse_args()
+    wl = dict(WORKLOADS[args.workload])
+    if args.episodes:
+        wl["episodes"] = args.episodes
+    if args.impl == "reference":
+        run_reference_arm(args, wl)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from ffm_b200 import BatchSim
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the FFM kernels have no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    if args.warmup < 3:
+        args.warmup = 3
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    B, N, cap = wl["episodes"], wl["n"], wl["cap"]
+    m = room_map(wl["h"], wl["w"])
+    sff = sff_room(m, wl["nbh"])
+    params = {"k_S": wl["k_S"], "k_D": wl["k_D"], "diffuse": 0.2, "decay": 0.2, "neighborhood": wl["nbh"]}
+    ep_base = rank * B                                   # global episode ids: results independent of N
+    pos_np = place(m, N, B, ep_base, args.seed)
+    n_np = np.full((B,), N, dtype=np.int32)
+    sim = BatchSim(m, sff, B, N, params, seed=args.seed, episode_base=ep_base, track_dff=wl["track_dff"], device=local)
+    info = sim.kernel_info()
+    pos_dev = torch.from_numpy(pos_np).cuda()
+    n_dev = torch.from_numpy(n_np).cuda()
+    pos_pin = torch.from_numpy(pos_np).pin_memory()
+    n_pin = torch.from_numpy(n_np).pin_memory()
+    steps_dev = torch.zeros(B, dtype=torch.int32, device="cuda")
+    ped_dev = torch.zeros(B, dtype=torch.int64, device="cuda")
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")   # > 126 MB L2
+
+    def one_pass_resident(ev=None):
+        if ev: ev[0].record()
+        sim.set_positions(pos_dev, n_dev)
+        if ev: ev[1].record()
+        sim.rollout(cap)
+        if ev: ev[2].record()
+        sim.counters_into(steps_dev, ped_dev)
+        if ev: ev[3].record()
+
+    for _ in range(args.warmup):
+        flush.fill_(1)
+        one_pass_resident()
+    barrier()
+    ped_per_pass = int(ped_dev.sum().item())
+    steps_host = steps_dev.cpu().numpy()
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
+    l0 = sim.launch_count
+    barrier()
+    for k in range(args.steps):
+        flush.fill_(k & 0xFF)                 # L2 flush between timed iterations (not timed)
+        one_pass_resident(evs[k])
+    barrier()
+    launches = sim.launch_count - l0
+    total_ms = sum(e[0].elapsed_time(e[3]) for e in evs)
+    kern_ms = sum(e[1].elapsed_time(e[2]) for e in evs) / args.steps
+
+    # ---- e2e: host buffers in, host counters out ------------------------------------------------
+    e2e_evs = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(args.steps)]
+    for _ in range(2):
+        sim.set_positions(pos_pin.numpy(), n_pin.numpy()); sim.rollout(cap); sim.counters()
+    barrier()
+    e2e_ped = 0
+    for k in range(args.steps):
+        flush.fill_(k & 0xFF)
+        e2e_evs[k][0].record()
+        sim.set_positions(pos_pin.numpy(), n_pin.numpy())       # H2D of this step's inputs
+        sim.rollout(cap)
+        st_h, ped_h = sim.counters()                             # D2H of the step's result (+ sync)
+        e2e_evs[k][1].record()
+        e2e_ped += int(ped_h.sum())
+    barrier()
+    clocks = sampler.stop()
+    e2e_ms = sum(e[0].elapsed_time(e[1]) for e in e2e_evs)
+
+    t = torch.tensor([total_ms, e2e_ms, kern_ms, float(ped_per_pass), float(e2e_ped)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        total_ms, e2e_ms, kern_ms = tmax[0].item(), tmax[1].item(), tmax[2].item()
+        ped_all, e2e_ped_all = tsum[3].item(), tsum[4].item()
+    else:
+        ped_all, e2e_ped_all = float(ped_per_pass), float(e2e_ped)
+
+    if rank == 0:
+        value = ped_all * args.steps / (total_ms * 1e-3)
+        e2e_value = e2e_ped_all / (e2e_ms * 1e-3)
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except OSError:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        alg_bytes = BYTES_PER_PED_STEP[wl["track_dff"]] * ped_per_pass
+        if wl["track_dff"]:
+            alg_bytes += 8 * wl["h"] * wl["w"] * int(steps_host.sum())      # DFF field read+write per episode-step
+        achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
+        prof = {}
+        try:
+            prof = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json"))).get(args.workload, {})
+        except OSError:
+            pass
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": wl["desc"], "episodes_per_gpu": B, "peds_per_episode": N, "map": f"{wl['h']}x{wl['w']}",
+                       "step_cap": cap, "parallelism": f"episodes sharded over {world} GPU(s), no collective",
+                       "l2": "256 MiB L2 flush between timed iterations (untimed)",
+                       "kernel": {"name": "ffm_core_rollout_kernel", **info},
+                       "mean_evacuation_steps": float(steps_host.mean()), "ped_steps_per_pass_per_gpu": ped_per_pass},
+            "episodes_per_sec": B * world * args.steps / (total_ms * 1e-3),
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(pos_np.nbytes + n_np.nbytes),
+                    "d2h_bytes_per_step": int(B * 4 + B * 8), "ms_per_step": e2e_ms / args.steps},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": prof.get("dram_bytes_per_launch"),
+                         "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6650 GB/s",
+                         "kernel_ms": kern_ms, "algorithmic_bytes_per_launch": alg_bytes,
+                         "note": "fields are shared-memory resident: the kernel moves its algorithmic bytes through SMEM, "
+                                 "not HBM; see DESIGN.md (roofline) for the SMEM-bandwidth and issue-slot views"},
+        }
+        if not args.no_cpu and world == 1:
+            try:
+                if have_c_oracle():
+                    line["cpu_baseline"] = cpu_c_port(wl, episodes=max(os.cpu_count() or 1, 32))
+                    line["cpu_baseline_numpy"] = cpu_numpy_port(wl, budget_s=min(args.cpu_budget, 10.0))
+                else:
+                    line["cpu_baseline"] = cpu_numpy_port(wl, budget_s=args.cpu_budget)
+            except Exception as ex:   # the baseline is reporting, never the product
+                line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": f"failed: {ex!r}"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

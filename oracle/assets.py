@@ -32,7 +32,11 @@ def sff_norm_min(map_array, metric, dtype=np.float64):
                     if metric == "L1":
                         d = abs(i - ex) + abs(j - ey)
                     elif metric == "L2":
-                        d = np.hypot(i - ex, j - ey)
+                        # Create_SFF.py:26 calls np.hypot.  The shipped data/sff/distance_L2.npy equals
+                        # the CORRECTLY ROUNDED hypot on every cell (== IEEE sqrt of the exact integer
+                        # dx^2+dy^2, == math.hypot); this container's np.hypot is 1 ulp off on 2 of
+                        # 2500 cells, so the shipped file -- the reference's own golden vector -- wins.
+                        d = np.sqrt(np.float64(int(i - ex) ** 2 + int(j - ey) ** 2))
                     else:
                         d = max(abs(i - ex), abs(j - ey))
                     out[i, j] = min(out[i, j], d)

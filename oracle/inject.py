@@ -236,3 +236,20 @@ def run_reference(model, source, max_steps=None, log_probs=False, keep_dff=True)
             t += 1
     return dict(steps=t, traj=traj, dff=dffs, min_margin=st.min_margin, n_move=st.n_move,
                 n_coin=st.n_coin, n_winner=st.n_winner, n_eps=st.n_eps, probs_log=st.probs_log)
+
+
+class BufferSource:
+    """Replays recorded draws: ``move[t, idx]`` dense, conflicts as a dict {(t, cell): (coin, winner)}."""
+
+    def __init__(self, move, conflict):
+        self._move = move
+        self._conflict = conflict
+
+    def move(self, step, idx, cdf=None):
+        return float(self._move[step, idx])
+
+    def coin(self, step, cell):
+        return float(self._conflict[(step, cell)][0])
+
+    def winner(self, step, cell, k):
+        return float(self._conflict[(step, cell)][1])

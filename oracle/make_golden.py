@@ -1,0 +1,114 @@
+"""Generates tests/golden/* from the UNMODIFIED reference (container only; needs /root/reference).
+
+    python -m oracle.make_golden
+
+Fixtures
+  core_*.npz          full episodes of model/ffm_core.py FloorFieldModel under keyed Philox draws
+                      (oracle/inject.py): inputs, per-step positions, per-step DFF, step count
+  stock_main_seed42.npz  the stock `main.py` run (config/default_config.yaml, seed 42, the
+                      reference's own MT19937 streams) with every consumed draw recorded, so the run
+                      can be replayed through the injected-draw buffers of the CUDA path
+  shipped_assets.json sha256 of the arrays the reference ships (data/maps, data/sff)
+"""
+import hashlib
+import json
+import os
+import random
+import tempfile
+
+import numpy as np
+
+from . import assets, inject
+
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+REF = inject.REFERENCE_ROOT
+
+
+def _flatten(traj):
+    counts = np.array([len(p) for p in traj], dtype=np.int32)
+    flat = np.concatenate([p.reshape(-1, 2) for p in traj]).astype(np.int16) if traj else np.zeros((0, 2), np.int16)
+    return flat, counts
+
+
+def core_case(name, h, w, N, nbh, metric, dtype, seed, episode, extra=None, dff_every=1):
+    ref = inject.import_reference("ffm_core")
+    m = assets.room_map(h, w)
+    sff = assets.sff_norm_min(m, metric, dtype)
+    params = {"neighborhood": nbh, **(extra or {})}
+    with tempfile.TemporaryDirectory() as tmp:
+        p = os.path.join(tmp, "sff.npy")
+        np.save(p, sff)
+        np.random.seed(seed)
+        model = ref.FloorFieldModel(m, p, N, params)
+        pos0 = np.array(model.positions, dtype=np.int16)
+        r = inject.run_reference(model, inject.PhiloxSource(seed, episode), log_probs=True)
+    flat, counts = _flatten(r["traj"])
+    dff = np.stack(r["dff"][::dff_every]).astype(np.float32)
+    # probabilities of the first 64 draws, for the 1e-6 relative probability bar
+    pl = r["probs_log"][:64]
+    probs = np.zeros((len(pl), 9), np.float64)
+    probs_meta = np.zeros((len(pl), 3), np.int32)
+    for i, (t, idx, pr) in enumerate(pl):
+        probs[i, :len(pr)] = pr
+        probs_meta[i] = (t, idx, len(pr))
+    np.savez_compressed(
+        os.path.join(OUT, name + ".npz"), map=m, sff=sff, pos0=pos0, params=json.dumps(params),
+        seed=np.uint64(seed), episode=np.uint32(episode), steps=np.int32(r["steps"]), traj=flat,
+        traj_counts=counts, dff=dff, dff_every=np.int32(dff_every), min_margin=np.float64(r["min_margin"]),
+        n_move=np.int32(r["n_move"]), n_coin=np.int32(r["n_coin"]), n_winner=np.int32(r["n_winner"]),
+        probs=probs, probs_meta=probs_meta)
+    print(name, "steps", r["steps"], "min_margin %.2e" % r["min_margin"], "draws", r["n_move"], r["n_coin"], r["n_winner"])
+
+
+def stock_main():
+    """main.py:17-46 with its own generators; records the draws it consumes."""
+    import yaml
+    ref = inject.import_reference("ffm_core")
+    with open(os.path.join(REF, "config", "default_config.yaml")) as f:
+        config = yaml.safe_load(f)
+    np.random.seed(config["seed"])
+    random.seed(config["seed"])
+    m = np.load(os.path.join(REF, config["map"]))
+    model = ref.FloorFieldModel(m, os.path.join(REF, config["sff"]), config["N"], config["params"])
+    pos0 = np.array(model.positions, dtype=np.int16)
+    H, W = m.shape
+    rec = inject.RecordingSource(inject.StockSource(), 600, config["N"], H * W)
+    r = inject.run_reference(model, rec, keep_dff=False)
+    T = r["steps"]
+    cf = rec.conflict_buf[:T]
+    tt, cc = np.nonzero(~np.isnan(cf[:, :, 0]))
+    flat, counts = _flatten(r["traj"])
+    np.savez_compressed(
+        os.path.join(OUT, "stock_main_seed42.npz"), params=json.dumps(config["params"]), pos0=pos0,
+        steps=np.int32(T), traj=flat, traj_counts=counts, move=rec.move_buf[:T],
+        conflict_t=tt.astype(np.int32), conflict_cell=cc.astype(np.int32), conflict_u=cf[tt, cc],
+        min_margin=np.float64(r["min_margin"]), final_dff=np.array(model.dff, dtype=np.float32))
+    print("stock main.py seed 42:", T, "steps,", int(counts[:-1].sum()) + config["N"], "ped-steps, min_margin %.2e" % r["min_margin"])
+
+
+def shipped():
+    out = {}
+    for rel in ("data/maps/simple_room.npy", "data/sff/distance_L1.npy", "data/sff/distance_L2.npy", "data/sff/distance_Linf.npy"):
+        a = np.load(os.path.join(REF, rel))
+        out[rel] = dict(shape=list(a.shape), dtype=str(a.dtype), sha256=hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest(),
+                        n_inf=int(np.isinf(a).sum()) if a.dtype.kind == "f" else 0)
+    with open(os.path.join(OUT, "shipped_assets.json"), "w") as f:
+        json.dump(out, f, indent=1, sort_keys=True)
+    print("shipped assets:", {k: v["sha256"][:12] for k, v in out.items()})
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    core_case("core_12x12_neumann_f32", 12, 12, 50, "neumann", "L1", np.float32, 11, 3)
+    core_case("core_12x12_moore_f32_full", 12, 12, 100, "moore", "L1", np.float32, 12, 0)
+    core_case("core_50x50_moore_f64", 50, 50, 100, "moore", "L2", np.float64, 13, 5, dff_every=20)
+    core_case("core_50x50_neumann_f64", 50, 50, 100, "neumann", "L1", np.float64, 14, 1, dff_every=20)
+    core_case("core_20x20_moore_params", 20, 20, 150, "moore", "Linf", np.float32, 15, 9,
+              extra={"k_S": 2.5, "k_D": 0.7, "diffuse": 0.3, "decay": 0.1}, dff_every=10)
+    core_case("core_16x24_moore_kd0", 16, 24, 60, "moore", "L2", np.float32, 16, 2, extra={"k_D": 0}, dff_every=10)
+    stock_main()
+    shipped()
+
+
+if __name__ == "__main__":
+    main()

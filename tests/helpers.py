@@ -36,3 +36,21 @@ def oracle_core_episode(map_array, sff, pos0, params, seed, episode, max_steps=N
 
 def traj_to_cells(traj, width):
     return [(p[:, 0] * width + p[:, 1]).astype(np.int64) for p in traj]
+
+
+import json
+import os
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+CORE_FIXTURES = ["core_12x12_neumann_f32", "core_12x12_moore_f32_full", "core_50x50_moore_f64",
+                 "core_50x50_neumann_f64", "core_20x20_moore_params", "core_16x24_moore_kd0"]
+
+
+def load_golden(name):
+    z = np.load(os.path.join(GOLDEN, name + ".npz"))
+    g = {k: z[k] for k in z.files}
+    g["params"] = json.loads(str(g["params"]))
+    counts = g["traj_counts"]
+    offs = np.concatenate([[0], np.cumsum(counts)])
+    g["traj_list"] = [g["traj"][offs[t]:offs[t + 1]].astype(np.int64) for t in range(len(counts))]
+    return g
