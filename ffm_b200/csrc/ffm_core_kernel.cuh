@@ -1,16 +1,29 @@
 // Persistent rollout kernel of the base floor-field CA: one CTA per episode, all steps in-kernel.
 //
 // Reproduces, per step, FloorFieldModel.step() + update_dff() of the reference
-// (model/ffm_core.py:36-117) and, around it, the loop of run() (ffm_core.py:119-126):
+// (model/ffm_core.py:36-117) and, around it, the loop of run() (ffm_core.py:119-126).
 //
-//   phase A  candidate build, forced exit, SFF/DFF move probabilities, keyed draw -> target cell
-//            (ffm_core.py:40-88)
-//   phase B  same-target conflicts: lone claimant moves; k >= 2 claimants -> coin, then the
-//            floor(u*k)-th claimant in ascending agent index moves; DFF footprint += 1
-//            (ffm_core.py:90-98)
-//   phase C  exit removal as a STABLE compaction, so alive rank == the reference's array index
-//            (ffm_core.py:101-102), occupancy/owner grid update, optional trajectory row
-//   phase D  DFF decay + diffusion with NumPy's float32 rounding sequence (ffm_core.py:106-117)
+// The reference walks the pedestrians one by one; here a step is four block-wide phases over
+// shared-memory state, with the expensive work compacted onto dense work lists so that warps run
+// with full lanes even when most of a packed crowd cannot move:
+//
+//   A1 (every live slot)   8/4 neighbour cells -> candidate mask (passable and unoccupied at time t,
+//                          ffm_core.py:52-60).  No candidate: no request, no draw (:63).  An exit
+//                          among the candidates: forced request, no draw (:66-72) -> request list.
+//                          Otherwise -> draw list.
+//   A2 (draw list)         score = -k_S*sff + k_D*dff, exp(score - max), NumPy-ordered sum,
+//                          normalise, float64 CDF, keyed uniform -> target (:74-88) -> request list
+//   B  (request list)      same-target conflicts: lone claimant moves; k >= 2 claimants -> coin, then
+//                          the floor(u*k)-th claimant in ascending agent index moves; DFF footprint
+//                          += 1 (:90-98).  Claimants are found by looking at the owners of the
+//                          target's neighbour cells (no atomics, deterministic).
+//   C  (moved requests)    apply: owner grid, position; pedestrians that reached an exit clear their
+//                          alive bit (:101-102)
+//   D  (every cell)        DFF decay + diffusion with NumPy's float32 rounding sequence (:106-117)
+//
+// Pedestrians keep a stable SLOT; the reference's array index (which shifts when somebody leaves,
+// :102) is the slot's alive rank = prefix popcount over the alive bitmap, recomputed only in steps
+// where somebody left.  Slots are physically re-packed when a quarter of them are dead.
 //
 // HBM is touched only by the prologue (fields + positions in), the epilogue (state out) and the
 // optional trajectory rows; everything a step reads or writes lives in shared memory when the
@@ -18,16 +31,15 @@
 //
 // Shared-memory state of an episode
 //   grid  u16[HW + 2*(W+1)]  bits 15..14 cell type (0 free, 1 wall, 2 exit, 3 other), bits 13..0
-//                            1 + alive rank of the pedestrian standing there (0 = empty); a guard
-//                            band of W+1 "wall" entries on both ends absorbs the neighbour reads
-//                            of border (exit) cells
+//                            1 + slot of the pedestrian standing there (0 = empty); a guard band of
+//                            W+1 "wall" entries on both ends absorbs neighbour reads of border cells
 //   score S[HW]              -k_S * sff  (S = float | double, the dtype NumPy computes in)
 //   dffA/dffB f32[HW]        dynamic floor field, ping-pong
-//   posA/posB PosT[n_max]    linear cell per pedestrian, alive-rank order, ping-pong
-//                            (PosT = u16 when H*W <= 65536, else u32)
-//   tgt   PosT[n_max]        requested cell this step (all-ones = no request)
-//   nxt   PosT[n_max]        cell after conflict resolution
-//   wcnt  u32[n_max/32+2]    survivors per 32-pedestrian group (compaction scan input)
+//   pos   PosT[n_max]        linear cell per slot (PosT = u16 when H*W <= 65536, else u32)
+//   tgt   PosT[n_max]        requested cell this step per slot (all-ones = no request)
+//   work  u32[n_max]         draw list: slot | candidate mask << 16
+//   req   u16[n_max]         request list: slot | 0x8000 once the request is granted
+//   alive u32[n_max/32+1]    alive bitmap;  wpre u32[n_max/32+1] exclusive prefix popcounts
 #pragma once
 #include "ffm_device.cuh"
 
@@ -35,6 +47,7 @@ namespace ffm {
 
 constexpr uint32_t TYPE_SHIFT = 14;
 constexpr uint32_t OCC_MASK = 0x3FFFu;
+constexpr uint32_t TYPE_BITS = 3u << TYPE_SHIFT;
 constexpr uint32_t TYPE_FREE = 0, TYPE_WALL = 1, TYPE_EXIT = 2, TYPE_OTHER = 3;
 constexpr int MAX_PEDS = 16382;
 
@@ -44,7 +57,7 @@ struct RolloutParams {
     const uint16_t* type_grid;   // [HW + 2*(W+1)] type bits only, guard band included
     const void* score;           // [HW] S
     float kd, c0, c1, thr;
-    uint32_t* pos;               // [B][n_max] linear cells (always u32 in HBM)
+    uint32_t* pos;               // [B][n_max] linear cells, alive-rank order (always u32 in HBM)
     int32_t* n_alive;            // [B]
     int32_t* t_done;             // [B]
     unsigned long long* ped_steps;  // [B]
@@ -61,7 +74,7 @@ struct RolloutParams {
 };
 
 struct SmemLayout {
-    uint32_t grid, score, dffA, dffB, posA, posB, tgt, nxt, wcnt, total;
+    uint32_t score, dffA, dffB, grid, pos, tgt, work, req, alive, wpre, ctr, total;
 };
 
 __host__ __device__ inline uint32_t align16(uint32_t x) { return (x + 15u) & ~15u; }
@@ -69,17 +82,20 @@ __host__ __device__ inline uint32_t align16(uint32_t x) { return (x + 15u) & ~15
 __host__ __device__ inline SmemLayout make_layout(int HW, int W, int n_max, int sizeof_score, bool dff,
                                                   bool fields_in_smem) {
     const uint32_t ps = (HW <= 65536) ? 2u : 4u;   // sizeof(PosT)
+    const uint32_t nw = (uint32_t)(n_max + 31) / 32 + 1;
     SmemLayout L;
     uint32_t o = 0;
     L.score = o; if (fields_in_smem) o = align16(o + (uint32_t)HW * sizeof_score);
     L.dffA = o;  if (fields_in_smem && dff) o = align16(o + (uint32_t)HW * 4u);
     L.dffB = o;  if (fields_in_smem && dff) o = align16(o + (uint32_t)HW * 4u);
     L.grid = o;  o = align16(o + (uint32_t)(HW + 2 * (W + 1)) * 2u);
-    L.posA = o;  o = align16(o + (uint32_t)n_max * ps);
-    L.posB = o;  o = align16(o + (uint32_t)n_max * ps);
+    L.pos = o;   o = align16(o + (uint32_t)n_max * ps);
     L.tgt = o;   o = align16(o + (uint32_t)n_max * ps);
-    L.nxt = o;   o = align16(o + (uint32_t)n_max * ps);
-    L.wcnt = o;  o = align16(o + (uint32_t)(n_max / 32 + 2) * 4u);
+    L.work = o;  o = align16(o + (uint32_t)n_max * 4u);
+    L.req = o;   o = align16(o + (uint32_t)n_max * 2u);
+    L.alive = o; o = align16(o + nw * 4u);
+    L.wpre = o;  o = align16(o + nw * 4u);
+    L.ctr = o;   o = align16(o + 8u * 4u);
     L.total = o;
     return L;
 }
@@ -89,9 +105,26 @@ template <int NBR> __device__ __forceinline__ int nbr_dr(int k);
 template <int NBR> __device__ __forceinline__ int nbr_dc(int k);
 template <> __device__ __forceinline__ int nbr_dr<4>(int k) { return k == 0 ? -1 : (k == 1 ? 1 : 0); }
 template <> __device__ __forceinline__ int nbr_dc<4>(int k) { return k == 2 ? -1 : (k == 3 ? 1 : 0); }
-template <> __device__ __forceinline__ int nbr_dr<8>(int k) { return k < 3 ? -1 : (k < 5 ? 0 : 1); }
-template <> __device__ __forceinline__ int nbr_dc<8>(int k) {
-    return (k == 0 || k == 3 || k == 5) ? -1 : ((k == 1 || k == 6) ? 0 : 1);
+template <> __device__ __forceinline__ int nbr_dr<8>(int k) { const int q = k + (k >= 4 ? 1 : 0); return q / 3 - 1; }
+template <> __device__ __forceinline__ int nbr_dc<8>(int k) { const int q = k + (k >= 4 ? 1 : 0); return q % 3 - 1; }
+template <int NBR> __device__ __forceinline__ int nbr_off(int k, int W) { return nbr_dr<NBR>(k) * W + nbr_dc<NBR>(k); }
+
+__device__ __forceinline__ uint32_t lanemask_lt() {
+    uint32_t m;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+    return m;
+}
+
+// Warp-aggregated append of `value` to a shared-memory list (one atomic per warp).  All 32 lanes
+// must call it; lanes with pred == false append nothing.
+template <typename T>
+__device__ __forceinline__ void warp_append(bool pred, T value, T* list, uint32_t* counter, int lane) {
+    const uint32_t bal = __ballot_sync(0xffffffffu, pred);
+    if (bal == 0u) return;
+    uint32_t base = 0;
+    if (lane == 0) base = atomicAdd(counter, (uint32_t)__popc(bal));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (pred) list[base + __popc(bal & lanemask_lt())] = value;
 }
 
 template <typename S, typename PosT, int NBR, bool DFF, bool FIELDS_IN_SMEM, int THREADS>
@@ -104,14 +137,17 @@ ffm_core_rollout_kernel(const RolloutParams P) {
     const int W = P.W, HW = P.HW, H = P.H;
     const int G = W + 1;  // guard band
     const SmemLayout L = make_layout(HW, W, P.n_max, (int)sizeof(S), DFF, FIELDS_IN_SMEM);
+    constexpr uint32_t NONE_CELL = (uint32_t)(PosT)~(PosT)0;
+    constexpr uint32_t EXIT_EMPTY = TYPE_EXIT << TYPE_SHIFT;
 
     uint16_t* grid = reinterpret_cast<uint16_t*>(smem_raw + L.grid) + G;   // grid[-G .. HW+G)
-    constexpr uint32_t NONE_CELL = (uint32_t)(PosT)~(PosT)0;
-    PosT* posA = reinterpret_cast<PosT*>(smem_raw + L.posA);
-    PosT* posB = reinterpret_cast<PosT*>(smem_raw + L.posB);
+    PosT* pos = reinterpret_cast<PosT*>(smem_raw + L.pos);
     PosT* tgt = reinterpret_cast<PosT*>(smem_raw + L.tgt);
-    PosT* nxt = reinterpret_cast<PosT*>(smem_raw + L.nxt);
-    uint32_t* wcnt = reinterpret_cast<uint32_t*>(smem_raw + L.wcnt);
+    uint32_t* work = reinterpret_cast<uint32_t*>(smem_raw + L.work);
+    uint16_t* req = reinterpret_cast<uint16_t*>(smem_raw + L.req);
+    uint32_t* alive = reinterpret_cast<uint32_t*>(smem_raw + L.alive);
+    uint32_t* wpre = reinterpret_cast<uint32_t*>(smem_raw + L.wpre);
+    uint32_t* ctr = reinterpret_cast<uint32_t*>(smem_raw + L.ctr);   // [parity][n_work, n_req, n_exit, -]
 
     const S* score;
     float* dffA = nullptr;
@@ -135,23 +171,26 @@ ffm_core_rollout_kernel(const RolloutParams P) {
         }
     }
 
-    // ---- prologue: occupancy/owner grid and positions ------------------------------------------
+    // ---- prologue: owner grid, positions, alive bitmap ------------------------------------------
     for (int c = tid; c < HW + 2 * G; c += THREADS) grid[c - G] = P.type_grid[c];
-    int n = P.n_alive[e];
+    int n = P.n_alive[e];        // pedestrians still inside
+    int n_slots = n;             // slots in use (live + dead since the last re-pack)
     const int t0 = P.t_done[e];
     uint32_t* gpos = P.pos + (size_t)e * P.n_max;
-    for (int i = tid; i < n; i += THREADS) posA[i] = (PosT)gpos[i];
+    for (int i = tid; i < n; i += THREADS) pos[i] = (PosT)gpos[i];
+    for (int w = tid; w <= (n + 31) / 32; w += THREADS) {
+        const int lo = w * 32;
+        alive[w] = (lo + 32 <= n) ? 0xffffffffu : (lo < n ? ((1u << (n - lo)) - 1u) : 0u);
+        wpre[w] = (uint32_t)(lo < n ? lo : n);
+    }
+    if (tid < 8) ctr[tid] = 0u;
     __syncthreads();
-    for (int i = tid; i < n; i += THREADS) grid[posA[i]] |= (uint16_t)(i + 1);
+    for (int i = tid; i < n; i += THREADS) grid[pos[i]] |= (uint16_t)(i + 1);
     __syncthreads();
 
     const uint32_t episode = P.episode_base + (uint32_t)e;
     const double* mv_draws = P.move_draws ? P.move_draws + (size_t)e * P.draw_steps * P.n_max : nullptr;
     const double* cf_draws = P.conflict_draws ? P.conflict_draws + (size_t)e * P.draw_steps * HW * 2 : nullptr;
-
-    int off[NBR];
-#pragma unroll
-    for (int k = 0; k < NBR; ++k) off[k] = nbr_dr<NBR>(k) * W + nbr_dc<NBR>(k);
 
     unsigned long long ped_steps = 0;
     int tl = 0;
@@ -160,168 +199,245 @@ ffm_core_rollout_kernel(const RolloutParams P) {
         ped_steps += (unsigned long long)n;
         const int di = (int)t - P.draw_first;   // row in the injected-draw buffers
         const bool inj = di >= 0 && di < P.draw_steps;
+        uint32_t* cnt = ctr + ((tl & 1) << 2);          // this step's counters
+        if (tid == 0) {                                   // next step's counters (idle this step)
+            uint32_t* nx = ctr + (((tl + 1) & 1) << 2);
+            nx[0] = 0u; nx[1] = 0u; nx[2] = 0u;
+        }
 
-        // ================= phase A: choose a target cell ========================================
-        for (int i = tid; i < n; i += THREADS) {
-            const uint32_t c = posA[i];
-            uint32_t m = 0, ex = 0;
+        // ================= A1: candidate masks, forced exits ====================================
+        for (int base = 0; base < n_slots; base += THREADS) {
+            const int s = base + tid;
+            bool need_draw = false, forced = false;
+            uint32_t m = 0;
+            if (s < n_slots && ((alive[s >> 5] >> (s & 31)) & 1u)) {
+                const int c = (int)pos[s];
+                uint32_t ex = 0;
 #pragma unroll
-            for (int k = 0; k < NBR; ++k) {
-                const uint32_t g = grid[(int)c + off[k]];
-                // passable (map 0 or 3, ffm_core.py:52-53) and not occupied at time t (:57-60)
-                const bool is_exit = g == (TYPE_EXIT << TYPE_SHIFT);
-                if (g == 0u || is_exit) m |= 1u << k;
-                if (is_exit) ex |= 1u << k;
-            }
-            uint32_t target = NONE_CELL;
-            if (m != 0u) {
-                if ((grid[c] >> TYPE_SHIFT) == TYPE_EXIT) ex |= 1u << NBR;   // "stay" joins the candidates (:64)
-                if (ex != 0u) {
-                    // forced exit: first exit cell in candidate order, no draw (:66-72)
-                    const int k = __ffs(ex) - 1;
-                    target = (k == NBR) ? c : (uint32_t)((int)c + off[k]);
-                } else {
-                    const uint32_t mfull = m | (1u << NBR);
-                    const int ncand = __popc(mfull);
-                    S p[NBR + 1];
-                    S mx = neg_inf<S>();
-#pragma unroll
-                    for (int k = 0; k <= NBR; ++k) {
-                        p[k] = neg_inf<S>();
-                        if ((mfull >> k) & 1u) {
-                            const int cc = (k == NBR) ? (int)c : (int)c + off[k];
-                            S s = score[cc];                                   // -k_S * sff
-                            if (DFF) s = add_rn(s, (S)mul_rn(P.kd, dffA[cc]));  // + k_D * dff  (:77)
-                            p[k] = s;
-                            mx = max_t(mx, s);
-                        }
+                for (int k = 0; k < NBR; ++k) {
+                    const uint32_t g = grid[c + nbr_off<NBR>(k, W)];
+                    // passable (map 0 or 3, ffm_core.py:52-53) and not occupied at time t (:57-60)
+                    if (g == 0u || g == EXIT_EMPTY) m |= 1u << k;
+                    if (g == EXIT_EMPTY) ex |= 1u << k;
+                }
+                uint32_t target = NONE_CELL;
+                if (m != 0u) {
+                    if ((grid[c] >> TYPE_SHIFT) == TYPE_EXIT) ex |= 1u << NBR;   // "stay" joins the candidates (:64)
+                    if (ex != 0u) {
+                        // forced exit: first exit cell in candidate order, no draw (:66-72)
+                        const int k = __ffs(ex) - 1;
+                        target = (k == NBR) ? (uint32_t)c : (uint32_t)(c + nbr_off<NBR>(k, W));
+                        forced = true;
+                    } else {
+                        need_draw = true;
                     }
+                }
+                tgt[s] = (PosT)target;
+            }
+            warp_append<uint32_t>(need_draw, (uint32_t)s | (m << 16), work, &cnt[0], lane);
+            warp_append<uint16_t>(forced, (uint16_t)s, req, &cnt[1], lane);
+        }
+        __syncthreads();
+
+        // ================= A2: move probabilities and keyed draw (draw list) ====================
+        const int n_work = (int)cnt[0];
+        for (int base = 0; base < n_work; base += THREADS) {
+            const int wi = base + tid;
+            bool requested = false;
+            int s = 0;
+            if (wi < n_work) {
+                const uint32_t wv = work[wi];
+                s = (int)(wv & 0xFFFFu);
+                const uint32_t mfull = (wv >> 16) | (1u << NBR);
+                const int ncand = __popc(mfull);
+                const int c = (int)pos[s];
+                S p[NBR + 1];
+                S mx = neg_inf<S>();
+#pragma unroll
+                for (int k = 0; k <= NBR; ++k) {
+                    p[k] = neg_inf<S>();
+                    if ((mfull >> k) & 1u) {
+                        const int cc = (k == NBR) ? c : c + nbr_off<NBR>(k, W);
+                        S sc = score[cc];                                    // -k_S * sff
+                        if (DFF) sc = add_rn(sc, (S)mul_rn(P.kd, dffA[cc])); // + k_D * dff   (:77)
+                        p[k] = sc;
+                        mx = max_t(mx, sc);
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k <= NBR; ++k)
+                    if ((mfull >> k) & 1u) p[k] = exp_t(add_rn(p[k], -mx));   // exp(score - max) (:80)
+                const S sum = np_sum_masked<S, NBR + 1>(p, mfull, ncand);       // probs.sum() (:81)
+                uint32_t target = NONE_CELL;
+                if (isfinite(sum) && sum != (S)0) {                             // (:82)
+                    double tot = 0.0;
 #pragma unroll
                     for (int k = 0; k <= NBR; ++k)
-                        if ((mfull >> k) & 1u) p[k] = exp_t(add_rn(p[k], -mx));  // exp(score - max) (:80)
-                    const S sum = np_sum_masked<S, NBR + 1>(p, mfull, ncand);      // probs.sum() (:81)
-                    if (isfinite(sum) && sum != (S)0) {                            // (:82)
-                        double tot = 0.0;
+                        if ((mfull >> k) & 1u) {
+                            p[k] = div_rn(p[k], sum);                           // probs /= sum (:83)
+                            tot = __dadd_rn(tot, (double)p[k]);                 // choice(): cdf = cumsum(p)
+                        }
+                    // the reference's array index of this pedestrian = alive rank of its slot
+                    const uint32_t rank = wpre[s >> 5] + (uint32_t)__popc(alive[s >> 5] & ((1u << (s & 31)) - 1u));
+                    const double u = (inj && mv_draws) ? mv_draws[(size_t)di * P.n_max + rank]
+                                                       : draw_u0(P.seed, episode, t, STREAM_MOVE, rank);
+                    // searchsorted(cdf / cdf[-1], u, 'right'): first candidate whose cdf exceeds u.
+                    // cdf_j = fl(run_j / tot); run_j * fl(1/tot) is within 2 ulp of it, so only a
+                    // draw within 1e-15 of a boundary needs the exact division.
+                    const double inv = __drcp_rn(tot);
+                    double run = 0.0;
+                    int slot = NBR;                                             // last cdf == 1.0 > u
+                    bool done = false;
 #pragma unroll
-                        for (int k = 0; k <= NBR; ++k)
-                            if ((mfull >> k) & 1u) {
-                                p[k] = div_rn(p[k], sum);                          // probs /= sum (:83)
-                                tot = __dadd_rn(tot, (double)p[k]);                // choice(): cdf = cumsum(p)
-                            }
-                        const double u = (inj && mv_draws)
-                                             ? mv_draws[(size_t)di * P.n_max + i]
-                                             : draw_u0(P.seed, episode, t, STREAM_MOVE, (uint32_t)i);
-                        // searchsorted(cdf / cdf[-1], u, 'right') == #{j : cdf_j / tot <= u}
-                        double run = 0.0;
-                        int j = 0;
-#pragma unroll
-                        for (int k = 0; k <= NBR; ++k)
-                            if ((mfull >> k) & 1u) {
-                                run = __dadd_rn(run, (double)p[k]);
-                                j += (__ddiv_rn(run, tot) <= u) ? 1 : 0;
-                            }
-                        if (j >= ncand) j = ncand - 1;
-                        const int slot = (int)__fns(mfull, 0, j + 1);
-                        target = (slot == NBR) ? c : (uint32_t)((int)c + off[slot]);
-                    }
+                    for (int k = 0; k < NBR; ++k)
+                        if ((mfull >> k) & 1u) {
+                            run = __dadd_rn(run, (double)p[k]);
+                            const double q = __dmul_rn(run, inv);
+                            bool le = q <= u;
+                            if (fabs(q - u) < 1e-15) le = __ddiv_rn(run, tot) <= u;
+                            if (!le && !done) { slot = k; done = true; }
+                        }
+                    target = (slot == NBR) ? (uint32_t)c : (uint32_t)(c + nbr_off<NBR>(slot, W));
+                    requested = true;
                 }
+                tgt[s] = (PosT)target;
             }
-            tgt[i] = (PosT)target;
+            warp_append<uint16_t>(requested, (uint16_t)s, req, &cnt[1], lane);
         }
         __syncthreads();
 
-        // ================= phase B: resolve same-target conflicts ===============================
-        for (int base = 0; base < n; base += THREADS) {
-            const int i = base + tid;
-            const bool active = i < n;
-            bool kept = false;
-            if (active) {
-                const uint32_t c = posA[i];
-                const uint32_t T = tgt[i];
-                uint32_t newc = c;
-                if (T != NONE_CELL) {
-                    bool moved;
-                    if (T == c) {
-                        moved = true;   // nobody else can request an occupied cell: lone claimant
+        // ================= B: resolve same-target conflicts (request list) ======================
+        const int n_req = (int)cnt[1];
+        for (int j = tid; j < n_req; j += THREADS) {
+            const int s = (int)req[j];
+            const int c = (int)pos[s];
+            const uint32_t T = tgt[s];
+            bool moved;
+            if (T == (uint32_t)c) {
+                moved = true;   // nobody else can request an occupied cell: lone claimant of "stay"
+            } else {
+                int k = 0, r = 0;
+#pragma unroll
+                for (int q = 0; q < NBR; ++q) {
+                    const uint32_t occ = grid[(int)T + nbr_off<NBR>(q, W)] & OCC_MASK;
+                    if (occ != 0u) {
+                        const int o = (int)occ - 1;
+                        if ((uint32_t)tgt[o] == T) { ++k; r += (o < s) ? 1 : 0; }
+                    }
+                }
+                if (k == 1) {
+                    moved = true;                                             // (:91-93)
+                } else {
+                    Draw2 d;
+                    if (inj && cf_draws) {
+                        d.u0 = cf_draws[((size_t)di * HW + T) * 2];
+                        d.u1 = cf_draws[((size_t)di * HW + T) * 2 + 1];
                     } else {
-                        int k = 0, r = 0;
-#pragma unroll
-                        for (int q = 0; q < NBR; ++q) {
-                            const uint32_t occ = grid[(int)T + off[q]] & OCC_MASK;
-                            if (occ != 0u) {
-                                const int j = (int)occ - 1;
-                                if (tgt[j] == T) { ++k; r += (j < i) ? 1 : 0; }
-                            }
-                        }
-                        if (k == 1) {
-                            moved = true;                                         // (:91-93)
-                        } else {
-                            Draw2 d;
-                            if (inj && cf_draws) {
-                                d.u0 = cf_draws[((size_t)di * HW + T) * 2];
-                                d.u1 = cf_draws[((size_t)di * HW + T) * 2 + 1];
-                            } else {
-                                d = draw2(P.seed, episode, t, STREAM_CONFLICT, T);
-                            }
-                            // coin (:95), then agents[int(u * k)] in ascending agent index (:96)
-                            moved = (d.u0 < 0.5) && ((int)(d.u1 * (double)k) == r);
-                        }
+                        d = draw2(P.seed, episode, t, STREAM_CONFLICT, T);
                     }
-                    if (moved) {
-                        newc = T;
-                        if (DFF) dffA[c] = __fadd_rn(dffA[c], 1.0f);               // footprint (:93,98)
-                    }
+                    // coin (:95), then agents[int(u * k)] in ascending agent index (:96)
+                    moved = (d.u0 < 0.5) && ((int)(d.u1 * (double)k) == r);
                 }
-                kept = (grid[newc] >> TYPE_SHIFT) != TYPE_EXIT;                    // (:101)
-                nxt[i] = (PosT)newc;
             }
-            const uint32_t bal = __ballot_sync(0xffffffffu, kept);
-            if (lane == 0 && i < n) wcnt[i >> 5] = __popc(bal);
+            if (moved) {
+                if (DFF) dffA[c] = __fadd_rn(dffA[c], 1.0f);                  // footprint (:93,98)
+                if (T != (uint32_t)c) req[j] = (uint16_t)(s | 0x8000);        // to be applied in C
+            }
         }
         __syncthreads();
 
-        // ================= phase C: stable compaction + grid update =============================
-        const int ngroups = (n + 31) >> 5;
-        int n_new = 0;
-        for (int base = 0; base < n; base += THREADS) {
-            const int i = base + tid;
-            const bool active = i < n;
-            const int v = i >> 5;   // warp-uniform
-            // exclusive prefix of wcnt[0..v) and grand total, by warp-wide reduction
-            int before = 0, total = 0;
-            for (int w0 = 0; w0 < ngroups; w0 += 32) {
-                const int w = w0 + lane;
-                const int x = (w < ngroups) ? (int)wcnt[w] : 0;
-                int xb = (w < v) ? x : 0, xt = x;
-#pragma unroll
-                for (int s = 16; s > 0; s >>= 1) {
-                    xb += __shfl_xor_sync(0xffffffffu, xb, s);
-                    xt += __shfl_xor_sync(0xffffffffu, xt, s);
-                }
-                before += xb;
-                total += xt;
-            }
-            n_new = total;
-            const uint32_t newc = active ? (uint32_t)nxt[i] : 0u;
-            // only this thread writes grid[newc] in this phase, so its type bits are stable
-            const bool kept = active && (grid[newc] >> TYPE_SHIFT) != TYPE_EXIT;
-            const uint32_t bal = __ballot_sync(0xffffffffu, kept);
-            if (active) {
-                const uint32_t c = posA[i];
-                if (newc != c) grid[c] &= (uint16_t)(3u << TYPE_SHIFT);
-                if (kept) {
-                    const int ni = before + __popc(bal & ((1u << lane) - 1u));
-                    posB[ni] = (PosT)newc;
-                    grid[newc] = (uint16_t)((grid[newc] & (3u << TYPE_SHIFT)) | (uint32_t)(ni + 1));
+        // ================= C: apply granted moves, exits ========================================
+        for (int base = 0; base < n_req; base += THREADS) {
+            const int j = base + tid;
+            bool leaves = false;
+            if (j < n_req) {
+                const uint32_t rv = req[j];
+                if (rv & 0x8000u) {
+                    const int s = (int)(rv & 0x7FFFu);
+                    const int c = (int)pos[s];
+                    const uint32_t T = tgt[s];
+                    grid[c] &= (uint16_t)TYPE_BITS;
+                    if ((grid[T] >> TYPE_SHIFT) == TYPE_EXIT) {                // (:101-102)
+                        leaves = true;
+                        atomicAnd(&alive[s >> 5], ~(1u << (s & 31)));
+                    } else {
+                        grid[T] |= (uint16_t)(s + 1);
+                        pos[s] = (PosT)T;
+                    }
                 }
             }
+            const uint32_t bal = __ballot_sync(0xffffffffu, leaves);
+            if (bal != 0u && lane == 0) atomicAdd(&cnt[2], (uint32_t)__popc(bal));
         }
-
-        // ================= phase D: DFF decay + diffusion =======================================
         if (DFF) {
             // new = c0 * dff (ffm_core.py:109); the neighbour terms read this scaled field (:111)
             for (int c = tid; c < HW; c += THREADS) dffA[c] = __fmul_rn(P.c0, dffA[c]);
-            __syncthreads();
+        }
+        __syncthreads();
+
+        const int n_exit = (int)cnt[2];
+        if (n_exit > 0) {
+            n -= n_exit;
+            const int nwords = (n_slots + 31) >> 5;
+            if (4 * n <= 3 * n_slots && n_slots > 32) {
+                // ---- re-pack: slot := alive rank (stable), tgt[] is free to serve as scratch -----
+                if (tid < 32) {
+                    uint32_t carry = 0;
+                    for (int w0 = 0; w0 < nwords; w0 += 32) {
+                        const int w = w0 + lane;
+                        const uint32_t x = (w < nwords) ? (uint32_t)__popc(alive[w]) : 0u;
+                        uint32_t inc = x;
+#pragma unroll
+                        for (int d = 1; d < 32; d <<= 1) {
+                            const uint32_t y = __shfl_up_sync(0xffffffffu, inc, d);
+                            if (lane >= d) inc += y;
+                        }
+                        if (w < nwords) wpre[w] = carry + inc - x;
+                        carry += __shfl_sync(0xffffffffu, inc, 31);
+                    }
+                }
+                __syncthreads();
+                for (int s = tid; s < n_slots; s += THREADS)
+                    if ((alive[s >> 5] >> (s & 31)) & 1u) {
+                        const uint32_t rank = wpre[s >> 5] + (uint32_t)__popc(alive[s >> 5] & ((1u << (s & 31)) - 1u));
+                        tgt[rank] = pos[s];
+                    }
+                __syncthreads();
+                for (int i = tid; i < n; i += THREADS) {
+                    const PosT c = tgt[i];
+                    pos[i] = c;
+                    grid[c] = (uint16_t)((grid[c] & TYPE_BITS) | (uint32_t)(i + 1));
+                }
+                for (int w = tid; w <= (n + 31) / 32; w += THREADS) {
+                    const int lo = w * 32;
+                    alive[w] = (lo + 32 <= n) ? 0xffffffffu : (lo < n ? ((1u << (n - lo)) - 1u) : 0u);
+                    wpre[w] = (uint32_t)(lo < n ? lo : n);
+                }
+                n_slots = n;
+                __syncthreads();
+            } else {
+                // ---- alive ranks changed: refresh the word prefix -------------------------------
+                if (tid < 32) {
+                    uint32_t carry = 0;
+                    for (int w0 = 0; w0 < nwords; w0 += 32) {
+                        const int w = w0 + lane;
+                        const uint32_t x = (w < nwords) ? (uint32_t)__popc(alive[w]) : 0u;
+                        uint32_t inc = x;
+#pragma unroll
+                        for (int d = 1; d < 32; d <<= 1) {
+                            const uint32_t y = __shfl_up_sync(0xffffffffu, inc, d);
+                            if (lane >= d) inc += y;
+                        }
+                        if (w < nwords) wpre[w] = carry + inc - x;
+                        carry += __shfl_sync(0xffffffffu, inc, 31);
+                    }
+                }
+                __syncthreads();
+            }
+        }
+
+        // ================= D: DFF diffusion ======================================================
+        if (DFF) {
             for (int c = tid; c < HW; c += THREADS) {
                 const int r = c / W, col = c - r * W;
                 float acc = dffA[c];
@@ -329,27 +445,33 @@ ffm_core_rollout_kernel(const RolloutParams P) {
                 for (int k = 0; k < NBR; ++k) {
                     const int rr = r + nbr_dr<NBR>(k), cc = col + nbr_dc<NBR>(k);
                     const float v = (rr >= 0 && rr < H && cc >= 0 && cc < W) ? dffA[rr * W + cc] : 0.0f;
-                    acc = __fadd_rn(acc, __fmul_rn(P.c1, v));                      // (:112-113)
+                    acc = __fadd_rn(acc, __fmul_rn(P.c1, v));                  // (:112-113)
                 }
-                if (acc < P.thr) acc = 0.0f;                                       // (:116-117)
+                if (acc < P.thr) acc = 0.0f;                                   // (:116-117)
                 dffB[c] = acc;
             }
             float* tmp = dffA; dffA = dffB; dffB = tmp;
+            __syncthreads();
         }
-        __syncthreads();
 
         // trajectory row: positions after this step, alive-rank order (ffm_core.py:125)
         if (P.traj != nullptr && tl < P.traj_steps) {
             uint32_t* row = P.traj + ((size_t)e * P.traj_steps + tl) * P.n_max;
-            for (int i = tid; i < n_new; i += THREADS) row[i] = posB[i];
-            if (tid == 0) P.traj_n[(size_t)e * P.traj_steps + tl] = n_new;
+            for (int s = tid; s < n_slots; s += THREADS)
+                if ((alive[s >> 5] >> (s & 31)) & 1u) {
+                    const uint32_t rank = wpre[s >> 5] + (uint32_t)__popc(alive[s >> 5] & ((1u << (s & 31)) - 1u));
+                    row[rank] = (uint32_t)pos[s];
+                }
+            if (tid == 0) P.traj_n[(size_t)e * P.traj_steps + tl] = n;
         }
-        PosT* tp = posA; posA = posB; posB = tp;
-        n = n_new;
     }
 
-    // ---- epilogue: state back to HBM ------------------------------------------------------------
-    for (int i = tid; i < n; i += THREADS) gpos[i] = posA[i];
+    // ---- epilogue: state back to HBM, alive-rank order -------------------------------------------
+    for (int s = tid; s < n_slots; s += THREADS)
+        if ((alive[s >> 5] >> (s & 31)) & 1u) {
+            const uint32_t rank = wpre[s >> 5] + (uint32_t)__popc(alive[s >> 5] & ((1u << (s & 31)) - 1u));
+            gpos[rank] = (uint32_t)pos[s];
+        }
     if (DFF) {
         if (dffA != dff_home)
             for (int c = tid; c < HW; c += THREADS) dff_home[c] = dffA[c];
