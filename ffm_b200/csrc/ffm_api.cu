@@ -5,6 +5,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -68,22 +69,32 @@ namespace ffm {
 // (the first product of ffm_core.py:77; elementwise, so hoisting it out of the step is exact).
 template <typename S>
 __global__ void prep_fields_kernel(const uint8_t* map, const S* sff, uint16_t* type_grid, S* score, int H, int W,
-                                   S neg_ks, int32_t* err) {
+                                   int nbr, S neg_ks, int32_t* err) {
     const int HW = H * W, G = W + 1;
     for (int x = blockIdx.x * blockDim.x + threadIdx.x; x < HW + 2 * G; x += gridDim.x * blockDim.x) {
         const int c = x - G;
-        uint32_t type = TYPE_WALL;
+        uint32_t cell = WALL_CELL;      // guard band and every non-passable code (1, 2): blocked
         if (c >= 0 && c < HW) {
             const uint8_t m = map[c];
-            type = (m == FFM_CELL_FREE) ? TYPE_FREE : (m == FFM_CELL_WALL) ? TYPE_WALL : (m == FFM_CELL_EXIT) ? TYPE_EXIT : TYPE_OTHER;
             if (m > 3) atomicOr(err, 1);
             const int r = c / W, col = c - r * W;
             // the step never bounds-checks neighbours (nor does ffm_core.py:45-53, which "relies on
             // border walls"): a free cell on the border would let a pedestrian read outside the map
             if ((r == 0 || r == H - 1 || col == 0 || col == W - 1) && m == FFM_CELL_FREE) atomicOr(err, 2);
+            if (m == FFM_CELL_EXIT) cell = TYPE_EXIT << TYPE_SHIFT;
+            if (m == FFM_CELL_FREE) {
+                bool near = false;   // static flag: some neighbour (of the model's neighbourhood) is an exit
+                for (int dr = -1; dr <= 1; ++dr)
+                    for (int dc = -1; dc <= 1; ++dc) {
+                        if ((dr == 0 && dc == 0) || (nbr == 4 && dr != 0 && dc != 0)) continue;
+                        const int rr = r + dr, cc = col + dc;
+                        if (rr >= 0 && rr < H && cc >= 0 && cc < W && map[rr * W + cc] == FFM_CELL_EXIT) near = true;
+                    }
+                cell = (near ? TYPE_NEAR_EXIT : TYPE_FREE) << TYPE_SHIFT;
+            }
             score[c] = mul_rn(neg_ks, sff[c]);
         }
-        type_grid[x] = (uint16_t)(type << TYPE_SHIFT);
+        type_grid[x] = (uint16_t)cell;
     }
 }
 
@@ -99,7 +110,8 @@ __global__ void pack_positions_kernel(const int32_t* pos_rc, const int32_t* n, c
         const int2 rc = reinterpret_cast<const int2*>(pos_rc)[x];
         if (rc.x < 0 || rc.x >= H || rc.y < 0 || rc.y >= W) { atomicOr(err, 8); continue; }
         const int c = rc.x * W + rc.y;
-        if ((type_grid[c + G] >> TYPE_SHIFT) != TYPE_FREE) atomicOr(err, 16);   // initialize_agents(): map == 0 cells only
+        const uint32_t ty = type_grid[c + G] >> TYPE_SHIFT;
+        if (ty != TYPE_FREE && ty != TYPE_NEAR_EXIT) atomicOr(err, 16);   // initialize_agents(): map == 0 cells only
         pos[x] = (uint32_t)c;
     }
 }
@@ -224,6 +236,10 @@ int ffm_create(const ffm_config_t* cfg, ffm_sim_t* out) {
     }
     const int work = N > HW / 8 ? N : HW / 8;
     s->threads = work <= 128 ? 128 : (work <= 1024 ? 256 : (work <= 4096 ? 512 : 1024));
+    if (const char* ev = getenv("FFM_THREADS")) {   // tuning override: 128 | 256 | 512 | 1024
+        const int v = atoi(ev);
+        if (v == 128 || v == 256 || v == 512 || v == 1024) s->threads = v;
+    }
     s->kernel = pick_kernel(cfg->sff_dtype == FFM_F64, HW <= 65536, cfg->neighborhood, dff, s->fields_in_smem, s->threads);
     cudaError_t ce = cudaFuncSetAttribute(s->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, s->smem_bytes);
     if (ce != cudaSuccess) { delete s; return fail(FFM_E_CUDA, "cudaFuncSetAttribute(smem=%d): %s", s->smem_bytes, cudaGetErrorString(ce)); }
@@ -281,9 +297,9 @@ int ffm_set_fields(ffm_sim_t s, const uint8_t* map, const void* sff, int space, 
     if ((rc = copy_in(s->d_sff, sff, (size_t)HW * ssz, space, st))) return rc;
     const int blocks = (HW + 2 * (W + 1) + 255) / 256;
     if (s->cfg.sff_dtype == FFM_F64)
-        ffm::prep_fields_kernel<double><<<blocks, 256, 0, st>>>(s->d_map, (const double*)s->d_sff, s->d_type_grid, (double*)s->d_score, H, W, -s->cfg.k_S, s->d_err);
+        ffm::prep_fields_kernel<double><<<blocks, 256, 0, st>>>(s->d_map, (const double*)s->d_sff, s->d_type_grid, (double*)s->d_score, H, W, s->cfg.neighborhood, -s->cfg.k_S, s->d_err);
     else
-        ffm::prep_fields_kernel<float><<<blocks, 256, 0, st>>>(s->d_map, (const float*)s->d_sff, s->d_type_grid, (float*)s->d_score, H, W, (float)(-s->cfg.k_S), s->d_err);
+        ffm::prep_fields_kernel<float><<<blocks, 256, 0, st>>>(s->d_map, (const float*)s->d_sff, s->d_type_grid, (float*)s->d_score, H, W, s->cfg.neighborhood, (float)(-s->cfg.k_S), s->d_err);
     CU(cudaGetLastError());
     s->launches++;
     if ((rc = check_device_flag(s, st))) return rc;

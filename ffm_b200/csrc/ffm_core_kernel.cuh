@@ -30,9 +30,12 @@
 // fields fit (FIELDS_IN_SMEM), otherwise SFF scores / DFF stay in global memory (L2-resident).
 //
 // Shared-memory state of an episode
-//   grid  u16[HW + 2*(W+1)]  bits 15..14 cell type (0 free, 1 wall, 2 exit, 3 other), bits 13..0
-//                            1 + slot of the pedestrian standing there (0 = empty); a guard band of
-//                            W+1 "wall" entries on both ends absorbs neighbour reads of border cells
+//   grid  u16[HW + 2*(W+1)]  bits 15..14 cell type (0 free, 1 blocked, 2 exit, 3 free cell next to an
+//                            exit), bits 13..0 = 1 + slot of the pedestrian standing there, 0 = empty,
+//                            0x3FFF on blocked cells (walls look "occupied": one test per neighbour);
+//                            a guard band of W+1 blocked entries on both ends absorbs neighbour reads
+//                            of border cells
+//   claim u8[HW]             requests per target cell this step (zeroed again by the requesters)
 //   score S[HW]              -k_S * sff  (S = float | double, the dtype NumPy computes in)
 //   dffA/dffB f32[HW]        dynamic floor field, ping-pong
 //   pos   PosT[n_max]        linear cell per slot (PosT = u16 when H*W <= 65536, else u32)
@@ -48,7 +51,8 @@ namespace ffm {
 constexpr uint32_t TYPE_SHIFT = 14;
 constexpr uint32_t OCC_MASK = 0x3FFFu;
 constexpr uint32_t TYPE_BITS = 3u << TYPE_SHIFT;
-constexpr uint32_t TYPE_FREE = 0, TYPE_WALL = 1, TYPE_EXIT = 2, TYPE_OTHER = 3;
+constexpr uint32_t TYPE_FREE = 0, TYPE_WALL = 1, TYPE_EXIT = 2, TYPE_NEAR_EXIT = 3;
+constexpr uint32_t WALL_CELL = (TYPE_WALL << TYPE_SHIFT) | OCC_MASK;
 constexpr int MAX_PEDS = 16382;
 
 struct RolloutParams {
@@ -74,7 +78,7 @@ struct RolloutParams {
 };
 
 struct SmemLayout {
-    uint32_t score, dffA, dffB, grid, pos, tgt, work, req, alive, wpre, ctr, total;
+    uint32_t score, dffA, dffB, grid, claim, pos, tgt, work, req, alive, wpre, ctr, total;
 };
 
 __host__ __device__ inline uint32_t align16(uint32_t x) { return (x + 15u) & ~15u; }
@@ -89,6 +93,7 @@ __host__ __device__ inline SmemLayout make_layout(int HW, int W, int n_max, int 
     L.dffA = o;  if (fields_in_smem && dff) o = align16(o + (uint32_t)HW * 4u);
     L.dffB = o;  if (fields_in_smem && dff) o = align16(o + (uint32_t)HW * 4u);
     L.grid = o;  o = align16(o + (uint32_t)(HW + 2 * (W + 1)) * 2u);
+    L.claim = o; o = align16(o + (uint32_t)HW);
     L.pos = o;   o = align16(o + (uint32_t)n_max * ps);
     L.tgt = o;   o = align16(o + (uint32_t)n_max * ps);
     L.work = o;  o = align16(o + (uint32_t)n_max * 4u);
@@ -108,6 +113,21 @@ template <> __device__ __forceinline__ int nbr_dc<4>(int k) { return k == 2 ? -1
 template <> __device__ __forceinline__ int nbr_dr<8>(int k) { const int q = k + (k >= 4 ? 1 : 0); return q / 3 - 1; }
 template <> __device__ __forceinline__ int nbr_dc<8>(int k) { const int q = k + (k >= 4 ? 1 : 0); return q % 3 - 1; }
 template <int NBR> __device__ __forceinline__ int nbr_off(int k, int W) { return nbr_dr<NBR>(k) * W + nbr_dc<NBR>(k); }
+
+// same, for a neighbour index only known at run time (2-bit lookup tables of dr+1 / dc+1)
+template <int NBR> __device__ __forceinline__ int nbr_off_rt(int k, int W);
+template <> __device__ __forceinline__ int nbr_off_rt<8>(int k, int W) {
+    const int dr = (int)((0xA940u >> (2 * k)) & 3u) - 1, dc = (int)((0x9224u >> (2 * k)) & 3u) - 1;
+    return dr * W + dc;
+}
+template <> __device__ __forceinline__ int nbr_off_rt<4>(int k, int W) {
+    const int dr = (int)((0x58u >> (2 * k)) & 3u) - 1, dc = (int)((0x85u >> (2 * k)) & 3u) - 1;
+    return dr * W + dc;
+}
+
+// exact cdf comparison for a draw that lands within 1e-15 of a boundary (practically never taken;
+// kept out of line so the division sequence stays off the hot path)
+__device__ __noinline__ bool cdf_le_exact(double run, double tot, double u) { return __ddiv_rn(run, tot) <= u; }
 
 __device__ __forceinline__ uint32_t lanemask_lt() {
     uint32_t m;
@@ -148,6 +168,8 @@ ffm_core_rollout_kernel(const RolloutParams P) {
     uint32_t* alive = reinterpret_cast<uint32_t*>(smem_raw + L.alive);
     uint32_t* wpre = reinterpret_cast<uint32_t*>(smem_raw + L.wpre);
     uint32_t* ctr = reinterpret_cast<uint32_t*>(smem_raw + L.ctr);   // [parity][n_work, n_req, n_exit, -]
+    uint8_t* claim = smem_raw + L.claim;
+    uint32_t* claim32 = reinterpret_cast<uint32_t*>(smem_raw + L.claim);
 
     const S* score;
     float* dffA = nullptr;
@@ -184,6 +206,7 @@ ffm_core_rollout_kernel(const RolloutParams P) {
         wpre[w] = (uint32_t)(lo < n ? lo : n);
     }
     if (tid < 8) ctr[tid] = 0u;
+    for (int c = tid; c < (HW + 3) / 4; c += THREADS) claim32[c] = 0u;
     __syncthreads();
     for (int i = tid; i < n; i += THREADS) grid[pos[i]] |= (uint16_t)(i + 1);
     __syncthreads();
@@ -212,22 +235,27 @@ ffm_core_rollout_kernel(const RolloutParams P) {
             uint32_t m = 0;
             if (s < n_slots && ((alive[s >> 5] >> (s & 31)) & 1u)) {
                 const int c = (int)pos[s];
-                uint32_t ex = 0;
+                // passable (map 0 or 3, ffm_core.py:52-53) and not occupied at time t (:57-60):
+                // blocked cells carry 0x3FFF in the owner bits, so "owner bits == 0" is the whole test
 #pragma unroll
-                for (int k = 0; k < NBR; ++k) {
-                    const uint32_t g = grid[c + nbr_off<NBR>(k, W)];
-                    // passable (map 0 or 3, ffm_core.py:52-53) and not occupied at time t (:57-60)
-                    if (g == 0u || g == EXIT_EMPTY) m |= 1u << k;
-                    if (g == EXIT_EMPTY) ex |= 1u << k;
-                }
+                for (int k = 0; k < NBR; ++k)
+                    if ((grid[c + nbr_off<NBR>(k, W)] & OCC_MASK) == 0u) m |= 1u << k;
                 uint32_t target = NONE_CELL;
                 if (m != 0u) {
-                    if ((grid[c] >> TYPE_SHIFT) == TYPE_EXIT) ex |= 1u << NBR;   // "stay" joins the candidates (:64)
+                    const uint32_t own_type = grid[c] >> TYPE_SHIFT;
+                    uint32_t ex = 0;
+                    if (own_type >= TYPE_EXIT) {          // on an exit, or a free cell next to one (static flag)
+                        if (own_type == TYPE_EXIT) ex |= 1u << NBR;   // "stay" joins the candidates (:64)
+#pragma unroll
+                        for (int k = 0; k < NBR; ++k)
+                            if (grid[c + nbr_off<NBR>(k, W)] == EXIT_EMPTY) ex |= 1u << k;
+                    }
                     if (ex != 0u) {
                         // forced exit: first exit cell in candidate order, no draw (:66-72)
                         const int k = __ffs(ex) - 1;
-                        target = (k == NBR) ? (uint32_t)c : (uint32_t)(c + nbr_off<NBR>(k, W));
+                        target = (k == NBR) ? (uint32_t)c : (uint32_t)(c + nbr_off_rt<NBR>(k, W));
                         forced = true;
+                        if (k != NBR) atomicAdd(&claim32[target >> 2], 1u << (8 * (target & 3u)));
                     } else {
                         need_draw = true;
                     }
@@ -240,6 +268,8 @@ ffm_core_rollout_kernel(const RolloutParams P) {
         __syncthreads();
 
         // ================= A2: move probabilities and keyed draw (draw list) ====================
+        // Candidates are walked in COMPACTED order (set bits of the mask, then "stay"), which is the
+        // order of the reference's neighbor_coords array (:54,60,64) -- and keeps lanes busy.
         const int n_work = (int)cnt[0];
         for (int base = 0; base < n_work; base += THREADS) {
             const int wi = base + tid;
@@ -248,34 +278,49 @@ ffm_core_rollout_kernel(const RolloutParams P) {
             if (wi < n_work) {
                 const uint32_t wv = work[wi];
                 s = (int)(wv & 0xFFFFu);
-                const uint32_t mfull = (wv >> 16) | (1u << NBR);
-                const int ncand = __popc(mfull);
+                uint32_t mm = wv >> 16;
+                const int ncand = __popc(mm) + 1;
                 const int c = (int)pos[s];
+                int cell[NBR + 1];
                 S p[NBR + 1];
                 S mx = neg_inf<S>();
 #pragma unroll
-                for (int k = 0; k <= NBR; ++k) {
-                    p[k] = neg_inf<S>();
-                    if ((mfull >> k) & 1u) {
-                        const int cc = (k == NBR) ? c : c + nbr_off<NBR>(k, W);
+                for (int j = 0; j <= NBR; ++j)
+                    if (j < ncand) {
+                        int cc = c;
+                        if (j < ncand - 1) {
+                            const int k = __ffs(mm) - 1;
+                            mm &= mm - 1u;
+                            cc = c + nbr_off_rt<NBR>(k, W);
+                        }
+                        cell[j] = cc;
                         S sc = score[cc];                                    // -k_S * sff
                         if (DFF) sc = add_rn(sc, (S)mul_rn(P.kd, dffA[cc])); // + k_D * dff   (:77)
-                        p[k] = sc;
+                        p[j] = sc;
                         mx = max_t(mx, sc);
                     }
-                }
 #pragma unroll
-                for (int k = 0; k <= NBR; ++k)
-                    if ((mfull >> k) & 1u) p[k] = exp_t(add_rn(p[k], -mx));   // exp(score - max) (:80)
-                const S sum = np_sum_masked<S, NBR + 1>(p, mfull, ncand);       // probs.sum() (:81)
+                for (int j = 0; j <= NBR; ++j)
+                    if (j < ncand) p[j] = exp_t(add_rn(p[j], -mx));          // exp(score - max) (:80)
+                S sum;                                                        // probs.sum() (:81), NumPy order
+                if (NBR == 8 && ncand >= 8) {
+                    sum = add_rn(add_rn(add_rn(p[0], p[1]), add_rn(p[2], p[3])),
+                                 add_rn(add_rn(p[4], p[5]), add_rn(p[6], p[7])));
+                    if (ncand == 9) sum = add_rn(sum, p[NBR]);
+                } else {
+                    sum = (S)0;
+#pragma unroll
+                    for (int j = 0; j <= NBR; ++j)
+                        if (j < ncand) sum = add_rn(sum, p[j]);
+                }
                 uint32_t target = NONE_CELL;
-                if (isfinite(sum) && sum != (S)0) {                             // (:82)
+                if (isfinite(sum) && sum != (S)0) {                           // (:82)
                     double tot = 0.0;
 #pragma unroll
-                    for (int k = 0; k <= NBR; ++k)
-                        if ((mfull >> k) & 1u) {
-                            p[k] = div_rn(p[k], sum);                           // probs /= sum (:83)
-                            tot = __dadd_rn(tot, (double)p[k]);                 // choice(): cdf = cumsum(p)
+                    for (int j = 0; j <= NBR; ++j)
+                        if (j < ncand) {
+                            p[j] = div_rn(p[j], sum);                         // probs /= sum (:83)
+                            tot = __dadd_rn(tot, (double)p[j]);               // choice(): cdf = cumsum(p)
                         }
                     // the reference's array index of this pedestrian = alive rank of its slot
                     const uint32_t rank = wpre[s >> 5] + (uint32_t)__popc(alive[s >> 5] & ((1u << (s & 31)) - 1u));
@@ -286,19 +331,19 @@ ffm_core_rollout_kernel(const RolloutParams P) {
                     // draw within 1e-15 of a boundary needs the exact division.
                     const double inv = __drcp_rn(tot);
                     double run = 0.0;
-                    int slot = NBR;                                             // last cdf == 1.0 > u
+                    target = (uint32_t)c;                                     // last cdf == 1.0 > u: "stay"
                     bool done = false;
 #pragma unroll
-                    for (int k = 0; k < NBR; ++k)
-                        if ((mfull >> k) & 1u) {
-                            run = __dadd_rn(run, (double)p[k]);
+                    for (int j = 0; j < NBR; ++j)
+                        if (j < ncand - 1 && !done) {
+                            run = __dadd_rn(run, (double)p[j]);
                             const double q = __dmul_rn(run, inv);
                             bool le = q <= u;
-                            if (fabs(q - u) < 1e-15) le = __ddiv_rn(run, tot) <= u;
-                            if (!le && !done) { slot = k; done = true; }
+                            if (fabs(q - u) < 1e-15) le = cdf_le_exact(run, tot, u);
+                            if (!le) { target = (uint32_t)cell[j]; done = true; }
                         }
-                    target = (slot == NBR) ? (uint32_t)c : (uint32_t)(c + nbr_off<NBR>(slot, W));
                     requested = true;
+                    if (target != (uint32_t)c) atomicAdd(&claim32[target >> 2], 1u << (8 * (target & 3u)));
                 }
                 tgt[s] = (PosT)target;
             }
@@ -316,18 +361,18 @@ ffm_core_rollout_kernel(const RolloutParams P) {
             if (T == (uint32_t)c) {
                 moved = true;   // nobody else can request an occupied cell: lone claimant of "stay"
             } else {
-                int k = 0, r = 0;
-#pragma unroll
-                for (int q = 0; q < NBR; ++q) {
-                    const uint32_t occ = grid[(int)T + nbr_off<NBR>(q, W)] & OCC_MASK;
-                    if (occ != 0u) {
-                        const int o = (int)occ - 1;
-                        if ((uint32_t)tgt[o] == T) { ++k; r += (o < s) ? 1 : 0; }
-                    }
-                }
+                const int k = (int)claim[T];
                 if (k == 1) {
                     moved = true;                                             // (:91-93)
                 } else {
+                    // rank among the claimants in ascending agent index: the claimants are owners of
+                    // T's neighbour cells whose request is T
+                    int r = 0;
+#pragma unroll
+                    for (int q = 0; q < NBR; ++q) {
+                        const uint32_t o = (grid[(int)T + nbr_off<NBR>(q, W)] & OCC_MASK) - 1u;
+                        if (o < (uint32_t)s && (uint32_t)tgt[o] == T) ++r;    // o < s also excludes empty / blocked
+                    }
                     Draw2 d;
                     if (inj && cf_draws) {
                         d.u0 = cf_draws[((size_t)di * HW + T) * 2];
@@ -352,12 +397,13 @@ ffm_core_rollout_kernel(const RolloutParams P) {
             bool leaves = false;
             if (j < n_req) {
                 const uint32_t rv = req[j];
+                const int s = (int)(rv & 0x7FFFu);
+                const int c = (int)pos[s];
+                const uint32_t T = tgt[s];
+                if (T != (uint32_t)c) claim[T] = 0;                            // leave the counters clean
                 if (rv & 0x8000u) {
-                    const int s = (int)(rv & 0x7FFFu);
-                    const int c = (int)pos[s];
-                    const uint32_t T = tgt[s];
                     grid[c] &= (uint16_t)TYPE_BITS;
-                    if ((grid[T] >> TYPE_SHIFT) == TYPE_EXIT) {                // (:101-102)
+                    if (grid[T] == EXIT_EMPTY) {                               // (:101-102)
                         leaves = true;
                         atomicAnd(&alive[s >> 5], ~(1u << (s & 31)));
                     } else {
