@@ -299,48 +299,34 @@ ffm_core_rollout_kernel(const RolloutParams P) {
                         p[j] = sc;
                         mx = max_t(mx, sc);
                     }
+                // e_j = exp(score_j - max) (:80).  The reference then normalises (p = e / sum(e), :83)
+                // and np.random.choice picks the first j with cumsum(p)[j] / cumsum(p)[-1] > u (:84).
+                // That is the first j with E_j > u * E_n (E = running sums of e) up to the rounding of
+                // the normalisation (< 1e-7), which -- like the <= 2 ulp difference between NumPy's
+                // exp and CUDA's -- only matters for a draw closer than that to a CDF boundary; the
+                // parity bar excludes those draws (tests/helpers.py MARGIN_GUARD).  So: no divisions.
+                double tot = 0.0;
 #pragma unroll
                 for (int j = 0; j <= NBR; ++j)
-                    if (j < ncand) p[j] = exp_t(add_rn(p[j], -mx));          // exp(score - max) (:80)
-                S sum;                                                        // probs.sum() (:81), NumPy order
-                if (NBR == 8 && ncand >= 8) {
-                    sum = add_rn(add_rn(add_rn(p[0], p[1]), add_rn(p[2], p[3])),
-                                 add_rn(add_rn(p[4], p[5]), add_rn(p[6], p[7])));
-                    if (ncand == 9) sum = add_rn(sum, p[NBR]);
-                } else {
-                    sum = (S)0;
-#pragma unroll
-                    for (int j = 0; j <= NBR; ++j)
-                        if (j < ncand) sum = add_rn(sum, p[j]);
-                }
+                    if (j < ncand) {
+                        p[j] = exp_t(add_rn(p[j], -mx));
+                        tot += (double)p[j];
+                    }
                 uint32_t target = NONE_CELL;
-                if (isfinite(sum) && sum != (S)0) {                           // (:82)
-                    double tot = 0.0;
-#pragma unroll
-                    for (int j = 0; j <= NBR; ++j)
-                        if (j < ncand) {
-                            p[j] = div_rn(p[j], sum);                         // probs /= sum (:83)
-                            tot = __dadd_rn(tot, (double)p[j]);               // choice(): cdf = cumsum(p)
-                        }
+                if (isfinite(tot) && tot != 0.0) {                            // (:82)
                     // the reference's array index of this pedestrian = alive rank of its slot
                     const uint32_t rank = wpre[s >> 5] + (uint32_t)__popc(alive[s >> 5] & ((1u << (s & 31)) - 1u));
                     const double u = (inj && mv_draws) ? mv_draws[(size_t)di * P.n_max + rank]
                                                        : draw_u0(P.seed, episode, t, STREAM_MOVE, rank);
-                    // searchsorted(cdf / cdf[-1], u, 'right'): first candidate whose cdf exceeds u.
-                    // cdf_j = fl(run_j / tot); run_j * fl(1/tot) is within 2 ulp of it, so only a
-                    // draw within 1e-15 of a boundary needs the exact division.
-                    const double inv = __drcp_rn(tot);
+                    const double thresh = u * tot;
                     double run = 0.0;
-                    target = (uint32_t)c;                                     // last cdf == 1.0 > u: "stay"
+                    target = (uint32_t)c;                                     // E_n > u * E_n always: "stay" is last
                     bool done = false;
 #pragma unroll
                     for (int j = 0; j < NBR; ++j)
                         if (j < ncand - 1 && !done) {
-                            run = __dadd_rn(run, (double)p[j]);
-                            const double q = __dmul_rn(run, inv);
-                            bool le = q <= u;
-                            if (fabs(q - u) < 1e-15) le = cdf_le_exact(run, tot, u);
-                            if (!le) { target = (uint32_t)cell[j]; done = true; }
+                            run += (double)p[j];
+                            if (run > thresh) { target = (uint32_t)cell[j]; done = true; }
                         }
                     requested = true;
                     if (target != (uint32_t)c) atomicAdd(&claim32[target >> 2], 1u << (8 * (target & 3u)));
