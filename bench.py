@@ -218,7 +218,7 @@ def run_reference_arm(args, wl):
     for it in range(args.warmup + args.steps):
         t0 = time.perf_counter()
         if have_c_oracle() and not args.numpy_port:
-            last = cpu_c_port(wl, episodes=max(cores, 32), seed=1234 + it, cores=cores)
+            last = cpu_c_port(wl, episodes=max(4 * cores, 32), seed=1234 + it, cores=cores)
         else:
             last = cpu_numpy_port(wl, budget_s=args.cpu_budget, seed=1234 + it, cores=cores)
         if it >= args.warmup:
@@ -393,7 +393,7 @@ def main():
         if not args.no_cpu and world == 1:
             try:
                 if have_c_oracle():
-                    line["cpu_baseline"] = cpu_c_port(wl, episodes=max(os.cpu_count() or 1, 32))
+                    line["cpu_baseline"] = cpu_c_port(wl, episodes=max(4 * (os.cpu_count() or 1), 32))
                     line["cpu_baseline_numpy"] = cpu_numpy_port(wl, budget_s=min(args.cpu_budget, 10.0))
                 else:
                     line["cpu_baseline"] = cpu_numpy_port(wl, budget_s=args.cpu_budget)
