@@ -47,6 +47,7 @@ typedef struct {
     uint64_t seed; uint32_t episode_base; int max_steps, track_dff;
     int32_t* steps; int64_t* ped_steps; double* min_margin; int32_t* final_pos; int32_t* final_n; float* final_dff;
     int32_t* traj; int32_t* traj_n; int traj_steps;
+    double guard; double* move_out; int move_out_steps;   /* guarded recording of the move draws */
     int next; pthread_mutex_t mu;
 } job_t;
 
@@ -140,9 +141,21 @@ static void run_episode(job_t* J, int e) {
             if (!ok) continue;
             const double last = cdf[nc - 1];
             double u0, u1; draw2(J->seed, episode, (uint32_t)t, STREAM_MOVE, (uint32_t)i, &u0, &u1);
+            for (int j = 0; j < nc; ++j) cdf[j] /= last;
+            if (J->guard > 0.0) {
+                /* recorder of SURVEY.md 8(c): a draw within `guard` of a CDF boundary is re-drawn (next
+                 * attempt = same key, entity + attempt * 65536) so that the recorded stream is insensitive
+                 * to last-ulp differences of exp between implementations */
+                for (uint32_t attempt = 1;; ++attempt) {
+                    double mg = INFINITY;
+                    for (int j = 0; j < nc; ++j) { const double d = fabs(cdf[j] - u0); if (d < mg) mg = d; }
+                    if (mg >= J->guard) break;
+                    draw2(J->seed, episode, (uint32_t)t, STREAM_MOVE, (uint32_t)i + attempt * 65536u, &u0, &u1);
+                }
+            }
+            if (J->move_out && t < J->move_out_steps) J->move_out[((size_t)e * J->move_out_steps + t) * J->n_max + i] = u0;
             int idx = 0;
             for (int j = 0; j < nc; ++j) {
-                cdf[j] /= last;
                 if (cdf[j] <= u0) idx++;                                    /* searchsorted(..., 'right') */
                 const double mg = fabs(cdf[j] - u0);
                 if (mg < min_margin) min_margin = mg;
@@ -219,7 +232,8 @@ int ffm_oracle_core_run(const uint8_t* map, const void* sff, int sff_f64, int H,
                         float c0, float c1, float thr, const int32_t* pos_rc, const int32_t* n, int B, int n_max,
                         uint64_t seed, uint32_t episode_base, int max_steps, int track_dff, int threads,
                         int32_t* steps, int64_t* ped_steps, double* min_margin, int32_t* final_pos, int32_t* final_n,
-                        float* final_dff, int32_t* traj, int32_t* traj_n, int traj_steps) {
+                        float* final_dff, int32_t* traj, int32_t* traj_n, int traj_steps,
+                        double guard, double* move_out, int move_out_steps) {
     job_t J;
     memset(&J, 0, sizeof(J));
     J.map = map; J.sff = sff; J.sff_f64 = sff_f64; J.H = H; J.W = W; J.nbr = nbr; J.k_S = k_S; J.k_D = k_D;
@@ -227,6 +241,7 @@ int ffm_oracle_core_run(const uint8_t* map, const void* sff, int sff_f64, int H,
     J.episode_base = episode_base; J.max_steps = max_steps; J.track_dff = track_dff;
     J.steps = steps; J.ped_steps = ped_steps; J.min_margin = min_margin; J.final_pos = final_pos; J.final_n = final_n;
     J.final_dff = final_dff; J.traj = traj; J.traj_n = traj_n; J.traj_steps = traj_steps;
+    J.guard = guard; J.move_out = move_out; J.move_out_steps = move_out_steps;
     pthread_mutex_init(&J.mu, NULL);
     if (threads < 1) threads = 1;
     if (threads > 256) threads = 256;

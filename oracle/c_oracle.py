@@ -29,9 +29,11 @@ def lib():
 
 
 def run_core_batch(map_array, sff, pos_rc, n, params, seed=0, episode_base=0, max_steps=1 << 30, threads=1,
-                   track_dff=True, traj_steps=0, want_state=False):
+                   track_dff=True, traj_steps=0, want_state=False, guard=0.0, record_moves=0):
     """B episodes of model/ffm_core.py semantics.  pos_rc int32 [B, n_max, 2], n int32 [B].
-    -> (steps int32 [B], ped_steps int64 [B])  or, with want_state / traj_steps, a dict."""
+    -> (steps int32 [B], ped_steps int64 [B])  or, with want_state / traj_steps, a dict.
+    guard > 0 re-draws move uniforms closer than `guard` to a CDF boundary; record_moves = T returns
+    the uniforms actually used as move_draws float64 [B, T, n_max] (0 where nothing was drawn)."""
     m = np.ascontiguousarray(map_array, dtype=np.uint8)
     H, W = m.shape
     sff = np.asarray(sff)
@@ -53,6 +55,7 @@ def run_core_batch(map_array, sff, pos_rc, n, params, seed=0, episode_base=0, ma
     fdff = np.zeros((B, H, W), np.float32) if want_state else None
     traj = np.full((B, traj_steps, n_max), -1, np.int32) if traj_steps else None
     traj_n = np.zeros((B, traj_steps), np.int32) if traj_steps else None
+    moves = np.zeros((B, record_moves, n_max), np.float64) if record_moves else None
 
     def ptr(a):
         return C.c_void_p(a.ctypes.data) if a is not None else C.c_void_p(0)
@@ -62,8 +65,9 @@ def run_core_batch(map_array, sff, pos_rc, n, params, seed=0, episode_base=0, ma
         C.c_double(float(p["k_D"])), C.c_float(float(c0)), C.c_float(float(c1)), C.c_float(float(thr)), ptr(pos_rc), ptr(n),
         C.c_int(B), C.c_int(n_max), C.c_uint64(int(seed) & 0xFFFFFFFFFFFFFFFF), C.c_uint32(int(episode_base)),
         C.c_int(int(min(max_steps, 2**31 - 1))), C.c_int(int(bool(track_dff))), C.c_int(int(threads)), ptr(steps), ptr(ped),
-        ptr(margin), ptr(fpos), ptr(fn), ptr(fdff), ptr(traj), ptr(traj_n), C.c_int(int(traj_steps)))
-    if want_state or traj_steps:
+        ptr(margin), ptr(fpos), ptr(fn), ptr(fdff), ptr(traj), ptr(traj_n), C.c_int(int(traj_steps)),
+        C.c_double(float(guard)), ptr(moves), C.c_int(int(record_moves)))
+    if want_state or traj_steps or record_moves:
         return dict(steps=steps, ped_steps=ped, min_margin=margin, final_pos=fpos, final_n=fn, final_dff=fdff,
-                    traj=traj, traj_n=traj_n)
+                    traj=traj, traj_n=traj_n, move_draws=moves)
     return steps, ped

@@ -16,63 +16,72 @@ def _c2(nbh="moore"):
 
 
 @pytest.mark.parametrize("k_D,track", [(0, False), (1, True)])
-def test_c2_full_episodes_match_c_oracle(cuda_device, k_D, track):
+def test_c2_recorded_draws_bit_exact(cuda_device, k_D, track):
+    """North-star protocol at full size: both sides consume the same RECORDED move uniforms (recorder
+    re-draws anything within 1e-5 of a CDF boundary); conflicts use the keyed streams.
+    Every episode must then agree bit for bit: steps, ped-steps, trajectories, DFF."""
     import bench
     import torch
     from ffm_b200 import BatchSim
     from oracle import c_oracle
 
     m, sff = _c2()
-    B, N, seed, base = 48, 1024, 0x5EED0002, 4096 * 3
+    B, N, seed, base, T = 6, 1024, 0x5EED0002, 4096 * 3, 2600
     params = {"k_S": 3, "k_D": k_D, "neighborhood": "moore"}
     pos = bench.place(m, N, B, base, seed)
     n = np.full((B,), N, np.int32)
-    T = 4096
-    ref = c_oracle.run_core_batch(m, sff, pos, n, params, seed=seed, episode_base=base, max_steps=T, threads=8,
-                                  track_dff=track, traj_steps=T if False else 0, want_state=True)
+    ref = c_oracle.run_core_batch(m, sff, pos, n, params, seed=seed, episode_base=base, max_steps=T, threads=6,
+                                  track_dff=track, traj_steps=T, want_state=True, guard=1e-5, record_moves=T)
+    assert (ref["steps"] < T).all() and (ref["min_margin"] >= 1e-5).all()
     sim = BatchSim(m, sff, B, N, params, seed=seed, episode_base=base, track_dff=track)
     sim.set_positions(pos, n)
-    rec = 8
-    sim.rollout(T)
+    cells, cnt = sim.rollout(T, draws=dict(move=torch.from_numpy(ref["move_draws"]).cuda()), record=T)
     torch.cuda.synchronize()
     steps, ped = sim.counters()
-    ok = ref["min_margin"] >= MARGIN_GUARD
-    assert ok.sum() >= B - 4, f"too many knife-edge episodes: {(~ok).sum()}"
-    assert np.array_equal(steps[ok], ref["steps"][ok])
-    assert np.array_equal(ped[ok], ref["ped_steps"][ok])
-    assert (sim.get_positions()[1] == 0).all()
+    assert np.array_equal(steps, ref["steps"]) and np.array_equal(ped, ref["ped_steps"])
+    cells, cnt = cells.cpu().numpy(), cnt.cpu().numpy()
+    for e in range(B):
+        s = int(ref["steps"][e])
+        assert np.array_equal(cnt[e, :s], ref["traj_n"][e, :s])
+        mask = np.arange(N)[None, :] < cnt[e, :s, None]
+        assert np.array_equal(cells[e, :s][mask], ref["traj"][e, :s][mask]), e
     if track:
-        dff = sim.get_dff()
-        for e in np.nonzero(ok)[0]:
-            assert np.array_equal(dff[e].view(np.uint32), ref["final_dff"][e].view(np.uint32)), e
+        assert np.array_equal(sim.get_dff().view(np.uint32), ref["final_dff"].view(np.uint32))
 
 
-def test_c2_trajectories_match_c_oracle(cuda_device):
+def test_c2_keyed_streams_agree_up_to_knife_edges(cuda_device):
+    """Pure Philox mode at full size (~4.5e5 draws per episode): an episode may differ from the oracle
+    only if the oracle saw a draw closer than MARGIN_GUARD to a CDF boundary (exp differs by <= 2 ulp
+    between libm and CUDA); the evacuation-time distributions must agree (KS)."""
     import bench
     import torch
+    from scipy import stats
     from ffm_b200 import BatchSim
     from oracle import c_oracle
 
     m, sff = _c2()
-    B, N, seed = 4, 1024, 77
-    params = {"k_S": 3, "k_D": 1, "neighborhood": "moore"}
-    pos = bench.place(m, N, B, 0, seed)
+    B, N, seed, base = 96, 1024, 0x5EED0002, 0
+    params = {"k_S": 3, "k_D": 0, "neighborhood": "moore"}
+    pos = bench.place(m, N, B, base, seed)
     n = np.full((B,), N, np.int32)
-    T = 2400
-    ref = c_oracle.run_core_batch(m, sff, pos, n, params, seed=seed, max_steps=T, threads=4, traj_steps=T, want_state=True)
-    sim = BatchSim(m, sff, B, N, params, seed=seed)
+    ref = c_oracle.run_core_batch(m, sff, pos, n, params, seed=seed, episode_base=base, max_steps=4096, threads=8,
+                                  track_dff=False, want_state=True)
+    sim = BatchSim(m, sff, B, N, params, seed=seed, episode_base=base, track_dff=False)
     sim.set_positions(pos, n)
-    cells, cnt = sim.rollout(T, record=T)
+    sim.rollout(4096)
     torch.cuda.synchronize()
-    cells, cnt = cells.cpu().numpy(), cnt.cpu().numpy()
-    for e in range(B):
-        if ref["min_margin"][e] < MARGIN_GUARD:
-            continue
-        s = int(ref["steps"][e])
-        assert np.array_equal(cnt[e, :s], ref["traj_n"][e, :s])
-        for t in range(s):
-            k = cnt[e, t]
-            assert np.array_equal(cells[e, t, :k], ref["traj"][e, t, :k]), (e, t)
+    steps, ped = sim.counters()
+    differ = (steps != ref["steps"]) | (ped != ref["ped_steps"])
+    knife = ref["min_margin"] < MARGIN_GUARD
+    assert not (differ & ~knife).any(), "an episode without a knife-edge draw differs from the oracle"
+    assert differ.mean() < 0.5
+    # independent seeds: evacuation-time distribution, KS bound 0.2 at n = 96 vs 96 (p ~ 0.04 level)
+    sim2 = BatchSim(m, sff, B, N, params, seed=seed + 1, episode_base=10_000, track_dff=False)
+    sim2.set_positions(bench.place(m, N, B, 10_000, seed + 1), n)
+    sim2.rollout(4096)
+    steps2, _ = sim2.counters()
+    assert stats.ks_2samp(steps2, ref["steps"]).statistic < 0.2
+    assert abs(steps2.mean() - ref["steps"].mean()) < 0.02 * ref["steps"].mean()
 
 
 def test_properties_at_full_size(cuda_device):
