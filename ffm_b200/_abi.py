@@ -12,6 +12,7 @@ FFM_HOST, FFM_DEVICE = 0, 1
 FFM_NEUMANN, FFM_MOORE = 4, 8
 FFM_F32, FFM_F64 = 0, 1
 E_INVALID, E_CUDA, E_UNSUPPORTED, E_STATE = -1, -2, -3, -4
+SFF_L1, SFF_L2, SFF_LINF, SFF_BFS4, SFF_BFS8, SFF_DIJKSTRA8 = range(6)
 
 
 class Config(C.Structure):
@@ -50,6 +51,8 @@ SIGNATURES = {
     "ffm_get_dff": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "ffm_rollout": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(Draws), C.POINTER(RolloutOut), C.c_void_p]),
     "ffm_get_counters": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "ffm_sff_generate": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int,
+                                   C.c_int32, C.c_void_p, C.POINTER(C.c_int32)]),
     "ffm_launch_count": (C.c_int64, [C.c_void_p]),
     "ffm_kernel_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32),
                                   C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),

@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "ffm_core_kernel.cuh"
+#include "ffm_sff_kernels.cuh"
 
 namespace {
 
@@ -408,6 +409,92 @@ int ffm_get_counters(ffm_sim_t s, int32_t* steps, int64_t* ped_steps, int space,
     if (ped_steps && (rc = copy_out(ped_steps, s->d_ped_steps, (size_t)s->cfg.n_episodes * 8, space, st))) return rc;
     if (space == FFM_HOST && (rc = check_device_flag(s, st))) return rc;
     return FFM_OK;
+}
+
+int ffm_sff_generate(const uint8_t* maps, int32_t n_maps, int32_t H, int32_t W, int32_t mode, int32_t out_dtype, void* out,
+                     int space, int32_t device, void* stream, int32_t* rounds_out) {
+    if (!maps || !out) return fail(FFM_E_INVALID, "null argument");
+    if (n_maps < 1 || H < 1 || W < 1) return fail(FFM_E_INVALID, "bad shape");
+    if (mode < FFM_SFF_L1 || mode > FFM_SFF_DIJKSTRA8) return fail(FFM_E_INVALID, "unknown SFF mode %d", mode);
+    if (out_dtype != FFM_F32 && out_dtype != FFM_F64) return fail(FFM_E_INVALID, "out_dtype must be FFM_F32 or FFM_F64");
+    cudaStream_t st = (cudaStream_t)stream;
+    CU(cudaSetDevice(device));
+    const size_t HW = (size_t)H * W, total = HW * n_maps;
+    const size_t osz = out_dtype == FFM_F64 ? 8 : 4;
+    uint8_t* d_maps = nullptr; void* d_out = nullptr; float* d_dist = nullptr; uint8_t* d_dirty = nullptr;
+    int32_t* d_exits = nullptr; int32_t* d_counts = nullptr; int* d_any = nullptr;
+    int rc = FFM_OK, rounds = 0;
+#define SFF_CU(call)                                                                        \
+    do {                                                                                    \
+        cudaError_t e_ = (call);                                                            \
+        if (e_ != cudaSuccess) { rc = fail(FFM_E_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); goto done; } \
+    } while (0)
+    {
+        const uint8_t* mp = maps;
+        if (space == FFM_HOST) {
+            SFF_CU(cudaMalloc((void**)&d_maps, total));
+            SFF_CU(cudaMemcpyAsync(d_maps, maps, total, cudaMemcpyHostToDevice, st));
+            mp = d_maps;
+            SFF_CU(cudaMalloc(&d_out, total * osz));
+        } else {
+            d_out = out;
+        }
+        const int bx = (int)((HW + 255) / 256 < 148 * 8 ? (HW + 255) / 256 : 148 * 8);
+        if (mode <= FFM_SFF_LINF) {
+            SFF_CU(cudaMalloc((void**)&d_exits, (size_t)n_maps * ffm::SFF_MAX_EXITS * 2 * sizeof(int32_t)));
+            SFF_CU(cudaMalloc((void**)&d_counts, (size_t)n_maps * sizeof(int32_t)));
+            SFF_CU(cudaMemsetAsync(d_counts, 0, (size_t)n_maps * sizeof(int32_t), st));
+            ffm::sff_collect_exits_kernel<<<dim3(bx, n_maps), 256, 0, st>>>(mp, d_exits, d_counts, H, W);
+            if (out_dtype == FFM_F64)
+                ffm::sff_norm_min_kernel<double><<<dim3(bx, n_maps), 256, 0, st>>>(mp, d_exits, d_counts, H, W, mode, (double*)d_out);
+            else
+                ffm::sff_norm_min_kernel<float><<<dim3(bx, n_maps), 256, 0, st>>>(mp, d_exits, d_counts, H, W, mode, (float*)d_out);
+            SFF_CU(cudaGetLastError());
+            std::vector<int32_t> counts(n_maps);
+            SFF_CU(cudaMemcpyAsync(counts.data(), d_counts, (size_t)n_maps * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+            SFF_CU(cudaStreamSynchronize(st));
+            for (int i = 0; i < n_maps; ++i)
+                if (counts[i] > ffm::SFF_MAX_EXITS) { rc = fail(FFM_E_UNSUPPORTED, "map %d has %d exit cells (max %d)", i, counts[i], ffm::SFF_MAX_EXITS); goto done; }
+        } else {
+            const int tiles_x = (W + ffm::SFF_TILE - 1) / ffm::SFF_TILE, tiles_y = (H + ffm::SFF_TILE - 1) / ffm::SFF_TILE;
+            const size_t ntiles = (size_t)tiles_x * tiles_y * n_maps;
+            if (tiles_y > 65535 || n_maps > 65535) { rc = fail(FFM_E_UNSUPPORTED, "too many tiles / maps for one launch"); goto done; }
+            SFF_CU(cudaMalloc((void**)&d_dist, total * sizeof(float)));
+            SFF_CU(cudaMalloc((void**)&d_dirty, 2 * ntiles));
+            SFF_CU(cudaMalloc((void**)&d_any, sizeof(int)));
+            SFF_CU(cudaMemsetAsync(d_dirty, 0, 2 * ntiles, st));
+            ffm::sff_relax_init_kernel<<<dim3(bx, n_maps), 256, 0, st>>>(mp, d_dist, d_dirty, H, W, tiles_x, tiles_y);
+            const float INF = __builtin_huge_valf();
+            const float w_axis = 1.0f;
+            const float w_diag = mode == FFM_SFF_BFS4 ? INF : (mode == FFM_SFF_BFS8 ? 1.0f : (float)1.4142135623730951);
+            uint8_t* din = d_dirty; uint8_t* dout = d_dirty + ntiles;
+            for (;;) {
+                int any = 0;
+                SFF_CU(cudaMemsetAsync(d_any, 0, sizeof(int), st));
+                SFF_CU(cudaMemsetAsync(dout, 0, ntiles, st));
+                ffm::sff_relax_tile_kernel<<<dim3(tiles_x, tiles_y, n_maps), 256, 0, st>>>(mp, d_dist, din, dout, d_any, H, W, tiles_x, tiles_y, w_axis, w_diag);
+                SFF_CU(cudaGetLastError());
+                ++rounds;
+                SFF_CU(cudaMemcpyAsync(&any, d_any, sizeof(int), cudaMemcpyDeviceToHost, st));
+                SFF_CU(cudaStreamSynchronize(st));
+                if (!any) break;
+                uint8_t* t = din; din = dout; dout = t;
+                if (rounds > 4 * (tiles_x + tiles_y) * ffm::SFF_TILE) { rc = fail(FFM_E_CUDA, "SFF relaxation did not converge"); goto done; }
+            }
+            const int cb = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+            if (out_dtype == FFM_F64) ffm::sff_convert_kernel<double><<<cb, 256, 0, st>>>(d_dist, (double*)d_out, total);
+            else ffm::sff_convert_kernel<float><<<cb, 256, 0, st>>>(d_dist, (float*)d_out, total);
+            SFF_CU(cudaGetLastError());
+        }
+        if (space == FFM_HOST) SFF_CU(cudaMemcpyAsync(out, d_out, total * osz, cudaMemcpyDeviceToHost, st));
+        SFF_CU(cudaStreamSynchronize(st));
+    }
+done:
+#undef SFF_CU
+    if (space == FFM_HOST) { cudaFree(d_maps); cudaFree(d_out); }
+    cudaFree(d_dist); cudaFree(d_dirty); cudaFree(d_exits); cudaFree(d_counts); cudaFree(d_any);
+    if (rounds_out) *rounds_out = rounds;
+    return rc;
 }
 
 int64_t ffm_launch_count(ffm_sim_t s) { return s ? s->launches : 0; }

@@ -1,0 +1,188 @@
+// Static-floor-field generation on the GPU.
+//
+//  * sff_norm_min_kernel      obstacle-blind min-over-exits norm distance -- exact counterpart of the
+//                             reference generators (Create_SFF.py:14-33: L1 / np.hypot / Linf, float64,
+//                             inf on non-walkable cells; create_12x12_map_and_sff.py:36-50: L1, float32)
+//  * sff_relax_tile_kernel    geodesic (obstacle-aware) distance from the exits, 4-/8-connected unit
+//                             steps (= wavefront BFS levels) or (1, sqrt 2)-weighted 8-connected steps
+//                             (= Dijkstra), computed as the least fixpoint of
+//                                 d[c] = min(d[c], min_nb fl32(d[nb] + w))
+//                             by block-asynchronous relaxation: a CTA owns a 32x32 tile in shared
+//                             memory, relaxes it to local convergence, writes it back and marks the
+//                             neighbouring tiles dirty if its rim changed; rounds repeat over dirty
+//                             tiles until none is left.  Any relaxation order reaches the same fixpoint
+//                             (fl32(d + w) is monotone in d), so the result is bit-identical to a
+//                             float32 Dijkstra -- the oracle (oracle/c/ffm_oracle.c geodesic).
+//                             North-star item 2 (the reference has no obstacle-aware generator).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace ffm {
+
+enum { SFF_L1 = 0, SFF_L2 = 1, SFF_LINF = 2, SFF_BFS4 = 3, SFF_BFS8 = 4, SFF_DIJKSTRA8 = 5 };
+
+constexpr int SFF_TILE = 32;
+
+// one thread per cell; exits (row, col) pairs of this map in global memory
+constexpr int SFF_MAX_EXITS = 4096;
+
+// exit cells of every map -> exits[map][SFF_MAX_EXITS] (row, col), counts[map] (order is irrelevant to a min)
+__global__ void sff_collect_exits_kernel(const uint8_t* __restrict__ maps, int32_t* __restrict__ exits,
+                                         int32_t* __restrict__ counts, int H, int W) {
+    const int mapi = blockIdx.y;
+    const size_t HW = (size_t)H * W;
+    for (size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x; c < HW; c += (size_t)gridDim.x * blockDim.x)
+        if (maps[mapi * HW + c] == 3) {                               // np.argwhere(cell_map == 3), Create_SFF.py:8
+            const int k = atomicAdd(&counts[mapi], 1);
+            if (k < SFF_MAX_EXITS) {
+                exits[((size_t)mapi * SFF_MAX_EXITS + k) * 2] = (int)(c / W);
+                exits[((size_t)mapi * SFF_MAX_EXITS + k) * 2 + 1] = (int)(c % W);
+            }
+        }
+}
+
+template <typename OutT>
+__global__ void sff_norm_min_kernel(const uint8_t* __restrict__ maps, const int32_t* __restrict__ exits_all,
+                                    const int32_t* __restrict__ counts, int H, int W, int metric, OutT* __restrict__ out) {
+    const int mapi = blockIdx.y;
+    const size_t HW = (size_t)H * W;
+    const uint8_t* map = maps + mapi * HW;
+    const int32_t* exits = exits_all + (size_t)mapi * SFF_MAX_EXITS * 2;
+    const int e0 = 0, e1 = min(counts[mapi], SFF_MAX_EXITS);
+    for (size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x; c < HW; c += (size_t)gridDim.x * blockDim.x) {
+        const int i = (int)(c / W), j = (int)(c - (size_t)i * W);
+        const uint8_t m = map[c];
+        double best = __longlong_as_double(0x7ff0000000000000LL);
+        if (m == 0 || m == 3) {                                       // Create_SFF.py:21
+            for (int e = e0; e < e1; ++e) {
+                const int dx = abs(i - exits[2 * e]), dy = abs(j - exits[2 * e + 1]);
+                double d;
+                if (metric == SFF_L1) d = (double)(dx + dy);          // :24
+                else if (metric == SFF_LINF) d = (double)max(dx, dy); // :28
+                else d = __dsqrt_rn((double)((long long)dx * dx + (long long)dy * dy));   // :26, correctly rounded hypot
+                best = fmin(best, d);                                 // :31-33
+            }
+        }
+        out[mapi * HW + c] = (OutT)best;
+    }
+}
+
+// initial field: 0 on exits, +inf elsewhere; every tile that holds an exit starts dirty
+__global__ void sff_relax_init_kernel(const uint8_t* __restrict__ maps, float* __restrict__ dist, uint8_t* __restrict__ dirty,
+                                      int H, int W, int tiles_x, int tiles_y) {
+    const int mapi = blockIdx.y;
+    const size_t HW = (size_t)H * W;
+    for (size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x; c < HW; c += (size_t)gridDim.x * blockDim.x) {
+        const bool ex = maps[mapi * HW + c] == 3;
+        dist[mapi * HW + c] = ex ? 0.0f : __int_as_float(0x7f800000);
+        if (ex) {
+            const int r = (int)(c / W), col = (int)(c - (size_t)r * W);
+            dirty[((size_t)mapi * tiles_y + r / SFF_TILE) * tiles_x + col / SFF_TILE] = 1;
+        }
+    }
+}
+
+// One relaxation round: CTA (x, y, map) = tile.  dirty_in says which tiles must run; dirty_out collects
+// the tiles to run next round; *any_out is set when something is left to do.
+__global__ void __launch_bounds__(256)
+sff_relax_tile_kernel(const uint8_t* __restrict__ maps, float* __restrict__ dist, const uint8_t* __restrict__ dirty_in,
+                      uint8_t* __restrict__ dirty_out, int* __restrict__ any_out, int H, int W, int tiles_x, int tiles_y,
+                      float w_axis, float w_diag) {
+    const int tx = blockIdx.x, ty = blockIdx.y, mapi = blockIdx.z;
+    const size_t tile_id = ((size_t)mapi * tiles_y + ty) * tiles_x + tx;
+    if (!dirty_in[tile_id]) return;
+    constexpr int T = SFF_TILE, P = SFF_TILE + 2;
+    __shared__ float d[P][P + 1];
+    __shared__ uint8_t pass[T][T];
+    __shared__ int rim_changed[4];   // top, bottom, left, right
+    const size_t HW = (size_t)H * W;
+    const uint8_t* map = maps + mapi * HW;
+    float* g = dist + mapi * HW;
+    const int r0 = ty * T, c0 = tx * T;
+    const float INF = __int_as_float(0x7f800000);
+    if (threadIdx.x < 4) rim_changed[threadIdx.x] = 0;
+    for (int x = threadIdx.x; x < P * P; x += blockDim.x) {
+        const int lr = x / P, lc = x - lr * P;
+        const int r = r0 + lr - 1, c = c0 + lc - 1;
+        float v = INF;
+        if (r >= 0 && r < H && c >= 0 && c < W) v = g[(size_t)r * W + c];
+        d[lr][lc] = v;
+        if (lr >= 1 && lr <= T && lc >= 1 && lc <= T) {
+            uint8_t p = 0;
+            if (r < H && c < W) { const uint8_t m = map[(size_t)r * W + c]; p = (m == 0 || m == 3) ? 1 : 0; }
+            pass[lr - 1][lc - 1] = p;
+        }
+    }
+    __syncthreads();
+    // 256 threads x 4 cells; in-place (Gauss-Seidel style) min-relaxation: a concurrently updated
+    // neighbour is read as either its old or its new value, both valid upper bounds of the fixpoint
+    volatile float (*vd)[P + 1] = d;
+    bool any_change = false;
+    for (int it = 0; it < 4 * T * T; ++it) {
+        bool ch = false;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int x = threadIdx.x + q * 256;
+            const int lr = x / T, lc = x - lr * T;
+            if (!pass[lr][lc]) continue;
+            const int a = lr + 1, b = lc + 1;
+            float best = vd[a][b];
+            const float old = best;
+            best = fminf(best, __fadd_rn(vd[a - 1][b], w_axis));
+            best = fminf(best, __fadd_rn(vd[a + 1][b], w_axis));
+            best = fminf(best, __fadd_rn(vd[a][b - 1], w_axis));
+            best = fminf(best, __fadd_rn(vd[a][b + 1], w_axis));
+            if (w_diag < INF) {
+                best = fminf(best, __fadd_rn(vd[a - 1][b - 1], w_diag));
+                best = fminf(best, __fadd_rn(vd[a - 1][b + 1], w_diag));
+                best = fminf(best, __fadd_rn(vd[a + 1][b - 1], w_diag));
+                best = fminf(best, __fadd_rn(vd[a + 1][b + 1], w_diag));
+            }
+            if (best < old) { vd[a][b] = best; ch = true; }
+        }
+        if (!__syncthreads_or(ch ? 1 : 0)) break;
+        any_change = true;
+    }
+    (void)any_change;
+    // write back; detect rim changes to wake the neighbours
+    for (int x = threadIdx.x; x < T * T; x += blockDim.x) {
+        const int lr = x / T, lc = x - lr * T;
+        const int r = r0 + lr, c = c0 + lc;
+        if (r < H && c < W) {
+            const float v = d[lr + 1][lc + 1];
+            const size_t gi = (size_t)r * W + c;
+            if (v < g[gi]) {
+                g[gi] = v;
+                if (lr == 0) rim_changed[0] = 1;
+                if (lr == T - 1) rim_changed[1] = 1;
+                if (lc == 0) rim_changed[2] = 1;
+                if (lc == T - 1) rim_changed[3] = 1;
+            }
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        // a changed rim wakes the three tiles on that side (safe superset: corners included)
+        bool any = false;
+        auto mark = [&](int ny, int nx) {
+            if (ny >= 0 && ny < tiles_y && nx >= 0 && nx < tiles_x) {
+                dirty_out[((size_t)mapi * tiles_y + ny) * tiles_x + nx] = 1;
+                any = true;
+            }
+        };
+        if (rim_changed[0]) for (int dx = -1; dx <= 1; ++dx) mark(ty - 1, tx + dx);
+        if (rim_changed[1]) for (int dx = -1; dx <= 1; ++dx) mark(ty + 1, tx + dx);
+        if (rim_changed[2]) for (int dy = -1; dy <= 1; ++dy) mark(ty + dy, tx - 1);
+        if (rim_changed[3]) for (int dy = -1; dy <= 1; ++dy) mark(ty + dy, tx + 1);
+        if (any) *any_out = 1;
+    }
+}
+
+template <typename OutT>
+__global__ void sff_convert_kernel(const float* __restrict__ dist, OutT* __restrict__ out, size_t n) {
+    for (size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x; c < n; c += (size_t)gridDim.x * blockDim.x)
+        out[c] = (OutT)dist[c];
+}
+
+}  // namespace ffm

@@ -123,6 +123,19 @@ int ffm_rollout(ffm_sim_t sim, int32_t max_steps, const ffm_draws_t *draws, cons
  * Either pointer may be NULL. */
 int ffm_get_counters(ffm_sim_t sim, int32_t *steps, int64_t *ped_steps, int space, void *stream);
 
+/* Static-floor-field generation for n_maps maps (uint8 [n_maps][H][W]) -> out [n_maps][H][W] of
+ * out_dtype (FFM_F32 | FFM_F64), +inf on non-walkable and unreachable cells.
+ *   FFM_SFF_L1 / L2 / LINF   obstacle-blind min-over-exits norm: Create_SFF.py:14-33 (L2 = correctly
+ *                            rounded hypot, as in the shipped data/sff/distance_L2.npy),
+ *                            create_12x12_map_and_sff.py:36-50
+ *   FFM_SFF_BFS4 / BFS8      geodesic distance in 4-/8-connected unit steps (wavefront BFS levels)
+ *   FFM_SFF_DIJKSTRA8        geodesic distance with step costs (1, float32(sqrt 2)), float32 sums
+ * `rounds` (may be NULL) receives the number of relaxation rounds the geodesic modes needed.
+ * Synchronous with respect to the host on return. */
+enum { FFM_SFF_L1 = 0, FFM_SFF_L2 = 1, FFM_SFF_LINF = 2, FFM_SFF_BFS4 = 3, FFM_SFF_BFS8 = 4, FFM_SFF_DIJKSTRA8 = 5 };
+int ffm_sff_generate(const uint8_t *maps, int32_t n_maps, int32_t height, int32_t width, int32_t mode, int32_t out_dtype,
+                     void *out, int space, int32_t device, void *stream, int32_t *rounds);
+
 /* number of kernels this handle has launched so far (bench.py "gpu_launches") */
 int64_t ffm_launch_count(ffm_sim_t sim);
 

@@ -251,3 +251,72 @@ int ffm_oracle_core_run(const uint8_t* map, const void* sff, int sff_f64, int H,
     pthread_mutex_destroy(&J.mu);
     return 0;
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * Geodesic static floor field: textbook Dijkstra (binary heap, lazy deletion) from all exit cells
+ * over walkable cells (map 0 or 3), float32 path sums d[v] = fl32(d[u] + w), step costs
+ * (w_axis, w_diag); w_diag < 0 disables diagonal steps.  Unit costs give BFS levels.  This is the
+ * oracle of the GPU relaxation kernel (ffm_b200/csrc/ffm_sff_kernels.cuh); on obstacle-free rooms it
+ * coincides with the reference's Create_SFF.py L1 (4-connected) / Linf (8-connected) fields.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct { float d; int32_t c; } heap_item;
+
+static void heap_push(heap_item* h, int* n, heap_item it) {
+    int i = (*n)++;
+    while (i > 0) {
+        int p = (i - 1) / 2;
+        if (h[p].d <= it.d) break;
+        h[i] = h[p]; i = p;
+    }
+    h[i] = it;
+}
+static heap_item heap_pop(heap_item* h, int* n) {
+    heap_item top = h[0], last = h[--(*n)];
+    int i = 0;
+    for (;;) {
+        int l = 2 * i + 1, r = l + 1, m = i;
+        float md = last.d;
+        if (l < *n && h[l].d < md) { m = l; md = h[l].d; }
+        if (r < *n && h[r].d < md) { m = r; }
+        if (m == i) break;
+        h[i] = h[m]; i = m;
+    }
+    h[i] = last;
+    return top;
+}
+
+int ffm_oracle_geodesic(const uint8_t* map, int H, int W, float w_axis, float w_diag, float* out) {
+    const size_t HW = (size_t)H * W;
+    size_t cap = HW * 9 + 16;
+    heap_item* heap = (heap_item*)malloc(sizeof(heap_item) * cap);
+    if (!heap) return -1;
+    int hn = 0;
+    for (size_t c = 0; c < HW; ++c) {
+        out[c] = INFINITY;
+        if (map[c] == 3) { out[c] = 0.0f; heap_item it = {0.0f, (int32_t)c}; heap_push(heap, &hn, it); }
+    }
+    while (hn > 0) {
+        heap_item it = heap_pop(heap, &hn);
+        if (it.d > out[it.c]) continue;
+        const int r = it.c / W, col = it.c % W;
+        for (int dr = -1; dr <= 1; ++dr)
+            for (int dc = -1; dc <= 1; ++dc) {
+                if (dr == 0 && dc == 0) continue;
+                const int diag = (dr != 0 && dc != 0);
+                if (diag && w_diag < 0.0f) continue;
+                const int rr = r + dr, cc = col + dc;
+                if (rr < 0 || rr >= H || cc < 0 || cc >= W) continue;
+                const uint8_t m = map[(size_t)rr * W + cc];
+                if (!(m == 0 || m == 3)) continue;
+                const float w = diag ? w_diag : w_axis;
+                const float nd = it.d + w;
+                if (nd < out[(size_t)rr * W + cc]) {
+                    out[(size_t)rr * W + cc] = nd;
+                    heap_item ni = {nd, (int32_t)(rr * W + cc)};
+                    heap_push(heap, &hn, ni);
+                }
+            }
+    }
+    free(heap);
+    return 0;
+}

@@ -71,3 +71,17 @@ def run_core_batch(map_array, sff, pos_rc, n, params, seed=0, episode_base=0, ma
         return dict(steps=steps, ped_steps=ped, min_margin=margin, final_pos=fpos, final_n=fn, final_dff=fdff,
                     traj=traj, traj_n=traj_n, move_draws=moves)
     return steps, ped
+
+
+def geodesic(map_array, mode):
+    """Geodesic SFF (float32; inf on non-walkable / unreachable cells).  mode: "bfs4" | "bfs8" | "dijkstra8"."""
+    m = np.ascontiguousarray(map_array, dtype=np.uint8)
+    H, W = m.shape
+    out = np.empty((H, W), np.float32)
+    w_diag = {"bfs4": -1.0, "bfs8": 1.0, "dijkstra8": float(np.float32(np.sqrt(2.0)))}[mode]
+    L = lib()
+    L.ffm_oracle_geodesic.restype = C.c_int
+    rc = L.ffm_oracle_geodesic(C.c_void_p(m.ctypes.data), C.c_int(H), C.c_int(W), C.c_float(1.0), C.c_float(w_diag),
+                               C.c_void_p(out.ctypes.data))
+    assert rc == 0
+    return out

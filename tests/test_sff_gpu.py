@@ -1,0 +1,70 @@
+"""GPU SFF generation (ffm_sff_generate) against the reference's shipped fields and the oracles."""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+from helpers import GOLDEN
+from oracle import assets, c_oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def test_shipped_distance_files_bit_exact(cuda_device):
+    """Regenerates data/sff/distance_{L1,L2,Linf}.npy (float64, 195 inf) from the 50x50 room."""
+    from ffm_b200.sff import generate_sff
+    with open(os.path.join(GOLDEN, "shipped_assets.json")) as f:
+        want = json.load(f)
+    m = assets.room_map(50, 50)
+    for metric in ("L1", "L2", "Linf"):
+        got = generate_sff(m, metric, np.float64)
+        meta = want[f"data/sff/distance_{metric}.npy"]
+        assert got.dtype == np.float64 and int(np.isinf(got).sum()) == meta["n_inf"] == 195
+        assert hashlib.sha256(got.tobytes()).hexdigest() == meta["sha256"], metric
+
+
+def test_12x12_l1_float32(cuda_device):
+    from ffm_b200.sff import generate_sff
+    m = assets.room_map(12, 12)
+    got = generate_sff(m, "L1", np.float32)
+    assert got.dtype == np.float32 and np.array_equal(got, assets.sff_norm_min(m, "L1", np.float32))
+
+
+@pytest.mark.parametrize("metric", ["L1", "L2", "Linf"])
+def test_norm_min_multi_exit_batch(cuda_device, metric):
+    from ffm_b200.sff import generate_sff
+    maps = np.stack([assets.obstacle_map_c5(70, 90, index=i, n_exits=8) for i in range(3)])
+    got = generate_sff(maps, metric, np.float64)
+    for i in range(3):
+        assert np.array_equal(got[i], assets.sff_norm_min_fast(maps[i], metric, np.float64)), i
+
+
+@pytest.mark.parametrize("mode", ["bfs4", "bfs8", "dijkstra8"])
+@pytest.mark.parametrize("shape", [(33, 47), (200, 160)])
+def test_geodesic_bit_exact(cuda_device, mode, shape):
+    from ffm_b200.sff import generate_sff
+    maps = np.stack([assets.obstacle_map_c5(shape[0], shape[1], index=i, n_exits=4) for i in range(2)])
+    maps[1, 5:9, 5:9] = 2
+    maps[1, 6:8, 6:8] = 0           # enclosed pocket: unreachable -> inf
+    got, rounds = generate_sff(maps, mode, np.float32, return_rounds=True)
+    assert rounds >= 1
+    for i in range(2):
+        want = c_oracle.geodesic(maps[i], mode)
+        assert np.array_equal(got[i].view(np.uint32), want.view(np.uint32)), (mode, i)
+    assert np.isinf(got[1, 6, 6])
+
+
+def test_geodesic_c3_and_c5_maps(cuda_device):
+    """The C3 floor plan (256x256 rooms with doors) and one C5 map (1024x1024, 20% obstacles)."""
+    import torch
+    from ffm_b200.sff import generate_sff
+    m3 = assets.rooms_map_c3()
+    got = generate_sff(m3, "bfs8", np.float32)
+    assert np.array_equal(got, c_oracle.geodesic(m3, "bfs8"))
+    assert np.isfinite(got[(m3 == 0)]).all()
+    m5 = assets.obstacle_map_c5(1024, 1024, index=0)
+    for mode in ("bfs4", "dijkstra8"):
+        got = generate_sff(torch.from_numpy(m5).cuda(), mode, np.float32).cpu().numpy()
+        assert np.array_equal(got.view(np.uint32), c_oracle.geodesic(m5, mode).view(np.uint32)), mode
