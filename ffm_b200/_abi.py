@@ -7,11 +7,13 @@ import os
 
 from . import build as _build
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 FFM_HOST, FFM_DEVICE = 0, 1
 FFM_NEUMANN, FFM_MOORE = 4, 8
 FFM_F32, FFM_F64 = 0, 1
 E_INVALID, E_CUDA, E_UNSUPPORTED, E_STATE = -1, -2, -3, -4
+MODEL_CORE, MODEL_UNIFIED_CRITIC, MODEL_UNIFIED_ACTOR, MODEL_UNIFIED_BOTH, MODEL_TRAINED = range(5)
+LEARN_NONE, LEARN_EXACT, LEARN_BATCHED = range(3)
 SFF_L1, SFF_L2, SFF_LINF, SFF_BFS4, SFF_BFS8, SFF_DIJKSTRA8 = range(6)
 
 
@@ -25,6 +27,10 @@ class Config(C.Structure):
         ("k_S", C.c_double), ("k_D", C.c_double),
         ("dff_c0", C.c_float), ("dff_c1", C.c_float), ("dff_threshold", C.c_float), ("reserved1", C.c_float),
         ("seed", C.c_uint64), ("episode_base", C.c_uint32), ("reserved2", C.c_uint32),
+        ("model", C.c_int32), ("learn", C.c_int32), ("block_size", C.c_int32), ("reserved3", C.c_int32),
+        ("k_A", C.c_double), ("gamma", C.c_double), ("alpha_v", C.c_double), ("alpha_h", C.c_double),
+        ("exit_reward", C.c_double), ("step_penalty", C.c_double), ("collision_penalty", C.c_double),
+        ("epsilon", C.c_double), ("sff_min", C.c_double), ("sff_max", C.c_double),
     ]
 
 
@@ -51,6 +57,12 @@ SIGNATURES = {
     "ffm_get_dff": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "ffm_rollout": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(Draws), C.POINTER(RolloutOut), C.c_void_p]),
     "ffm_get_counters": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "ffm_tables_shape": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "ffm_tables_set": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "ffm_tables_get": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "ffm_tables_bind_deltas": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ffm_tables_apply_deltas": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "ffm_set_epsilon": (C.c_int, [C.c_void_p, C.c_double]),
     "ffm_sff_generate": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int,
                                    C.c_int32, C.c_void_p, C.POINTER(C.c_int32)]),
     "ffm_launch_count": (C.c_int64, [C.c_void_p]),

@@ -12,6 +12,7 @@
 
 #include "ffm_core_kernel.cuh"
 #include "ffm_sff_kernels.cuh"
+#include "ffm_unified_kernel.cuh"
 
 namespace {
 
@@ -59,6 +60,13 @@ struct ffm_sim_s {
     int32_t* d_pos_rc;   // staging for (row, col) pairs
     int32_t* d_err;      // device-side validation flag
     const void* kernel;  // selected rollout kernel
+    // unified / trained models
+    int S, A, nby;
+    double* d_V; uint8_t* d_vseen; double* d_H; uint8_t* d_hseen;
+    double* d_dV; double* d_dH;          // borrowed (caller-owned) delta tables
+    ffm::HStats* d_hstats;
+    double* d_blk_lo; double* d_blk_hi; int* d_blk_any;
+    double epsilon;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -74,7 +82,7 @@ __global__ void prep_fields_kernel(const uint8_t* map, const S* sff, uint16_t* t
     const int HW = H * W, G = W + 1;
     for (int x = blockIdx.x * blockDim.x + threadIdx.x; x < HW + 2 * G; x += gridDim.x * blockDim.x) {
         const int c = x - G;
-        uint32_t cell = WALL_CELL;      // guard band and every non-passable code (1, 2): blocked
+        uint32_t cell = WALL_CELL;      // guard band and the non-passable codes: blocked
         if (c >= 0 && c < HW) {
             const uint8_t m = map[c];
             if (m > 3) atomicOr(err, 1);
@@ -83,6 +91,7 @@ __global__ void prep_fields_kernel(const uint8_t* map, const S* sff, uint16_t* t
             // border walls"): a free cell on the border would let a pedestrian read outside the map
             if ((r == 0 || r == H - 1 || col == 0 || col == W - 1) && m == FFM_CELL_FREE) atomicOr(err, 2);
             if (m == FFM_CELL_EXIT) cell = TYPE_EXIT << TYPE_SHIFT;
+            if (m == FFM_CELL_PED) cell = PEDMARK_CELL;   // blocked, and "a pedestrian" to _encode_state (ffm_unified.py:235)
             if (m == FFM_CELL_FREE) {
                 bool near = false;   // static flag: some neighbour (of the model's neighbourhood) is an exit
                 for (int dr = -1; dr <= 1; ++dr)
@@ -162,6 +171,19 @@ const void* pick_kernel(bool f64, bool small, int nbr, bool dff, bool fs, int th
     return f64 ? pick_pos<double>(small, nbr, dff, fs, threads) : pick_pos<float>(small, nbr, dff, fs, threads);
 }
 
+template <typename S, int NBR, bool FS>
+const void* upick_threads(int threads) {
+    if (threads >= 256) return (const void*)ffm::ffm_unified_rollout_kernel<S, NBR, FS, 256>;
+    return (const void*)ffm::ffm_unified_rollout_kernel<S, NBR, FS, 128>;
+}
+template <typename S, int NBR>
+const void* upick_fs(bool fs, int threads) { return fs ? upick_threads<S, NBR, true>(threads) : upick_threads<S, NBR, false>(threads); }
+template <typename S>
+const void* upick_nbr(int nbr, bool fs, int threads) { return nbr == 4 ? upick_fs<S, 4>(fs, threads) : upick_fs<S, 8>(fs, threads); }
+const void* upick_kernel(bool f64, int nbr, bool fs, int threads) {
+    return f64 ? upick_nbr<double>(nbr, fs, threads) : upick_nbr<float>(nbr, fs, threads);
+}
+
 int check_device_flag(ffm_sim_t s, cudaStream_t st) {
     int32_t flag = 0;
     CU(cudaMemcpyAsync(&flag, s->d_err, sizeof(flag), cudaMemcpyDeviceToHost, st));
@@ -204,6 +226,16 @@ int ffm_create(const ffm_config_t* cfg, ffm_sim_t* out) {
     if (cfg->n_episodes < 1) return fail(FFM_E_INVALID, "n_episodes must be >= 1");
     if (cfg->n_max < 1 || cfg->n_max > ffm::MAX_PEDS) return fail(FFM_E_UNSUPPORTED, "n_max must be in [1, %d]", ffm::MAX_PEDS);
     if (!cfg->track_dff && cfg->k_D != 0.0) return fail(FFM_E_INVALID, "track_dff = 0 requires k_D == 0");
+    if (cfg->model < FFM_MODEL_CORE || cfg->model > FFM_MODEL_TRAINED) return fail(FFM_E_INVALID, "unknown model %d", cfg->model);
+    const bool unified = cfg->model != FFM_MODEL_CORE;
+    if (unified) {
+        if (cfg->block_size < 1) return fail(FFM_E_INVALID, "block_size must be >= 1");
+        if (cfg->learn < FFM_LEARN_NONE || cfg->learn > FFM_LEARN_BATCHED) return fail(FFM_E_INVALID, "unknown learn mode %d", cfg->learn);
+        if (cfg->learn == FFM_LEARN_EXACT && cfg->n_episodes != 1)
+            return fail(FFM_E_INVALID, "FFM_LEARN_EXACT reproduces the reference's sequential table updates and needs n_episodes == 1");
+        if (cfg->model == FFM_MODEL_TRAINED && cfg->learn != FFM_LEARN_NONE) return fail(FFM_E_INVALID, "the trained-actor model does not learn");
+        if (!cfg->track_dff) return fail(FFM_E_INVALID, "the unified models always track the DFF");
+    }
     int ndev = 0;
     CU(cudaGetDeviceCount(&ndev));
     if (cfg->device < 0 || cfg->device >= ndev) return fail(FFM_E_INVALID, "device %d not present (%d visible)", cfg->device, ndev);
@@ -223,17 +255,18 @@ int ffm_create(const ffm_config_t* cfg, ffm_sim_t* out) {
 
     // kernel variant: fields in shared memory when they fit, and as many threads as pedestrians
     // (rounded to a supported CTA size) without starving co-resident CTAs
-    ffm::SmemLayout Lin = ffm::make_layout(HW, W, N, ssz, dff, true);
-    ffm::SmemLayout Lout = ffm::make_layout(HW, W, N, ssz, dff, false);
-    if ((int)Lin.total <= MAX_SMEM_OPTIN) {
+    const int tot_in = unified ? (int)ffm::make_ulayout(HW, W, N, ssz, true).total : (int)ffm::make_layout(HW, W, N, ssz, dff, true).total;
+    const int tot_out = unified ? (int)ffm::make_ulayout(HW, W, N, ssz, false).total : (int)ffm::make_layout(HW, W, N, ssz, dff, false).total;
+    struct { int total; } Lout = {tot_out};
+    if (tot_in <= MAX_SMEM_OPTIN) {
         s->fields_in_smem = true;
-        s->smem_bytes = (int)Lin.total;
-    } else if ((int)Lout.total <= MAX_SMEM_OPTIN) {
+        s->smem_bytes = tot_in;
+    } else if (tot_out <= MAX_SMEM_OPTIN) {
         s->fields_in_smem = false;
-        s->smem_bytes = (int)Lout.total;
+        s->smem_bytes = tot_out;
     } else {
         delete s;
-        return fail(FFM_E_UNSUPPORTED, "episode state (%u B) does not fit the 227 KB of shared memory of one SM", Lout.total);
+        return fail(FFM_E_UNSUPPORTED, "episode state (%d B) does not fit the 227 KB of shared memory of one SM", Lout.total);
     }
     const int work = N > HW / 8 ? N : HW / 8;
     s->threads = work <= 128 ? 128 : (work <= 1024 ? 256 : (work <= 4096 ? 512 : 1024));
@@ -241,7 +274,16 @@ int ffm_create(const ffm_config_t* cfg, ffm_sim_t* out) {
         const int v = atoi(ev);
         if (v == 128 || v == 256 || v == 512 || v == 1024) s->threads = v;
     }
-    s->kernel = pick_kernel(cfg->sff_dtype == FFM_F64, HW <= 65536, cfg->neighborhood, dff, s->fields_in_smem, s->threads);
+    if (unified) {
+        s->threads = N <= 128 ? 128 : 256;
+        s->kernel = upick_kernel(cfg->sff_dtype == FFM_F64, cfg->neighborhood, s->fields_in_smem, s->threads);
+        s->A = cfg->neighborhood + 1;
+        s->nby = (W + cfg->block_size - 1) / cfg->block_size;
+        s->S = ((cfg->height + cfg->block_size - 1) / cfg->block_size) * s->nby * 256;
+        s->epsilon = cfg->epsilon;
+    } else {
+        s->kernel = pick_kernel(cfg->sff_dtype == FFM_F64, HW <= 65536, cfg->neighborhood, dff, s->fields_in_smem, s->threads);
+    }
     cudaError_t ce = cudaFuncSetAttribute(s->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, s->smem_bytes);
     if (ce != cudaSuccess) { delete s; return fail(FFM_E_CUDA, "cudaFuncSetAttribute(smem=%d): %s", s->smem_bytes, cudaGetErrorString(ce)); }
     int occ = 0;
@@ -268,6 +310,21 @@ int ffm_create(const ffm_config_t* cfg, ffm_sim_t* out) {
         ALLOC(s->d_dff, (size_t)B * HW * 4);
         if (!s->fields_in_smem) ALLOC(s->d_dff_tmp, (size_t)B * HW * 4);
     }
+    if (unified) {
+        ALLOC(s->d_V, (size_t)s->S * 8);
+        ALLOC(s->d_vseen, (size_t)s->S);
+        ALLOC(s->d_H, (size_t)s->S * s->A * 8);
+        ALLOC(s->d_hseen, (size_t)s->S);
+        ALLOC(s->d_hstats, sizeof(ffm::HStats));
+        ALLOC(s->d_blk_lo, 148 * 8);
+        ALLOC(s->d_blk_hi, 148 * 8);
+        ALLOC(s->d_blk_any, 148 * 4);
+        cudaMemset(s->d_V, 0, (size_t)s->S * 8);
+        cudaMemset(s->d_vseen, 0, (size_t)s->S);
+        cudaMemset(s->d_H, 0, (size_t)s->S * s->A * 8);
+        cudaMemset(s->d_hseen, 0, (size_t)s->S);
+        cudaMemset(s->d_hstats, 0, sizeof(ffm::HStats));
+    }
 #undef ALLOC
     cudaMemset(s->d_err, 0, 4);
     cudaMemset(s->d_n, 0, (size_t)B * 4);
@@ -283,6 +340,8 @@ int ffm_destroy(ffm_sim_t s) {
     cudaFree(s->d_map); cudaFree(s->d_type_grid); cudaFree(s->d_sff); cudaFree(s->d_score);
     cudaFree(s->d_pos); cudaFree(s->d_pos_rc); cudaFree(s->d_n); cudaFree(s->d_t);
     cudaFree(s->d_ped_steps); cudaFree(s->d_err); cudaFree(s->d_dff); cudaFree(s->d_dff_tmp);
+    cudaFree(s->d_V); cudaFree(s->d_vseen); cudaFree(s->d_H); cudaFree(s->d_hseen); cudaFree(s->d_hstats);
+    cudaFree(s->d_blk_lo); cudaFree(s->d_blk_hi); cudaFree(s->d_blk_any);
     delete s;
     return FFM_OK;
 }
@@ -375,6 +434,34 @@ int ffm_rollout(ffm_sim_t s, int32_t max_steps, const ffm_draws_t* draws, const 
     if (draws && draws->space != FFM_DEVICE) return fail(FFM_E_INVALID, "recorded draws must live in device memory");
     cudaStream_t st = (cudaStream_t)stream;
     CU(cudaSetDevice(s->cfg.device));
+    if (s->cfg.model != FFM_MODEL_CORE) {
+        if (s->cfg.learn == FFM_LEARN_BATCHED && !s->d_dV) return fail(FFM_E_STATE, "FFM_LEARN_BATCHED needs ffm_tables_bind_deltas first");
+        ffm::UnifiedParams U;
+        memset(&U, 0, sizeof(U));
+        U.H = s->cfg.height; U.W = s->cfg.width; U.HW = s->HW; U.n_max = s->cfg.n_max; U.B = s->cfg.n_episodes;
+        U.max_steps = max_steps;
+        U.mode = s->cfg.model - 1; U.learn = s->cfg.learn;
+        U.block_size = s->cfg.block_size; U.nby = s->nby; U.S = s->S;
+        U.type_grid = s->d_type_grid; U.score = s->d_score;
+        U.kd = (float)s->cfg.k_D; U.c0 = s->cfg.dff_c0; U.c1 = s->cfg.dff_c1; U.thr = s->cfg.dff_threshold;
+        U.kA = s->cfg.k_A; U.gamma = s->cfg.gamma; U.alpha_v = s->cfg.alpha_v; U.alpha_h = s->cfg.alpha_h;
+        U.exit_reward = s->cfg.exit_reward; U.step_penalty = s->cfg.step_penalty; U.collision_penalty = s->cfg.collision_penalty;
+        U.epsilon = s->epsilon; U.sff_min = s->cfg.sff_min; U.sff_max = s->cfg.sff_max;
+        U.pos = s->d_pos; U.n_alive = s->d_n; U.t_done = s->d_t; U.ped_steps = s->d_ped_steps;
+        U.dff = s->d_dff; U.dff_tmp = s->d_dff_tmp;
+        U.V = s->d_V; U.v_seen = s->d_vseen; U.Hm = s->d_H; U.h_seen = s->d_hseen; U.dV = s->d_dV; U.dH = s->d_dH;
+        U.hstats = s->d_hstats;
+        U.seed = s->cfg.seed; U.episode_base = s->cfg.episode_base;
+        if (draws) { U.move_draws = draws->move; U.conflict_draws = draws->conflict; U.draw_steps = draws->steps; U.draw_first = draws->first_step; }
+        if (out && out->traj_cells) {
+            if (!out->traj_n) return fail(FFM_E_INVALID, "traj_cells without traj_n");
+            U.traj = out->traj_cells; U.traj_n = out->traj_n; U.traj_steps = out->traj_steps;
+        }
+        void* uargs[] = {&U};
+        CU(cudaLaunchKernel(s->kernel, dim3(s->cfg.n_episodes), dim3(s->threads), uargs, (size_t)s->smem_bytes, st));
+        s->launches++;
+        return FFM_OK;
+    }
     ffm::RolloutParams P;
     memset(&P, 0, sizeof(P));
     P.H = s->cfg.height; P.W = s->cfg.width; P.HW = s->HW; P.n_max = s->cfg.n_max; P.B = s->cfg.n_episodes;
@@ -408,6 +495,75 @@ int ffm_get_counters(ffm_sim_t s, int32_t* steps, int64_t* ped_steps, int space,
     if (steps && (rc = copy_out(steps, s->d_t, (size_t)s->cfg.n_episodes * 4, space, st))) return rc;
     if (ped_steps && (rc = copy_out(ped_steps, s->d_ped_steps, (size_t)s->cfg.n_episodes * 8, space, st))) return rc;
     if (space == FFM_HOST && (rc = check_device_flag(s, st))) return rc;
+    return FFM_OK;
+}
+
+int ffm_tables_shape(ffm_sim_t s, int32_t* n_states, int32_t* n_actions) {
+    if (!s) return fail(FFM_E_INVALID, "null argument");
+    if (s->cfg.model == FFM_MODEL_CORE) return fail(FFM_E_STATE, "the base model has no tables");
+    if (n_states) *n_states = s->S;
+    if (n_actions) *n_actions = s->A;
+    return FFM_OK;
+}
+
+int ffm_tables_set(ffm_sim_t s, const double* V, const uint8_t* v_seen, const double* H, const uint8_t* h_seen, int space, void* stream) {
+    if (!s) return fail(FFM_E_INVALID, "null argument");
+    if (s->cfg.model == FFM_MODEL_CORE) return fail(FFM_E_STATE, "the base model has no tables");
+    cudaStream_t st = (cudaStream_t)stream;
+    CU(cudaSetDevice(s->cfg.device));
+    int rc;
+    if (V && (rc = copy_in(s->d_V, V, (size_t)s->S * 8, space, st))) return rc;
+    if (v_seen && (rc = copy_in(s->d_vseen, v_seen, (size_t)s->S, space, st))) return rc;
+    if (H && (rc = copy_in(s->d_H, H, (size_t)s->S * s->A * 8, space, st))) return rc;
+    if (h_seen && (rc = copy_in(s->d_hseen, h_seen, (size_t)s->S, space, st))) return rc;
+    if (H || h_seen) {   // extremes of the H table must be rescanned before the next use
+        ffm::HStats hs; hs.hmin = 0; hs.hmax = 0; hs.dirty = 1; hs.any = 0;
+        CU(cudaMemcpyAsync(s->d_hstats, &hs, sizeof(hs), cudaMemcpyHostToDevice, st));
+    }
+    CU(cudaStreamSynchronize(st));
+    return FFM_OK;
+}
+
+int ffm_tables_get(ffm_sim_t s, double* V, uint8_t* v_seen, double* H, uint8_t* h_seen, int space, void* stream) {
+    if (!s) return fail(FFM_E_INVALID, "null argument");
+    if (s->cfg.model == FFM_MODEL_CORE) return fail(FFM_E_STATE, "the base model has no tables");
+    cudaStream_t st = (cudaStream_t)stream;
+    CU(cudaSetDevice(s->cfg.device));
+    int rc;
+    if (V && (rc = copy_out(V, s->d_V, (size_t)s->S * 8, space, st))) return rc;
+    if (v_seen && (rc = copy_out(v_seen, s->d_vseen, (size_t)s->S, space, st))) return rc;
+    if (H && (rc = copy_out(H, s->d_H, (size_t)s->S * s->A * 8, space, st))) return rc;
+    if (h_seen && (rc = copy_out(h_seen, s->d_hseen, (size_t)s->S, space, st))) return rc;
+    return FFM_OK;
+}
+
+int ffm_tables_bind_deltas(ffm_sim_t s, double* dV, double* dH) {
+    if (!s || !dV) return fail(FFM_E_INVALID, "null argument");
+    if (s->cfg.model == FFM_MODEL_CORE) return fail(FFM_E_STATE, "the base model has no tables");
+    s->d_dV = dV;
+    s->d_dH = dH;
+    return FFM_OK;
+}
+
+int ffm_tables_apply_deltas(ffm_sim_t s, void* stream) {
+    if (!s) return fail(FFM_E_INVALID, "null argument");
+    if (!s->d_dV) return fail(FFM_E_STATE, "no delta tables bound");
+    cudaStream_t st = (cudaStream_t)stream;
+    CU(cudaSetDevice(s->cfg.device));
+    const bool has_h = s->cfg.model == FFM_MODEL_UNIFIED_ACTOR || s->cfg.model == FFM_MODEL_UNIFIED_BOTH;
+    if (has_h && !s->d_dH) return fail(FFM_E_STATE, "actor learning needs a dH table");
+    const int blocks = 148;
+    ffm::unified_apply_deltas_kernel<<<blocks, 256, 0, st>>>(s->d_V, s->d_dV, has_h ? s->d_H : nullptr, s->d_dH, s->d_hseen, s->S, s->A,
+                                                            s->d_hstats, s->d_blk_lo, s->d_blk_hi, s->d_blk_any);
+    if (has_h) ffm::unified_finish_stats_kernel<<<1, 32, 0, st>>>(s->d_hstats, s->d_blk_lo, s->d_blk_hi, s->d_blk_any, blocks);
+    CU(cudaGetLastError());
+    s->launches += has_h ? 2 : 1;
+    return FFM_OK;
+}
+
+int ffm_set_epsilon(ffm_sim_t s, double epsilon) {
+    if (!s) return fail(FFM_E_INVALID, "null argument");
+    s->epsilon = epsilon < 0.0 ? 0.0 : (epsilon > 1.0 ? 1.0 : epsilon);   // np.clip (ffm_unified.py:867)
     return FFM_OK;
 }
 

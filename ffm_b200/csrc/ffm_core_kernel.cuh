@@ -53,7 +53,7 @@ constexpr uint32_t OCC_MASK = 0x3FFFu;
 constexpr uint32_t TYPE_BITS = 3u << TYPE_SHIFT;
 constexpr uint32_t TYPE_FREE = 0, TYPE_WALL = 1, TYPE_EXIT = 2, TYPE_NEAR_EXIT = 3;
 constexpr uint32_t WALL_CELL = (TYPE_WALL << TYPE_SHIFT) | OCC_MASK;
-constexpr int MAX_PEDS = 16382;
+constexpr int MAX_PEDS = 16380;   // owner ids 1..16380; 0x3FFE / 0x3FFF mark blocked cells
 
 struct RolloutParams {
     int H, W, HW, n_max, B;

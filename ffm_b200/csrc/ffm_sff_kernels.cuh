@@ -12,7 +12,7 @@
 //                             neighbouring tiles dirty if its rim changed; rounds repeat over dirty
 //                             tiles until none is left.  Any relaxation order reaches the same fixpoint
 //                             (fl32(d + w) is monotone in d), so the result is bit-identical to a
-//                             float32 Dijkstra -- the oracle (oracle/c/ffm_oracle.c geodesic).
+//                             float32 Dijkstra (which is what the CPU checker of the test-suite runs).
 //                             North-star item 2 (the reference has no obstacle-aware generator).
 #pragma once
 #include <cuda_runtime.h>

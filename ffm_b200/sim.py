@@ -37,11 +37,21 @@ class BatchSim:
                   configuration): the DFF cannot influence any move and is not computed at all.
     """
 
+    DEFAULTS = CORE_DEFAULTS
+
+    def _configure(self, cfg):
+        """Hook for subclasses: fill the model-specific part of the ffm_config_t."""
+        cfg.model = _abi.MODEL_CORE
+
+    def _score_field(self, sff):
+        """The SFF array the kernels score with (and its dtype decides float32 vs float64 arithmetic)."""
+        return sff if sff.dtype == np.float32 else sff.astype(np.float64)
+
     def __init__(self, map_array, sff, n_episodes, n_max, params=None, seed=0, episode_base=0,
                  track_dff=None, device=None):
         if not torch.cuda.is_available():
             raise RuntimeError("ffm_b200 needs a CUDA device (no CPU fallback)")
-        self.params = dict(CORE_DEFAULTS) if params is None else {**CORE_DEFAULTS, **params}
+        self.params = dict(self.DEFAULTS) if params is None else {**self.DEFAULTS, **params}
         self.map_array = np.ascontiguousarray(np.asarray(map_array).astype(np.uint8))   # ffm_core.py:16
         if self.map_array.ndim != 2:
             raise ValueError("map_array must be 2-D")
@@ -49,7 +59,7 @@ class BatchSim:
         if sff.shape != self.map_array.shape:
             raise ValueError("sff shape differs from map shape")
         # NumPy computes the scores in promote(sff.dtype, float32): float32 stays, all else -> float64
-        self.sff = np.ascontiguousarray(sff if sff.dtype == np.float32 else sff.astype(np.float64))
+        self.sff = np.ascontiguousarray(self._score_field(sff))
         self.H, self.W = self.map_array.shape
         self.B, self.n_max = int(n_episodes), int(n_max)
         self.neighbors = list(NEUMANN) if self.params["neighborhood"] == "neumann" else list(MOORE)
@@ -67,13 +77,14 @@ class BatchSim:
         cfg.sff_dtype = _abi.FFM_F32 if self.sff.dtype == np.float32 else _abi.FFM_F64
         cfg.n_episodes, cfg.n_max = self.B, self.n_max
         cfg.track_dff = int(self.track_dff)
-        cfg.k_S, cfg.k_D = float(self.params["k_S"]), k_D
+        cfg.k_S, cfg.k_D = float(self.params.get("k_S", 0.0)), k_D
         # scalars are formed in Python floats and cast to float32 when they meet the float32 field
         cfg.dff_c0 = float(np.float32((1 - decay) * (1 - diffuse)))                      # ffm_core.py:109
         cfg.dff_c1 = float(np.float32(decay * (1 - diffuse) / len(self.neighbors)))      # ffm_core.py:113
         cfg.dff_threshold = float(np.float32(1e-4))                                      # ffm_core.py:116
         cfg.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
         cfg.episode_base = int(episode_base) & 0xFFFFFFFF
+        self._configure(cfg)
         self._lib = _abi.lib()
         self._h = C.c_void_p()
         _abi.check(self._lib.ffm_create(C.byref(cfg), C.byref(self._h)))
@@ -188,3 +199,121 @@ class BatchSim:
         a, b, c, d = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32()
         _abi.check(self._lib.ffm_kernel_info(self._h, C.byref(a), C.byref(b), C.byref(c), C.byref(d)))
         return dict(smem_bytes=a.value, threads=b.value, ctas_per_sm=c.value, fields_in_smem=bool(d.value))
+
+
+UNIFIED_DEFAULTS = {                      # ffm_unified.py:36-53
+    "k_S": 10, "k_D": 1, "k_A": 10, "diffuse": 0.2, "decay": 0.2, "neighborhood": "neumann",
+    "alpha_v": 0.1, "gamma": 0.95, "exit_reward": 100.0, "step_penalty": 0.0, "collision_penalty": -1.0,
+    "block_size": 5, "alpha_h": 0.1, "epsilon": 0.0,
+}
+TRAINED_DEFAULTS = {"k_D": 1, "k_A": 10, "diffuse": 0.2, "decay": 0.2, "neighborhood": "neumann", "block_size": 5}  # ffm_trained_core.py:29-36
+_MODES = {"critic_only": _abi.MODEL_UNIFIED_CRITIC, "actor_only": _abi.MODEL_UNIFIED_ACTOR, "both": _abi.MODEL_UNIFIED_BOTH,
+          "trained": _abi.MODEL_TRAINED}
+_LEARN = {"none": _abi.LEARN_NONE, "exact": _abi.LEARN_EXACT, "batched": _abi.LEARN_BATCHED}
+
+
+class UnifiedSim(BatchSim):
+    """B episodes of ``FloorFieldModelUnified`` (model/ffm_unified.py) or of the trained-actor model
+    (model/ffm_trained_core.py) sharing map, SFF, parameters and the V / H tables.
+
+    mode   "critic_only" | "actor_only" | "both" | "trained"
+    learn  "exact"   the reference's sequential per-agent table updates (n_episodes must be 1)
+           "batched" synchronous batched TD: rollouts accumulate alpha*delta into ``dV`` / ``dH`` against
+                     frozen tables; ``apply_deltas()`` (after the caller's all-reduce) folds them in
+           "none"    frozen tables
+    Tables are dense: state id = (bx*nby + by)*256 + rU*64 + rD*16 + rL*4 + rR (``key_to_id``).
+    """
+
+    DEFAULTS = UNIFIED_DEFAULTS
+
+    def __init__(self, map_array, sff, n_episodes, n_max, mode="critic_only", learn="exact", params=None, seed=0,
+                 episode_base=0, device=None):
+        if mode not in _MODES:
+            raise ValueError(f"learning_mode must be one of {sorted(_MODES)}, got {mode}")
+        self.mode, self.learn = mode, learn
+        if mode == "trained":
+            self.DEFAULTS = TRAINED_DEFAULTS
+        super().__init__(map_array, sff, n_episodes, n_max, params, seed, episode_base, True, device)
+        S, A = C.c_int32(), C.c_int32()
+        _abi.check(self._lib.ffm_tables_shape(self._h, C.byref(S), C.byref(A)))
+        self.S, self.A = S.value, A.value
+        self.bs = int(self.params["block_size"])
+        self.nby = -(-self.W // self.bs)
+        self.dV = self.dH = None
+        if learn == "batched":
+            dev = f"cuda:{self.device}"
+            self.dV = torch.zeros(self.S, dtype=torch.float64, device=dev)
+            self.dH = torch.zeros((self.S, self.A), dtype=torch.float64, device=dev)
+            _abi.check(self._lib.ffm_tables_bind_deltas(self._h, _ptr(self.dV), _ptr(self.dH)))
+
+    def _score_field(self, sff):
+        if self.mode == "critic_only":
+            return sff if sff.dtype == np.float32 else sff.astype(np.float64)           # file dtype kept (ffm_unified.py:70)
+        return np.where(np.isinf(sff), 0.0, sff).astype(np.float32)                       # ffm_unified.py:72-76
+
+    def _configure(self, cfg):
+        p = self.params
+        cfg.model = _MODES[self.mode]
+        cfg.learn = _LEARN[self.learn]
+        cfg.block_size = int(p["block_size"])
+        cfg.k_A = float(p.get("k_A", 0.0))
+        cfg.gamma, cfg.alpha_v, cfg.alpha_h = float(p.get("gamma", 0.0)), float(p.get("alpha_v", 0.0)), float(p.get("alpha_h", 0.0))
+        cfg.exit_reward = float(p.get("exit_reward", 0.0))
+        cfg.step_penalty = float(p.get("step_penalty", 0.0))
+        cfg.collision_penalty = float(p.get("collision_penalty", 0.0))
+        cfg.epsilon = float(p.get("epsilon", 0.0) or 0.0)
+        cfg.sff_min, cfg.sff_max = float(np.min(self.sff)), float(np.max(self.sff))       # ffm_unified.py:425-426
+
+    # -- tables ----------------------------------------------------------------------------------
+    def key_to_id(self, key):
+        r, (bx, by) = key
+        return (int(bx) * self.nby + int(by)) * 256 + int(r[0]) * 64 + int(r[1]) * 16 + int(r[2]) * 4 + int(r[3])
+
+    def id_to_key(self, sid):
+        blk, code = divmod(int(sid), 256)
+        return ((code >> 6, (code >> 4) & 3, (code >> 2) & 3, code & 3), (blk // self.nby, blk % self.nby))
+
+    def get_tables(self):
+        """-> (V float64 [S], v_seen bool [S], H float64 [S, A], h_seen bool [S]) NumPy copies."""
+        V = np.empty(self.S, np.float64); vs = np.empty(self.S, np.uint8)
+        H = np.empty((self.S, self.A), np.float64); hs = np.empty(self.S, np.uint8)
+        _abi.check(self._lib.ffm_tables_get(self._h, _ptr(V), _ptr(vs), _ptr(H), _ptr(hs), _abi.FFM_HOST, _stream()))
+        return V, vs.astype(bool), H, hs.astype(bool)
+
+    def set_tables(self, V=None, v_seen=None, H=None, h_seen=None):
+        conv = lambda a, dt, shape: None if a is None else np.ascontiguousarray(np.asarray(a, dtype=dt).reshape(shape))
+        V, H = conv(V, np.float64, (self.S,)), conv(H, np.float64, (self.S, self.A))
+        vs, hs = conv(v_seen, np.uint8, (self.S,)), conv(h_seen, np.uint8, (self.S,))
+        _abi.check(self._lib.ffm_tables_set(self._h, _ptr(V), _ptr(vs), _ptr(H), _ptr(hs), _abi.FFM_HOST, _stream()))
+
+    def v_dict(self):
+        """The reference's ``dict(self.V)`` (ffm_unified.py:821)."""
+        V, vs, _, _ = self.get_tables()
+        return {self.id_to_key(s): float(V[s]) for s in np.flatnonzero(vs)}
+
+    def h_dict(self):
+        """The reference's ``dict(self.H)`` (ffm_unified.py:855): rows as lists of Python floats."""
+        _, _, H, hs = self.get_tables()
+        return {self.id_to_key(s): [float(v) for v in H[s]] for s in np.flatnonzero(hs)}
+
+    def load_v_dict(self, d):
+        V = np.zeros(self.S, np.float64); vs = np.zeros(self.S, np.uint8)
+        for k, v in d.items():
+            V[self.key_to_id(k)] = v
+            vs[self.key_to_id(k)] = 1
+        self.set_tables(V=V, v_seen=vs)
+
+    def load_h_dict(self, d):
+        H = np.zeros((self.S, self.A), np.float64); hs = np.zeros(self.S, np.uint8)
+        for k, v in d.items():
+            if len(v) == self.A:
+                H[self.key_to_id(k)] = v
+                hs[self.key_to_id(k)] = 1
+        self.set_tables(H=H, h_seen=hs)
+
+    def set_epsilon(self, epsilon):
+        _abi.check(self._lib.ffm_set_epsilon(self._h, float(epsilon)))
+
+    def apply_deltas(self):
+        """V += dV, H += dH, deltas zeroed, H extremes refreshed (call after all-reducing dV / dH)."""
+        _abi.check(self._lib.ffm_tables_apply_deltas(self._h, _stream()))

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define FFM_ABI_VERSION 1
+#define FFM_ABI_VERSION 2
 
 enum {
     FFM_OK = 0,
@@ -42,6 +42,22 @@ enum { FFM_F32 = 0, FFM_F64 = 1 };             /* dtype of the SFF file (ffm_cor
 /* map cell codes, Create_Map.py:9-19 / ffm_unified.py:283-286 */
 enum { FFM_CELL_FREE = 0, FFM_CELL_PED = 1, FFM_CELL_WALL = 2, FFM_CELL_EXIT = 3 };
 
+/* which reference class a handle reproduces */
+enum {
+    FFM_MODEL_CORE = 0,           /* model/ffm_core.py FloorFieldModel */
+    FFM_MODEL_UNIFIED_CRITIC = 1, /* model/ffm_unified.py learning_mode="critic_only" */
+    FFM_MODEL_UNIFIED_ACTOR = 2,  /*                       learning_mode="actor_only" */
+    FFM_MODEL_UNIFIED_BOTH = 3,   /*                       learning_mode="both" */
+    FFM_MODEL_TRAINED = 4         /* model/ffm_trained_core.py FloorFieldModel (frozen H table) */
+};
+/* how the unified model's tables are updated */
+enum {
+    FFM_LEARN_NONE = 0,    /* tables frozen (evaluation rollouts; any number of episodes) */
+    FFM_LEARN_EXACT = 1,   /* the reference's sequential per-agent updates; n_episodes must be 1 */
+    FFM_LEARN_BATCHED = 2  /* synchronous batched TD: deltas accumulated against frozen tables, applied
+                              by ffm_tables_apply_deltas (after the caller's cross-GPU all-reduce) */
+};
+
 typedef struct ffm_sim_s *ffm_sim_t;
 
 /* Static configuration of a batch of B independent episodes on one map.
@@ -53,7 +69,7 @@ typedef struct ffm_config {
     int32_t neighborhood;  /* FFM_NEUMANN | FFM_MOORE          params["neighborhood"] */
     int32_t sff_dtype;     /* FFM_F32 | FFM_F64                dtype move scores are computed in */
     int32_t n_episodes;    /* B */
-    int32_t n_max;         /* capacity: pedestrians per episode (<= 16382) */
+    int32_t n_max;         /* capacity: pedestrians per episode (<= 16380) */
     int32_t track_dff;     /* 0: k_D == 0 and the caller never reads .dff -> DFF skipped entirely */
     int32_t reserved0;
     double k_S;            /* params["k_S"]   score = -k_S*sff + k_D*dff   ffm_core.py:77 */
@@ -65,6 +81,16 @@ typedef struct ffm_config {
     uint64_t seed;         /* Philox key */
     uint32_t episode_base; /* global id of episode 0 of this handle (multi-GPU sharding) */
     uint32_t reserved2;
+    /* ---- unified / trained models only (ffm_unified.py:36-53, ffm_trained_core.py:29-36) ---- */
+    int32_t model;         /* FFM_MODEL_* */
+    int32_t learn;         /* FFM_LEARN_* */
+    int32_t block_size;    /* params["block_size"] */
+    int32_t reserved3;
+    double k_A;            /* params["k_A"] */
+    double gamma, alpha_v, alpha_h;
+    double exit_reward, step_penalty, collision_penalty;
+    double epsilon;        /* params["epsilon"] / set_epsilon() */
+    double sff_min, sff_max; /* float(np.min/max(self.sff)) of the inf->0 float32 SFF (ffm_unified.py:425-426) */
 } ffm_config_t;
 
 /* Optional recorded uniforms that override the keyed Philox streams (parity tests: "both sides
@@ -122,6 +148,24 @@ int ffm_rollout(ffm_sim_t sim, int32_t max_steps, const ffm_draws_t *draws, cons
  * ffm_core.py:126) and pedestrian-steps processed (sum over steps of the alive count).
  * Either pointer may be NULL. */
 int ffm_get_counters(ffm_sim_t sim, int32_t *steps, int64_t *ped_steps, int space, void *stream);
+
+/* ---- tables of the unified / trained models ----------------------------------------------------
+ * Dense images of the reference's dicts: state id = (bx*nby + by)*256 + rU*64 + rD*16 + rL*4 + rR with
+ * bx = row / block_size, by = col / block_size, nby = ceil(width / block_size)
+ * (key ((rU,rD,rL,rR),(bx,by)) of _encode_state, ffm_unified.py:188-269).
+ *   V      double [S]        self.V            v_seen uint8 [S]  key present (a defaultdict read inserts)
+ *   H      double [S][A]     self.H rows       h_seen uint8 [S]  row present;  A = neighbours + 1
+ * Any pointer may be NULL (left untouched / not returned). */
+int ffm_tables_shape(ffm_sim_t sim, int32_t *n_states, int32_t *n_actions);
+int ffm_tables_set(ffm_sim_t sim, const double *V, const uint8_t *v_seen, const double *H, const uint8_t *h_seen,
+                   int space, void *stream);   /* set_v_table() :823-830, pretrained_v_path :84-110, h_table_path */
+int ffm_tables_get(ffm_sim_t sim, double *V, uint8_t *v_seen, double *H, uint8_t *h_seen, int space,
+                   void *stream);              /* get_v_table() :814-821, get_h_table() :847-857 */
+/* FFM_LEARN_BATCHED: caller-owned device buffers dV double [S], dH double [S][A] the rollouts accumulate
+ * alpha*delta into (the caller all-reduces them across GPUs), then V += dV, H += dH, deltas zeroed. */
+int ffm_tables_bind_deltas(ffm_sim_t sim, double *dV, double *dH);
+int ffm_tables_apply_deltas(ffm_sim_t sim, void *stream);
+int ffm_set_epsilon(ffm_sim_t sim, double epsilon);   /* set_epsilon() :859-867 */
 
 /* Static-floor-field generation for n_maps maps (uint8 [n_maps][H][W]) -> out [n_maps][H][W] of
  * out_dtype (FFM_F32 | FFM_F64), +inf on non-walkable and unreachable cells.

@@ -86,6 +86,104 @@ def stock_main():
     print("stock main.py seed 42:", T, "steps,", int(counts[:-1].sum()) + config["N"], "ped-steps, min_margin %.2e" % r["min_margin"])
 
 
+UNI_PARAMS = dict(k_S=10, k_D=1, k_A=10, alpha_v=0.01, alpha_h=0.1, gamma=0.99, exit_reward=100.0, step_penalty=-1.0,
+                  collision_penalty=-1.0, neighborhood="neumann", block_size=1)   # run_unified_*_training.py MODEL_PARAMS
+
+
+def _tables_to_arrays(o_like, vdict, hdict, A):
+    """dict tables -> (ids, values) arrays using the dense state id of oracle/unified_numpy.py."""
+    vid = np.array(sorted(o_like.key_to_id(k) for k in vdict), np.int64)
+    vval = np.array([vdict[o_like.id_to_key(i)] for i in vid], np.float64)
+    hid = np.array(sorted(o_like.key_to_id(k) for k in hdict), np.int64) if hdict else np.zeros(0, np.int64)
+    hval = np.array([hdict[o_like.id_to_key(i)] for i in hid], np.float64).reshape(-1, A)
+    return vid, vval, hid, hval
+
+
+def unified_case(name, mode, h, w, N, episodes, seed, params, eps=0.0, radius=None, max_steps=300, sff_dtype=np.float32,
+                 v_from=None):
+    """Multi-episode learning run of the reference FloorFieldModelUnified under keyed draws: tables carry
+    over the episodes exactly as in run_unified_critic_training.py:216-222."""
+    import contextlib, io, pickle
+    from . import unified_numpy
+    ref = inject.import_reference("ffm_unified")
+    m = assets.room_map(h, w)
+    sff = assets.sff_norm_min(m, "L1", sff_dtype)
+    vtab = None
+    with tempfile.TemporaryDirectory() as tmp:
+        p = os.path.join(tmp, "sff.npy")
+        np.save(p, sff)
+        vpath = None
+        if v_from is not None:
+            z = np.load(os.path.join(OUT, v_from + ".npz"))
+            helper = unified_numpy.UnifiedOracle(m, sff, np.zeros((0, 2)), "critic_only", params)
+            vtab = {helper.id_to_key(i): float(v) for i, v in zip(z["v_ids"], z["v_vals"])}
+            vpath = os.path.join(tmp, "v.pkl")
+            with open(vpath, "wb") as f:      # the reference expects pickled-bytes keys (ffm_unified.py:91-107)
+                pickle.dump({pickle.dumps(k): v for k, v in vtab.items()}, f)
+        np.random.seed(seed)
+        with contextlib.redirect_stdout(io.StringIO()):
+            model = ref.FloorFieldModelUnified(m, p, N, learning_mode=mode, pretrained_v_path=vpath, params=params)
+        if mode != "critic_only":
+            model.set_epsilon(eps)
+        exit_pos = tuple(int(v) for v in np.argwhere(m == 3)[0])
+        pos0s, trajs, counts, steps, margins = [], [], [], [], []
+        for ep in range(episodes):
+            model.reset(exit_pos=exit_pos if radius else None, radius=radius)
+            pos0s.append(np.array(model.positions, dtype=np.int16).reshape(-1, 2))
+            r = inject.run_reference(model, inject.PhiloxSource(seed, ep), max_steps=max_steps, keep_dff=False)
+            flat, cnt = _flatten(r["traj"])
+            trajs.append(flat); counts.append(cnt); steps.append(r["steps"]); margins.append(r["min_margin"])
+    helper = unified_numpy.UnifiedOracle(m, sff, np.zeros((0, 2)), mode, params)
+    A = helper.A
+    vid, vval, hid, hval = _tables_to_arrays(helper, dict(model.V), dict(model.H) if model.H is not None else {}, A)
+    save = dict(map=m, sff=sff, params=json.dumps(params), mode=mode, seed=np.uint64(seed), eps=np.float64(eps),
+                max_steps=np.int32(max_steps), episodes=np.int32(episodes), steps=np.array(steps, np.int32),
+                min_margin=np.array(margins), v_ids=vid, v_vals=vval, h_ids=hid, h_vals=hval,
+                final_dff=np.array(model.dff, np.float32), v_from=v_from or "")
+    for ep in range(episodes):
+        save[f"pos0_{ep}"] = pos0s[ep]; save[f"traj_{ep}"] = trajs[ep]; save[f"counts_{ep}"] = counts[ep]
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **save)
+    print(name, "steps", steps, "min_margin %.1e" % min(margins), "|V|", len(vid), "|H|", len(hid))
+
+
+def trained_case(name, h, w, N, seed, params, h_from, max_steps=120):
+    """model/ffm_trained_core.py FloorFieldModel with the H table learned in fixture `h_from`."""
+    import contextlib, io, pickle
+    from . import unified_numpy
+    ref = inject.import_reference("ffm_trained_core")
+    m = assets.room_map(h, w)
+    sff = assets.sff_norm_min(m, "L1", np.float32)
+    z = np.load(os.path.join(OUT, h_from + ".npz"))
+    helper = unified_numpy.UnifiedOracle(m, sff, np.zeros((0, 2)), "trained", params)
+    htab = {helper.id_to_key(i): [float(x) for x in row] for i, row in zip(z["h_ids"], z["h_vals"])}
+    with tempfile.TemporaryDirectory() as tmp:
+        p = os.path.join(tmp, "sff.npy"); np.save(p, sff)
+        hp = os.path.join(tmp, "h.pkl")
+        with open(hp, "wb") as f:
+            pickle.dump({pickle.dumps(k): v for k, v in htab.items()}, f)   # ffm_trained_core.py:55-59
+        np.random.seed(seed)
+        with contextlib.redirect_stdout(io.StringIO()):
+            model = ref.FloorFieldModel(m, p, N, hp, params)
+        pos0 = np.array(model.positions, dtype=np.int16)
+        r = inject.run_reference(model, inject.PhiloxSource(seed, 0), max_steps=max_steps, keep_dff=False)
+    flat, cnt = _flatten(r["traj"])
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), map=m, sff=sff, params=json.dumps(params), seed=np.uint64(seed),
+                        h_from=h_from, pos0=pos0, traj=flat, counts=cnt, steps=np.int32(r["steps"]), max_steps=np.int32(max_steps),
+                        min_margin=np.float64(r["min_margin"]), final_dff=np.array(model.dff, np.float32))
+    print(name, "steps", r["steps"], "min_margin %.1e" % r["min_margin"])
+
+
+def unified_all():
+    unified_case("uni_critic_12x12", "critic_only", 12, 12, 30, 5, 21, UNI_PARAMS, radius=7)
+    unified_case("uni_critic_moore_bs5", "critic_only", 12, 12, 45, 3, 22, {**UNI_PARAMS, "neighborhood": "moore", "block_size": 5})
+    unified_case("uni_critic_20x20_f64", "critic_only", 20, 20, 40, 2, 23, {**UNI_PARAMS, "block_size": 3}, sff_dtype=np.float64)
+    unified_case("uni_actor_eps", "actor_only", 12, 12, 16, 3, 24, UNI_PARAMS, eps=0.2, max_steps=60, v_from="uni_critic_12x12")
+    unified_case("uni_actor_greedy", "actor_only", 12, 12, 16, 2, 25, UNI_PARAMS, eps=0.0, max_steps=60)
+    unified_case("uni_both", "both", 12, 12, 20, 3, 26, UNI_PARAMS, eps=0.1, max_steps=60)
+    unified_case("uni_both_moore", "both", 12, 12, 20, 2, 27, {**UNI_PARAMS, "neighborhood": "moore", "block_size": 2}, eps=0.05, max_steps=50)
+    trained_case("trained_12x12", 12, 12, 30, 28, {"k_D": 1, "k_A": 10, "neighborhood": "neumann", "block_size": 1}, "uni_actor_eps")
+
+
 def shipped():
     out = {}
     for rel in ("data/maps/simple_room.npy", "data/sff/distance_L1.npy", "data/sff/distance_L2.npy", "data/sff/distance_Linf.npy"):
@@ -108,6 +206,7 @@ def main():
     core_case("core_16x24_moore_kd0", 16, 24, 60, "moore", "L2", np.float32, 16, 2, extra={"k_D": 0}, dff_every=10)
     stock_main()
     shipped()
+    unified_all()
 
 
 if __name__ == "__main__":

@@ -54,3 +54,23 @@ def load_golden(name):
     offs = np.concatenate([[0], np.cumsum(counts)])
     g["traj_list"] = [g["traj"][offs[t]:offs[t + 1]].astype(np.int64) for t in range(len(counts))]
     return g
+
+
+UNIFIED_FIXTURES = ["uni_critic_12x12", "uni_critic_moore_bs5", "uni_critic_20x20_f64", "uni_actor_eps",
+                    "uni_actor_greedy", "uni_both", "uni_both_moore"]
+
+
+def load_unified(name):
+    z = np.load(os.path.join(GOLDEN, name + ".npz"))
+    g = {k: z[k] for k in z.files}
+    g["params"] = json.loads(str(g["params"]))
+    g["mode"] = str(g["mode"])
+    g["v_from"] = str(g["v_from"]) if "v_from" in g else ""
+    E = int(g["episodes"]) if "episodes" in g else 1
+    g["ep"] = []
+    for ep in range(E):
+        counts = g[f"counts_{ep}"]
+        offs = np.concatenate([[0], np.cumsum(counts)])
+        g["ep"].append(dict(pos0=g[f"pos0_{ep}"].astype(np.int64),
+                            traj=[g[f"traj_{ep}"][offs[t]:offs[t + 1]].astype(np.int64) for t in range(len(counts))]))
+    return g
