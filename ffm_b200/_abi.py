@@ -63,6 +63,7 @@ SIGNATURES = {
     "ffm_tables_bind_deltas": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "ffm_tables_apply_deltas": (C.c_int, [C.c_void_p, C.c_void_p]),
     "ffm_set_epsilon": (C.c_int, [C.c_void_p, C.c_double]),
+    "ffm_set_episode_base": (C.c_int, [C.c_void_p, C.c_uint32]),
     "ffm_sff_generate": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int,
                                    C.c_int32, C.c_void_p, C.POINTER(C.c_int32)]),
     "ffm_launch_count": (C.c_int64, [C.c_void_p]),

@@ -567,6 +567,12 @@ int ffm_set_epsilon(ffm_sim_t s, double epsilon) {
     return FFM_OK;
 }
 
+int ffm_set_episode_base(ffm_sim_t s, uint32_t episode_base) {
+    if (!s) return fail(FFM_E_INVALID, "null argument");
+    s->cfg.episode_base = episode_base;
+    return FFM_OK;
+}
+
 int ffm_sff_generate(const uint8_t* maps, int32_t n_maps, int32_t H, int32_t W, int32_t mode, int32_t out_dtype, void* out,
                      int space, int32_t device, void* stream, int32_t* rounds_out) {
     if (!maps || !out) return fail(FFM_E_INVALID, "null argument");

@@ -190,6 +190,9 @@ class BatchSim:
         _abi.check(self._lib.ffm_rollout(self._h, int(max_steps), dptr, optr, _stream()))
         return ret
 
+    def set_episode_base(self, episode_base):
+        _abi.check(self._lib.ffm_set_episode_base(self._h, int(episode_base) & 0xFFFFFFFF))
+
     # -- introspection -------------------------------------------------------------------------
     @property
     def launch_count(self):

@@ -166,6 +166,8 @@ int ffm_tables_get(ffm_sim_t sim, double *V, uint8_t *v_seen, double *H, uint8_t
 int ffm_tables_bind_deltas(ffm_sim_t sim, double *dV, double *dH);
 int ffm_tables_apply_deltas(ffm_sim_t sim, void *stream);
 int ffm_set_epsilon(ffm_sim_t sim, double epsilon);   /* set_epsilon() :859-867 */
+/* global id of episode 0 for the following rollouts (a drop-in object advances it on every reset()) */
+int ffm_set_episode_base(ffm_sim_t sim, uint32_t episode_base);
 
 /* Static-floor-field generation for n_maps maps (uint8 [n_maps][H][W]) -> out [n_maps][H][W] of
  * out_dtype (FFM_F32 | FFM_F64), +inf on non-walkable and unreachable cells.

@@ -65,3 +65,78 @@ def test_run_and_attribute_assignment(cuda_device, tmp_path):
         FloorFieldModel(m, p, 500, {"seed": 5})            # more pedestrians than free cells (ffm_core.py:25)
     with pytest.raises(FileNotFoundError):
         FloorFieldModel(m, os.path.join(tmp_path, "missing.npy"), 3)
+
+
+def test_unified_dropin_like_training_driver(cuda_device, tmp_path):
+    """run_unified_critic_training.py:164-225 / run_unified_actor_training.py:193-268 usage pattern: one
+    model object, `.N = n`, reset(exit_pos, radius), run(max_steps), table accessors; compared with
+    the oracle driven through the same episodes."""
+    import pickle
+    from ffm_b200.model.ffm_unified import FloorFieldModelUnified
+    from oracle import unified_numpy
+
+    m = assets.room_map(12, 12)
+    sff = assets.sff_norm_min(m, "L1", np.float32)
+    p = os.path.join(tmp_path, "sff.npy")
+    np.save(p, sff)
+    params = dict(k_S=10, k_D=1, k_A=10, alpha_v=0.01, alpha_h=0.1, gamma=0.99, exit_reward=100.0, step_penalty=-1.0,
+                  collision_penalty=-1.0, neighborhood="neumann", block_size=1, seed=4242)
+    with pytest.raises(ValueError):
+        FloorFieldModelUnified(m, p, 5, learning_mode="bogus", params=params)
+    np.random.seed(3)
+    model = FloorFieldModelUnified(m, p, 10, learning_mode="critic_only", params=params)
+    o = unified_numpy.UnifiedOracle(m, sff, np.zeros((0, 2)), "critic_only", params)
+    ep = 1                                            # episode 0 was the constructor's placement
+    for N in (1, 10, 25):
+        model.N = N
+        for _ in range(2):
+            model.reset(exit_pos=(0, 6), radius=7)
+            o.positions, o.t, o.source = model.positions.copy(), 0, PhiloxSource(4242, ep)
+            o.dff[:] = 0
+            steps = model.run(max_steps=300)
+            r = o.run(max_steps=300)
+            ep += 1
+            assert steps == r["steps"] and model.positions.shape[0] == 0
+    assert model.get_v_table_size() == int(o.v_seen.sum()) and model.get_h_table() is None
+    v = model.get_v_table()
+    assert v == o.v_dict()
+    vp = os.path.join(tmp_path, "V.pkl")
+    with open(vp, "wb") as f:
+        pickle.dump({pickle.dumps(k): x for k, x in v.items()}, f)      # legacy bytes-key format (ffm_unified.py:91-107)
+
+    actor = FloorFieldModelUnified(m, p, 8, learning_mode="actor_only", pretrained_v_path=vp, params=params)
+    assert actor.initial_v_size == len(v)
+    actor.set_epsilon(0.3)
+    actor.reset(exit_pos=(0, 6), radius=5)
+    steps, traj = actor.run(max_steps=40, return_trajectory=True)
+    assert steps == len(traj) and traj.dtype == object
+    init, cur, new = actor.get_v_table_size()
+    assert init == len(v) and cur == init + new
+    rows, total = actor.get_h_table_size()
+    assert total == rows * 5 and len(actor.get_h_table()) == rows and all(len(x) == 5 for x in actor.get_h_table().values())
+
+
+def test_trained_dropin_like_run_trained_ffm(cuda_device, tmp_path):
+    """run_trained_ffm.py:199-243: positions / dff assigned per episode, run(max_steps)."""
+    import json
+    import pickle
+    from helpers import GOLDEN
+    from ffm_b200.model.ffm_trained_core import FloorFieldModel
+    from oracle import unified_numpy
+
+    z = np.load(os.path.join(GOLDEN, "trained_12x12.npz"))
+    hz = np.load(os.path.join(GOLDEN, str(z["h_from"]) + ".npz"))
+    params = {**json.loads(str(z["params"])), "seed": int(z["seed"])}
+    helper = unified_numpy.UnifiedOracle(z["map"], z["sff"], np.zeros((0, 2)), "trained", params)
+    htab = {helper.id_to_key(i): [float(x) for x in row] for i, row in zip(hz["h_ids"], hz["h_vals"])}
+    hp, sp = os.path.join(tmp_path, "H.pkl"), os.path.join(tmp_path, "sff.npy")
+    with open(hp, "wb") as f:
+        pickle.dump({pickle.dumps(k): v for k, v in htab.items()}, f)
+    np.save(sp, z["sff"])
+    model = FloorFieldModel(z["map"], sp, len(z["pos0"]), hp, params)
+    model._episode = 0                                 # replay the fixture's episode 0
+    model.positions = z["pos0"].astype(np.int64)
+    model.dff = np.zeros_like(model.map_array, dtype=np.float32)
+    steps = model.run(save_prefix=None, save_interval=100, max_steps=int(z["max_steps"]))
+    assert steps == int(z["steps"])
+    assert np.array_equal(model.dff.view(np.uint32), z["final_dff"].view(np.uint32))
