@@ -1,0 +1,60 @@
+"""Multi-rank host logic on CPU (gloo, world_size 2): episode partition and the delta all-reduce."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from ffm_b200 import sharding
+
+
+def test_shard_range_partitions_exactly():
+    for total in (1, 7, 8, 4096, 4099):
+        for ws in (1, 2, 3, 8):
+            spans = [sharding.shard_range(total, r, ws) for r in range(ws)]
+            assert spans[0][0] == 0 and sum(c for _, c in spans) == total
+            for (a, ca), (b, _) in zip(spans, spans[1:]):
+                assert a + ca == b
+            assert max(c for _, c in spans) - min(c for _, c in spans) <= 1
+
+
+def _worker(rank, ws, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(ws))
+    dist.init_process_group("gloo", rank=rank, world_size=ws)
+    try:
+        first, count = sharding.shard_range(10, None, None)
+        S, A = 64, 5
+        g = torch.Generator().manual_seed(100 + rank)
+        dV = torch.rand(S, dtype=torch.float64, generator=g)
+        dH = torch.rand(S, A, dtype=torch.float64, generator=g)
+        seen = torch.zeros(S, dtype=torch.uint8)
+        seen[rank::3] = 1
+        sharding.allreduce_deltas([dV, dH], [seen])
+        out.put((rank, first, count, dV.numpy().copy(), dH.numpy().copy(), seen.numpy().copy()))
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_delta_allreduce_gloo_world2():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in procs], key=lambda x: x[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert (res[0][1], res[0][2]) == (0, 5) and (res[1][1], res[1][2]) == (5, 5)
+    want_v = sum(torch.rand(64, dtype=torch.float64, generator=torch.Generator().manual_seed(100 + r)).numpy() for r in range(2))
+    assert np.allclose(res[0][3], want_v) and np.array_equal(res[0][3], res[1][3])
+    assert np.array_equal(res[0][4], res[1][4])
+    want_seen = np.zeros(64, np.uint8); want_seen[0::3] = 1; want_seen[1::3] = 1
+    assert np.array_equal(res[0][5], want_seen) and np.array_equal(res[1][5], want_seen)
