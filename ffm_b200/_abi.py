@@ -60,7 +60,7 @@ SIGNATURES = {
     "ffm_tables_shape": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "ffm_tables_set": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "ffm_tables_get": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
-    "ffm_tables_bind_deltas": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ffm_tables_bind_deltas": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ffm_tables_apply_deltas": (C.c_int, [C.c_void_p, C.c_void_p]),
     "ffm_set_epsilon": (C.c_int, [C.c_void_p, C.c_double]),
     "ffm_set_episode_base": (C.c_int, [C.c_void_p, C.c_uint32]),

@@ -63,7 +63,7 @@ struct ffm_sim_s {
     // unified / trained models
     int S, A, nby;
     double* d_V; uint8_t* d_vseen; double* d_H; uint8_t* d_hseen;
-    double* d_dV; double* d_dH;          // borrowed (caller-owned) delta tables
+    double* d_dV; double* d_dN; double* d_dH;   // borrowed (caller-owned) delta tables
     ffm::HStats* d_hstats;
     double* d_blk_lo; double* d_blk_hi; int* d_blk_any;
     double epsilon;
@@ -449,7 +449,7 @@ int ffm_rollout(ffm_sim_t s, int32_t max_steps, const ffm_draws_t* draws, const 
         U.epsilon = s->epsilon; U.sff_min = s->cfg.sff_min; U.sff_max = s->cfg.sff_max;
         U.pos = s->d_pos; U.n_alive = s->d_n; U.t_done = s->d_t; U.ped_steps = s->d_ped_steps;
         U.dff = s->d_dff; U.dff_tmp = s->d_dff_tmp;
-        U.V = s->d_V; U.v_seen = s->d_vseen; U.Hm = s->d_H; U.h_seen = s->d_hseen; U.dV = s->d_dV; U.dH = s->d_dH;
+        U.V = s->d_V; U.v_seen = s->d_vseen; U.Hm = s->d_H; U.h_seen = s->d_hseen; U.dV = s->d_dV; U.dN = s->d_dN; U.dH = s->d_dH;
         U.hstats = s->d_hstats;
         U.seed = s->cfg.seed; U.episode_base = s->cfg.episode_base;
         if (draws) { U.move_draws = draws->move; U.conflict_draws = draws->conflict; U.draw_steps = draws->steps; U.draw_first = draws->first_step; }
@@ -537,10 +537,11 @@ int ffm_tables_get(ffm_sim_t s, double* V, uint8_t* v_seen, double* H, uint8_t* 
     return FFM_OK;
 }
 
-int ffm_tables_bind_deltas(ffm_sim_t s, double* dV, double* dH) {
-    if (!s || !dV) return fail(FFM_E_INVALID, "null argument");
+int ffm_tables_bind_deltas(ffm_sim_t s, double* dV, double* dN, double* dH) {
+    if (!s || !dV || !dN) return fail(FFM_E_INVALID, "null argument");
     if (s->cfg.model == FFM_MODEL_CORE) return fail(FFM_E_STATE, "the base model has no tables");
     s->d_dV = dV;
+    s->d_dN = dN;
     s->d_dH = dH;
     return FFM_OK;
 }
@@ -553,7 +554,7 @@ int ffm_tables_apply_deltas(ffm_sim_t s, void* stream) {
     const bool has_h = s->cfg.model == FFM_MODEL_UNIFIED_ACTOR || s->cfg.model == FFM_MODEL_UNIFIED_BOTH;
     if (has_h && !s->d_dH) return fail(FFM_E_STATE, "actor learning needs a dH table");
     const int blocks = 148;
-    ffm::unified_apply_deltas_kernel<<<blocks, 256, 0, st>>>(s->d_V, s->d_dV, has_h ? s->d_H : nullptr, s->d_dH, s->d_hseen, s->S, s->A,
+    ffm::unified_apply_deltas_kernel<<<blocks, 256, 0, st>>>(s->d_V, s->d_dV, s->d_dN, s->cfg.alpha_v, has_h ? s->d_H : nullptr, s->d_dH, s->d_hseen, s->S, s->A,
                                                             s->d_hstats, s->d_blk_lo, s->d_blk_hi, s->d_blk_any);
     if (has_h) ffm::unified_finish_stats_kernel<<<1, 32, 0, st>>>(s->d_hstats, s->d_blk_lo, s->d_blk_hi, s->d_blk_any, blocks);
     CU(cudaGetLastError());

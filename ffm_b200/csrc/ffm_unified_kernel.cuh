@@ -62,7 +62,7 @@ struct UnifiedParams {
     float* dff; float* dff_tmp;
     double* V; uint8_t* v_seen;  // [S]
     double* Hm; uint8_t* h_seen; // [S][A], [S]
-    double* dV; double* dH;      // batched mode delta tables
+    double* dV; double* dN; double* dH;   // batched mode: sum of TD errors, visit counts [S]; sum of alpha_h*delta [S][A]
     HStats* hstats;
     unsigned long long seed; uint32_t episode_base;
     const double* move_draws; const double* conflict_draws; int draw_steps, draw_first;
@@ -517,7 +517,8 @@ ffm_unified_rollout_kernel(const UnifiedParams P) {
                     const uint32_t w = info[i], sid = st[i];
                     const double v_next = (w & INFO_EXIT) ? 0.0 : P.V[nst[i]];
                     const double td = __dadd_rn(__dadd_rn(agent_reward(P, w), __dmul_rn(P.gamma, v_next)), -P.V[sid]);
-                    atomicAdd(&P.dV[sid], __dmul_rn(P.alpha_v, td));
+                    atomicAdd(&P.dV[sid], td);
+                    atomicAdd(&P.dN[sid], 1.0);
                     if (learn_actor) {
                         P.h_seen[sid] = 1;
                         const uint32_t a = w & INFO_SLOT_MASK;
@@ -599,15 +600,21 @@ ffm_unified_rollout_kernel(const UnifiedParams P) {
     }
 }
 
-// V += dV, H += dH, deltas zeroed, extremes of H recomputed (batched learning, between launches)
-__global__ void unified_apply_deltas_kernel(double* V, double* dV, double* Hm, double* dH, const uint8_t* h_seen, int S, int A,
+// Batched learning, between launches.  A state visited n times in the sync with TD errors d_1..d_n against
+// the frozen table receives V += (1 - (1 - alpha_v)^n) * mean(d): what n sequential updates towards the same
+// targets would give (a plain sum would multiply the step size by n and diverge for well-visited states).
+// H accumulates alpha_h * delta like the reference (:777).  Deltas zeroed, extremes of H recomputed.
+__global__ void unified_apply_deltas_kernel(double* V, double* dV, double* dN, double alpha_v, double* Hm, double* dH,
+                                            const uint8_t* h_seen, int S, int A,
                                             HStats* hstats, double* block_lo, double* block_hi, int* block_any) {
     const double DINF = __longlong_as_double(0x7ff0000000000000LL);
     double lo = DINF, hi = -DINF;
     int any = 0;
     for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < S; s += gridDim.x * blockDim.x) {
-        V[s] += dV[s];
+        const double cnt = dN[s];
+        if (cnt > 0.0) V[s] += (1.0 - pow(1.0 - alpha_v, cnt)) * (dV[s] / cnt);
         dV[s] = 0.0;
+        dN[s] = 0.0;
         if (Hm != nullptr) {
             for (int a = 0; a < A; ++a) {
                 const double v = Hm[(size_t)s * A + a] + dH[(size_t)s * A + a];

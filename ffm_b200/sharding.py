@@ -39,7 +39,7 @@ class BatchedLearner:
     """Synchronous batched TD learning of the unified model (BASELINE config 4).
 
     Each sync: every rank rolls out its B episodes against the frozen tables (kernel mode
-    FFM_LEARN_BATCHED accumulates alpha*delta into dV / dH with atomics), the deltas and key flags are
+    FFM_LEARN_BATCHED accumulates TD errors, visit counts and alpha_h*delta into dV / dN / dH with atomics), the deltas and key flags are
     all-reduced over ranks, and every rank applies the same update -- so all ranks hold identical
     tables without ever broadcasting them.  This is a different algorithm from the reference's
     sequential per-agent updates ("sequential learning semantics"); it is judged
@@ -62,12 +62,20 @@ class BatchedLearner:
         rank, ws = world()
         if ws > 1:
             _abi.check(s._lib.ffm_tables_get(s._h, None, _ptr(self._vseen), None, _ptr(self._hseen), _abi.FFM_DEVICE, _stream()))
-            allreduce_deltas([s.dV, s.dH], [self._vseen, self._hseen])
+            allreduce_deltas([s.dV, s.dN, s.dH], [self._vseen, self._hseen])
             _abi.check(s._lib.ffm_tables_set(s._h, None, _ptr(self._vseen), None, _ptr(self._hseen), _abi.FFM_DEVICE, _stream()))
         s.apply_deltas()
 
-    def round(self, pos_rc, n, max_steps):
+    def round(self, pos_rc, n, max_steps, sync_every=None):
+        """One batch of episodes.  sync_every = K folds the deltas in every K CA steps (value information then
+        travels K-step-wise within an episode, closer to the reference's per-agent updates); None = once,
+        at the end.  The number of syncs is fixed by max_steps so that all ranks stay in lock-step."""
         self.sim.set_positions(pos_rc, n)
-        self.sim.rollout(max_steps)
-        self.sync()
+        if sync_every is None:
+            self.sim.rollout(max_steps)
+            self.sync()
+        else:
+            for _ in range(0, max_steps, sync_every):
+                self.sim.rollout(min(sync_every, max_steps))
+                self.sync()
         return self.sim.counters()

@@ -221,8 +221,9 @@ class UnifiedSim(BatchSim):
 
     mode   "critic_only" | "actor_only" | "both" | "trained"
     learn  "exact"   the reference's sequential per-agent table updates (n_episodes must be 1)
-           "batched" synchronous batched TD: rollouts accumulate alpha*delta into ``dV`` / ``dH`` against
-                     frozen tables; ``apply_deltas()`` (after the caller's all-reduce) folds them in
+           "batched" synchronous batched TD: rollouts accumulate TD errors / visit counts / alpha_h*delta into
+                     ``dV`` / ``dN`` / ``dH`` against frozen tables; ``apply_deltas()`` (after the caller's
+                     all-reduce) folds them in
            "none"    frozen tables
     Tables are dense: state id = (bx*nby + by)*256 + rU*64 + rD*16 + rL*4 + rR (``key_to_id``).
     """
@@ -242,12 +243,13 @@ class UnifiedSim(BatchSim):
         self.S, self.A = S.value, A.value
         self.bs = int(self.params["block_size"])
         self.nby = -(-self.W // self.bs)
-        self.dV = self.dH = None
+        self.dV = self.dN = self.dH = None
         if learn == "batched":
             dev = f"cuda:{self.device}"
             self.dV = torch.zeros(self.S, dtype=torch.float64, device=dev)
+            self.dN = torch.zeros(self.S, dtype=torch.float64, device=dev)
             self.dH = torch.zeros((self.S, self.A), dtype=torch.float64, device=dev)
-            _abi.check(self._lib.ffm_tables_bind_deltas(self._h, _ptr(self.dV), _ptr(self.dH)))
+            _abi.check(self._lib.ffm_tables_bind_deltas(self._h, _ptr(self.dV), _ptr(self.dN), _ptr(self.dH)))
 
     def _score_field(self, sff):
         if self.mode == "critic_only":

@@ -58,7 +58,7 @@ def test_batched_td_tracks_sequential_td(cuda_device):
     learner = BatchedLearner(batched)
     for r in range(E // B):
         batched.set_episode_base(r * B)
-        learner.round(*pack_positions(pos[r * B:(r + 1) * B], N), 300)
+        learner.round(*pack_positions(pos[r * B:(r + 1) * B], N), 96, sync_every=4)
     Vb, sb, _, _ = batched.get_tables()
     assert np.array_equal(se, sb)                       # the dynamics do not depend on V: same states visited
     big = se & (np.abs(Ve) > 5.0)
@@ -66,7 +66,7 @@ def test_batched_td_tracks_sequential_td(cuda_device):
     corr = np.corrcoef(Ve[big], Vb[big])[0, 1]
     assert corr > 0.97, corr
     rel = np.abs(Ve[big] - Vb[big]) / np.abs(Ve[big])
-    assert np.median(rel) < 0.15, np.median(rel)
+    assert np.median(rel) < 0.2, np.median(rel)
 
 
 def test_batched_actor_learning_runs_and_keeps_tables_finite(cuda_device):
