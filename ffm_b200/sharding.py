@@ -46,9 +46,10 @@ class BatchedLearner:
     statistically, while FFM_LEARN_EXACT reproduces the reference bit for bit on one episode.
     """
 
-    def __init__(self, sim):
+    def __init__(self, sim, distributed=True):
         assert sim.learn == "batched"
         self.sim = sim
+        self.distributed = distributed      # False: never touch the process group (single-rank reference runs)
         dev = sim.dV.device
         self._vseen = torch.zeros(sim.S, dtype=torch.uint8, device=dev)
         self._hseen = torch.zeros(sim.S, dtype=torch.uint8, device=dev)
@@ -59,7 +60,7 @@ class BatchedLearner:
         from . import _abi
         from .sim import _ptr, _stream
         s = self.sim
-        rank, ws = world()
+        rank, ws = world() if self.distributed else (0, 1)
         if ws > 1:
             _abi.check(s._lib.ffm_tables_get(s._h, None, _ptr(self._vseen), None, _ptr(self._hseen), _abi.FFM_DEVICE, _stream()))
             allreduce_deltas([s.dV, s.dN, s.dH], [self._vseen, self._hseen])

@@ -64,7 +64,7 @@ def main():
     assert torch.equal(lo, hi), "ranks hold different V tables"
     if rank == 0:
         one = UnifiedSim(m, sff, E, Np, mode="both", learn="batched", params=P, seed=7, episode_base=0, device=local)
-        l1 = BatchedLearner(one)
+        l1 = BatchedLearner(one, distributed=False)
         for r in range(3):
             one.set_episode_base(r * E)
             l1.round(*pack_positions(pos, Np), 100)
