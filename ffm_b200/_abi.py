@@ -41,7 +41,8 @@ class Draws(C.Structure):
 
 class RolloutOut(C.Structure):
     _fields_ = [("traj_cells", C.c_void_p), ("traj_n", C.c_void_p), ("traj_steps", C.c_int32),
-                ("reserved", C.c_int32)]
+                ("reserved", C.c_int32), ("rec_state", C.c_void_p), ("rec_action", C.c_void_p),
+                ("rec_reward", C.c_void_p), ("rec_len", C.c_void_p)]
 
 
 # name -> (restype, argtypes); tests/test_abi.py checks this table against the header
@@ -66,6 +67,8 @@ SIGNATURES = {
     "ffm_set_episode_base": (C.c_int, [C.c_void_p, C.c_uint32]),
     "ffm_sff_generate": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int,
                                    C.c_int32, C.c_void_p, C.POINTER(C.c_int32)]),
+    "ffm_rollout_returns": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_double, C.c_void_p,
+                                      C.c_int32, C.c_void_p]),
     "ffm_launch_count": (C.c_int64, [C.c_void_p]),
     "ffm_kernel_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32),
                                   C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),

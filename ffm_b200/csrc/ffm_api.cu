@@ -457,6 +457,10 @@ int ffm_rollout(ffm_sim_t s, int32_t max_steps, const ffm_draws_t* draws, const 
             if (!out->traj_n) return fail(FFM_E_INVALID, "traj_cells without traj_n");
             U.traj = out->traj_cells; U.traj_n = out->traj_n; U.traj_steps = out->traj_steps;
         }
+        if (out) {
+            U.rec_state = out->rec_state; U.rec_action = out->rec_action; U.rec_reward = out->rec_reward; U.rec_len = out->rec_len;
+            U.traj_steps = out->traj_steps;
+        }
         void* uargs[] = {&U};
         CU(cudaLaunchKernel(s->kernel, dim3(s->cfg.n_episodes), dim3(s->threads), uargs, (size_t)s->smem_bytes, st));
         s->launches++;
@@ -658,6 +662,18 @@ done:
     cudaFree(d_dist); cudaFree(d_dirty); cudaFree(d_exits); cudaFree(d_counts); cudaFree(d_any);
     if (rounds_out) *rounds_out = rounds;
     return rc;
+}
+
+int ffm_rollout_returns(const float* reward, const int32_t* len, int32_t B, int32_t T, int32_t N, double gamma, double* returns,
+                        int32_t device, void* stream) {
+    if (!reward || !len || !returns) return fail(FFM_E_INVALID, "null argument");
+    if (B < 1 || T < 1 || N < 1) return fail(FFM_E_INVALID, "bad shape");
+    CU(cudaSetDevice(device));
+    const long long total = (long long)B * ((N + 3) / 4);
+    const int blocks = (int)((total + 255) / 256 < 148LL * 8 ? (total + 255) / 256 : 148LL * 8);
+    ffm::rollout_returns_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(reward, len, B, T, N, gamma, returns);
+    CU(cudaGetLastError());
+    return FFM_OK;
 }
 
 int64_t ffm_launch_count(ffm_sim_t s) { return s ? s->launches : 0; }

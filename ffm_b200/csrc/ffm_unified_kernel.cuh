@@ -67,10 +67,11 @@ struct UnifiedParams {
     unsigned long long seed; uint32_t episode_base;
     const double* move_draws; const double* conflict_draws; int draw_steps, draw_first;
     uint32_t* traj; int32_t* traj_n; int traj_steps;
+    uint32_t* rec_state; uint8_t* rec_action; float* rec_reward; int32_t* rec_len;   // rollout buffer [B][traj_steps][n_max]
 };
 
 struct USmemLayout {
-    uint32_t score, dffA, dffB, grid, claim, pos, posB, tgt, st, nst, info, td, wcnt, red, misc, total;
+    uint32_t score, dffA, dffB, grid, claim, pos, posB, tgt, st, nst, info, orig, origB, td, wcnt, red, misc, total;
 };
 
 __host__ __device__ inline USmemLayout make_ulayout(int HW, int W, int n_max, int sizeof_score, bool fields_in_smem) {
@@ -87,6 +88,8 @@ __host__ __device__ inline USmemLayout make_ulayout(int HW, int W, int n_max, in
     L.st = o;    o = align16(o + (uint32_t)n_max * 4u);
     L.nst = o;   o = align16(o + (uint32_t)n_max * 4u);
     L.info = o;  o = align16(o + (uint32_t)n_max * 4u);
+    L.orig = o;  o = align16(o + (uint32_t)n_max * 2u);
+    L.origB = o; o = align16(o + (uint32_t)n_max * 2u);
     L.td = o;    o = align16(o + (uint32_t)n_max * 8u);
     L.wcnt = o;  o = align16(o + (uint32_t)(n_max / 32 + 2) * 4u);
     L.red = o;   o = align16(o + 32u * 8u * 2u + 32u * 4u);
@@ -170,6 +173,8 @@ ffm_unified_rollout_kernel(const UnifiedParams P) {
     uint32_t* st = reinterpret_cast<uint32_t*>(smem_raw + L.st);
     uint32_t* nst = reinterpret_cast<uint32_t*>(smem_raw + L.nst);
     uint32_t* info = reinterpret_cast<uint32_t*>(smem_raw + L.info);
+    uint16_t* orig = reinterpret_cast<uint16_t*>(smem_raw + L.orig);    // column of the rollout buffer (index at launch)
+    uint16_t* origB = reinterpret_cast<uint16_t*>(smem_raw + L.origB);
     double* tdv = reinterpret_cast<double*>(smem_raw + L.td);
     uint32_t* wcnt = reinterpret_cast<uint32_t*>(smem_raw + L.wcnt);
     double* red_lo = reinterpret_cast<double*>(smem_raw + L.red);
@@ -199,7 +204,9 @@ ffm_unified_rollout_kernel(const UnifiedParams P) {
     int n = P.n_alive[e];
     const int t0 = P.t_done[e];
     uint32_t* gpos = P.pos + (size_t)e * P.n_max;
-    for (int i = tid; i < n; i += THREADS) pos[i] = gpos[i];
+    const bool recording = P.rec_reward != nullptr || P.rec_state != nullptr || P.rec_action != nullptr;
+    for (int i = tid; i < n; i += THREADS) { pos[i] = gpos[i]; orig[i] = (uint16_t)i; }
+    if (P.rec_len != nullptr) for (int i = tid; i < P.n_max; i += THREADS) P.rec_len[(size_t)e * P.n_max + i] = 0;
     __syncthreads();
     for (int i = tid; i < n; i += THREADS) grid[pos[i]] |= (uint16_t)(i + 1);
     __syncthreads();
@@ -445,6 +452,14 @@ ffm_unified_rollout_kernel(const UnifiedParams P) {
                 nc = T;
             }
             posB[i] = nc;
+            if (recording && tl < P.traj_steps) {                        // rollout buffer row: coalesced over pedestrians
+                const size_t at = ((size_t)e * P.traj_steps + tl) * P.n_max + orig[i];
+                const uint32_t w = info[i];
+                if (P.rec_state) P.rec_state[at] = st[i];
+                if (P.rec_action) P.rec_action[at] = (uint8_t)(w & INFO_SLOT_MASK);
+                if (P.rec_reward) P.rec_reward[at] = (float)agent_reward(P, w);
+                if (P.rec_len) P.rec_len[(size_t)e * P.n_max + orig[i]] = tl + 1;
+            }
         }
         __syncthreads();
 
@@ -562,9 +577,11 @@ ffm_unified_rollout_kernel(const UnifiedParams P) {
                 const int ni = before + __popc(bal & ((1u << lane) - 1u));
                 const uint32_t c = posB[i];
                 pos[ni] = c;
+                origB[ni] = orig[i];
                 grid[c] = (uint16_t)((grid[c] & TYPE_BITS) | (uint32_t)(ni + 1));
             }
         }
+        { uint16_t* tmpo = orig; orig = origB; origB = tmpo; }
         // ================= D: DFF decay + diffusion (:779-798) ==================================
         for (int c = tid; c < HW; c += THREADS) dffA[c] = __fmul_rn(P.c0, dffA[c]);
         __syncthreads();
@@ -597,6 +614,56 @@ ffm_unified_rollout_kernel(const UnifiedParams P) {
         P.n_alive[e] = n;
         P.t_done[e] = t0 + tl;
         P.ped_steps[e] += ped_steps;
+    }
+}
+
+// Discounted returns of a rollout buffer: G[b][t][n] = r[b][t][n] + gamma * G[b][t+1][n] over each path
+// (ffm_learning_core.py:262-278, 350-355: `G = r + self.gamma * G`, float64).  HBM-bound streaming kernel:
+// one thread owns 4 adjacent pedestrians of an episode, reads float4 reward rows and writes 2 x double2
+// return rows walking the time axis backwards; rows are contiguous over pedestrians -> fully coalesced.
+__global__ void __launch_bounds__(256)
+rollout_returns_kernel(const float* __restrict__ reward, const int32_t* __restrict__ len, int B, int T, int N, double gamma,
+                       double* __restrict__ G) {
+    const int groups = (N + 3) / 4;
+    const long long total = (long long)B * groups;
+    for (long long x = (long long)blockIdx.x * blockDim.x + threadIdx.x; x < total; x += (long long)gridDim.x * blockDim.x) {
+        const int b = (int)(x / groups), n0 = (int)(x - (long long)b * groups) * 4;
+        const bool vec = (N % 4 == 0);
+        int L[4];
+        int Lmax = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            L[k] = (n0 + k < N) ? min(len[(size_t)b * N + n0 + k], T) : 0;
+            Lmax = max(Lmax, L[k]);
+        }
+        double g[4] = {0.0, 0.0, 0.0, 0.0};
+        const size_t base = (size_t)b * T * N + n0;
+        for (int t = T - 1; t >= Lmax; --t) {          // beyond every path's end: zeros
+            if (vec) {
+                reinterpret_cast<double2*>(G + base + (size_t)t * N)[0] = make_double2(0.0, 0.0);
+                reinterpret_cast<double2*>(G + base + (size_t)t * N)[1] = make_double2(0.0, 0.0);
+            } else {
+                for (int k = 0; k < 4 && n0 + k < N; ++k) G[base + (size_t)t * N + k] = 0.0;
+            }
+        }
+#pragma unroll 4
+        for (int t = Lmax - 1; t >= 0; --t) {
+            float r[4];
+            if (vec) {
+                const float4 v = __ldg(reinterpret_cast<const float4*>(reward + base + (size_t)t * N));
+                r[0] = v.x; r[1] = v.y; r[2] = v.z; r[3] = v.w;
+            } else {
+                for (int k = 0; k < 4; ++k) r[k] = (n0 + k < N) ? reward[base + (size_t)t * N + k] : 0.0f;
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) g[k] = (t < L[k]) ? __dadd_rn((double)r[k], __dmul_rn(gamma, g[k])) : 0.0;
+            if (vec) {
+                reinterpret_cast<double2*>(G + base + (size_t)t * N)[0] = make_double2(g[0], g[1]);
+                reinterpret_cast<double2*>(G + base + (size_t)t * N)[1] = make_double2(g[2], g[3]);
+            } else {
+                for (int k = 0; k < 4 && n0 + k < N; ++k) G[base + (size_t)t * N + k] = g[k];
+            }
+        }
     }
 }
 

@@ -150,7 +150,7 @@ class BatchSim:
         _abi.check(self._lib.ffm_get_counters(self._h, _ptr(steps_t), _ptr(ped_steps_t), _abi.FFM_DEVICE, _stream()))
 
     # -- stepping ------------------------------------------------------------------------------
-    def rollout(self, max_steps, draws=None, record=0):
+    def rollout(self, max_steps, draws=None, record=0, record_buffer=False):
         """Run up to ``max_steps`` CA steps per episode (asynchronous on the current stream).
 
         draws   optional dict(move=float64 [B, T, n_max], conflict=float64 [B, T, H*W, 2],
@@ -181,12 +181,23 @@ class BatchSim:
             self._keep = [mv, cf]
         optr, ret = None, None
         if record:
-            cells = torch.zeros((self.B, record, self.n_max), dtype=torch.int32, device=f"cuda:{self.device}")
-            cnt = torch.zeros((self.B, record), dtype=torch.int32, device=f"cuda:{self.device}")
+            dev = f"cuda:{self.device}"
             o = _abi.RolloutOut()
-            o.traj_cells, o.traj_n, o.traj_steps = cells.data_ptr(), cnt.data_ptr(), int(record)
+            o.traj_steps = int(record)
+            if record_buffer:
+                # rollout buffer of the unified models: state / action / reward per agent-step, SoA [B, T, n_max]
+                rs = torch.zeros((self.B, record, self.n_max), dtype=torch.int32, device=dev)
+                ra = torch.zeros((self.B, record, self.n_max), dtype=torch.uint8, device=dev)
+                rr = torch.zeros((self.B, record, self.n_max), dtype=torch.float32, device=dev)
+                rl = torch.zeros((self.B, self.n_max), dtype=torch.int32, device=dev)
+                o.rec_state, o.rec_action, o.rec_reward, o.rec_len = rs.data_ptr(), ra.data_ptr(), rr.data_ptr(), rl.data_ptr()
+                ret = dict(state=rs, action=ra, reward=rr, length=rl)
+            else:
+                cells = torch.zeros((self.B, record, self.n_max), dtype=torch.int32, device=dev)
+                cnt = torch.zeros((self.B, record), dtype=torch.int32, device=dev)
+                o.traj_cells, o.traj_n = cells.data_ptr(), cnt.data_ptr()
+                ret = (cells, cnt)
             optr = C.byref(o)
-            ret = (cells, cnt)
         _abi.check(self._lib.ffm_rollout(self._h, int(max_steps), dptr, optr, _stream()))
         return ret
 
@@ -322,3 +333,15 @@ class UnifiedSim(BatchSim):
     def apply_deltas(self):
         """V += dV, H += dH, deltas zeroed, H extremes refreshed (call after all-reducing dV / dH)."""
         _abi.check(self._lib.ffm_tables_apply_deltas(self._h, _stream()))
+
+
+def rollout_returns(reward, length, gamma):
+    """Discounted returns G[b, t, n] = r + gamma * G[b, t+1, n] (float64) of a rollout buffer
+    (reward float32 [B, T, N], length int32 [B, N], CUDA tensors) -- ffm_learning_core.py:262-278."""
+    assert reward.is_cuda and reward.dtype == torch.float32 and reward.is_contiguous() and reward.dim() == 3
+    assert length.is_cuda and length.dtype == torch.int32 and length.is_contiguous()
+    B, T, N = reward.shape
+    out = torch.empty((B, T, N), dtype=torch.float64, device=reward.device)
+    _abi.check(_abi.lib().ffm_rollout_returns(_ptr(reward), _ptr(length), B, T, N, float(gamma), _ptr(out),
+                                              reward.device.index or 0, _stream()))
+    return out

@@ -116,6 +116,18 @@ typedef struct ffm_rollout_out {
     int32_t *traj_n;
     int32_t traj_steps;
     int32_t reserved;
+    /* Rollout buffer of the unified models (SoA, one column per pedestrian = its index at the start of the
+     * launch, rows = steps of this launch, [B][traj_steps][n_max]); any may be NULL:
+     *   rec_state  uint32  state id of the agent-step           states[idx]      ffm_unified.py:293-294
+     *   rec_action uint8   chosen slot (neighbours.., stay)     actions[idx]     :343,510
+     *   rec_reward float32 step_penalty + exit + collisions     reward           :636-648
+     *   rec_len    int32 [B][n_max] steps the pedestrian was inside during this launch (its path length)
+     * -- the per-agent (state, action, reward) path lists of ffm_learning_core.py:79-81,221-222 in array form,
+     * input of ffm_rollout_returns. */
+    uint32_t *rec_state;
+    uint8_t *rec_action;
+    float *rec_reward;
+    int32_t *rec_len;
 } ffm_rollout_out_t;
 
 int ffm_abi_version(void);
@@ -184,6 +196,13 @@ int ffm_set_episode_base(ffm_sim_t sim, uint32_t episode_base);
 enum { FFM_SFF_L1 = 0, FFM_SFF_L2 = 1, FFM_SFF_LINF = 2, FFM_SFF_BFS4 = 3, FFM_SFF_BFS8 = 4, FFM_SFF_DIJKSTRA8 = 5 };
 int ffm_sff_generate(const uint8_t *maps, int32_t n_maps, int32_t height, int32_t width, int32_t mode, int32_t out_dtype,
                      void *out, int space, int32_t device, void *stream, int32_t *rounds);
+
+/* Discounted returns of a rollout buffer (device pointers): for every path (b, n) of length len[b][n],
+ *   G[b][t][n] = reward[b][t][n] + gamma * G[b][t+1][n],  G beyond the path's end = 0      (float64)
+ * -- the reverse scan `G = r + self.gamma * G` of ffm_learning_core.py:262-278, 350-355.  reward / G are
+ * [B][T][N] (time-major per episode: consecutive pedestrians are consecutive in memory). */
+int ffm_rollout_returns(const float *reward, const int32_t *len, int32_t n_episodes, int32_t steps, int32_t n_max,
+                        double gamma, double *returns, int32_t device, void *stream);
 
 /* number of kernels this handle has launched so far (bench.py "gpu_launches") */
 int64_t ffm_launch_count(ffm_sim_t sim);

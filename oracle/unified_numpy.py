@@ -96,6 +96,7 @@ class UnifiedOracle:
         self.source = source
         self.t = 0
         self.min_margin = np.inf
+        self.step_log = None     # set to [] to record (states, chosen slots, rewards) per step in agent order
 
     # -- keys -------------------------------------------------------------------------------------
     def state_id(self, x, y, state_map):
@@ -241,6 +242,9 @@ class UnifiedOracle:
                     nstate[idx] = self.state_id(nxt[idx, 0], nxt[idx, 1], nmap)
             g, av = p["gamma"], p["alpha_v"]
             td = np.zeros(n, np.float64)
+            if self.step_log is not None:
+                self.step_log.append(dict(states=states.copy(), slots=chosen_slot.copy(),
+                                          rewards=np.array([self._reward(will_exit[i], int(coll[i])) for i in range(n)], np.float64)))
             for idx in range(n):                                                  # sequential TD(0) (:633-665)
                 r = self._reward(will_exit[idx], int(coll[idx]))
                 v_next = 0.0 if will_exit[idx] else self._v(nstate[idx])
