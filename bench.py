@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Benchmark of the FFM hot path: pedestrian-steps/s of batched evacuation episodes (BASELINE.json).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c3|c1] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c2dff|c3|c1] [--impl ours|reference]
 
 A "step" is one pass of the hot path over one batch: B episodes placed, then rolled out by the
 persistent kernel until everybody has left (or the step cap).  Workload `c2` (the configuration the
@@ -46,6 +46,8 @@ WORKLOADS = {
                desc="C2: 4096 episodes/GPU, 64x64 single-exit room, SFF only, Moore, 1024 peds/episode, to evacuation (cap 4096)"),
     "c2dff": dict(h=64, w=64, n=1024, episodes=4096, cap=4096, nbh="moore", k_S=3, k_D=1, track_dff=True,
                   desc="C2 geometry with DFF on (k_D=1, diffuse=decay=0.2)"),
+    "c3": dict(h=256, w=256, n=10000, episodes=148, cap=2048, nbh="moore", k_S=3, k_D=1, track_dff=True, plan="c3",
+               desc="C3: 148 episodes/GPU, 256x256 floor plan (3x3 rooms, 4 exits), geodesic SFF, DFF on, Moore, 10000 peds/episode, cap 2048"),
     "c1": dict(h=12, w=12, n=100, episodes=4096, cap=4096, nbh="neumann", k_S=3, k_D=1, track_dff=True,
                desc="C1 geometry batched: 12x12 room, neumann, N=100, DFF on"),
 }
@@ -54,42 +56,17 @@ WORKLOADS = {
 # ------------------------------------------------------------------------------------------------
 # workload construction (product-side code only; no oracle)
 # ------------------------------------------------------------------------------------------------
-def room_map(h, w):
-    """Walled room with one exit in the middle of the top wall (the layout of Create_Map.py:9-19)."""
-    m = np.zeros((h, w), dtype=np.uint8)
-    m[0, :] = 2; m[-1, :] = 2; m[:, 0] = 2; m[:, -1] = 2
-    m[0, w // 2] = 3
-    return m
+from ffm_b200.workloads import place, room_map, rooms_map_c3, sff_room  # noqa: E402
 
 
-def sff_room(m, nbh):
-    """Obstacle-blind distance to the exit: Linf for Moore, L1 for von Neumann (Create_SFF.py:24,28);
-    float32, inf on non-walkable cells."""
-    h, w = m.shape
-    er, ec = np.argwhere(m == 3)[0]
-    rr, cc = np.meshgrid(np.arange(h), np.arange(w), indexing="ij")
-    d = np.maximum(abs(rr - er), abs(cc - ec)) if nbh == "moore" else abs(rr - er) + abs(cc - ec)
-    out = np.full((h, w), np.inf, dtype=np.float32)
-    walk = (m == 0) | (m == 3)
-    out[walk] = d[walk]
-    return out
-
-
-def place(m, n, episodes, episode_base, seed):
-    """Uniform placement without replacement on free cells, keyed by GLOBAL episode id (Philox stream
-    PLACE): the n free cells with the smallest keys, in key order.  int32 [episodes, n, 2]."""
-    from ffm_b200 import philox
-    free = np.argwhere(m == 0).astype(np.int32)
-    out = np.empty((episodes, n, 2), dtype=np.int32)
-    ords = np.arange(len(free))
-    chunk = 256
-    for e0 in range(0, episodes, chunk):
-        e1 = min(episodes, e0 + chunk)
-        eps = (episode_base + np.arange(e0, e1))[:, None]
-        keys, _ = philox.draw2(seed, eps, 0, philox.STREAM_PLACE, ords[None, :])
-        sel = np.argsort(keys, axis=1, kind="stable")[:, :n]
-        out[e0:e1] = free[sel]
-    return out
+def build_fields(wl):
+    """(map, sff) of a workload; the C3 field is the geodesic 8-connected BFS distance generated on the GPU."""
+    if wl.get("plan") == "c3":
+        from ffm_b200.sff import generate_sff
+        m = rooms_map_c3(wl["h"], wl["w"])
+        return m, generate_sff(m, "bfs8", np.float32)
+    m = room_map(wl["h"], wl["w"])
+    return m, sff_room(m, wl["nbh"])
 
 
 # ------------------------------------------------------------------------------------------------
@@ -157,8 +134,8 @@ def _cpu_worker(args):
         def coin(self, t, c): return self.rs.random_sample()
         def winner(self, t, c, k): return self.rs.random_sample()
 
-    m = room_map(wl["h"], wl["w"])
-    o = ffm_numpy.CoreOracle(m, sff_room(m, wl["nbh"]), pos0,
+    m, sff = wl["_fields"]
+    o = ffm_numpy.CoreOracle(m, sff, pos0,
                              {"k_S": wl["k_S"], "k_D": wl["k_D"], "neighborhood": wl["nbh"]}, MT())
     t0 = time.perf_counter()
     ped = 0
@@ -171,7 +148,7 @@ def _cpu_worker(args):
 def cpu_numpy_port(wl, budget_s, seed=1234, cores=None):
     import multiprocessing as mp
     cores = cores or os.cpu_count() or 1
-    m = room_map(wl["h"], wl["w"])
+    m, _ = wl["_fields"]
     pos = place(m, wl["n"], cores, 0, seed)
     with mp.get_context("fork").Pool(cores) as pool:
         t0 = time.perf_counter()
@@ -188,10 +165,10 @@ def cpu_c_port(wl, episodes, seed=1234, cores=None):
     """C restatement (oracle/c), one episode per thread; full episodes."""
     from oracle import c_oracle
     cores = cores or os.cpu_count() or 1
-    m = room_map(wl["h"], wl["w"])
+    m, sff = wl["_fields"]
     pos = place(m, wl["n"], episodes, 0, seed)
     t0 = time.perf_counter()
-    steps, ped = c_oracle.run_core_batch(m, sff_room(m, wl["nbh"]), pos, np.full((episodes,), wl["n"], np.int32),
+    steps, ped = c_oracle.run_core_batch(m, sff, pos, np.full((episodes,), wl["n"], np.int32),
                                         {"k_S": wl["k_S"], "k_D": wl["k_D"], "neighborhood": wl["nbh"]},
                                         seed=seed, episode_base=0, max_steps=wl["cap"], threads=cores,
                                         track_dff=wl["track_dff"])
@@ -213,6 +190,13 @@ def run_reference_arm(args, wl):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    if wl.get("plan") == "c3":     # the C3 field is a geodesic distance: CPU-side Dijkstra of the oracle
+        from oracle import c_oracle
+        m = rooms_map_c3(wl["h"], wl["w"])
+        wl["_fields"] = (m, c_oracle.geodesic(m, "bfs8"))
+    else:
+        m = room_map(wl["h"], wl["w"])
+        wl["_fields"] = (m, sff_room(m, wl["nbh"]))
     cores = os.cpu_count() or 1
     times, vals, last = [], [], None
     for it in range(args.warmup + args.steps):
@@ -279,8 +263,8 @@ def main():
         torch.cuda.synchronize()
 
     B, N, cap = wl["episodes"], wl["n"], wl["cap"]
-    m = room_map(wl["h"], wl["w"])
-    sff = sff_room(m, wl["nbh"])
+    m, sff = build_fields(wl)
+    wl["_fields"] = (m, sff)
     params = {"k_S": wl["k_S"], "k_D": wl["k_D"], "diffuse": 0.2, "decay": 0.2, "neighborhood": wl["nbh"]}
     ep_base = rank * B                                   # global episode ids: results independent of N
     pos_np = place(m, N, B, ep_base, args.seed)

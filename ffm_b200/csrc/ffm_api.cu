@@ -147,7 +147,6 @@ namespace {
 template <typename S, typename PosT, int NBR, bool DFF, bool FS>
 const void* pick_threads(int threads) {
     if (threads == 1024) return (const void*)ffm::ffm_core_rollout_kernel<S, PosT, NBR, DFF, FS, 1024>;
-    if (threads == 512) return (const void*)ffm::ffm_core_rollout_kernel<S, PosT, NBR, DFF, FS, 512>;
     if (threads == 128) return (const void*)ffm::ffm_core_rollout_kernel<S, PosT, NBR, DFF, FS, 128>;
     return (const void*)ffm::ffm_core_rollout_kernel<S, PosT, NBR, DFF, FS, 256>;
 }
@@ -269,10 +268,10 @@ int ffm_create(const ffm_config_t* cfg, ffm_sim_t* out) {
         return fail(FFM_E_UNSUPPORTED, "episode state (%d B) does not fit the 227 KB of shared memory of one SM", Lout.total);
     }
     const int work = N > HW / 8 ? N : HW / 8;
-    s->threads = work <= 128 ? 128 : (work <= 1024 ? 256 : (work <= 4096 ? 512 : 1024));
-    if (const char* ev = getenv("FFM_THREADS")) {   // tuning override: 128 | 256 | 512 | 1024
+    s->threads = work <= 128 ? 128 : (work <= 2048 ? 256 : 1024);
+    if (const char* ev = getenv("FFM_THREADS")) {   // tuning override: 128 | 256 | 1024
         const int v = atoi(ev);
-        if (v == 128 || v == 256 || v == 512 || v == 1024) s->threads = v;
+        if (v == 128 || v == 256 || v == 1024) s->threads = v;
     }
     if (unified) {
         s->threads = N <= 128 ? 128 : 256;

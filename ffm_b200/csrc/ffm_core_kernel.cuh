@@ -35,13 +35,15 @@
 //                            0x3FFF on blocked cells (walls look "occupied": one test per neighbour);
 //                            a guard band of W+1 blocked entries on both ends absorbs neighbour reads
 //                            of border cells
-//   claim u8[HW]             requests per target cell this step (zeroed again by the requesters)
+//   claim u4[HW]             requests per target cell this step (nibbles, 8 cells per word; swept clean in C)
 //   score S[HW]              -k_S * sff  (S = float | double, the dtype NumPy computes in)
 //   dffA/dffB f32[HW]        dynamic floor field, ping-pong
 //   pos   PosT[n_max]        linear cell per slot (PosT = u16 when H*W <= 65536, else u32)
-//   tgt   PosT[n_max]        requested cell this step per slot (all-ones = no request)
-//   work  u32[n_max]         draw list: slot | candidate mask << 16
-//   req   u16[n_max]         request list: slot | 0x8000 once the request is granted
+//   tgt   PosT[n_max]        per slot: candidate mask between A1 and A2, then the requested cell
+//                            (all-ones = no request)
+//   list  u16[n_max]         ONE work list: A1 pushes the slots that must draw from the front and the
+//                            forced requests from the back; A2 turns each draw entry into a request
+//                            entry in place (0xFFFF = no request); | 0x8000 once the request is granted
 //   alive u32[n_max/32+1]    alive bitmap;  wpre u32[n_max/32+1] exclusive prefix popcounts
 #pragma once
 #include "ffm_device.cuh"
@@ -78,7 +80,7 @@ struct RolloutParams {
 };
 
 struct SmemLayout {
-    uint32_t score, dffA, dffB, grid, claim, pos, tgt, work, req, alive, wpre, ctr, total;
+    uint32_t score, dffA, dffB, grid, claim, pos, tgt, list, alive, wpre, ctr, total;
 };
 
 __host__ __device__ inline uint32_t align16(uint32_t x) { return (x + 15u) & ~15u; }
@@ -93,11 +95,10 @@ __host__ __device__ inline SmemLayout make_layout(int HW, int W, int n_max, int 
     L.dffA = o;  if (fields_in_smem && dff) o = align16(o + (uint32_t)HW * 4u);
     L.dffB = o;  if (fields_in_smem && dff) o = align16(o + (uint32_t)HW * 4u);
     L.grid = o;  o = align16(o + (uint32_t)(HW + 2 * (W + 1)) * 2u);
-    L.claim = o; o = align16(o + (uint32_t)HW);
+    L.claim = o; o = align16(o + ((uint32_t)HW + 7u) / 8u * 4u);
     L.pos = o;   o = align16(o + (uint32_t)n_max * ps);
     L.tgt = o;   o = align16(o + (uint32_t)n_max * ps);
-    L.work = o;  o = align16(o + (uint32_t)n_max * 4u);
-    L.req = o;   o = align16(o + (uint32_t)n_max * 2u);
+    L.list = o;  o = align16(o + (uint32_t)n_max * 2u);
     L.alive = o; o = align16(o + nw * 4u);
     L.wpre = o;  o = align16(o + nw * 4u);
     L.ctr = o;   o = align16(o + 8u * 4u);
@@ -137,14 +138,16 @@ __device__ __forceinline__ uint32_t lanemask_lt() {
 
 // Warp-aggregated append of `value` to a shared-memory list (one atomic per warp).  All 32 lanes
 // must call it; lanes with pred == false append nothing.
+// dir = +1 fills list[0], list[1], ...; dir = -1 fills list[last], list[last-1], ...
 template <typename T>
-__device__ __forceinline__ void warp_append(bool pred, T value, T* list, uint32_t* counter, int lane) {
+__device__ __forceinline__ void warp_append(bool pred, T value, T* list, uint32_t* counter, int lane, int dir = 1, int last = 0) {
     const uint32_t bal = __ballot_sync(0xffffffffu, pred);
     if (bal == 0u) return;
     uint32_t base = 0;
     if (lane == 0) base = atomicAdd(counter, (uint32_t)__popc(bal));
     base = __shfl_sync(0xffffffffu, base, 0);
-    if (pred) list[base + __popc(bal & lanemask_lt())] = value;
+    const int k = (int)base + __popc(bal & lanemask_lt());
+    if (pred) list[dir > 0 ? k : last - k] = value;
 }
 
 template <typename S, typename PosT, int NBR, bool DFF, bool FIELDS_IN_SMEM, int THREADS>
@@ -163,13 +166,13 @@ ffm_core_rollout_kernel(const RolloutParams P) {
     uint16_t* grid = reinterpret_cast<uint16_t*>(smem_raw + L.grid) + G;   // grid[-G .. HW+G)
     PosT* pos = reinterpret_cast<PosT*>(smem_raw + L.pos);
     PosT* tgt = reinterpret_cast<PosT*>(smem_raw + L.tgt);
-    uint32_t* work = reinterpret_cast<uint32_t*>(smem_raw + L.work);
-    uint16_t* req = reinterpret_cast<uint16_t*>(smem_raw + L.req);
+    uint16_t* list = reinterpret_cast<uint16_t*>(smem_raw + L.list);
+    const int list_last = P.n_max - 1;
     uint32_t* alive = reinterpret_cast<uint32_t*>(smem_raw + L.alive);
     uint32_t* wpre = reinterpret_cast<uint32_t*>(smem_raw + L.wpre);
     uint32_t* ctr = reinterpret_cast<uint32_t*>(smem_raw + L.ctr);   // [parity][n_work, n_req, n_exit, -]
-    uint8_t* claim = smem_raw + L.claim;
     uint32_t* claim32 = reinterpret_cast<uint32_t*>(smem_raw + L.claim);
+    const int claim_words = (HW + 7) / 8;
 
     const S* score;
     float* dffA = nullptr;
@@ -206,7 +209,7 @@ ffm_core_rollout_kernel(const RolloutParams P) {
         wpre[w] = (uint32_t)(lo < n ? lo : n);
     }
     if (tid < 8) ctr[tid] = 0u;
-    for (int c = tid; c < (HW + 3) / 4; c += THREADS) claim32[c] = 0u;
+    for (int c = tid; c < claim_words; c += THREADS) claim32[c] = 0u;
     __syncthreads();
     for (int i = tid; i < n; i += THREADS) grid[pos[i]] |= (uint16_t)(i + 1);
     __syncthreads();
@@ -255,15 +258,15 @@ ffm_core_rollout_kernel(const RolloutParams P) {
                         const int k = __ffs(ex) - 1;
                         target = (k == NBR) ? (uint32_t)c : (uint32_t)(c + nbr_off_rt<NBR>(k, W));
                         forced = true;
-                        if (k != NBR) atomicAdd(&claim32[target >> 2], 1u << (8 * (target & 3u)));
+                        if (k != NBR) atomicAdd(&claim32[target >> 3], 1u << (4 * (target & 7u)));
                     } else {
                         need_draw = true;
                     }
                 }
-                tgt[s] = (PosT)target;
+                tgt[s] = need_draw ? (PosT)m : (PosT)target;     // the mask rides in tgt[] until A2
             }
-            warp_append<uint32_t>(need_draw, (uint32_t)s | (m << 16), work, &cnt[0], lane);
-            warp_append<uint16_t>(forced, (uint16_t)s, req, &cnt[1], lane);
+            warp_append<uint16_t>(need_draw, (uint16_t)s, list, &cnt[0], lane);
+            warp_append<uint16_t>(forced, (uint16_t)s, list, &cnt[1], lane, -1, list_last);
         }
         __syncthreads();
 
@@ -273,12 +276,9 @@ ffm_core_rollout_kernel(const RolloutParams P) {
         const int n_work = (int)cnt[0];
         for (int base = 0; base < n_work; base += THREADS) {
             const int wi = base + tid;
-            bool requested = false;
-            int s = 0;
             if (wi < n_work) {
-                const uint32_t wv = work[wi];
-                s = (int)(wv & 0xFFFFu);
-                uint32_t mm = wv >> 16;
+                const int s = (int)list[wi];
+                uint32_t mm = (uint32_t)tgt[s];
                 const int ncand = __popc(mm) + 1;
                 const int c = (int)pos[s];
                 int cell[NBR + 1];
@@ -328,26 +328,28 @@ ffm_core_rollout_kernel(const RolloutParams P) {
                             run += (double)p[j];
                             if (run > thresh) { target = (uint32_t)cell[j]; done = true; }
                         }
-                    requested = true;
-                    if (target != (uint32_t)c) atomicAdd(&claim32[target >> 2], 1u << (8 * (target & 3u)));
+                    if (target != (uint32_t)c) atomicAdd(&claim32[target >> 3], 1u << (4 * (target & 7u)));
+                } else {
+                    list[wi] = (uint16_t)0xFFFFu;                             // no request after all (:82)
                 }
                 tgt[s] = (PosT)target;
             }
-            warp_append<uint16_t>(requested, (uint16_t)s, req, &cnt[1], lane);
         }
         __syncthreads();
 
         // ================= B: resolve same-target conflicts (request list) ======================
-        const int n_req = (int)cnt[1];
+        const int n_req = n_work + (int)cnt[1];
         for (int j = tid; j < n_req; j += THREADS) {
-            const int s = (int)req[j];
+            const int li = j < n_work ? j : list_last - (j - n_work);
+            const int s = (int)list[li];
+            if (s == 0xFFFF) continue;
             const int c = (int)pos[s];
             const uint32_t T = tgt[s];
             bool moved;
             if (T == (uint32_t)c) {
                 moved = true;   // nobody else can request an occupied cell: lone claimant of "stay"
             } else {
-                const int k = (int)claim[T];
+                const int k = (int)((claim32[T >> 3] >> (4 * (T & 7u))) & 0xFu);
                 if (k == 1) {
                     moved = true;                                             // (:91-93)
                 } else {
@@ -372,7 +374,7 @@ ffm_core_rollout_kernel(const RolloutParams P) {
             }
             if (moved) {
                 if (DFF) dffA[c] = __fadd_rn(dffA[c], 1.0f);                  // footprint (:93,98)
-                if (T != (uint32_t)c) req[j] = (uint16_t)(s | 0x8000);        // to be applied in C
+                if (T != (uint32_t)c) list[li] = (uint16_t)(s | 0x8000);      // to be applied in C
             }
         }
         __syncthreads();
@@ -382,12 +384,11 @@ ffm_core_rollout_kernel(const RolloutParams P) {
             const int j = base + tid;
             bool leaves = false;
             if (j < n_req) {
-                const uint32_t rv = req[j];
-                const int s = (int)(rv & 0x7FFFu);
-                const int c = (int)pos[s];
-                const uint32_t T = tgt[s];
-                if (T != (uint32_t)c) claim[T] = 0;                            // leave the counters clean
-                if (rv & 0x8000u) {
+                const uint32_t rv = list[j < n_work ? j : list_last - (j - n_work)];
+                if ((rv & 0x8000u) && rv != 0xFFFFu) {
+                    const int s = (int)(rv & 0x7FFFu);
+                    const int c = (int)pos[s];
+                    const uint32_t T = tgt[s];
                     grid[c] &= (uint16_t)TYPE_BITS;
                     if (grid[T] == EXIT_EMPTY) {                               // (:101-102)
                         leaves = true;
@@ -401,6 +402,7 @@ ffm_core_rollout_kernel(const RolloutParams P) {
             const uint32_t bal = __ballot_sync(0xffffffffu, leaves);
             if (bal != 0u && lane == 0) atomicAdd(&cnt[2], (uint32_t)__popc(bal));
         }
+        for (int c = tid; c < claim_words; c += THREADS) claim32[c] = 0u;    // claim counters clean for the next step
         if (DFF) {
             // new = c0 * dff (ffm_core.py:109); the neighbour terms read this scaled field (:111)
             for (int c = tid; c < HW; c += THREADS) dffA[c] = __fmul_rn(P.c0, dffA[c]);

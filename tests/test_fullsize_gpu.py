@@ -115,3 +115,42 @@ def test_properties_at_full_size(cuda_device):
     pb, kb = b.get_positions()
     assert np.array_equal(kb, k[B // 2:]) and np.array_equal(pb, p[B // 2:])
     assert np.array_equal(b.get_dff().view(np.uint32), a.get_dff()[B // 2:].view(np.uint32))
+
+
+def test_c3_floor_plan_matches_c_oracle(cuda_device):
+    """BASELINE configs[2] geometry: 256x256 rooms-and-doors plan, geodesic SFF (generated on the GPU), DFF on,
+    10 000 pedestrians; fields stay in global memory (L2) at this size.  Recorded-draw protocol, 200 steps."""
+    import torch
+    from ffm_b200 import BatchSim
+    from ffm_b200.sff import generate_sff
+    from ffm_b200.workloads import place, rooms_map_c3
+    from oracle import c_oracle
+
+    m = rooms_map_c3()
+    sff = generate_sff(m, "bfs8", np.float32)
+    assert np.array_equal(sff, c_oracle.geodesic(m, "bfs8"))
+    B, N, seed, T = 2, 10000, 0x5EED0003, 200
+    params = {"k_S": 3, "k_D": 1, "neighborhood": "moore"}
+    pos = place(m, N, B, 0, seed)
+    n = np.full((B,), N, np.int32)
+    ref = c_oracle.run_core_batch(m, sff, pos, n, params, seed=seed, max_steps=T, threads=2, traj_steps=T, want_state=True,
+                                  guard=1e-5, record_moves=T)
+    sim = BatchSim(m, sff, B, N, params, seed=seed)
+    assert not sim.kernel_info()["fields_in_smem"]
+    sim.set_positions(pos, n)
+    cells, cnt = sim.rollout(T, draws=dict(move=torch.from_numpy(ref["move_draws"]).cuda()), record=T)
+    torch.cuda.synchronize()
+    steps, ped = sim.counters()
+    assert np.array_equal(ped, ref["ped_steps"]) and (steps == T).all()
+    cells, cnt = cells.cpu().numpy(), cnt.cpu().numpy()
+    assert np.array_equal(cnt, ref["traj_n"])
+    for e in range(B):
+        for t in (0, 1, 50, T - 1):
+            k = cnt[e, t]
+            assert np.array_equal(cells[e, t, :k], ref["traj"][e, t, :k]), (e, t)
+    p_gpu, n_gpu = sim.get_positions()
+    assert np.array_equal(n_gpu, ref["final_n"])
+    W = 256
+    for e in range(B):
+        assert np.array_equal(p_gpu[e, :n_gpu[e], 0] * W + p_gpu[e, :n_gpu[e], 1], ref["final_pos"][e, :n_gpu[e]])
+    assert np.array_equal(sim.get_dff().view(np.uint32), ref["final_dff"].view(np.uint32))
