@@ -296,7 +296,7 @@ int ffm_create(const ffm_config_t* cfg, ffm_sim_t* out) {
         if (e_ != cudaSuccess) { ffm_destroy(s); return fail(FFM_E_CUDA, "cudaMalloc(%zu) failed: %s", (size_t)(bytes), cudaGetErrorString(e_)); } \
     } while (0)
     ALLOC(s->d_map, (size_t)HW);
-    ALLOC(s->d_type_grid, (size_t)(HW + 2 * (W + 1)) * 2);
+    ALLOC(s->d_type_grid, (size_t)(HW + 2 * (W + 1)) * 2 + 16);   // padded: the rollout kernel bulk-copies it in 16-byte units
     ALLOC(s->d_sff, (size_t)HW * ssz);
     ALLOC(s->d_score, (size_t)HW * ssz);
     ALLOC(s->d_pos, (size_t)B * N * 4);

@@ -80,7 +80,7 @@ struct RolloutParams {
 };
 
 struct SmemLayout {
-    uint32_t score, dffA, dffB, grid, claim, pos, tgt, list, alive, wpre, ctr, total;
+    uint32_t score, dffA, dffB, grid, claim, pos, tgt, list, alive, wpre, ctr, bar, total;
 };
 
 __host__ __device__ inline uint32_t align16(uint32_t x) { return (x + 15u) & ~15u; }
@@ -102,6 +102,7 @@ __host__ __device__ inline SmemLayout make_layout(int HW, int W, int n_max, int 
     L.alive = o; o = align16(o + nw * 4u);
     L.wpre = o;  o = align16(o + nw * 4u);
     L.ctr = o;   o = align16(o + 8u * 4u);
+    L.bar = o;   o = align16(o + 8u);
     L.total = o;
     return L;
 }
@@ -174,19 +175,38 @@ ffm_core_rollout_kernel(const RolloutParams P) {
     uint32_t* claim32 = reinterpret_cast<uint32_t*>(smem_raw + L.claim);
     const int claim_words = (HW + 7) / 8;
 
+    // ---- prologue: stage the episode's fields with TMA bulk copies (cp.async.bulk + mbarrier) ------
+    unsigned long long* bar = reinterpret_cast<unsigned long long*>(smem_raw + L.bar);
     const S* score;
     float* dffA = nullptr;
     float* dffB = nullptr;
     float* dff_home = DFF ? P.dff + (size_t)e * HW : nullptr;
+    const uint32_t grid_bytes = align16((uint32_t)(HW + 2 * G) * 2u);      // d_type_grid is padded to this size
+    const uint32_t score_bytes = (uint32_t)HW * (uint32_t)sizeof(S), dff_bytes = (uint32_t)HW * 4u;
+    const bool tma_fields = FIELDS_IN_SMEM && (score_bytes % 16u == 0u) && (dff_bytes % 16u == 0u);
+    if (tid == 0) mbar_init(bar, 1);
+    __syncthreads();
+    if (tid == 0) {
+        uint32_t bytes = grid_bytes;
+        if (tma_fields) bytes += score_bytes + (DFF ? dff_bytes : 0u);
+        mbar_arrive_expect_tx(bar, bytes);
+        bulk_copy_g2s(smem_raw + L.grid, P.type_grid, grid_bytes, bar);
+        if (tma_fields) {
+            bulk_copy_g2s(smem_raw + L.score, P.score, score_bytes, bar);
+            if (DFF) bulk_copy_g2s(smem_raw + L.dffA, dff_home, dff_bytes, bar);
+        }
+    }
     if (FIELDS_IN_SMEM) {
         S* s_sm = reinterpret_cast<S*>(smem_raw + L.score);
-        const S* s_g = reinterpret_cast<const S*>(P.score);
-        for (int c = tid; c < HW; c += THREADS) s_sm[c] = s_g[c];
         score = s_sm;
         if (DFF) {
             dffA = reinterpret_cast<float*>(smem_raw + L.dffA);
             dffB = reinterpret_cast<float*>(smem_raw + L.dffB);
-            for (int c = tid; c < HW; c += THREADS) dffA[c] = dff_home[c];
+        }
+        if (!tma_fields) {     // odd sizes: ordinary loads
+            const S* s_g = reinterpret_cast<const S*>(P.score);
+            for (int c = tid; c < HW; c += THREADS) s_sm[c] = s_g[c];
+            if (DFF) for (int c = tid; c < HW; c += THREADS) dffA[c] = dff_home[c];
         }
     } else {
         score = reinterpret_cast<const S*>(P.score);
@@ -196,8 +216,7 @@ ffm_core_rollout_kernel(const RolloutParams P) {
         }
     }
 
-    // ---- prologue: owner grid, positions, alive bitmap ------------------------------------------
-    for (int c = tid; c < HW + 2 * G; c += THREADS) grid[c - G] = P.type_grid[c];
+    // ---- owner grid, positions, alive bitmap -----------------------------------------------------
     int n = P.n_alive[e];        // pedestrians still inside
     int n_slots = n;             // slots in use (live + dead since the last re-pack)
     const int t0 = P.t_done[e];
@@ -210,6 +229,7 @@ ffm_core_rollout_kernel(const RolloutParams P) {
     }
     if (tid < 8) ctr[tid] = 0u;
     for (int c = tid; c < claim_words; c += THREADS) claim32[c] = 0u;
+    mbar_wait(bar, 0);          // the bulk copies have landed (phase 0 of the barrier completed)
     __syncthreads();
     for (int i = tid; i < n; i += THREADS) grid[pos[i]] |= (uint16_t)(i + 1);
     __syncthreads();
@@ -506,9 +526,14 @@ ffm_core_rollout_kernel(const RolloutParams P) {
             const uint32_t rank = wpre[s >> 5] + (uint32_t)__popc(alive[s >> 5] & ((1u << (s & 31)) - 1u));
             gpos[rank] = (uint32_t)pos[s];
         }
-    if (DFF) {
-        if (dffA != dff_home)
+    if (DFF && dffA != dff_home) {
+        if (tma_fields) {               // shared -> global bulk store of the final DFF
+            fence_proxy_async_smem();
+            __syncthreads();
+            if (tid == 0) { bulk_copy_s2g(dff_home, dffA, dff_bytes); bulk_commit_wait_all(); }
+        } else {
             for (int c = tid; c < HW; c += THREADS) dff_home[c] = dffA[c];
+        }
     }
     if (tid == 0) {
         P.n_alive[e] = n;
