@@ -151,6 +151,58 @@ __device__ __forceinline__ void warp_append(bool pred, T value, T* list, uint32_
     if (pred) list[dir > 0 ? k : last - k] = value;
 }
 
+// update_dff (ffm_core.py:106-117) in one pass: out = threshold(s + sum_k c1 * s[nb_k]) with s = c0 * in,
+// each product and sum rounded separately in the reference's neighbour order.  A thread walks down a
+// column strip with a 3-row register window, so a cell costs 3 loads instead of 9 and every product
+// c1 * s is formed once; out-of-map neighbours contribute exactly 0 (np.pad of the scaled field, :111).
+template <int NBR>
+__device__ __forceinline__ void dff_decay_diffuse(const float* __restrict__ in, float* __restrict__ out, int H, int W,
+                                                  float c0, float c1, float thr, int tid, int nthreads) {
+    const int cw = W < nthreads ? W : nthreads;          // columns handled per sweep
+    const int bands = W < nthreads ? nthreads / W : 1;   // row bands working in parallel on one column sweep
+    const int rpb = (H + bands - 1) / bands;
+    const int band = tid / cw, colb = tid - band * cw;
+    if (band >= bands) return;
+    const int r0 = band * rpb, r1 = min(H, r0 + rpb);
+    for (int col = colb; col < W; col += cw) {
+        const bool hasl = col > 0, hasr = col + 1 < W;
+        float up[3], uc[3], un[3], sc = 0.0f;            // c1*s of rows r-1, r, r+1 (left, centre, right); s of the centre
+        auto load_row = [&](int r, float (&u)[3], float& s_centre) {
+            float d0 = 0.0f, d1 = 0.0f, d2 = 0.0f;
+            if (r >= 0 && r < H) {
+                const float* row = in + (size_t)r * W + col;
+                d1 = row[0];
+                if (hasl) d0 = row[-1];
+                if (hasr) d2 = row[1];
+            }
+            const float s0 = __fmul_rn(c0, d0), s1 = __fmul_rn(c0, d1), s2 = __fmul_rn(c0, d2);   // (:109)
+            u[0] = __fmul_rn(c1, s0); u[1] = __fmul_rn(c1, s1); u[2] = __fmul_rn(c1, s2);         // (:113)
+            s_centre = s1;
+        };
+        float dummy;
+        load_row(r0 - 1, up, dummy);
+        load_row(r0, uc, sc);
+        for (int r = r0; r < r1; ++r) {
+            float sn;
+            load_row(r + 1, un, sn);
+            float acc = sc;
+            if (NBR == 8) {   // (-1,-1) (-1,0) (-1,1) (0,-1) (0,1) (1,-1) (1,0) (1,1)
+                acc = __fadd_rn(acc, up[0]); acc = __fadd_rn(acc, up[1]); acc = __fadd_rn(acc, up[2]);
+                acc = __fadd_rn(acc, uc[0]); acc = __fadd_rn(acc, uc[2]);
+                acc = __fadd_rn(acc, un[0]); acc = __fadd_rn(acc, un[1]); acc = __fadd_rn(acc, un[2]);
+            } else {          // (-1,0) (1,0) (0,-1) (0,1)
+                acc = __fadd_rn(acc, up[1]); acc = __fadd_rn(acc, un[1]);
+                acc = __fadd_rn(acc, uc[0]); acc = __fadd_rn(acc, uc[2]);
+            }
+            if (acc < thr) acc = 0.0f;                                                            // (:116-117)
+            out[(size_t)r * W + col] = acc;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { up[k] = uc[k]; uc[k] = un[k]; }
+            sc = sn;
+        }
+    }
+}
+
 template <typename S, typename PosT, int NBR, bool DFF, bool FIELDS_IN_SMEM, int THREADS>
 __global__ void __launch_bounds__(THREADS, (THREADS <= 256 && sizeof(S) == 4) ? 1280 / THREADS : 1)
 ffm_core_rollout_kernel(const RolloutParams P) {
@@ -423,10 +475,8 @@ ffm_core_rollout_kernel(const RolloutParams P) {
             if (bal != 0u && lane == 0) atomicAdd(&cnt[2], (uint32_t)__popc(bal));
         }
         for (int c = tid; c < claim_words; c += THREADS) claim32[c] = 0u;    // claim counters clean for the next step
-        if (DFF) {
-            // new = c0 * dff (ffm_core.py:109); the neighbour terms read this scaled field (:111)
-            for (int c = tid; c < HW; c += THREADS) dffA[c] = __fmul_rn(P.c0, dffA[c]);
-        }
+        // DFF decay + diffusion reads the bumped field (phase B wrote it before the last barrier) -> other buffer
+        if (DFF) dff_decay_diffuse<NBR>(dffA, dffB, H, W, P.c0, P.c1, P.thr, tid, THREADS);
         __syncthreads();
 
         const int n_exit = (int)cnt[2];
@@ -490,23 +540,7 @@ ffm_core_rollout_kernel(const RolloutParams P) {
             }
         }
 
-        // ================= D: DFF diffusion ======================================================
-        if (DFF) {
-            for (int c = tid; c < HW; c += THREADS) {
-                const int r = c / W, col = c - r * W;
-                float acc = dffA[c];
-#pragma unroll
-                for (int k = 0; k < NBR; ++k) {
-                    const int rr = r + nbr_dr<NBR>(k), cc = col + nbr_dc<NBR>(k);
-                    const float v = (rr >= 0 && rr < H && cc >= 0 && cc < W) ? dffA[rr * W + cc] : 0.0f;
-                    acc = __fadd_rn(acc, __fmul_rn(P.c1, v));                  // (:112-113)
-                }
-                if (acc < P.thr) acc = 0.0f;                                   // (:116-117)
-                dffB[c] = acc;
-            }
-            float* tmp = dffA; dffA = dffB; dffB = tmp;
-            __syncthreads();
-        }
+        if (DFF) { float* tmp = dffA; dffA = dffB; dffB = tmp; }      // phase D ran alongside C (above)
 
         // trajectory row: positions after this step, alive-rank order (ffm_core.py:125)
         if (P.traj != nullptr && tl < P.traj_steps) {

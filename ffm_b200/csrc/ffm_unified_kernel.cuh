@@ -583,20 +583,7 @@ ffm_unified_rollout_kernel(const UnifiedParams P) {
         }
         { uint16_t* tmpo = orig; orig = origB; origB = tmpo; }
         // ================= D: DFF decay + diffusion (:779-798) ==================================
-        for (int c = tid; c < HW; c += THREADS) dffA[c] = __fmul_rn(P.c0, dffA[c]);
-        __syncthreads();
-        for (int c = tid; c < HW; c += THREADS) {
-            const int r = c / W, col = c - r * W;
-            float acc = dffA[c];
-#pragma unroll
-            for (int k = 0; k < NBR; ++k) {
-                const int rr = r + nbr_dr<NBR>(k), cc = col + nbr_dc<NBR>(k);
-                const float v = (rr >= 0 && rr < H && cc >= 0 && cc < W) ? dffA[rr * W + cc] : 0.0f;
-                acc = __fadd_rn(acc, __fmul_rn(P.c1, v));
-            }
-            if (acc < P.thr) acc = 0.0f;
-            dffB[c] = acc;
-        }
+        dff_decay_diffuse<NBR>(dffA, dffB, H, W, P.c0, P.c1, P.thr, tid, THREADS);
         { float* tmp = dffA; dffA = dffB; dffB = tmp; }
         __syncthreads();
         n = n_new;
