@@ -69,6 +69,10 @@ def build_fields(wl):
     return m, sff_room(m, wl["nbh"])
 
 
+# full episodes per host thread in the C-port CPU sample (sized for ~10-30 s of CPU work per thread-second scale)
+CPU_C_EPISODES = {"c2": 64, "c2dff": 32, "c1": 2048, "c3": 1}
+
+
 # ------------------------------------------------------------------------------------------------
 # clocks
 # ------------------------------------------------------------------------------------------------
@@ -202,7 +206,7 @@ def run_reference_arm(args, wl):
     for it in range(args.warmup + args.steps):
         t0 = time.perf_counter()
         if have_c_oracle() and not args.numpy_port:
-            last = cpu_c_port(wl, episodes=max(4 * cores, 32), seed=1234 + it, cores=cores)
+            last = cpu_c_port(wl, episodes=CPU_C_EPISODES.get(args.workload, 64) * cores, seed=1234 + it, cores=cores)
         else:
             last = cpu_numpy_port(wl, budget_s=args.cpu_budget, seed=1234 + it, cores=cores)
         if it >= args.warmup:
@@ -368,7 +372,9 @@ def main():
                     "d2h_bytes_per_step": int(B * 4 + B * 8), "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": prof.get("dram_bytes_per_launch"),
+                         "traffic": prof.get("dram_bytes_per_launch") if B == prof.get("episodes") else None,
+                         "smem": {"wavefronts_pct_of_peak": prof.get("smem_wavefronts_pct_of_peak"),
+                                  "issue_active_pct": prof.get("issue_active_pct"), "source": prof.get("source")},
                          "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6650 GB/s",
                          "kernel_ms": kern_ms, "algorithmic_bytes_per_launch": alg_bytes,
                          "note": "fields are shared-memory resident: the kernel moves its algorithmic bytes through SMEM, "
@@ -377,7 +383,7 @@ def main():
         if not args.no_cpu and world == 1:
             try:
                 if have_c_oracle():
-                    line["cpu_baseline"] = cpu_c_port(wl, episodes=max(4 * (os.cpu_count() or 1), 32))
+                    line["cpu_baseline"] = cpu_c_port(wl, episodes=CPU_C_EPISODES.get(args.workload, 64) * (os.cpu_count() or 1))
                     line["cpu_baseline_numpy"] = cpu_numpy_port(wl, budget_s=min(args.cpu_budget, 10.0))
                 else:
                     line["cpu_baseline"] = cpu_numpy_port(wl, budget_s=args.cpu_budget)
