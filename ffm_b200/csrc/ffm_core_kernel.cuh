@@ -41,10 +41,9 @@
 //   pos   PosT[n_max]        linear cell per slot (PosT = u16 when H*W <= 65536, else u32)
 //   tgt   PosT[n_max]        per slot: candidate mask between A1 and A2, then the requested cell
 //                            (all-ones = no request)
-//   list  u16[n_max]         ONE work list: A1 pushes the slots that must draw among <= 3 candidates from
-//                            the front, those with more candidates and the forced requests (| 0x4000)
-//                            from the back; A2 turns each draw entry into a request entry in place
-//                            (0xFFFF = no request); | 0x8000 once the request is granted
+//   list  u16[n_max]         ONE work list: A1 pushes the slots that must draw from the front and the
+//                            forced requests from the back; A2 turns each draw entry into a request
+//                            entry in place (0xFFFF = no request); | 0x8000 once the request is granted
 //   alive u32[n_max/32+1]    alive bitmap;  wpre u32[n_max/32+1] exclusive prefix popcounts
 #pragma once
 #include "ffm_device.cuh"
@@ -150,67 +149,6 @@ __device__ __forceinline__ void warp_append(bool pred, T value, T* list, uint32_
     base = __shfl_sync(0xffffffffu, base, 0);
     const int k = (int)base + __popc(bal & lanemask_lt());
     if (pred) list[dir > 0 ? k : last - k] = value;
-}
-
-constexpr int A2_FEW = 3;   // candidate-count split of the draw list (incl. "stay")
-
-// Phase A2 for one pedestrian: SFF/DFF move probabilities and the keyed draw (ffm_core.py:74-88).
-// Candidates are walked in COMPACTED order (set bits of the mask, then "stay"), which is the order of the
-// reference's neighbor_coords array (:54,60,64).  MAXC bounds the number of candidates (unroll depth).
-template <typename S, typename PosT, int NBR, bool DFF, int MAXC>
-__device__ __forceinline__ uint32_t decide_move(const RolloutParams& P, int s, const PosT* pos, const PosT* tgt, const S* score,
-                                                const float* dffA, const uint32_t* alive, const uint32_t* wpre,
-                                                const double* mv_draws, bool inj, int di, uint32_t episode, uint32_t t, int W,
-                                                uint32_t none_cell) {
-    uint32_t mm = (uint32_t)tgt[s];                 // the candidate mask rides in tgt[] between A1 and A2
-    const int ncand = __popc(mm) + 1;
-    const int c = (int)pos[s];
-    int cell[MAXC];
-    S p[MAXC];
-    S mx = neg_inf<S>();
-#pragma unroll
-    for (int j = 0; j < MAXC; ++j)
-        if (j < ncand) {
-            int cc = c;
-            if (j < ncand - 1) {
-                const int k = __ffs(mm) - 1;
-                mm &= mm - 1u;
-                cc = c + nbr_off_rt<NBR>(k, W);
-            }
-            cell[j] = cc;
-            S sc = score[cc];                                    // -k_S * sff
-            if (DFF) sc = add_rn(sc, (S)mul_rn(P.kd, dffA[cc])); // + k_D * dff   (:77)
-            p[j] = sc;
-            mx = max_t(mx, sc);
-        }
-    // e_j = exp(score_j - max) (:80).  The reference then normalises (p = e / sum(e), :83) and
-    // np.random.choice picks the first j with cumsum(p)[j] / cumsum(p)[-1] > u (:84).  That is the first j
-    // with E_j > u * E_n (E = running sums of e) up to the rounding of the normalisation (< 1e-7), which --
-    // like the <= 2 ulp difference between NumPy's exp and CUDA's -- only matters for a draw closer than
-    // that to a CDF boundary; the parity bar excludes those draws (tests/helpers.py MARGIN_GUARD).
-    double tot = 0.0;
-#pragma unroll
-    for (int j = 0; j < MAXC; ++j)
-        if (j < ncand) {
-            p[j] = exp_t(add_rn(p[j], -mx));
-            tot += (double)p[j];
-        }
-    if (!(isfinite(tot) && tot != 0.0)) return none_cell;         // (:82)
-    // the reference's array index of this pedestrian = alive rank of its slot
-    const uint32_t rank = wpre[s >> 5] + (uint32_t)__popc(alive[s >> 5] & ((1u << (s & 31)) - 1u));
-    const double u = (inj && mv_draws) ? mv_draws[(size_t)di * P.n_max + rank]
-                                       : draw_u0(P.seed, episode, t, STREAM_MOVE, rank);
-    const double thresh = u * tot;
-    double run = 0.0;
-    uint32_t target = (uint32_t)c;                                // E_n > u * E_n always: "stay" is last
-    bool done = false;
-#pragma unroll
-    for (int j = 0; j < MAXC - 1; ++j)
-        if (j < ncand - 1 && !done) {
-            run += (double)p[j];
-            if (run > thresh) { target = (uint32_t)cell[j]; done = true; }
-        }
-    return target;
 }
 
 // update_dff (ffm_core.py:106-117) in one pass: out = threshold(s + sum_k c1 * s[nb_k]) with s = c0 * in,
@@ -399,43 +337,84 @@ ffm_core_rollout_kernel(const RolloutParams P) {
                 }
                 tgt[s] = need_draw ? (PosT)m : (PosT)target;     // the mask rides in tgt[] until A2
             }
-            const bool few = need_draw && __popc(m) < A2_FEW;
-            warp_append<uint16_t>(few, (uint16_t)s, list, &cnt[0], lane);
-            warp_append<uint16_t>((need_draw && !few) || forced, (uint16_t)(s | (forced ? 0x4000 : 0)), list, &cnt[1], lane, -1, list_last);
+            warp_append<uint16_t>(need_draw, (uint16_t)s, list, &cnt[0], lane);
+            warp_append<uint16_t>(forced, (uint16_t)s, list, &cnt[1], lane, -1, list_last);
         }
         __syncthreads();
 
-        // ================= A2: move probabilities and keyed draw (draw lists) ===================
-        // Two passes with different unroll depth: the front of the list holds pedestrians with at most
-        // A2_FEW candidates (2/3 of all draws in a packed crowd), the back those with more.
-        const int n_few = (int)cnt[0], n_back = (int)cnt[1];
-        for (int wi = tid; wi < n_few; wi += THREADS) {
-            const int s = (int)list[wi];
-            const uint32_t target = decide_move<S, PosT, NBR, DFF, A2_FEW>(P, s, pos, tgt, score, dffA, alive, wpre, mv_draws,
-                                                                             inj, di, episode, t, W, NONE_CELL);
-            if (target == NONE_CELL) list[wi] = (uint16_t)0xFFFFu;            // no request after all (:82)
-            else if (target != (uint32_t)pos[s]) atomicAdd(&claim32[target >> 3], 1u << (4 * (target & 7u)));
-            tgt[s] = (PosT)target;
-        }
-        for (int wi = tid; wi < n_back; wi += THREADS) {
-            const uint32_t rv = list[list_last - wi];
-            if (rv & 0x4000u) continue;                                        // forced request: nothing to decide
-            const int s = (int)rv;
-            const uint32_t target = decide_move<S, PosT, NBR, DFF, NBR + 1>(P, s, pos, tgt, score, dffA, alive, wpre, mv_draws,
-                                                                              inj, di, episode, t, W, NONE_CELL);
-            if (target == NONE_CELL) list[list_last - wi] = (uint16_t)0xFFFFu;
-            else if (target != (uint32_t)pos[s]) atomicAdd(&claim32[target >> 3], 1u << (4 * (target & 7u)));
-            tgt[s] = (PosT)target;
+        // ================= A2: move probabilities and keyed draw (draw list) ====================
+        // Candidates are walked in COMPACTED order (set bits of the mask, then "stay"), which is the
+        // order of the reference's neighbor_coords array (:54,60,64) -- and keeps lanes busy.
+        const int n_work = (int)cnt[0];
+        for (int base = 0; base < n_work; base += THREADS) {
+            const int wi = base + tid;
+            if (wi < n_work) {
+                const int s = (int)list[wi];
+                uint32_t mm = (uint32_t)tgt[s];
+                const int ncand = __popc(mm) + 1;
+                const int c = (int)pos[s];
+                int cell[NBR + 1];
+                S p[NBR + 1];
+                S mx = neg_inf<S>();
+#pragma unroll
+                for (int j = 0; j <= NBR; ++j)
+                    if (j < ncand) {
+                        int cc = c;
+                        if (j < ncand - 1) {
+                            const int k = __ffs(mm) - 1;
+                            mm &= mm - 1u;
+                            cc = c + nbr_off_rt<NBR>(k, W);
+                        }
+                        cell[j] = cc;
+                        S sc = score[cc];                                    // -k_S * sff
+                        if (DFF) sc = add_rn(sc, (S)mul_rn(P.kd, dffA[cc])); // + k_D * dff   (:77)
+                        p[j] = sc;
+                        mx = max_t(mx, sc);
+                    }
+                // e_j = exp(score_j - max) (:80).  The reference then normalises (p = e / sum(e), :83)
+                // and np.random.choice picks the first j with cumsum(p)[j] / cumsum(p)[-1] > u (:84).
+                // That is the first j with E_j > u * E_n (E = running sums of e) up to the rounding of
+                // the normalisation (< 1e-7), which -- like the <= 2 ulp difference between NumPy's
+                // exp and CUDA's -- only matters for a draw closer than that to a CDF boundary; the
+                // parity bar excludes those draws (tests/helpers.py MARGIN_GUARD).  So: no divisions.
+                double tot = 0.0;
+#pragma unroll
+                for (int j = 0; j <= NBR; ++j)
+                    if (j < ncand) {
+                        p[j] = exp_t(add_rn(p[j], -mx));
+                        tot += (double)p[j];
+                    }
+                uint32_t target = NONE_CELL;
+                if (isfinite(tot) && tot != 0.0) {                            // (:82)
+                    // the reference's array index of this pedestrian = alive rank of its slot
+                    const uint32_t rank = wpre[s >> 5] + (uint32_t)__popc(alive[s >> 5] & ((1u << (s & 31)) - 1u));
+                    const double u = (inj && mv_draws) ? mv_draws[(size_t)di * P.n_max + rank]
+                                                       : draw_u0(P.seed, episode, t, STREAM_MOVE, rank);
+                    const double thresh = u * tot;
+                    double run = 0.0;
+                    target = (uint32_t)c;                                     // E_n > u * E_n always: "stay" is last
+                    bool done = false;
+#pragma unroll
+                    for (int j = 0; j < NBR; ++j)
+                        if (j < ncand - 1 && !done) {
+                            run += (double)p[j];
+                            if (run > thresh) { target = (uint32_t)cell[j]; done = true; }
+                        }
+                    if (target != (uint32_t)c) atomicAdd(&claim32[target >> 3], 1u << (4 * (target & 7u)));
+                } else {
+                    list[wi] = (uint16_t)0xFFFFu;                             // no request after all (:82)
+                }
+                tgt[s] = (PosT)target;
+            }
         }
         __syncthreads();
 
         // ================= B: resolve same-target conflicts (request list) ======================
-        const int n_req = n_few + n_back;
+        const int n_req = n_work + (int)cnt[1];
         for (int j = tid; j < n_req; j += THREADS) {
-            const int li = j < n_few ? j : list_last - (j - n_few);
-            const uint32_t rv0 = list[li];
-            if (rv0 == 0xFFFFu) continue;
-            const int s = (int)(rv0 & 0x3FFFu);
+            const int li = j < n_work ? j : list_last - (j - n_work);
+            const int s = (int)list[li];
+            if (s == 0xFFFF) continue;
             const int c = (int)pos[s];
             const uint32_t T = tgt[s];
             bool moved;
@@ -477,9 +456,9 @@ ffm_core_rollout_kernel(const RolloutParams P) {
             const int j = base + tid;
             bool leaves = false;
             if (j < n_req) {
-                const uint32_t rv = list[j < n_few ? j : list_last - (j - n_few)];
+                const uint32_t rv = list[j < n_work ? j : list_last - (j - n_work)];
                 if ((rv & 0x8000u) && rv != 0xFFFFu) {
-                    const int s = (int)(rv & 0x3FFFu);
+                    const int s = (int)(rv & 0x7FFFu);
                     const int c = (int)pos[s];
                     const uint32_t T = tgt[s];
                     grid[c] &= (uint16_t)TYPE_BITS;
