@@ -1,5 +1,5 @@
 """Synthetic maps, fields and placements of the BASELINE configurations (product side; the parity
-tests build the same inputs independently in oracle/assets.py).
+tests build the same inputs independently on the checker side).
 
   C1/C2  walled room, one exit in the middle of the top wall (layout of Create_Map.py:9-19)
   C3     256x256 floor plan: border walls, 4 exits, 3x3 rooms separated by walls with 4-cell doors
