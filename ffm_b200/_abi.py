@@ -53,6 +53,7 @@ SIGNATURES = {
     "ffm_destroy": (C.c_int, [C.c_void_p]),
     "ffm_set_fields": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "ffm_set_positions": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "ffm_place": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "ffm_get_positions": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "ffm_set_dff": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "ffm_get_dff": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),

@@ -59,6 +59,8 @@ struct ffm_sim_s {
     float* d_dff_tmp;
     int32_t* d_pos_rc;   // staging for (row, col) pairs
     int32_t* d_err;      // device-side validation flag
+    uint32_t* d_free; int* d_free_count; int32_t* d_n_req;   // placement: eligible cells, their number, requested counts
+    int place_er, place_ec, place_radius, place_count;       // what d_free currently holds (-2: nothing)
     const void* kernel;  // selected rollout kernel
     // unified / trained models
     int S, A, nby;
@@ -124,6 +126,75 @@ __global__ void pack_positions_kernel(const int32_t* pos_rc, const int32_t* n, c
         if (ty != TYPE_FREE && ty != TYPE_NEAR_EXIT) atomicOr(err, 16);   // initialize_agents(): map == 0 cells only
         pos[x] = (uint32_t)c;
     }
+}
+
+// ---- initial placement (initialize_agents) ---------------------------------------------------------
+// eligible cells of the map in row-major order (np.argwhere(map == 0), optionally radius-limited)
+__global__ void collect_free_cells_kernel(const uint16_t* type_grid, int H, int W, int er, int ec, int radius, uint32_t* cells, int* count) {
+    // single CTA, ordered compaction by block-wide scan over chunks of blockDim.x cells
+    __shared__ int warp_tot[32];
+    __shared__ int base;
+    const int G = W + 1, HW = H * W, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) base = 0;
+    __syncthreads();
+    for (int c0 = 0; c0 < HW; c0 += blockDim.x) {
+        const int c = c0 + threadIdx.x;
+        bool ok = false;
+        if (c < HW) {
+            const uint32_t ty = type_grid[c + G] >> TYPE_SHIFT;
+            ok = (ty == TYPE_FREE || ty == TYPE_NEAR_EXIT);
+            if (ok && radius >= 0) { const int r = c / W, col = c - r * W; ok = abs(r - er) + abs(col - ec) <= radius; }
+        }
+        const uint32_t bal = __ballot_sync(0xffffffffu, ok);
+        if (lane == 0) warp_tot[warp] = __popc(bal);
+        __syncthreads();
+        int before = 0, total = 0;
+        for (int w = 0; w < (int)blockDim.x / 32; ++w) { if (w < warp) before += warp_tot[w]; total += warp_tot[w]; }
+        if (ok) cells[base + before + __popc(bal & ((1u << lane) - 1u))] = (uint32_t)c;
+        __syncthreads();
+        if (threadIdx.x == 0) base += total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *count = base;
+}
+
+// one CTA per episode: Philox key per eligible cell, bitonic sort of (key, ordinal) in shared memory, the
+// first n cells in key order become the pedestrians
+__global__ void __launch_bounds__(256)
+place_kernel(const uint32_t* cells, const int* count_ptr, const int32_t* n_req, uint32_t* pos, int32_t* n_out, int n_max,
+             unsigned long long seed, uint32_t episode_base, int npad) {
+    extern __shared__ __align__(16) unsigned char sm[];
+    unsigned long long* key = reinterpret_cast<unsigned long long*>(sm);
+    uint16_t* ord = reinterpret_cast<uint16_t*>(sm + (size_t)npad * 8);
+    const int e = blockIdx.x, F = *count_ptr;
+    const uint32_t episode = episode_base + (uint32_t)e;
+    for (int i = threadIdx.x; i < npad; i += blockDim.x) {
+        unsigned long long k = ~0ULL;
+        if (i < F) {
+            const uint4 o = philox4x32_10((uint32_t)i, 0u, episode, STREAM_PLACE, (uint32_t)seed, (uint32_t)(seed >> 32));
+            k = ((unsigned long long)(o.x >> 5) << 26) | (unsigned long long)(o.y >> 6);    // the 53 bits of u0: same order as the double
+        }
+        key[i] = k;
+        ord[i] = (uint16_t)i;
+    }
+    __syncthreads();
+    for (int size = 2; size <= npad; size <<= 1)
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int x = threadIdx.x; x < npad / 2; x += blockDim.x) {
+                const int i = 2 * x - (x & (stride - 1)), j = i + stride;
+                const bool up = (i & size) == 0;
+                const unsigned long long ki = key[i], kj = key[j];
+                const uint16_t oi = ord[i], oj = ord[j];
+                const bool gt = ki > kj || (ki == kj && oi > oj);          // ties by ordinal: a stable argsort
+                if (gt == up) { key[i] = kj; key[j] = ki; ord[i] = oj; ord[j] = oi; }
+            }
+            __syncthreads();
+        }
+    int n = n_req[e];
+    n = n < F ? n : F;                                                       // actual_N = min(N, available) (ffm_unified.py:160-162)
+    n = n < n_max ? n : n_max;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) pos[(size_t)e * n_max + i] = cells[ord[i]];
+    if (threadIdx.x == 0) n_out[e] = n;
 }
 
 __global__ void unpack_positions_kernel(const uint32_t* pos, const int32_t* n, int32_t* pos_rc, int B, int n_max, int W) {
@@ -305,6 +376,10 @@ int ffm_create(const ffm_config_t* cfg, ffm_sim_t* out) {
     ALLOC(s->d_t, (size_t)B * 4);
     ALLOC(s->d_ped_steps, (size_t)B * 8);
     ALLOC(s->d_err, 4);
+    ALLOC(s->d_free, (size_t)HW * 4);
+    ALLOC(s->d_free_count, 4);
+    ALLOC(s->d_n_req, (size_t)B * 4);
+    s->place_radius = -2;
     if (dff) {
         ALLOC(s->d_dff, (size_t)B * HW * 4);
         if (!s->fields_in_smem) ALLOC(s->d_dff_tmp, (size_t)B * HW * 4);
@@ -339,6 +414,7 @@ int ffm_destroy(ffm_sim_t s) {
     cudaFree(s->d_map); cudaFree(s->d_type_grid); cudaFree(s->d_sff); cudaFree(s->d_score);
     cudaFree(s->d_pos); cudaFree(s->d_pos_rc); cudaFree(s->d_n); cudaFree(s->d_t);
     cudaFree(s->d_ped_steps); cudaFree(s->d_err); cudaFree(s->d_dff); cudaFree(s->d_dff_tmp);
+    cudaFree(s->d_free); cudaFree(s->d_free_count); cudaFree(s->d_n_req);
     cudaFree(s->d_V); cudaFree(s->d_vseen); cudaFree(s->d_H); cudaFree(s->d_hseen); cudaFree(s->d_hstats);
     cudaFree(s->d_blk_lo); cudaFree(s->d_blk_hi); cudaFree(s->d_blk_any);
     delete s;
@@ -363,6 +439,45 @@ int ffm_set_fields(ffm_sim_t s, const uint8_t* map, const void* sff, int space, 
     s->launches++;
     if ((rc = check_device_flag(s, st))) return rc;
     s->have_fields = true;
+    s->place_radius = -2;
+    return FFM_OK;
+}
+
+int ffm_place(ffm_sim_t s, const int32_t* n, int32_t exit_row, int32_t exit_col, int32_t radius, void* stream) {
+    if (!s || !n) return fail(FFM_E_INVALID, "null argument");
+    if (!s->have_fields) return fail(FFM_E_STATE, "ffm_set_fields must precede ffm_place");
+    cudaStream_t st = (cudaStream_t)stream;
+    CU(cudaSetDevice(s->cfg.device));
+    const int B = s->cfg.n_episodes, N = s->cfg.n_max;
+    if (radius < 0) { radius = -1; exit_row = exit_col = 0; }
+    if (s->place_radius != radius || s->place_er != exit_row || s->place_ec != exit_col) {
+        ffm::collect_free_cells_kernel<<<1, 1024, 0, st>>>(s->d_type_grid, s->cfg.height, s->cfg.width, exit_row, exit_col, radius, s->d_free, s->d_free_count);
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(&s->place_count, s->d_free_count, 4, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        s->place_radius = radius; s->place_er = exit_row; s->place_ec = exit_col;
+        s->launches++;
+    }
+    for (int e = 0; e < B; ++e)
+        if (n[e] < 0) return fail(FFM_E_INVALID, "negative pedestrian count");
+    if (radius < 0)
+        for (int e = 0; e < B; ++e)
+            if (n[e] > s->place_count || n[e] > N)    // np.random.choice(len(free), N, replace=False) raises (ffm_core.py:25)
+                return fail(FFM_E_INVALID, "Cannot take a larger sample than population when 'replace=False' (%d pedestrians, %d free cells, capacity %d)", n[e], s->place_count, N);
+    int npad = 2;
+    while (npad < s->place_count) npad <<= 1;
+    if (npad > 16384) return fail(FFM_E_UNSUPPORTED, "%d eligible cells: device placement sorts at most 16384 per episode", s->place_count);
+    const size_t smem = (size_t)npad * 10;
+    CU(cudaFuncSetAttribute(ffm::place_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CU(cudaMemcpyAsync(s->d_n_req, n, (size_t)B * 4, cudaMemcpyHostToDevice, st));
+    CU(cudaMemsetAsync(s->d_t, 0, (size_t)B * 4, st));
+    CU(cudaMemsetAsync(s->d_ped_steps, 0, (size_t)B * 8, st));
+    if (s->d_dff) CU(cudaMemsetAsync(s->d_dff, 0, (size_t)B * s->HW * 4, st));
+    ffm::place_kernel<<<B, 256, smem, st>>>(s->d_free, s->d_free_count, s->d_n_req, s->d_pos, s->d_n, N, s->cfg.seed, s->cfg.episode_base, npad);
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(st));      // n[] is a host buffer of the caller
+    s->launches++;
+    s->have_positions = true;
     return FFM_OK;
 }
 

@@ -84,6 +84,7 @@ class BatchSim:
         cfg.dff_threshold = float(np.float32(1e-4))                                      # ffm_core.py:116
         cfg.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
         cfg.episode_base = int(episode_base) & 0xFFFFFFFF
+        self._seed_base = (int(seed), int(episode_base))
         self._configure(cfg)
         self._lib = _abi.lib()
         self._h = C.c_void_p()
@@ -119,6 +120,25 @@ class BatchSim:
         _abi.check(self._lib.ffm_set_positions(self._h, _ptr(pos_rc), _ptr(n), space, _stream()))
         if space == _abi.FFM_HOST:
             torch.cuda.current_stream().synchronize()   # host buffers may be freed by the caller
+
+    def place(self, n, exit_pos=None, radius=None):
+        """Device-side initialize_agents(): n[e] pedestrians per episode on distinct free cells, uniformly without
+        replacement (optionally within L1 `radius` of `exit_pos`, count clamped like ffm_unified.py:160-162),
+        keyed by the global episode id.  Resets DFF and counters.  Falls back to the host placement
+        (ffm_b200.workloads.place, same keys, same result) when the map has more than 16384 eligible cells."""
+        n = np.ascontiguousarray(np.broadcast_to(np.asarray(n, dtype=np.int32), (self.B,)))
+        er, ec, rad = (-1, -1, -1) if exit_pos is None or radius is None else (int(exit_pos[0]), int(exit_pos[1]), int(radius))
+        rc = self._lib.ffm_place(self._h, _ptr(n), er, ec, rad, _stream())
+        if rc == _abi.E_UNSUPPORTED and rad < 0:
+            from . import workloads
+            if len(set(n.tolist())) != 1:
+                raise _abi.FfmError(rc, "host placement fallback needs equal counts")
+            cfg_seed, base = self._seed_base
+            pos = workloads.place(self.map_array, int(n[0]), self.B, base, cfg_seed)
+            buf = np.full((self.B, self.n_max, 2), -1, np.int32)
+            buf[:, :int(n[0])] = pos
+            return self.set_positions(buf, n)
+        _abi.check(rc)
 
     def get_positions(self):
         """-> (pos_rc int32 [B, n_max, 2] with -1 padding, n int32 [B]) as NumPy arrays."""
@@ -203,6 +223,7 @@ class BatchSim:
 
     def set_episode_base(self, episode_base):
         _abi.check(self._lib.ffm_set_episode_base(self._h, int(episode_base) & 0xFFFFFFFF))
+        self._seed_base = (self._seed_base[0], int(episode_base))
 
     # -- introspection -------------------------------------------------------------------------
     @property
