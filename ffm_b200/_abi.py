@@ -58,6 +58,7 @@ SIGNATURES = {
     "ffm_set_dff": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "ffm_get_dff": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "ffm_rollout": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(Draws), C.POINTER(RolloutOut), C.c_void_p]),
+    "ffm_move_probs": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "ffm_get_counters": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "ffm_tables_shape": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "ffm_tables_set": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),

@@ -605,6 +605,47 @@ int ffm_rollout(ffm_sim_t s, int32_t max_steps, const ffm_draws_t* draws, const 
     return FFM_OK;
 }
 
+namespace {
+template <typename S, int NBR>
+const void* probs_pick_dff(bool dff) {
+    return dff ? (const void*)ffm::core_move_probs_kernel<S, NBR, true> : (const void*)ffm::core_move_probs_kernel<S, NBR, false>;
+}
+}  // namespace
+
+int ffm_move_probs(ffm_sim_t s, double* probs, int32_t* kind, int space, void* stream) {
+    if (!s || !probs || !kind) return fail(FFM_E_INVALID, "null argument");
+    if (s->cfg.model != FFM_MODEL_CORE) return fail(FFM_E_UNSUPPORTED, "ffm_move_probs covers the base model");
+    if (!s->have_fields || !s->have_positions) return fail(FFM_E_STATE, "fields and positions must be set first");
+    cudaStream_t st = (cudaStream_t)stream;
+    CU(cudaSetDevice(s->cfg.device));
+    const int B = s->cfg.n_episodes, N = s->cfg.n_max, A = s->cfg.neighborhood + 1;
+    double* d_probs = probs; int32_t* d_kind = kind;
+    if (space == FFM_HOST) {
+        CU(cudaMalloc((void**)&d_probs, (size_t)B * N * A * 8));
+        CU(cudaMalloc((void**)&d_kind, (size_t)B * N * 4));
+    }
+    ffm::RolloutParams P;
+    memset(&P, 0, sizeof(P));
+    P.H = s->cfg.height; P.W = s->cfg.width; P.HW = s->HW; P.n_max = N; P.B = B;
+    P.type_grid = s->d_type_grid; P.score = s->d_score; P.kd = (float)s->cfg.k_D;
+    P.pos = s->d_pos; P.n_alive = s->d_n; P.dff = s->d_dff;
+    const bool f64 = s->cfg.sff_dtype == FFM_F64, dff = s->d_dff != nullptr;
+    const void* k = f64 ? (s->cfg.neighborhood == 4 ? probs_pick_dff<double, 4>(dff) : probs_pick_dff<double, 8>(dff))
+                        : (s->cfg.neighborhood == 4 ? probs_pick_dff<float, 4>(dff) : probs_pick_dff<float, 8>(dff));
+    const size_t smem = (size_t)(s->HW + 2 * (s->cfg.width + 1)) * 2 + 16;
+    CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    void* args[] = {&P, &d_probs, &d_kind};
+    CU(cudaLaunchKernel(k, dim3(B), dim3(256), args, smem, st));
+    s->launches++;
+    int rc = FFM_OK;
+    if (space == FFM_HOST) {
+        rc = copy_out(probs, d_probs, (size_t)B * N * A * 8, FFM_HOST, st);
+        if (!rc) rc = copy_out(kind, d_kind, (size_t)B * N * 4, FFM_HOST, st);
+        cudaFree(d_probs); cudaFree(d_kind);
+    }
+    return rc;
+}
+
 int ffm_get_counters(ffm_sim_t s, int32_t* steps, int64_t* ped_steps, int space, void* stream) {
     if (!s) return fail(FFM_E_INVALID, "null argument");
     cudaStream_t st = (cudaStream_t)stream;

@@ -151,6 +151,42 @@ __device__ __forceinline__ void warp_append(bool pred, T value, T* list, uint32_
     if (pred) list[dir > 0 ? k : last - k] = value;
 }
 
+// Unnormalised move probabilities of one pedestrian (ffm_core.py:74-80): candidates in COMPACTED order (set bits
+// of the neighbour mask, then "stay"), e_j = exp(score_j - max_j score_j) with score = -k_S*sff + k_D*dff in the
+// dtype NumPy uses.  Returns sum_j e_j (float64); cell[j] / e[j] are filled for j < ncand.  The reference then
+// normalises (p = e / sum(e), :83) and np.random.choice picks the first j with cumsum(p)[j]/cumsum(p)[-1] > u
+// (:84) -- the first j with E_j > u * E_n (E = running sums of e) up to the rounding of the normalisation
+// (< 1e-7), which, like the <= 2 ulp difference between NumPy's exp and CUDA's, only matters for a draw closer
+// than that to a CDF boundary; the parity bar excludes those draws (tests/helpers.py MARGIN_GUARD).
+template <typename S, int NBR, bool DFF>
+__device__ __forceinline__ double move_weights(uint32_t mm, int ncand, int c, int W, const S* score, const float* dffA, float kd,
+                                               int (&cell)[NBR + 1], S (&e)[NBR + 1]) {
+    S mx = neg_inf<S>();
+#pragma unroll
+    for (int j = 0; j <= NBR; ++j)
+        if (j < ncand) {
+            int cc = c;
+            if (j < ncand - 1) {
+                const int k = __ffs(mm) - 1;
+                mm &= mm - 1u;
+                cc = c + nbr_off_rt<NBR>(k, W);
+            }
+            cell[j] = cc;
+            S sc = score[cc];                                    // -k_S * sff
+            if (DFF) sc = add_rn(sc, (S)mul_rn(kd, dffA[cc]));   // + k_D * dff   (:77)
+            e[j] = sc;
+            mx = max_t(mx, sc);
+        }
+    double tot = 0.0;
+#pragma unroll
+    for (int j = 0; j <= NBR; ++j)
+        if (j < ncand) {
+            e[j] = exp_t(add_rn(e[j], -mx));                     // exp(score - max) (:80)
+            tot += (double)e[j];
+        }
+    return tot;
+}
+
 // update_dff (ffm_core.py:106-117) in one pass: out = threshold(s + sum_k c1 * s[nb_k]) with s = c0 * in,
 // each product and sum rounded separately in the reference's neighbour order.  A thread walks down a
 // column strip with a 3-row register window, so a cell costs 3 loads instead of 9 and every product
@@ -355,35 +391,7 @@ ffm_core_rollout_kernel(const RolloutParams P) {
                 const int c = (int)pos[s];
                 int cell[NBR + 1];
                 S p[NBR + 1];
-                S mx = neg_inf<S>();
-#pragma unroll
-                for (int j = 0; j <= NBR; ++j)
-                    if (j < ncand) {
-                        int cc = c;
-                        if (j < ncand - 1) {
-                            const int k = __ffs(mm) - 1;
-                            mm &= mm - 1u;
-                            cc = c + nbr_off_rt<NBR>(k, W);
-                        }
-                        cell[j] = cc;
-                        S sc = score[cc];                                    // -k_S * sff
-                        if (DFF) sc = add_rn(sc, (S)mul_rn(P.kd, dffA[cc])); // + k_D * dff   (:77)
-                        p[j] = sc;
-                        mx = max_t(mx, sc);
-                    }
-                // e_j = exp(score_j - max) (:80).  The reference then normalises (p = e / sum(e), :83)
-                // and np.random.choice picks the first j with cumsum(p)[j] / cumsum(p)[-1] > u (:84).
-                // That is the first j with E_j > u * E_n (E = running sums of e) up to the rounding of
-                // the normalisation (< 1e-7), which -- like the <= 2 ulp difference between NumPy's
-                // exp and CUDA's -- only matters for a draw closer than that to a CDF boundary; the
-                // parity bar excludes those draws (tests/helpers.py MARGIN_GUARD).  So: no divisions.
-                double tot = 0.0;
-#pragma unroll
-                for (int j = 0; j <= NBR; ++j)
-                    if (j < ncand) {
-                        p[j] = exp_t(add_rn(p[j], -mx));
-                        tot += (double)p[j];
-                    }
+                const double tot = move_weights<S, NBR, DFF>(mm, ncand, c, W, score, dffA, P.kd, cell, p);
                 uint32_t target = NONE_CELL;
                 if (isfinite(tot) && tot != 0.0) {                            // (:82)
                     // the reference's array index of this pedestrian = alive rank of its slot
@@ -573,6 +581,61 @@ ffm_core_rollout_kernel(const RolloutParams P) {
         P.n_alive[e] = n;
         P.t_done[e] = t0 + tl;
         P.ped_steps[e] += ped_steps;
+    }
+}
+
+// Probe (parity tests, "move probabilities within 1e-6 relative"): the probability vector every pedestrian of
+// the CURRENT state would sample from, computed with the hot path's own arithmetic (move_weights), written in
+// SLOT order (neighbours in the reference's order, then "stay"; 0 for non-candidates).
+//   kind: 0 = no candidate, no request (:63);  1 = forced exit (one-hot, :66-72);  2 = draws from probs
+template <typename S, int NBR, bool DFF>
+__global__ void core_move_probs_kernel(const RolloutParams P, double* __restrict__ probs, int32_t* __restrict__ kind) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int e = blockIdx.x, W = P.W, HW = P.HW, G = W + 1;
+    uint16_t* grid = reinterpret_cast<uint16_t*>(smem_raw) + G;
+    for (int c = threadIdx.x; c < HW + 2 * G; c += blockDim.x) grid[c - G] = P.type_grid[c];
+    const int n = P.n_alive[e];
+    const uint32_t* gpos = P.pos + (size_t)e * P.n_max;
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) grid[gpos[i]] |= (uint16_t)(i + 1);
+    __syncthreads();
+    const S* score = reinterpret_cast<const S*>(P.score);
+    const float* dff = DFF ? P.dff + (size_t)e * HW : nullptr;
+    constexpr uint32_t EXIT_EMPTY = TYPE_EXIT << TYPE_SHIFT;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int c = (int)gpos[i];
+        double* out = probs + ((size_t)e * P.n_max + i) * (NBR + 1);
+#pragma unroll
+        for (int k = 0; k <= NBR; ++k) out[k] = 0.0;
+        uint32_t m = 0, ex = 0;
+#pragma unroll
+        for (int k = 0; k < NBR; ++k) {
+            const uint32_t g = grid[c + nbr_off<NBR>(k, W)];
+            if ((g & OCC_MASK) == 0u) m |= 1u << k;
+            if (g == EXIT_EMPTY) ex |= 1u << k;
+        }
+        int kd = 0;
+        if (m != 0u) {
+            if (ex != 0u) {
+                kd = 1;
+                out[__ffs(ex) - 1] = 1.0;
+            } else {
+                kd = 2;
+                int cell[NBR + 1];
+                S w[NBR + 1];
+                const int ncand = __popc(m) + 1;
+                const double tot = move_weights<S, NBR, DFF>(m, ncand, c, W, score, dff, P.kd, cell, w);
+                uint32_t mm = m;
+#pragma unroll
+                for (int j = 0; j <= NBR; ++j)
+                    if (j < ncand) {
+                        int slot = NBR;
+                        if (j < ncand - 1) { slot = __ffs(mm) - 1; mm &= mm - 1u; }
+                        out[slot] = (double)w[j] / tot;
+                    }
+            }
+        }
+        kind[(size_t)e * P.n_max + i] = kd;
     }
 }
 

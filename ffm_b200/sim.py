@@ -158,6 +158,15 @@ class BatchSim:
         _abi.check(self._lib.ffm_set_dff(self._h, _ptr(dff), _abi.FFM_HOST, _stream()))
         torch.cuda.current_stream().synchronize()
 
+    def move_probs(self):
+        """Probe: (probs float64 [B, n_max, neighbours+1] in slot order, kind int32 [B, n_max]) for the current state
+        -- the distribution each pedestrian samples from in the next step (0 no request, 1 forced exit, 2 sampled)."""
+        A = len(self.neighbors) + 1
+        probs = np.empty((self.B, self.n_max, A), np.float64)
+        kind = np.empty((self.B, self.n_max), np.int32)
+        _abi.check(self._lib.ffm_move_probs(self._h, _ptr(probs), _ptr(kind), _abi.FFM_HOST, _stream()))
+        return probs, kind
+
     def counters(self):
         """-> (steps int32 [B], ped_steps int64 [B]) since the last set_positions."""
         steps = np.empty((self.B,), dtype=np.int32)

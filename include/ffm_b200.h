@@ -164,6 +164,13 @@ int ffm_get_dff(ffm_sim_t sim, float *dff, int space, void *stream);
 int ffm_rollout(ffm_sim_t sim, int32_t max_steps, const ffm_draws_t *draws, const ffm_rollout_out_t *out,
                 void *stream);
 
+/* Probe for parity tests ("move probabilities within 1e-6 relative"), base model only: the probability vector
+ * every pedestrian of the CURRENT state would sample from in the next step (ffm_core.py:74-83), computed with
+ * the rollout kernel's own arithmetic.  probs double [B][n_max][neighborhood+1] in slot order (neighbours in
+ * get_neighbors() order, then "stay"; 0 for non-candidates); kind int32 [B][n_max]: 0 no candidate / no
+ * request (:63), 1 forced exit (one-hot, :66-72), 2 sampled. */
+int ffm_move_probs(ffm_sim_t sim, double *probs, int32_t *kind, int space, void *stream);
+
 /* per-episode counters since the last ffm_set_positions: steps executed (what run() returns,
  * ffm_core.py:126) and pedestrian-steps processed (sum over steps of the alive count).
  * Either pointer may be NULL. */
