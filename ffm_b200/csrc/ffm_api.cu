@@ -254,6 +254,11 @@ const void* upick_kernel(bool f64, int nbr, bool fs, int threads) {
     return f64 ? upick_nbr<double>(nbr, fs, threads) : upick_nbr<float>(nbr, fs, threads);
 }
 
+template <typename S, int NBR>
+const void* probs_pick_dff(bool dff) {
+    return dff ? (const void*)ffm::core_move_probs_kernel<S, NBR, true> : (const void*)ffm::core_move_probs_kernel<S, NBR, false>;
+}
+
 int check_device_flag(ffm_sim_t s, cudaStream_t st) {
     int32_t flag = 0;
     CU(cudaMemcpyAsync(&flag, s->d_err, sizeof(flag), cudaMemcpyDeviceToHost, st));
@@ -604,13 +609,6 @@ int ffm_rollout(ffm_sim_t s, int32_t max_steps, const ffm_draws_t* draws, const 
     s->launches++;
     return FFM_OK;
 }
-
-namespace {
-template <typename S, int NBR>
-const void* probs_pick_dff(bool dff) {
-    return dff ? (const void*)ffm::core_move_probs_kernel<S, NBR, true> : (const void*)ffm::core_move_probs_kernel<S, NBR, false>;
-}
-}  // namespace
 
 int ffm_move_probs(ffm_sim_t s, double* probs, int32_t* kind, int space, void* stream) {
     if (!s || !probs || !kind) return fail(FFM_E_INVALID, "null argument");
