@@ -332,16 +332,9 @@ int ffm_create(const ffm_config_t* cfg, ffm_sim_t* out) {
     // (rounded to a supported CTA size) without starving co-resident CTAs
     const int tot_in = unified ? (int)ffm::make_ulayout(HW, W, N, ssz, true).total : (int)ffm::make_layout(HW, W, N, ssz, dff, true).total;
     const int tot_out = unified ? (int)ffm::make_ulayout(HW, W, N, ssz, false).total : (int)ffm::make_layout(HW, W, N, ssz, dff, false).total;
-    struct { int total; } Lout = {tot_out};
-    if (tot_in <= MAX_SMEM_OPTIN) {
-        s->fields_in_smem = true;
-        s->smem_bytes = tot_in;
-    } else if (tot_out <= MAX_SMEM_OPTIN) {
-        s->fields_in_smem = false;
-        s->smem_bytes = tot_out;
-    } else {
+    if (tot_out > MAX_SMEM_OPTIN) {
         delete s;
-        return fail(FFM_E_UNSUPPORTED, "episode state (%d B) does not fit the 227 KB of shared memory of one SM", Lout.total);
+        return fail(FFM_E_UNSUPPORTED, "episode state (%d B) does not fit the 227 KB of shared memory of one SM", tot_out);
     }
     const int work = N > HW / 8 ? N : HW / 8;
     s->threads = work <= 128 ? 128 : (work <= 2048 ? 256 : 1024);
@@ -351,14 +344,31 @@ int ffm_create(const ffm_config_t* cfg, ffm_sim_t* out) {
     }
     if (unified) {
         s->threads = N <= 128 ? 128 : 256;
-        s->kernel = upick_kernel(cfg->sff_dtype == FFM_F64, cfg->neighborhood, s->fields_in_smem, s->threads);
         s->A = cfg->neighborhood + 1;
         s->nby = (W + cfg->block_size - 1) / cfg->block_size;
         s->S = ((cfg->height + cfg->block_size - 1) / cfg->block_size) * s->nby * 256;
         s->epsilon = cfg->epsilon;
-    } else {
-        s->kernel = pick_kernel(cfg->sff_dtype == FFM_F64, HW <= 65536, cfg->neighborhood, dff, s->fields_in_smem, s->threads);
     }
+    // Fields (score, DFF) in shared memory or left in global memory (L1/L2)?  Shared memory is faster per access
+    // but costs residency; measured on C2: SFF-only 6 vs 6 CTAs/SM -> shared +8 %, DFF-on 3 vs 6 CTAs/SM ->
+    // global +10 %.  Rule: shared unless the global variant keeps at least 1.5x as many CTAs resident.
+    auto kernel_for = [&](bool fs) {
+        return unified ? upick_kernel(cfg->sff_dtype == FFM_F64, cfg->neighborhood, fs, s->threads)
+                       : pick_kernel(cfg->sff_dtype == FFM_F64, HW <= 65536, cfg->neighborhood, dff, fs, s->threads);
+    };
+    auto occupancy = [&](const void* k, int smem) {
+        int occ = 0;
+        if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, s->threads, smem) != cudaSuccess) return 0;
+        return occ;
+    };
+    const int occ_out = occupancy(kernel_for(false), tot_out);
+    const int occ_in = tot_in <= MAX_SMEM_OPTIN ? occupancy(kernel_for(true), tot_in) : 0;
+    s->fields_in_smem = occ_in > 0 && 2 * occ_out < 3 * occ_in;
+    if (getenv("FFM_FIELDS_GLOBAL")) s->fields_in_smem = false;          // tuning overrides
+    if (getenv("FFM_FIELDS_SMEM") && occ_in > 0) s->fields_in_smem = true;
+    s->smem_bytes = s->fields_in_smem ? tot_in : tot_out;
+    s->kernel = kernel_for(s->fields_in_smem);
     cudaError_t ce = cudaFuncSetAttribute(s->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, s->smem_bytes);
     if (ce != cudaSuccess) { delete s; return fail(FFM_E_CUDA, "cudaFuncSetAttribute(smem=%d): %s", s->smem_bytes, cudaGetErrorString(ce)); }
     int occ = 0;

@@ -240,7 +240,7 @@ __device__ __forceinline__ void dff_decay_diffuse(const float* __restrict__ in, 
 }
 
 template <typename S, typename PosT, int NBR, bool DFF, bool FIELDS_IN_SMEM, int THREADS>
-__global__ void __launch_bounds__(THREADS, (THREADS <= 256 && sizeof(S) == 4) ? 1280 / THREADS : 1)
+__global__ void __launch_bounds__(THREADS, (THREADS <= 256 && sizeof(S) == 4) ? 1536 / THREADS : 1)
 ffm_core_rollout_kernel(const RolloutParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x;
