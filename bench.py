@@ -246,6 +246,12 @@ def main():
         run_reference_arm(args, wl)
         return
 
+    # stdout carries exactly ONE JSON line: anything a library writes to fd 1 meanwhile (NCCL prints its
+    # version banner there) is sent to stderr instead
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
     import torch
     import torch.distributed as dist
     from ffm_b200 import BatchSim
@@ -389,7 +395,8 @@ def main():
                     line["cpu_baseline"] = cpu_numpy_port(wl, budget_s=args.cpu_budget)
             except Exception as ex:   # the baseline is reporting, never the product
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": f"failed: {ex!r}"}
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 
