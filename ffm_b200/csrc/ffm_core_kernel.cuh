@@ -200,40 +200,27 @@ __device__ __forceinline__ void dff_decay_diffuse(const float* __restrict__ in, 
     const int band = tid / cw, colb = tid - band * cw;
     if (band >= bands) return;
     const int r0 = band * rpb, r1 = min(H, r0 + rpb);
-    // when a warp covers 32 consecutive columns of one band, the left/right terms come from the neighbouring
-    // lanes (c1*(c0*d) is a pure function of d, so the shuffled value is bit-identical to a local one): one load
-    // per cell instead of three; only the warp's edge lanes fetch their outer neighbour themselves
-    const bool shfl = (W % 32 == 0) && (nthreads % 32 == 0);   // then every warp is entirely inside one band and one column sweep
-    const int lane = tid & 31;
     for (int col = colb; col < W; col += cw) {
         const bool hasl = col > 0, hasr = col + 1 < W;
         float up[3], uc[3], un[3], sc = 0.0f;            // c1*s of rows r-1, r, r+1 (left, centre, right); s of the centre
-        auto raw = [&](int r, int cc) -> float { return (r >= 0 && r < H) ? in[(size_t)r * W + cc] : 0.0f; };
-        auto finish_row = [&](int r, float d1, float (&u)[3], float& s_centre) {
-            const float s1 = __fmul_rn(c0, d1);                                                   // (:109)
-            const float u1 = __fmul_rn(c1, s1);                                                   // (:113)
-            float u0, u2;
-            if (shfl) {
-                u0 = __shfl_up_sync(0xffffffffu, u1, 1);
-                u2 = __shfl_down_sync(0xffffffffu, u1, 1);
-                if (lane == 0) u0 = hasl ? __fmul_rn(c1, __fmul_rn(c0, raw(r, col - 1))) : 0.0f;
-                if (lane == 31) u2 = hasr ? __fmul_rn(c1, __fmul_rn(c0, raw(r, col + 1))) : 0.0f;
-            } else {
-                u0 = hasl ? __fmul_rn(c1, __fmul_rn(c0, raw(r, col - 1))) : 0.0f;
-                u2 = hasr ? __fmul_rn(c1, __fmul_rn(c0, raw(r, col + 1))) : 0.0f;
+        auto load_row = [&](int r, float (&u)[3], float& s_centre) {
+            float d0 = 0.0f, d1 = 0.0f, d2 = 0.0f;
+            if (r >= 0 && r < H) {
+                const float* row = in + (size_t)r * W + col;
+                d1 = row[0];
+                if (hasl) d0 = row[-1];
+                if (hasr) d2 = row[1];
             }
-            u[0] = u0; u[1] = u1; u[2] = u2;
+            const float s0 = __fmul_rn(c0, d0), s1 = __fmul_rn(c0, d1), s2 = __fmul_rn(c0, d2);   // (:109)
+            u[0] = __fmul_rn(c1, s0); u[1] = __fmul_rn(c1, s1); u[2] = __fmul_rn(c1, s2);         // (:113)
             s_centre = s1;
         };
         float dummy;
-        finish_row(r0 - 1, raw(r0 - 1, col), up, dummy);
-        finish_row(r0, raw(r0, col), uc, sc);
-        float d_ahead = raw(r0 + 1, col);                // software prefetch: the raw centre value of the next row
+        load_row(r0 - 1, up, dummy);
+        load_row(r0, uc, sc);
         for (int r = r0; r < r1; ++r) {
-            const float d_next = d_ahead;
-            d_ahead = raw(r + 2, col);
             float sn;
-            finish_row(r + 1, d_next, un, sn);
+            load_row(r + 1, un, sn);
             float acc = sc;
             if (NBR == 8) {   // (-1,-1) (-1,0) (-1,1) (0,-1) (0,1) (1,-1) (1,0) (1,1)
                 acc = __fadd_rn(acc, up[0]); acc = __fadd_rn(acc, up[1]); acc = __fadd_rn(acc, up[2]);
