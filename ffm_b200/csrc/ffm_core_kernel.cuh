@@ -45,9 +45,6 @@
 //                            forced requests from the back; A2 turns each draw entry into a request
 //                            entry in place (0xFFFF = no request); | 0x8000 once the request is granted
 //   alive u32[n_max/32+1]    alive bitmap;  wpre u32[n_max/32+1] exclusive prefix popcounts
-//   blocked u32[n_max/32+1]  slots whose neighbourhood held no candidate when last looked at; they are
-//                            skipped by A1 until a pedestrian leaves one of their neighbour cells (phase C
-//                            clears the bit of every owner around a vacated cell)
 #pragma once
 #include "ffm_device.cuh"
 
@@ -83,7 +80,7 @@ struct RolloutParams {
 };
 
 struct SmemLayout {
-    uint32_t score, dffA, dffB, grid, claim, pos, tgt, list, alive, wpre, blocked, ctr, bar, total;
+    uint32_t score, dffA, dffB, grid, claim, pos, tgt, list, alive, wpre, ctr, bar, total;
 };
 
 __host__ __device__ inline uint32_t align16(uint32_t x) { return (x + 15u) & ~15u; }
@@ -104,7 +101,6 @@ __host__ __device__ inline SmemLayout make_layout(int HW, int W, int n_max, int 
     L.list = o;  o = align16(o + (uint32_t)n_max * 2u);
     L.alive = o; o = align16(o + nw * 4u);
     L.wpre = o;  o = align16(o + nw * 4u);
-    L.blocked = o; o = align16(o + nw * 4u);
     L.ctr = o;   o = align16(o + 8u * 4u);
     L.bar = o;   o = align16(o + 8u);
     L.total = o;
@@ -263,7 +259,6 @@ ffm_core_rollout_kernel(const RolloutParams P) {
     const int list_last = P.n_max - 1;
     uint32_t* alive = reinterpret_cast<uint32_t*>(smem_raw + L.alive);
     uint32_t* wpre = reinterpret_cast<uint32_t*>(smem_raw + L.wpre);
-    uint32_t* blocked = reinterpret_cast<uint32_t*>(smem_raw + L.blocked);
     uint32_t* ctr = reinterpret_cast<uint32_t*>(smem_raw + L.ctr);   // [parity][n_work, n_req, n_exit, -]
     uint32_t* claim32 = reinterpret_cast<uint32_t*>(smem_raw + L.claim);
     const int claim_words = (HW + 7) / 8;
@@ -319,7 +314,6 @@ ffm_core_rollout_kernel(const RolloutParams P) {
         const int lo = w * 32;
         alive[w] = (lo + 32 <= n) ? 0xffffffffu : (lo < n ? ((1u << (n - lo)) - 1u) : 0u);
         wpre[w] = (uint32_t)(lo < n ? lo : n);
-        blocked[w] = 0u;
     }
     if (tid < 8) ctr[tid] = 0u;
     for (int c = tid; c < claim_words; c += THREADS) claim32[c] = 0u;
@@ -348,11 +342,9 @@ ffm_core_rollout_kernel(const RolloutParams P) {
         // ================= A1: candidate masks, forced exits ====================================
         for (int base = 0; base < n_slots; base += THREADS) {
             const int s = base + tid;
-            bool need_draw = false, forced = false, now_blocked = false;
+            bool need_draw = false, forced = false;
             uint32_t m = 0;
-            // one bitmap word per warp (base and THREADS are multiples of 32)
-            const uint32_t bword = (s < n_slots) ? blocked[s >> 5] : 0u;
-            if (s < n_slots && ((alive[s >> 5] >> (s & 31)) & 1u) && !((bword >> (s & 31)) & 1u)) {
+            if (s < n_slots && ((alive[s >> 5] >> (s & 31)) & 1u)) {
                 const int c = (int)pos[s];
                 // passable (map 0 or 3, ffm_core.py:52-53) and not occupied at time t (:57-60):
                 // blocked cells carry 0x3FFF in the owner bits, so "owner bits == 0" is the whole test
@@ -380,10 +372,7 @@ ffm_core_rollout_kernel(const RolloutParams P) {
                     }
                 }
                 tgt[s] = need_draw ? (PosT)m : (PosT)target;     // the mask rides in tgt[] until A2
-                now_blocked = (m == 0u);                           // no request, and none until a neighbour cell is vacated
             }
-            const uint32_t nbits = __ballot_sync(0xffffffffu, now_blocked);
-            if (lane == 0 && nbits != 0u) blocked[s >> 5] = bword | nbits;
             warp_append<uint16_t>(need_draw, (uint16_t)s, list, &cnt[0], lane);
             warp_append<uint16_t>(forced, (uint16_t)s, list, &cnt[1], lane, -1, list_last);
         }
@@ -481,13 +470,6 @@ ffm_core_rollout_kernel(const RolloutParams P) {
                     const int c = (int)pos[s];
                     const uint32_t T = tgt[s];
                     grid[c] &= (uint16_t)TYPE_BITS;
-                    // cell c is vacated: wake the blocked pedestrians around it (owners that stay put have stable
-                    // entries; owners that move this step are not blocked, so racing with their update is harmless)
-#pragma unroll
-                    for (int k = 0; k < NBR; ++k) {
-                        const uint32_t o = (grid[c + nbr_off<NBR>(k, W)] & OCC_MASK) - 1u;
-                        if (o < (uint32_t)n_slots && ((blocked[o >> 5] >> (o & 31)) & 1u)) atomicAnd(&blocked[o >> 5], ~(1u << (o & 31)));
-                    }
                     if (grid[T] == EXIT_EMPTY) {                               // (:101-102)
                         leaves = true;
                         atomicAnd(&alive[s >> 5], ~(1u << (s & 31)));
@@ -542,7 +524,6 @@ ffm_core_rollout_kernel(const RolloutParams P) {
                     const int lo = w * 32;
                     alive[w] = (lo + 32 <= n) ? 0xffffffffu : (lo < n ? ((1u << (n - lo)) - 1u) : 0u);
                     wpre[w] = (uint32_t)(lo < n ? lo : n);
-                    blocked[w] = 0u;                     // slots were renumbered: everybody looks again
                 }
                 n_slots = n;
                 __syncthreads();
