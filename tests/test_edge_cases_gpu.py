@@ -1,0 +1,134 @@
+"""Edge cases of the rollout kernels against the C / NumPy oracles: empty and single-pedestrian episodes, ragged
+batches, the maximum pedestrian capacity, maps above 65 536 cells (32-bit cell ids), obstacle maps with several
+exits, non-square maps, walls coded 1 (create_test_map of run_unified_critic_training.py:58-66)."""
+import numpy as np
+import pytest
+
+from helpers import MARGIN_GUARD, pack_positions, random_positions
+from oracle import assets, c_oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def _recorded(m, sff, pos, n, params, seed, T, base=0, threads=4, track=True):
+    return c_oracle.run_core_batch(m, sff, pos, n, params, seed=seed, episode_base=base, max_steps=T, threads=threads,
+                                   track_dff=track, traj_steps=T, want_state=True, guard=1e-5, record_moves=T)
+
+
+def _check_recorded(sim, ref, T, W):
+    import torch
+    cells, cnt = sim.rollout(T, draws=dict(move=torch.from_numpy(ref["move_draws"]).cuda()), record=T)
+    torch.cuda.synchronize()
+    steps, ped = sim.counters()
+    assert np.array_equal(steps, np.minimum(ref["steps"], T)) and np.array_equal(ped, ref["ped_steps"])
+    cells, cnt = cells.cpu().numpy(), cnt.cpu().numpy()
+    for e in range(len(steps)):
+        s = int(steps[e])
+        assert np.array_equal(cnt[e, :s], ref["traj_n"][e, :s]), e
+        mask = np.arange(cells.shape[2])[None, :] < cnt[e, :s, None]
+        assert np.array_equal(cells[e, :s][mask], ref["traj"][e, :s][mask]), e
+
+
+def test_empty_single_and_ragged_episodes(cuda_device):
+    from ffm_b200 import BatchSim
+    m = assets.room_map(16, 20)
+    sff = assets.sff_norm_min_fast(m, "L2", np.float32)
+    rng = np.random.RandomState(0)
+    counts = [0, 1, 2, 33, 64, 65, 100]
+    pos0 = [random_positions(m, k, rng) if k else np.zeros((0, 2), np.int64) for k in counts]
+    pos, n = pack_positions(pos0, 100)
+    ref = _recorded(m, sff, pos, n, {"neighborhood": "moore"}, 3, 400)
+    sim = BatchSim(m, sff, len(counts), 100, {"neighborhood": "moore"}, seed=3)
+    sim.set_positions(pos, n)
+    _check_recorded(sim, ref, 400, 20)
+    assert sim.counters()[0][0] == 0 and (sim.get_positions()[1] == 0).all()
+    assert np.array_equal(sim.get_dff().view(np.uint32), ref["final_dff"].view(np.uint32))
+
+
+def test_32bit_cell_ids_above_65536_cells(cuda_device):
+    """300 x 260 = 78 000 cells: PosT = uint32 variant, fields in global memory."""
+    from ffm_b200 import BatchSim
+    m = assets.obstacle_map_c5(300, 260, index=1, n_exits=4)
+    sff = c_oracle.geodesic(m, "bfs8")
+    rng = np.random.RandomState(1)
+    reach = np.argwhere((m == 0) & np.isfinite(sff))
+    pos0 = [reach[rng.choice(len(reach), 700, replace=False)] for _ in range(2)]
+    pos, n = pack_positions(pos0, 700)
+    params = {"neighborhood": "moore", "k_S": 2.0, "k_D": 1.0}
+    ref = _recorded(m, sff, pos, n, params, 5, 150)
+    sim = BatchSim(m, sff, 2, 700, params, seed=5)
+    sim.set_positions(pos, n)
+    _check_recorded(sim, ref, 150, 260)
+    assert np.array_equal(sim.get_dff().view(np.uint32), ref["final_dff"].view(np.uint32))
+
+
+def test_maximum_capacity_on_256x256(cuda_device):
+    """n_max = 16 380 pedestrians (the owner grid's 14-bit id space) on the C3 floor plan."""
+    from ffm_b200 import BatchSim
+    from ffm_b200.workloads import place, rooms_map_c3
+    m = rooms_map_c3()
+    sff = c_oracle.geodesic(m, "bfs8")
+    N = 16380
+    pos = place(m, N, 1, 0, 9)
+    n = np.array([N], np.int32)
+    params = {"neighborhood": "moore"}
+    ref = _recorded(m, sff, pos, n, params, 9, 40, threads=1)
+    sim = BatchSim(m, sff, 1, N, params, seed=9)
+    sim.set_positions(pos, n)
+    _check_recorded(sim, ref, 40, 256)
+    with pytest.raises(Exception):
+        BatchSim(m, sff, 1, N + 1, params)
+
+
+@pytest.mark.parametrize("nbh", ["neumann", "moore"])
+def test_obstacles_and_several_exits_full_episodes(cuda_device, nbh):
+    from ffm_b200 import BatchSim
+    m = assets.obstacle_map_c5(96, 80, index=3, n_exits=8)
+    sff = c_oracle.geodesic(m, "bfs4" if nbh == "neumann" else "dijkstra8").astype(np.float64)
+    rng = np.random.RandomState(2)
+    reach = np.argwhere((m == 0) & np.isfinite(sff))
+    pos0 = [reach[rng.choice(len(reach), 600 - 50 * e, replace=False)] for e in range(3)]
+    pos, n = pack_positions(pos0, 600)
+    params = {"neighborhood": nbh, "k_S": 1.5}
+    T = 1200
+    ref = _recorded(m, sff, pos, n, params, 21, T, base=5)
+    assert (ref["steps"] < T).all()
+    sim = BatchSim(m, sff, 3, 600, params, seed=21, episode_base=5)
+    sim.set_positions(pos, n)
+    _check_recorded(sim, ref, T, 80)
+    assert np.array_equal(sim.get_dff().view(np.uint32), ref["final_dff"].view(np.uint32))
+
+
+def test_unified_map_with_walls_coded_1(cuda_device):
+    """create_test_map (run_unified_critic_training.py:58-66) codes walls as 1: blocked for moves AND seen as
+    'pedestrian' by the diagonal test of _encode_state."""
+    import torch
+    from ffm_b200 import UnifiedSim
+    from oracle import unified_numpy
+    from oracle.inject import PhiloxSource
+    m = np.zeros((14, 14), np.uint8)
+    m[0, :] = 1; m[-1, :] = 1; m[:, 0] = 1; m[:, -1] = 1
+    m[7, 13] = 3
+    m[5:8, 6] = 1                                          # an interior wall coded 1
+    sff = np.ones(m.shape, np.float32) * 999                # create_test_sff: 999 on walls, L1 to the first exit
+    for i in range(14):
+        for j in range(14):
+            if m[i, j] in (0, 3):
+                sff[i, j] = abs(i - 7) + abs(j - 13)
+    P = dict(k_S=10, k_D=1, alpha_v=0.05, gamma=0.95, exit_reward=100.0, step_penalty=-1.0, collision_penalty=-1.0,
+             neighborhood="neumann", block_size=5)
+    rng = np.random.RandomState(3)
+    pos0 = random_positions(m, 30, rng)
+    o = unified_numpy.UnifiedOracle(m, sff, pos0, "critic_only", P, PhiloxSource(8, 0))
+    r = o.run(max_steps=300)
+    assert r["min_margin"] >= MARGIN_GUARD
+    sim = UnifiedSim(m, sff, 1, 30, mode="critic_only", learn="exact", params=P, seed=8)
+    sim.set_positions(*pack_positions([pos0], 30))
+    cells, cnt = sim.rollout(300, record=300)
+    torch.cuda.synchronize()
+    assert sim.counters()[0][0] == r["steps"]
+    cells, cnt = cells.cpu().numpy()[0], cnt.cpu().numpy()[0]
+    for t, want in enumerate(r["traj"]):
+        assert np.array_equal(cells[t, :cnt[t]], want[:, 0] * 14 + want[:, 1]), t
+    V, vs, _, _ = sim.get_tables()
+    assert np.array_equal(vs, o.v_seen) and np.array_equal(V.view(np.uint64), o.V.view(np.uint64))
