@@ -173,7 +173,8 @@ def injected(source, width, log_probs=False):
     o_pychoice, o_pyrandom = _pyrandom.choice, _pyrandom.random
 
     def _cell(frame):
-        t = frame.f_locals["target"]
+        loc = frame.f_locals
+        t = loc["target"] if "target" in loc else (loc["tx"], loc["ty"])    # ffm_learning_core.py:229 unpacks (tx, ty)
         return int(t[0]) * st.width + int(t[1])
 
     def choice(a, size=None, replace=True, p=None):

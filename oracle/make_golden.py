@@ -184,6 +184,51 @@ def unified_all():
     trained_case("trained_12x12", 12, 12, 30, 28, {"k_D": 1, "k_A": 10, "neighborhood": "neumann", "block_size": 1}, "uni_actor_eps")
 
 
+def mcq_case(name, h, w, N, seed, params, betas, sff_dtype=np.float64):
+    """Multi-episode run of model/ffm_learning_core.py (shared Q across episodes like main_learning.py:79-106)."""
+    from . import mcq_numpy
+    ref = inject.import_reference("ffm_learning_core")
+    m = assets.room_map(h, w)
+    sff = assets.sff_norm_min(m, "L1", sff_dtype)
+    with tempfile.TemporaryDirectory() as tmp:
+        p = os.path.join(tmp, "sff.npy")
+        np.save(p, sff)
+        np.random.seed(seed)
+        model = ref.FloorFieldModel(m, p, N, params)
+    Q, save, steps, margins = {}, {}, [], []
+    for ep, beta in enumerate(betas):
+        model.Q = Q
+        model.reset()
+        save[f"pos0_{ep}"] = np.array(model.positions, dtype=np.int16)
+        traj = []
+        with inject.injected(inject.PhiloxSource(seed, ep), w) as st:
+            t = 0
+            while model.positions.shape[0] > 0:
+                st.step = t
+                model.step(beta)
+                traj.append(np.array(model.positions, dtype=np.int64).reshape(-1, 2))
+                t += 1
+        flat, cnt = _flatten(traj)
+        save[f"traj_{ep}"], save[f"counts_{ep}"] = flat, cnt
+        steps.append(t); margins.append(st.min_margin)
+        Q = model.Q
+    helper = mcq_numpy.McqOracle(m, sff, np.zeros((0, 2)), params)
+    ids = np.array(sorted(helper.id_of(k) for k in Q), np.int64)
+    rows = np.stack([Q[helper.key_of(i)] for i in ids]).astype(np.float32)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), map=m, sff=sff, params=json.dumps(params), seed=np.uint64(seed),
+                        betas=np.array(betas, np.float64), alpha=np.float64(model.alpha), gamma=np.float64(model.gamma),
+                        steps=np.array(steps, np.int32), min_margin=np.array(margins), q_ids=ids, q_rows=rows,
+                        final_dff=np.array(model.dff, np.float32), **save)
+    print(name, "steps", steps, "min_margin %.1e" % min(margins), "|Q|", len(ids))
+
+
+def mcq_all():
+    mcq_case("mcq_12x12_penalties", 12, 12, 20, 31, {"max_steps": 60, "step_penalty": 0.01, "stop_penalty": 0.3, "collision_penalty": 0.7},
+             [1.0, 0.6, 0.2, 0.0], np.float32)
+    mcq_case("mcq_12x12_default", 12, 12, 40, 32, {"max_steps": 500}, [1.0, 0.5, 0.1])
+    mcq_case("mcq_20x20_kq", 20, 20, 30, 33, {"max_steps": 80, "k_Q": 2.0, "step_penalty": 0.05}, [0.8, 0.3])
+
+
 def shipped():
     out = {}
     for rel in ("data/maps/simple_room.npy", "data/sff/distance_L1.npy", "data/sff/distance_L2.npy", "data/sff/distance_Linf.npy"):
@@ -207,6 +252,7 @@ def main():
     stock_main()
     shipped()
     unified_all()
+    mcq_all()
 
 
 if __name__ == "__main__":

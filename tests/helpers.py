@@ -74,3 +74,19 @@ def load_unified(name):
         g["ep"].append(dict(pos0=g[f"pos0_{ep}"].astype(np.int64),
                             traj=[g[f"traj_{ep}"][offs[t]:offs[t + 1]].astype(np.int64) for t in range(len(counts))]))
     return g
+
+
+MCQ_FIXTURES = ["mcq_12x12_penalties", "mcq_12x12_default", "mcq_20x20_kq"]
+
+
+def load_mcq(name):
+    z = np.load(os.path.join(GOLDEN, name + ".npz"))
+    g = {k: z[k] for k in z.files}
+    g["params"] = json.loads(str(g["params"]))
+    g["ep"] = []
+    for ep in range(len(g["betas"])):
+        counts = g[f"counts_{ep}"]
+        offs = np.concatenate([[0], np.cumsum(counts)])
+        g["ep"].append(dict(pos0=g[f"pos0_{ep}"].astype(np.int64),
+                            traj=[g[f"traj_{ep}"][offs[t]:offs[t + 1]].astype(np.int64) for t in range(len(counts))]))
+    return g
