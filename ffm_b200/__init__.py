@@ -9,6 +9,6 @@ Layout
 The CUDA library is the only compute path; importing this package never falls back to a CPU
 implementation.
 """
-from .sim import BatchSim, UnifiedSim  # noqa: F401
+from .sim import BatchSim, McqSim, UnifiedSim  # noqa: F401
 
-__all__ = ["BatchSim", "UnifiedSim"]
+__all__ = ["BatchSim", "McqSim", "UnifiedSim"]

@@ -7,12 +7,12 @@ import os
 
 from . import build as _build
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 FFM_HOST, FFM_DEVICE = 0, 1
 FFM_NEUMANN, FFM_MOORE = 4, 8
 FFM_F32, FFM_F64 = 0, 1
 E_INVALID, E_CUDA, E_UNSUPPORTED, E_STATE = -1, -2, -3, -4
-MODEL_CORE, MODEL_UNIFIED_CRITIC, MODEL_UNIFIED_ACTOR, MODEL_UNIFIED_BOTH, MODEL_TRAINED = range(5)
+MODEL_CORE, MODEL_UNIFIED_CRITIC, MODEL_UNIFIED_ACTOR, MODEL_UNIFIED_BOTH, MODEL_TRAINED, MODEL_MCQ = range(6)
 LEARN_NONE, LEARN_EXACT, LEARN_BATCHED = range(3)
 SFF_L1, SFF_L2, SFF_LINF, SFF_BFS4, SFF_BFS8, SFF_DIJKSTRA8 = range(6)
 
@@ -31,6 +31,7 @@ class Config(C.Structure):
         ("k_A", C.c_double), ("gamma", C.c_double), ("alpha_v", C.c_double), ("alpha_h", C.c_double),
         ("exit_reward", C.c_double), ("step_penalty", C.c_double), ("collision_penalty", C.c_double),
         ("epsilon", C.c_double), ("sff_min", C.c_double), ("sff_max", C.c_double),
+        ("stop_penalty", C.c_double), ("timeout_penalty", C.c_double), ("step_cap", C.c_int32), ("reserved4", C.c_int32),
     ]
 
 
@@ -67,6 +68,10 @@ SIGNATURES = {
     "ffm_tables_apply_deltas": (C.c_int, [C.c_void_p, C.c_void_p]),
     "ffm_set_epsilon": (C.c_int, [C.c_void_p, C.c_double]),
     "ffm_set_episode_base": (C.c_int, [C.c_void_p, C.c_uint32]),
+    "ffm_q_shape": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
+    "ffm_q_get": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "ffm_q_set": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "ffm_set_beta": (C.c_int, [C.c_void_p, C.c_double]),
     "ffm_sff_generate": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int,
                                    C.c_int32, C.c_void_p, C.POINTER(C.c_int32)]),
     "ffm_rollout_returns": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_double, C.c_void_p,

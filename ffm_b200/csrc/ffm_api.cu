@@ -13,6 +13,7 @@
 #include "ffm_core_kernel.cuh"
 #include "ffm_sff_kernels.cuh"
 #include "ffm_unified_kernel.cuh"
+#include "ffm_mcq_kernel.cuh"
 
 namespace {
 
@@ -69,6 +70,11 @@ struct ffm_sim_s {
     ffm::HStats* d_hstats;
     double* d_blk_lo; double* d_blk_hi; int* d_blk_any;
     double epsilon;
+    // MC-Q model
+    long long qS;
+    float* d_Q; uint8_t* d_qseen;
+    uint32_t* d_path_state; uint8_t* d_path_code; int32_t* d_path_len; uint16_t* d_path_col;
+    double beta;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -301,8 +307,16 @@ int ffm_create(const ffm_config_t* cfg, ffm_sim_t* out) {
     if (cfg->n_episodes < 1) return fail(FFM_E_INVALID, "n_episodes must be >= 1");
     if (cfg->n_max < 1 || cfg->n_max > ffm::MAX_PEDS) return fail(FFM_E_UNSUPPORTED, "n_max must be in [1, %d]", ffm::MAX_PEDS);
     if (!cfg->track_dff && cfg->k_D != 0.0) return fail(FFM_E_INVALID, "track_dff = 0 requires k_D == 0");
-    if (cfg->model < FFM_MODEL_CORE || cfg->model > FFM_MODEL_TRAINED) return fail(FFM_E_INVALID, "unknown model %d", cfg->model);
-    const bool unified = cfg->model != FFM_MODEL_CORE;
+    if (cfg->model < FFM_MODEL_CORE || cfg->model > FFM_MODEL_MCQ) return fail(FFM_E_INVALID, "unknown model %d", cfg->model);
+    const bool mcq = cfg->model == FFM_MODEL_MCQ;
+    const bool unified = cfg->model != FFM_MODEL_CORE && !mcq;
+    if (mcq) {
+        if (cfg->neighborhood != FFM_NEUMANN) return fail(FFM_E_INVALID, "the MC-Q model moves on the von Neumann neighbourhood (ffm_learning_core.py:73)");
+        if (cfg->learn != FFM_LEARN_NONE && cfg->learn != FFM_LEARN_EXACT) return fail(FFM_E_INVALID, "the MC-Q model supports FFM_LEARN_NONE and FFM_LEARN_EXACT");
+        if (cfg->learn == FFM_LEARN_EXACT && cfg->n_episodes != 1) return fail(FFM_E_INVALID, "FFM_LEARN_EXACT needs n_episodes == 1");
+        if (cfg->step_cap < 1) return fail(FFM_E_INVALID, "step_cap (params[\"max_steps\"]) must be >= 1");
+        if (!cfg->track_dff) return fail(FFM_E_INVALID, "the MC-Q model always tracks the DFF");
+    }
     if (unified) {
         if (cfg->block_size < 1) return fail(FFM_E_INVALID, "block_size must be >= 1");
         if (cfg->learn < FFM_LEARN_NONE || cfg->learn > FFM_LEARN_BATCHED) return fail(FFM_E_INVALID, "unknown learn mode %d", cfg->learn);
@@ -330,8 +344,9 @@ int ffm_create(const ffm_config_t* cfg, ffm_sim_t* out) {
 
     // kernel variant: fields in shared memory when they fit, and as many threads as pedestrians
     // (rounded to a supported CTA size) without starving co-resident CTAs
-    const int tot_in = unified ? (int)ffm::make_ulayout(HW, W, N, ssz, true).total : (int)ffm::make_layout(HW, W, N, ssz, dff, true).total;
-    const int tot_out = unified ? (int)ffm::make_ulayout(HW, W, N, ssz, false).total : (int)ffm::make_layout(HW, W, N, ssz, dff, false).total;
+    const int tot_in = mcq ? (1 << 30) : unified ? (int)ffm::make_ulayout(HW, W, N, ssz, true).total : (int)ffm::make_layout(HW, W, N, ssz, dff, true).total;
+    const int tot_out = mcq ? (int)ffm::make_mlayout(HW, W, N).total
+                            : unified ? (int)ffm::make_ulayout(HW, W, N, ssz, false).total : (int)ffm::make_layout(HW, W, N, ssz, dff, false).total;
     if (tot_out > MAX_SMEM_OPTIN) {
         delete s;
         return fail(FFM_E_UNSUPPORTED, "episode state (%d B) does not fit the 227 KB of shared memory of one SM", tot_out);
@@ -352,7 +367,13 @@ int ffm_create(const ffm_config_t* cfg, ffm_sim_t* out) {
     // Fields (score, DFF) in shared memory or left in global memory (L1/L2)?  Shared memory is faster per access
     // but costs residency; measured on C2: SFF-only 6 vs 6 CTAs/SM -> shared +8 %, DFF-on 3 vs 6 CTAs/SM ->
     // global +10 %.  Rule: shared unless the global variant keeps at least 1.5x as many CTAs resident.
+    if (mcq) s->threads = N <= 128 ? 128 : 256;
     auto kernel_for = [&](bool fs) {
+        if (mcq) {
+            const bool f64 = cfg->sff_dtype == FFM_F64;
+            if (s->threads == 128) return f64 ? (const void*)ffm::ffm_mcq_rollout_kernel<double, 128> : (const void*)ffm::ffm_mcq_rollout_kernel<float, 128>;
+            return f64 ? (const void*)ffm::ffm_mcq_rollout_kernel<double, 256> : (const void*)ffm::ffm_mcq_rollout_kernel<float, 256>;
+        }
         return unified ? upick_kernel(cfg->sff_dtype == FFM_F64, cfg->neighborhood, fs, s->threads)
                        : pick_kernel(cfg->sff_dtype == FFM_F64, HW <= 65536, cfg->neighborhood, dff, fs, s->threads);
     };
@@ -399,6 +420,23 @@ int ffm_create(const ffm_config_t* cfg, ffm_sim_t* out) {
         ALLOC(s->d_dff, (size_t)B * HW * 4);
         if (!s->fields_in_smem) ALLOC(s->d_dff_tmp, (size_t)B * HW * 4);
     }
+    if (mcq) {
+        const int nby = (W + 2) / 3, nbx = (cfg->height + 2) / 3;
+        s->nby = nby;
+        s->qS = (long long)nbx * nby * (long long)ffm::MCQ_STATES_PER_BLOCK;
+        if (s->qS > 0xFFFFFFFFLL) { ffm_destroy(s); return fail(FFM_E_UNSUPPORTED, "Q table of %lld states exceeds 32-bit state ids", s->qS); }
+        ALLOC(s->d_Q, (size_t)s->qS * 5 * 4);
+        ALLOC(s->d_qseen, (size_t)s->qS);
+        if (!s->d_dff_tmp) ALLOC(s->d_dff_tmp, (size_t)B * HW * 4);
+        ALLOC(s->d_path_state, (size_t)B * (cfg->step_cap + 1) * N * 4);
+        ALLOC(s->d_path_code, (size_t)B * (cfg->step_cap + 1) * N);
+        ALLOC(s->d_path_len, (size_t)B * N * 4);
+        ALLOC(s->d_path_col, (size_t)B * N * 2);
+        cudaMemset(s->d_Q, 0, (size_t)s->qS * 5 * 4);
+        cudaMemset(s->d_qseen, 0, (size_t)s->qS);
+        cudaMemset(s->d_path_len, 0, (size_t)B * N * 4);
+        s->beta = 1.0;
+    }
     if (unified) {
         ALLOC(s->d_V, (size_t)s->S * 8);
         ALLOC(s->d_vseen, (size_t)s->S);
@@ -432,6 +470,7 @@ int ffm_destroy(ffm_sim_t s) {
     cudaFree(s->d_free); cudaFree(s->d_free_count); cudaFree(s->d_n_req);
     cudaFree(s->d_V); cudaFree(s->d_vseen); cudaFree(s->d_H); cudaFree(s->d_hseen); cudaFree(s->d_hstats);
     cudaFree(s->d_blk_lo); cudaFree(s->d_blk_hi); cudaFree(s->d_blk_any);
+    cudaFree(s->d_Q); cudaFree(s->d_qseen); cudaFree(s->d_path_state); cudaFree(s->d_path_code); cudaFree(s->d_path_len); cudaFree(s->d_path_col);
     delete s;
     return FFM_OK;
 }
@@ -563,6 +602,31 @@ int ffm_rollout(ffm_sim_t s, int32_t max_steps, const ffm_draws_t* draws, const 
     if (draws && draws->space != FFM_DEVICE) return fail(FFM_E_INVALID, "recorded draws must live in device memory");
     cudaStream_t st = (cudaStream_t)stream;
     CU(cudaSetDevice(s->cfg.device));
+    if (s->cfg.model == FFM_MODEL_MCQ) {
+        ffm::McqParams M;
+        memset(&M, 0, sizeof(M));
+        M.H = s->cfg.height; M.W = s->cfg.width; M.HW = s->HW; M.n_max = s->cfg.n_max; M.B = s->cfg.n_episodes;
+        M.max_steps = max_steps; M.step_cap = s->cfg.step_cap; M.learn = s->cfg.learn; M.nby = s->nby;
+        M.type_grid = s->d_type_grid; M.sff = s->d_sff;
+        M.kS = s->cfg.k_S; M.kD = s->cfg.k_D; M.kQ = s->cfg.k_A; M.beta = s->beta; M.alpha = s->cfg.alpha_v; M.gamma = s->cfg.gamma;
+        M.rw[ffm::RW_STEP] = -s->cfg.step_penalty; M.rw[ffm::RW_STOP] = -s->cfg.stop_penalty; M.rw[ffm::RW_COLL] = -s->cfg.collision_penalty;
+        M.rw[ffm::RW_EXIT] = s->cfg.exit_reward; M.rw[ffm::RW_TIMEOUT] = -s->cfg.timeout_penalty;
+        M.c0 = s->cfg.dff_c0; M.c1 = s->cfg.dff_c1; M.thr = s->cfg.dff_threshold;
+        M.pos = s->d_pos; M.n_alive = s->d_n; M.t_done = s->d_t; M.ped_steps = s->d_ped_steps;
+        M.dff = s->d_dff; M.dff_tmp = s->d_dff_tmp;
+        M.Q = s->d_Q; M.q_seen = s->d_qseen;
+        M.path_state = s->d_path_state; M.path_code = s->d_path_code; M.path_len = s->d_path_len; M.path_col = s->d_path_col;
+        M.seed = s->cfg.seed; M.episode_base = s->cfg.episode_base;
+        if (draws) { M.move_draws = draws->move; M.conflict_draws = draws->conflict; M.draw_steps = draws->steps; M.draw_first = draws->first_step; }
+        if (out && out->traj_cells) {
+            if (!out->traj_n) return fail(FFM_E_INVALID, "traj_cells without traj_n");
+            M.traj = out->traj_cells; M.traj_n = out->traj_n; M.traj_steps = out->traj_steps;
+        }
+        void* margs[] = {&M};
+        CU(cudaLaunchKernel(s->kernel, dim3(s->cfg.n_episodes), dim3(s->threads), margs, (size_t)s->smem_bytes, st));
+        s->launches++;
+        return FFM_OK;
+    }
     if (s->cfg.model != FFM_MODEL_CORE) {
         if (s->cfg.learn == FFM_LEARN_BATCHED && !s->d_dV) return fail(FFM_E_STATE, "FFM_LEARN_BATCHED needs ffm_tables_bind_deltas first");
         ffm::UnifiedParams U;
@@ -732,6 +796,40 @@ int ffm_tables_apply_deltas(ffm_sim_t s, void* stream) {
 int ffm_set_epsilon(ffm_sim_t s, double epsilon) {
     if (!s) return fail(FFM_E_INVALID, "null argument");
     s->epsilon = epsilon < 0.0 ? 0.0 : (epsilon > 1.0 ? 1.0 : epsilon);   // np.clip (ffm_unified.py:867)
+    return FFM_OK;
+}
+
+int ffm_q_shape(ffm_sim_t s, int64_t* n_states) {
+    if (!s || !n_states) return fail(FFM_E_INVALID, "null argument");
+    if (s->cfg.model != FFM_MODEL_MCQ) return fail(FFM_E_STATE, "only the MC-Q model has a Q table");
+    *n_states = s->qS;
+    return FFM_OK;
+}
+
+int ffm_q_get(ffm_sim_t s, float* Q, uint8_t* seen, int space, void* stream) {
+    if (!s) return fail(FFM_E_INVALID, "null argument");
+    if (s->cfg.model != FFM_MODEL_MCQ) return fail(FFM_E_STATE, "only the MC-Q model has a Q table");
+    CU(cudaSetDevice(s->cfg.device));
+    int rc;
+    if (Q && (rc = copy_out(Q, s->d_Q, (size_t)s->qS * 20, space, (cudaStream_t)stream))) return rc;
+    if (seen && (rc = copy_out(seen, s->d_qseen, (size_t)s->qS, space, (cudaStream_t)stream))) return rc;
+    return FFM_OK;
+}
+
+int ffm_q_set(ffm_sim_t s, const float* Q, const uint8_t* seen, int space, void* stream) {
+    if (!s) return fail(FFM_E_INVALID, "null argument");
+    if (s->cfg.model != FFM_MODEL_MCQ) return fail(FFM_E_STATE, "only the MC-Q model has a Q table");
+    CU(cudaSetDevice(s->cfg.device));
+    int rc;
+    if (Q && (rc = copy_in(s->d_Q, Q, (size_t)s->qS * 20, space, (cudaStream_t)stream))) return rc;
+    if (seen && (rc = copy_in(s->d_qseen, seen, (size_t)s->qS, space, (cudaStream_t)stream))) return rc;
+    CU(cudaStreamSynchronize((cudaStream_t)stream));
+    return FFM_OK;
+}
+
+int ffm_set_beta(ffm_sim_t s, double beta) {
+    if (!s) return fail(FFM_E_INVALID, "null argument");
+    s->beta = beta;
     return FFM_OK;
 }
 

@@ -375,3 +375,78 @@ def rollout_returns(reward, length, gamma):
     _abi.check(_abi.lib().ffm_rollout_returns(_ptr(reward), _ptr(length), B, T, N, float(gamma), _ptr(out),
                                               reward.device.index or 0, _stream()))
     return out
+
+
+MCQ_DEFAULTS = {"k_S": 3.0, "k_D": 1.0, "k_Q": 1.0, "diffuse": 0.2, "decay": 0.2, "neighborhood": "neumann",
+                "step_penalty": 0.0, "stop_penalty": 0.0, "collision_penalty": 0.0, "exit_reward": 100.0,
+                "timeout_penalty": 50.0, "max_steps": 500}        # ffm_learning_core.py:45-59
+
+
+class McqSim(BatchSim):
+    """B episodes of the target-centric Monte-Carlo Q-learning model (model/ffm_learning_core.py).
+
+    learn  "exact"  the reference's reverse Monte-Carlo backups at arrivals / timeouts (n_episodes must be 1)
+           "none"   frozen Q table, any number of episodes
+    The Q table is dense: state id = ((tx//3)*nby + ty//3) * 4**9 + sum(v_i * 4**i) over the 3x3 window around the
+    target cell (``key_to_id``); rows float32 [5] in the reference's action order FROM_UP/DOWN/LEFT/RIGHT/SELF.
+    """
+
+    DEFAULTS = MCQ_DEFAULTS
+
+    def __init__(self, map_array, sff, n_episodes, n_max, learn="exact", params=None, seed=0, episode_base=0,
+                 alpha=0.1, gamma=0.99, device=None):
+        self.learn, self.alpha, self.gamma = learn, float(alpha), float(gamma)
+        if params is not None and params.get("neighborhood", "neumann") != "neumann":
+            params = {**params, "neighborhood": "neumann"}          # the model forces von Neumann (ffm_learning_core.py:72-73)
+        super().__init__(map_array, sff, n_episodes, n_max, params, seed, episode_base, True, device)
+        S = C.c_int64()
+        _abi.check(self._lib.ffm_q_shape(self._h, C.byref(S)))
+        self.S = S.value
+        self.nby = -(-self.W // 3)
+
+    def _configure(self, cfg):
+        p = self.params
+        cfg.model = _abi.MODEL_MCQ
+        cfg.learn = _LEARN[self.learn]
+        cfg.k_A = float(p["k_Q"])
+        cfg.alpha_v, cfg.gamma = self.alpha, self.gamma
+        cfg.step_penalty, cfg.stop_penalty = float(p["step_penalty"]), float(p["stop_penalty"])
+        cfg.collision_penalty, cfg.exit_reward = float(p["collision_penalty"]), float(p["exit_reward"])
+        cfg.timeout_penalty, cfg.step_cap = float(p["timeout_penalty"]), int(p["max_steps"])
+        # _update_dff (ffm_learning_core.py:307-321) is always Moore: the neighbour weight divides by 8
+        decay, diffuse = float(p["decay"]), float(p["diffuse"])
+        cfg.dff_c0 = float(np.float32((1.0 - decay) * (1.0 - diffuse)))
+        cfg.dff_c1 = float(np.float32(decay * (1.0 - diffuse) / 8))
+
+    def set_beta(self, beta):
+        _abi.check(self._lib.ffm_set_beta(self._h, float(beta)))
+
+    def key_to_id(self, key):
+        cells, (bx, by) = key
+        return (int(bx) * self.nby + int(by)) * 4 ** 9 + sum(int(v) << (2 * k) for k, v in enumerate(bytes(cells)))
+
+    def id_to_key(self, sid):
+        blk, code = divmod(int(sid), 4 ** 9)
+        return (bytes((code >> (2 * k)) & 3 for k in range(9)), (blk // self.nby, blk % self.nby))
+
+    def get_q(self):
+        """-> (ids int64 [K], rows float32 [K, 5]) of the rows that exist."""
+        seen = np.empty(self.S, np.uint8)
+        _abi.check(self._lib.ffm_q_get(self._h, None, _ptr(seen), _abi.FFM_HOST, _stream()))
+        ids = np.flatnonzero(seen)
+        Q = np.empty((self.S, 5), np.float32)
+        _abi.check(self._lib.ffm_q_get(self._h, _ptr(Q), None, _abi.FFM_HOST, _stream()))
+        return ids, Q[ids].copy()
+
+    def q_dict(self):
+        """The reference's ``self.Q``: {(combined3x3 bytes, (bx, by)): float32[5]}."""
+        ids, rows = self.get_q()
+        return {self.id_to_key(i): rows[k] for k, i in enumerate(ids)}
+
+    def load_q_dict(self, d):
+        Q = np.zeros((self.S, 5), np.float32)
+        seen = np.zeros(self.S, np.uint8)
+        for k, v in d.items():
+            Q[self.key_to_id(k)] = v
+            seen[self.key_to_id(k)] = 1
+        _abi.check(self._lib.ffm_q_set(self._h, _ptr(Q), _ptr(seen), _abi.FFM_HOST, _stream()))

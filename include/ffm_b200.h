@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define FFM_ABI_VERSION 2
+#define FFM_ABI_VERSION 3
 
 enum {
     FFM_OK = 0,
@@ -48,7 +48,8 @@ enum {
     FFM_MODEL_UNIFIED_CRITIC = 1, /* model/ffm_unified.py learning_mode="critic_only" */
     FFM_MODEL_UNIFIED_ACTOR = 2,  /*                       learning_mode="actor_only" */
     FFM_MODEL_UNIFIED_BOTH = 3,   /*                       learning_mode="both" */
-    FFM_MODEL_TRAINED = 4         /* model/ffm_trained_core.py FloorFieldModel (frozen H table) */
+    FFM_MODEL_TRAINED = 4,        /* model/ffm_trained_core.py FloorFieldModel (frozen H table) */
+    FFM_MODEL_MCQ = 5             /* model/ffm_learning_core.py FloorFieldModel (target-centric Monte-Carlo Q-learning) */
 };
 /* how the unified model's tables are updated */
 enum {
@@ -91,6 +92,11 @@ typedef struct ffm_config {
     double exit_reward, step_penalty, collision_penalty;
     double epsilon;        /* params["epsilon"] / set_epsilon() */
     double sff_min, sff_max; /* float(np.min/max(self.sff)) of the inf->0 float32 SFF (ffm_unified.py:425-426) */
+    /* ---- FFM_MODEL_MCQ only (ffm_learning_core.py:45-59, :76-77): k_A carries k_Q, alpha_v carries alpha,
+     *      step_penalty / collision_penalty / exit_reward are the (positive) costs / reward of the params dict ---- */
+    double stop_penalty, timeout_penalty;
+    int32_t step_cap;      /* params["max_steps"]: finalize_timeouts() when the step counter reaches it */
+    int32_t reserved4;
 } ffm_config_t;
 
 /* Optional recorded uniforms that override the keyed Philox streams (parity tests: "both sides
@@ -198,6 +204,15 @@ int ffm_tables_apply_deltas(ffm_sim_t sim, void *stream);
 int ffm_set_epsilon(ffm_sim_t sim, double epsilon);   /* set_epsilon() :859-867 */
 /* global id of episode 0 for the following rollouts (a drop-in object advances it on every reset()) */
 int ffm_set_episode_base(ffm_sim_t sim, uint32_t episode_base);
+
+/* ---- Q table of FFM_MODEL_MCQ -----------------------------------------------------------------------
+ * Dense image of self.Q (ffm_learning_core.py:75): state id = ((tx/3)*nby + ty/3) * 4^9 + sum_i v_i * 4^i over the
+ * row-major 3x3 window around the TARGET cell (v = map code with OOB = 2, +1 on occupied free cells,
+ * _combined3x3_at_target :115-140), nby = ceil(width/3);  Q float32 [S][5], seen uint8 [S] (row exists). */
+int ffm_q_shape(ffm_sim_t sim, int64_t *n_states);
+int ffm_q_get(ffm_sim_t sim, float *Q, uint8_t *seen, int space, void *stream);
+int ffm_q_set(ffm_sim_t sim, const float *Q, const uint8_t *seen, int space, void *stream);   /* model.Q = shared_Q, main_learning.py:81 */
+int ffm_set_beta(ffm_sim_t sim, double beta);   /* the beta argument of step(beta), ffm_learning_core.py:145 */
 
 /* Static-floor-field generation for n_maps maps (uint8 [n_maps][H][W]) -> out [n_maps][H][W] of
  * out_dtype (FFM_F32 | FFM_F64), +inf on non-walkable and unreachable cells.
