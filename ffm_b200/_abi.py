@@ -72,6 +72,7 @@ SIGNATURES = {
     "ffm_q_get": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "ffm_q_set": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "ffm_set_beta": (C.c_int, [C.c_void_p, C.c_double]),
+    "ffm_mcq_finalize_timeouts": (C.c_int, [C.c_void_p, C.c_void_p]),
     "ffm_sff_generate": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int,
                                    C.c_int32, C.c_void_p, C.POINTER(C.c_int32)]),
     "ffm_rollout_returns": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_double, C.c_void_p,

@@ -598,7 +598,7 @@ int ffm_get_dff(ffm_sim_t s, float* dff, int space, void* stream) {
 int ffm_rollout(ffm_sim_t s, int32_t max_steps, const ffm_draws_t* draws, const ffm_rollout_out_t* out, void* stream) {
     if (!s) return fail(FFM_E_INVALID, "null argument");
     if (!s->have_fields || !s->have_positions) return fail(FFM_E_STATE, "fields and positions must be set before ffm_rollout");
-    if (max_steps < 0) return fail(FFM_E_INVALID, "max_steps < 0");
+    if (max_steps < 0 && !(max_steps == -1 && s->cfg.model == FFM_MODEL_MCQ)) return fail(FFM_E_INVALID, "max_steps < 0");
     if (draws && draws->space != FFM_DEVICE) return fail(FFM_E_INVALID, "recorded draws must live in device memory");
     cudaStream_t st = (cudaStream_t)stream;
     CU(cudaSetDevice(s->cfg.device));
@@ -606,7 +606,8 @@ int ffm_rollout(ffm_sim_t s, int32_t max_steps, const ffm_draws_t* draws, const 
         ffm::McqParams M;
         memset(&M, 0, sizeof(M));
         M.H = s->cfg.height; M.W = s->cfg.width; M.HW = s->HW; M.n_max = s->cfg.n_max; M.B = s->cfg.n_episodes;
-        M.max_steps = max_steps; M.step_cap = s->cfg.step_cap; M.learn = s->cfg.learn; M.nby = s->nby;
+        M.max_steps = max_steps < 0 ? 0 : max_steps; M.step_cap = s->cfg.step_cap; M.learn = s->cfg.learn; M.nby = s->nby;
+        M.force_finalize = max_steps < 0 ? 1 : 0;
         M.type_grid = s->d_type_grid; M.sff = s->d_sff;
         M.kS = s->cfg.k_S; M.kD = s->cfg.k_D; M.kQ = s->cfg.k_A; M.beta = s->beta; M.alpha = s->cfg.alpha_v; M.gamma = s->cfg.gamma;
         M.rw[ffm::RW_STEP] = -s->cfg.step_penalty; M.rw[ffm::RW_STOP] = -s->cfg.stop_penalty; M.rw[ffm::RW_COLL] = -s->cfg.collision_penalty;
@@ -825,6 +826,12 @@ int ffm_q_set(ffm_sim_t s, const float* Q, const uint8_t* seen, int space, void*
     if (seen && (rc = copy_in(s->d_qseen, seen, (size_t)s->qS, space, (cudaStream_t)stream))) return rc;
     CU(cudaStreamSynchronize((cudaStream_t)stream));
     return FFM_OK;
+}
+
+int ffm_mcq_finalize_timeouts(ffm_sim_t s, void* stream) {
+    if (!s) return fail(FFM_E_INVALID, "null argument");
+    if (s->cfg.model != FFM_MODEL_MCQ) return fail(FFM_E_STATE, "only the MC-Q model finalizes timeouts");
+    return ffm_rollout(s, -1, nullptr, nullptr, stream);    // zero steps, then the timeout records + backups
 }
 
 int ffm_set_beta(ffm_sim_t s, double beta) {

@@ -35,6 +35,7 @@ struct McqParams {
     int max_steps;           // steps to run in this launch
     int step_cap;            // params["max_steps"]: finalize_timeouts when the step counter reaches it
     int learn;               // ULEARN_NONE | ULEARN_EXACT
+    int force_finalize;      // finalize_timeouts() called by the driver before the cap (main_learning.py:96-97)
     int nby;
     const uint16_t* type_grid;
     const void* sff;         // [HW] S: the SFF itself (float32 or float64 as loaded)
@@ -162,6 +163,22 @@ ffm_mcq_rollout_kernel(const McqParams P) {
     const bool learn = P.learn == ULEARN_EXACT;
     const double wq = __dmul_rn(1.0 - P.beta, P.kQ);       // (1 - beta) * k_Q
     const int doff[4] = {-W, W, -1, 1};                     // UP, DOWN, LEFT, RIGHT (:73)
+    // finalize_timeouts() (:326-360): every remaining agent appends (state of its own cell, STOP, -timeout_penalty)
+    // as record `row` of its path and is backed up, in index order
+    auto finalize = [&](int row) {
+        for (int i = tid; i < n; i += THREADS) {
+            const int c = (int)pos[i];
+            const int r = c / W, col = c - r * W;
+            const size_t at = pbase + (size_t)row * pstride + orig[i];
+            P.path_state[at] = mcq_state(grid, r, col, H, W, P.nby);
+            P.path_code[at] = (uint8_t)(4 | (RW_TIMEOUT << 4));
+            plen[orig[i]] = row + 1;
+        }
+        __syncthreads();
+        if (tid == 0 && learn)
+            for (int i = 0; i < n; ++i) mcq_backup(P, e, orig[i], row + 1);
+        __syncthreads();
+    };
     unsigned long long ped_steps = 0;
     int tl = 0;
     for (; tl < P.max_steps && n > 0; ++tl) {
@@ -378,21 +395,9 @@ ffm_mcq_rollout_kernel(const McqParams P) {
         __syncthreads();
         n = n_new;
 
-        // ================= timeouts at the step cap (:284-285, :326-360) ========================
+        // ================= timeouts at the step cap (:284-285) ==================================
         if (tstep + 1 >= P.step_cap && n > 0) {
-            for (int i = tid; i < n; i += THREADS) {
-                const int c = (int)pos[i];
-                const int r = c / W, col = c - r * W;
-                const uint32_t sid = mcq_state(grid, r, col, H, W, P.nby);
-                const size_t at = pbase + (size_t)(tstep + 1) * pstride + orig[i];
-                P.path_state[at] = sid;
-                P.path_code[at] = (uint8_t)(4 | (RW_TIMEOUT << 4));
-                plen[orig[i]] = tstep + 2;
-            }
-            __syncthreads();
-            if (tid == 0 && learn)
-                for (int i = 0; i < n; ++i) mcq_backup(P, e, orig[i], tstep + 2);       // index order (:338)
-            __syncthreads();
+            finalize(tstep + 1);
             n = 0;                                                                      // everybody is cleared (:357-360)
         }
         if (P.traj != nullptr && tl < P.traj_steps) {
@@ -402,6 +407,10 @@ ffm_mcq_rollout_kernel(const McqParams P) {
         }
     }
 
+    if (P.force_finalize && n > 0 && t0 + tl <= P.step_cap) {
+        finalize(t0 + tl);
+        n = 0;
+    }
     for (int i = tid; i < n; i += THREADS) { gpos[i] = pos[i]; gcol[i] = orig[i]; }
     if (dffA != dff_home)
         for (int c = tid; c < HW; c += THREADS) dff_home[c] = dffA[c];

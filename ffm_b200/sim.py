@@ -421,6 +421,10 @@ class McqSim(BatchSim):
     def set_beta(self, beta):
         _abi.check(self._lib.ffm_set_beta(self._h, float(beta)))
 
+    def finalize_timeouts(self):
+        """finalize_timeouts() (ffm_learning_core.py:326-360) before the step cap."""
+        _abi.check(self._lib.ffm_mcq_finalize_timeouts(self._h, _stream()))
+
     def key_to_id(self, key):
         cells, (bx, by) = key
         return (int(bx) * self.nby + int(by)) * 4 ** 9 + sum(int(v) << (2 * k) for k, v in enumerate(bytes(cells)))

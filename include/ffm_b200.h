@@ -213,6 +213,7 @@ int ffm_q_shape(ffm_sim_t sim, int64_t *n_states);
 int ffm_q_get(ffm_sim_t sim, float *Q, uint8_t *seen, int space, void *stream);
 int ffm_q_set(ffm_sim_t sim, const float *Q, const uint8_t *seen, int space, void *stream);   /* model.Q = shared_Q, main_learning.py:81 */
 int ffm_set_beta(ffm_sim_t sim, double beta);   /* the beta argument of step(beta), ffm_learning_core.py:145 */
+int ffm_mcq_finalize_timeouts(ffm_sim_t sim, void *stream);   /* finalize_timeouts(), ffm_learning_core.py:326-360 */
 
 /* Static-floor-field generation for n_maps maps (uint8 [n_maps][H][W]) -> out [n_maps][H][W] of
  * out_dtype (FFM_F32 | FFM_F64), +inf on non-walkable and unreachable cells.

@@ -140,3 +140,45 @@ def test_trained_dropin_like_run_trained_ffm(cuda_device, tmp_path):
     steps = model.run(save_prefix=None, save_interval=100, max_steps=int(z["max_steps"]))
     assert steps == int(z["steps"])
     assert np.array_equal(model.dff.view(np.uint32), z["final_dff"].view(np.uint32))
+
+
+def test_mcq_dropin_like_main_learning(cuda_device, tmp_path):
+    """main_learning.py:60-106: a NEW model per episode, alpha / gamma assigned after construction, the Q dict handed
+    from episode to episode, finalize_timeouts() when the driver's own step limit hits first."""
+    from ffm_b200.model.ffm_learning_core import FloorFieldModel
+    from oracle import mcq_numpy
+
+    m = assets.room_map(12, 12)
+    sff = assets.sff_norm_min(m, "L1", np.float64)
+    p = os.path.join(tmp_path, "sff.npy")
+    np.save(p, sff)
+    params = {"max_steps": 500, "step_penalty": 0.01, "stop_penalty": 0.3, "collision_penalty": 0.7, "seed": 99}
+    o, shared_Q = None, {}
+    for ep, (beta, limit) in enumerate([(1.0, 0), (0.5, 30), (0.2, 0)]):
+        np.random.seed(100 + ep)
+        model = FloorFieldModel(m, p, 15, {**params, "episode": 10 * ep})
+        model.alpha, model.gamma = 0.2, 0.95
+        model.Q = shared_Q
+        model.reset()
+        pos0 = np.array(model.positions, dtype=np.int64)
+        if o is None:
+            o = mcq_numpy.McqOracle(m, sff, pos0, params, None, alpha=0.2, gamma=0.95)
+        o.reset(pos0)
+        o.source = PhiloxSource(99, 10 * ep + 1)                 # reset() advanced the episode key once
+        step = 0
+        while model.positions.shape[0] > 0 and (limit == 0 or step < limit):
+            model.step(beta)
+            o.step(beta)
+            step += 1
+            if o.min_margin >= MARGIN_GUARD:
+                assert np.array_equal(np.asarray(model.positions, dtype=np.int64).reshape(-1, 2), o.positions), (ep, step)
+        if model.positions.shape[0] > 0:
+            model.finalize_timeouts()
+            o.finalize_timeouts()
+        assert model.positions.shape[0] == 0
+        shared_Q = model.Q
+        want = o.q_dict()
+        if o.min_margin >= MARGIN_GUARD:
+            assert set(shared_Q) == set(want)
+            assert all(np.array_equal(shared_Q[k].view(np.uint32), want[k].view(np.uint32)) for k in want), ep
+    model.save_Q(os.path.join(tmp_path, "Q.pkl"))
