@@ -602,6 +602,8 @@ int ffm_rollout(ffm_sim_t s, int32_t max_steps, const ffm_draws_t* draws, const 
     if (draws && draws->space != FFM_DEVICE) return fail(FFM_E_INVALID, "recorded draws must live in device memory");
     cudaStream_t st = (cudaStream_t)stream;
     CU(cudaSetDevice(s->cfg.device));
+    // the opt-in shared-memory size is per-function state shared by all handles: re-assert ours before launching
+    CU(cudaFuncSetAttribute(s->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, s->smem_bytes));
     if (s->cfg.model == FFM_MODEL_MCQ) {
         ffm::McqParams M;
         memset(&M, 0, sizeof(M));

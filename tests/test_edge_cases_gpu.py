@@ -137,3 +137,20 @@ def test_unified_map_with_walls_coded_1(cuda_device):
         assert np.array_equal(cells[t, :cnt[t]], want[:, 0] * 14 + want[:, 1]), t
     V, vs, _, _ = sim.get_tables()
     assert np.array_equal(vs, o.v_seen) and np.array_equal(V.view(np.uint64), o.V.view(np.uint64))
+
+
+def test_handles_of_one_kernel_variant_with_different_shared_memory(cuda_device):
+    """The opt-in dynamic shared-memory size is per-function state: a later, smaller handle must not break an
+    earlier, larger one that runs the same kernel instantiation."""
+    from ffm_b200 import BatchSim
+    m = assets.room_map(40, 40)
+    sff = assets.sff_norm_min_fast(m, "Linf", np.float32)
+    rng = np.random.RandomState(0)
+    big = BatchSim(m, sff, 2, 1400, {"k_D": 0}, seed=1, track_dff=False)
+    small = BatchSim(m, sff, 2, 300, {"k_D": 0}, seed=1, track_dff=False)
+    assert big.kernel_info()["smem_bytes"] > small.kernel_info()["smem_bytes"]
+    assert big.kernel_info()["threads"] == small.kernel_info()["threads"]
+    for sim, N in ((big, 1400), (small, 300), (big, 1400)):
+        sim.set_positions(*pack_positions([random_positions(m, N, rng) for _ in range(2)], N))
+        sim.rollout(3000)
+        assert (sim.get_positions()[1] == 0).all()
