@@ -164,43 +164,84 @@ __global__ void collect_free_cells_kernel(const uint16_t* type_grid, int H, int 
     if (threadIdx.x == 0) *count = base;
 }
 
-// one CTA per episode: Philox key per eligible cell, bitonic sort of (key, ordinal) in shared memory, the
-// first n cells in key order become the pedestrians
+// one CTA per episode: the n cells with the smallest Philox keys, in key order.
+//   1. histogram of the keys' top 12 bits over all F eligible cells -> the bin b in which the n-th smallest key lies
+//   2. the cells of bins <= b (n .. n + |bin b| of them) are collected and bitonic-sorted by (key, ordinal) in
+//      shared memory -- ties by ordinal make it the stable argsort of the host placement
+//   3. the first n become the pedestrians, in key order
+// Works for any F (the keys are recomputed instead of stored); `cap` = capacity of the candidate buffer (power of 2).
 __global__ void __launch_bounds__(256)
 place_kernel(const uint32_t* cells, const int* count_ptr, const int32_t* n_req, uint32_t* pos, int32_t* n_out, int n_max,
-             unsigned long long seed, uint32_t episode_base, int npad) {
+             unsigned long long seed, uint32_t episode_base, int cap, int32_t* err) {
     extern __shared__ __align__(16) unsigned char sm[];
     unsigned long long* key = reinterpret_cast<unsigned long long*>(sm);
-    uint16_t* ord = reinterpret_cast<uint16_t*>(sm + (size_t)npad * 8);
-    const int e = blockIdx.x, F = *count_ptr;
+    uint32_t* ord = reinterpret_cast<uint32_t*>(sm + (size_t)cap * 8);
+    uint32_t* hist = reinterpret_cast<uint32_t*>(sm + (size_t)cap * 12);      // 4096 bins
+    __shared__ uint32_t part[256];
+    __shared__ int s_bin, s_m;
+    const int e = blockIdx.x, F = *count_ptr, tid = threadIdx.x, lane = tid & 31;
     const uint32_t episode = episode_base + (uint32_t)e;
-    for (int i = threadIdx.x; i < npad; i += blockDim.x) {
-        unsigned long long k = ~0ULL;
-        if (i < F) {
-            const uint4 o = philox4x32_10((uint32_t)i, 0u, episode, STREAM_PLACE, (uint32_t)seed, (uint32_t)(seed >> 32));
-            k = ((unsigned long long)(o.x >> 5) << 26) | (unsigned long long)(o.y >> 6);    // the 53 bits of u0: same order as the double
-        }
-        key[i] = k;
-        ord[i] = (uint16_t)i;
+    int n = n_req[e];
+    n = n < F ? n : F;                                                       // actual_N = min(N, available) (ffm_unified.py:160-162)
+    n = n < n_max ? n : n_max;
+    auto key_of = [&](int i) {
+        const uint4 o = philox4x32_10((uint32_t)i, 0u, episode, STREAM_PLACE, (uint32_t)seed, (uint32_t)(seed >> 32));
+        return ((unsigned long long)(o.x >> 5) << 26) | (unsigned long long)(o.y >> 6);     // the 53 bits of u0: same order as the double
+    };
+    for (int i = tid; i < 4096; i += 256) hist[i] = 0u;
+    if (tid == 0) { s_bin = 4095; s_m = 0; }
+    __syncthreads();
+    for (int i = tid; i < F; i += 256) atomicAdd(&hist[(uint32_t)(key_of(i) >> 41)], 1u);
+    __syncthreads();
+    // bin of the n-th smallest key: thread t sums bins [16t, 16t+16), then a serial scan over the 256 partial sums
+    uint32_t loc = 0;
+    for (int k = 0; k < 16; ++k) loc += hist[tid * 16 + k];
+    part[tid] = loc;
+    __syncthreads();
+    if (tid == 0 && n > 0) {
+        uint32_t cum = 0;
+        int t = 0;
+        while (t < 255 && cum + part[t] < (uint32_t)n) { cum += part[t]; ++t; }
+        int bb = t * 16;
+        while (bb < t * 16 + 15 && cum + hist[bb] < (uint32_t)n) { cum += hist[bb]; ++bb; }
+        s_bin = bb;
     }
     __syncthreads();
-    for (int size = 2; size <= npad; size <<= 1)
+    const uint32_t bsel = (uint32_t)s_bin;
+    for (int base = 0; base < F; base += 256) {
+        const int i = base + tid;
+        unsigned long long k = 0;
+        const bool take = n > 0 && i < F && (uint32_t)((k = key_of(i)) >> 41) <= bsel;
+        const uint32_t bal = __ballot_sync(0xffffffffu, take);
+        if (bal != 0u) {
+            int b0 = 0;
+            if (lane == 0) b0 = atomicAdd(&s_m, __popc(bal));
+            b0 = __shfl_sync(0xffffffffu, b0, 0);
+            const int at = b0 + __popc(bal & ((1u << lane) - 1u));
+            if (take && at < cap) { key[at] = k; ord[at] = (uint32_t)i; }
+        }
+    }
+    __syncthreads();
+    const int m = s_m;
+    if (m > cap) { if (tid == 0) atomicOr(err, 32); return; }                 // candidate buffer too small (practically unreachable)
+    int mpad = 2;
+    while (mpad < m) mpad <<= 1;
+    for (int i = m + tid; i < mpad; i += 256) { key[i] = ~0ULL; ord[i] = 0xFFFFFFFFu; }
+    __syncthreads();
+    for (int size = 2; size <= mpad; size <<= 1)
         for (int stride = size >> 1; stride > 0; stride >>= 1) {
-            for (int x = threadIdx.x; x < npad / 2; x += blockDim.x) {
+            for (int x = tid; x < mpad / 2; x += 256) {
                 const int i = 2 * x - (x & (stride - 1)), j = i + stride;
                 const bool up = (i & size) == 0;
                 const unsigned long long ki = key[i], kj = key[j];
-                const uint16_t oi = ord[i], oj = ord[j];
-                const bool gt = ki > kj || (ki == kj && oi > oj);          // ties by ordinal: a stable argsort
+                const uint32_t oi = ord[i], oj = ord[j];
+                const bool gt = ki > kj || (ki == kj && oi > oj);             // ties by ordinal: a stable argsort
                 if (gt == up) { key[i] = kj; key[j] = ki; ord[i] = oj; ord[j] = oi; }
             }
             __syncthreads();
         }
-    int n = n_req[e];
-    n = n < F ? n : F;                                                       // actual_N = min(N, available) (ffm_unified.py:160-162)
-    n = n < n_max ? n : n_max;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) pos[(size_t)e * n_max + i] = cells[ord[i]];
-    if (threadIdx.x == 0) n_out[e] = n;
+    for (int i = tid; i < n; i += 256) pos[(size_t)e * n_max + i] = cells[ord[i]];
+    if (tid == 0) n_out[e] = n;
 }
 
 __global__ void unpack_positions_kernel(const uint32_t* pos, const int32_t* n, int32_t* pos_rc, int B, int n_max, int W) {
@@ -276,6 +317,7 @@ int check_device_flag(ffm_sim_t s, cudaStream_t st) {
     if (flag & 4) return fail(FFM_E_INVALID, "pedestrian count outside [0, n_max]");
     if (flag & 8) return fail(FFM_E_INVALID, "pedestrian position outside the map");
     if (flag & 16) return fail(FFM_E_INVALID, "pedestrian placed on a cell that is not free (map != 0)");
+    if (flag & 32) return fail(FFM_E_UNSUPPORTED, "device placement: candidate buffer overflow");
     return fail(FFM_E_INVALID, "device validation flag %d", flag);
 }
 
@@ -518,16 +560,20 @@ int ffm_place(ffm_sim_t s, const int32_t* n, int32_t exit_row, int32_t exit_col,
         for (int e = 0; e < B; ++e)
             if (n[e] > s->place_count || n[e] > N)    // np.random.choice(len(free), N, replace=False) raises (ffm_core.py:25)
                 return fail(FFM_E_INVALID, "Cannot take a larger sample than population when 'replace=False' (%d pedestrians, %d free cells, capacity %d)", n[e], s->place_count, N);
+    int nmax_req = 0;
+    for (int e = 0; e < B; ++e) nmax_req = n[e] > nmax_req ? n[e] : nmax_req;
+    nmax_req = nmax_req < N ? nmax_req : N;
+    const int want = (s->place_count < nmax_req + 2048 ? s->place_count : nmax_req + 2048);   // n .. n + |threshold bin| candidates
     int npad = 2;
-    while (npad < s->place_count) npad <<= 1;
-    if (npad > 16384) return fail(FFM_E_UNSUPPORTED, "%d eligible cells: device placement sorts at most 16384 per episode", s->place_count);
-    const size_t smem = (size_t)npad * 10;
+    while (npad < want) npad <<= 1;
+    if (npad > 16384) npad = 16384;
+    const size_t smem = (size_t)npad * 12 + 4096 * 4;
     CU(cudaFuncSetAttribute(ffm::place_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CU(cudaMemcpyAsync(s->d_n_req, n, (size_t)B * 4, cudaMemcpyHostToDevice, st));
     CU(cudaMemsetAsync(s->d_t, 0, (size_t)B * 4, st));
     CU(cudaMemsetAsync(s->d_ped_steps, 0, (size_t)B * 8, st));
     if (s->d_dff) CU(cudaMemsetAsync(s->d_dff, 0, (size_t)B * s->HW * 4, st));
-    ffm::place_kernel<<<B, 256, smem, st>>>(s->d_free, s->d_free_count, s->d_n_req, s->d_pos, s->d_n, N, s->cfg.seed, s->cfg.episode_base, npad);
+    ffm::place_kernel<<<B, 256, smem, st>>>(s->d_free, s->d_free_count, s->d_n_req, s->d_pos, s->d_n, N, s->cfg.seed, s->cfg.episode_base, npad, s->d_err);
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(st));      // n[] is a host buffer of the caller
     s->launches++;

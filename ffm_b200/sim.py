@@ -124,21 +124,11 @@ class BatchSim:
     def place(self, n, exit_pos=None, radius=None):
         """Device-side initialize_agents(): n[e] pedestrians per episode on distinct free cells, uniformly without
         replacement (optionally within L1 `radius` of `exit_pos`, count clamped like ffm_unified.py:160-162),
-        keyed by the global episode id.  Resets DFF and counters.  Falls back to the host placement
-        (ffm_b200.workloads.place, same keys, same result) when the map has more than 16384 eligible cells."""
+        keyed by the global episode id.  Resets DFF and counters."""
         n = np.ascontiguousarray(np.broadcast_to(np.asarray(n, dtype=np.int32), (self.B,)))
         er, ec, rad = (-1, -1, -1) if exit_pos is None or radius is None else (int(exit_pos[0]), int(exit_pos[1]), int(radius))
-        rc = self._lib.ffm_place(self._h, _ptr(n), er, ec, rad, _stream())
-        if rc == _abi.E_UNSUPPORTED and rad < 0:
-            from . import workloads
-            if len(set(n.tolist())) != 1:
-                raise _abi.FfmError(rc, "host placement fallback needs equal counts")
-            cfg_seed, base = self._seed_base
-            pos = workloads.place(self.map_array, int(n[0]), self.B, base, cfg_seed)
-            buf = np.full((self.B, self.n_max, 2), -1, np.int32)
-            buf[:, :int(n[0])] = pos
-            return self.set_positions(buf, n)
-        _abi.check(rc)
+        _abi.check(self._lib.ffm_place(self._h, _ptr(n), er, ec, rad, _stream()))
+        self._lib.ffm_get_positions(self._h, None, None, _abi.FFM_HOST, _stream())   # surfaces device-side errors
 
     def get_positions(self):
         """-> (pos_rc int32 [B, n_max, 2] with -1 padding, n int32 [B]) as NumPy arrays."""

@@ -155,8 +155,8 @@ int ffm_set_positions(ffm_sim_t sim, const int32_t *pos_rc, const int32_t *n, in
  * <= radius, and n clamped to their number, :160-162) drawn uniformly without replacement -- the cells with the
  * n smallest Philox keys (stream PLACE, entity = ordinal of the cell among the eligible cells in row-major
  * order, keyed by the GLOBAL episode id), in key order.  Replaces ffm_set_positions for batched runs; zeroes
- * the DFF and the counters.  n: int32 [B] host array.  FFM_E_UNSUPPORTED when the eligible cells exceed 16384
- * (the per-episode sort runs in one SM's shared memory). */
+ * the DFF and the counters.  n: int32 [B] host array.  Any map size: a histogram of the keys selects the n + few
+ * smallest, which are then sorted in one SM's shared memory. */
 int ffm_place(ffm_sim_t sim, const int32_t *n, int32_t exit_row, int32_t exit_col, int32_t radius, void *stream);
 /* `.positions` read (main.py:44,46) */
 int ffm_get_positions(ffm_sim_t sim, int32_t *pos_rc, int32_t *n, int space, void *stream);
