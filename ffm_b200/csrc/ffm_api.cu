@@ -459,7 +459,7 @@ int ffm_create(const ffm_config_t* cfg, ffm_sim_t* out) {
     ALLOC(s->d_n_req, (size_t)B * 4);
     s->place_radius = -2;
     if (dff) {
-        // one allocation for both DFF buffers so that a single L2 access-policy window can cover them
+        // both DFF buffers in one allocation
         const bool two = !s->fields_in_smem || mcq;
         ALLOC(s->d_dff, (size_t)B * HW * 4 * (two ? 2 : 1));
         if (two) s->d_dff_tmp = s->d_dff + (size_t)B * HW;
@@ -649,25 +649,6 @@ int ffm_rollout(ffm_sim_t s, int32_t max_steps, const ffm_draws_t* draws, const 
     if (draws && draws->space != FFM_DEVICE) return fail(FFM_E_INVALID, "recorded draws must live in device memory");
     cudaStream_t st = (cudaStream_t)stream;
     CU(cudaSetDevice(s->cfg.device));
-    if (s->d_dff_tmp && getenv("FFM_L2_PERSIST")) {
-        // experiment: keep the DFF ping-pong buffers (the per-step working set when the fields live in global
-        // memory) resident in L2
-        static bool limit_set = false;
-        int maxp = 0, maxw = 0;
-        cudaDeviceGetAttribute(&maxp, cudaDevAttrMaxPersistingL2CacheSize, s->cfg.device);
-        cudaDeviceGetAttribute(&maxw, cudaDevAttrMaxAccessPolicyWindowSize, s->cfg.device);
-        if (!limit_set) { cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)maxp); limit_set = true; }
-        cudaStreamAttrValue av;
-        memset(&av, 0, sizeof(av));
-        size_t bytes = (size_t)s->cfg.n_episodes * s->HW * 8;
-        if (bytes > (size_t)maxw) bytes = (size_t)maxw;
-        av.accessPolicyWindow.base_ptr = s->d_dff;
-        av.accessPolicyWindow.num_bytes = bytes;
-        av.accessPolicyWindow.hitRatio = bytes <= (size_t)maxp ? 1.0f : (float)maxp / (float)bytes;
-        av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-        av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-        cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &av);
-    }
     // the opt-in shared-memory size is per-function state shared by all handles: re-assert ours before launching
     CU(cudaFuncSetAttribute(s->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, s->smem_bytes));
     if (s->cfg.model == FFM_MODEL_MCQ) {
