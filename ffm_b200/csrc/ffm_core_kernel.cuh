@@ -127,10 +127,6 @@ template <> __device__ __forceinline__ int nbr_off_rt<4>(int k, int W) {
     return dr * W + dc;
 }
 
-// exact cdf comparison for a draw that lands within 1e-15 of a boundary (practically never taken;
-// kept out of line so the division sequence stays off the hot path)
-__device__ __noinline__ bool cdf_le_exact(double run, double tot, double u) { return __ddiv_rn(run, tot) <= u; }
-
 __device__ __forceinline__ uint32_t lanemask_lt() {
     uint32_t m;
     asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));

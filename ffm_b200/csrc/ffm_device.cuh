@@ -2,10 +2,8 @@
 //
 //  * Philox4x32-10 counter-based draws (Salmon et al., SC'11) keyed (entity, step, episode, stream)
 //    -- the replacement for the reference's process-global generators (model/ffm_core.py:84,95,96).
-//  * IEEE helpers that pin NumPy's evaluation order: separate multiply and add (no FMA
-//    contraction), NumPy's pairwise float sum for n <= 9 (numpy/_core/src/umath/loops_utils.h.src
-//    pairwise_sum: n < 8 sequential; 8 <= n: 8 accumulators folded ((0+1)+(2+3))+((4+5)+(6+7)),
-//    remainder added sequentially).
+//  * IEEE helpers that pin NumPy's evaluation order: separate multiply and add (no FMA contraction).
+//  * TMA bulk-copy / mbarrier wrappers (inline PTX).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -98,31 +96,5 @@ __device__ __forceinline__ double max_t(double a, double b) { return fmax(a, b);
 template <typename S> __device__ __forceinline__ S neg_inf();
 template <> __device__ __forceinline__ float  neg_inf<float>()  { return -__int_as_float(0x7f800000); }
 template <> __device__ __forceinline__ double neg_inf<double>() { return -__longlong_as_double(0x7ff0000000000000LL); }
-
-// NumPy add.reduce over the COMPACTED candidate list (entries of p whose bit is set in mask, in
-// slot order; slot NS-1 = "stay" is always present).  n = popcount(mask) <= 9.
-template <typename S, int NS>
-__device__ __forceinline__ S np_sum_masked(const S (&p)[NS], uint32_t mask, int n) {
-    if (NS == 9 && n >= 8) {
-        S a[8];
-        if (n == 9) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) a[j] = p[j];
-        } else {
-            const int miss = __ffs(~mask & 0xFFu) - 1;   // the one absent neighbour slot
-#pragma unroll
-            for (int j = 0; j < 8; ++j) a[j] = (j < miss) ? p[j] : p[(j + 1 < NS) ? j + 1 : NS - 1];
-        }
-        S r = add_rn(add_rn(add_rn(a[0], a[1]), add_rn(a[2], a[3])),
-                     add_rn(add_rn(a[4], a[5]), add_rn(a[6], a[7])));
-        if (n == 9) r = add_rn(r, p[NS - 1]);
-        return r;
-    }
-    S r = (S)0;
-#pragma unroll
-    for (int k = 0; k < NS; ++k)
-        if ((mask >> k) & 1u) r = add_rn(r, p[k]);
-    return r;
-}
 
 }  // namespace ffm

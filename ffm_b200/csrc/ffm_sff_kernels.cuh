@@ -118,7 +118,6 @@ sff_relax_tile_kernel(const uint8_t* __restrict__ maps, float* __restrict__ dist
     // 256 threads x 4 cells; in-place (Gauss-Seidel style) min-relaxation: a concurrently updated
     // neighbour is read as either its old or its new value, both valid upper bounds of the fixpoint
     volatile float (*vd)[P + 1] = d;
-    bool any_change = false;
     for (int it = 0; it < 4 * T * T; ++it) {
         bool ch = false;
 #pragma unroll
@@ -142,9 +141,7 @@ sff_relax_tile_kernel(const uint8_t* __restrict__ maps, float* __restrict__ dist
             if (best < old) { vd[a][b] = best; ch = true; }
         }
         if (!__syncthreads_or(ch ? 1 : 0)) break;
-        any_change = true;
     }
-    (void)any_change;
     // write back; detect rim changes to wake the neighbours
     for (int x = threadIdx.x; x < T * T; x += blockDim.x) {
         const int lr = x / T, lc = x - lr * T;
