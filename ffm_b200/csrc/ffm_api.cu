@@ -903,6 +903,17 @@ int ffm_sff_generate(const uint8_t* maps, int32_t n_maps, int32_t H, int32_t W, 
     if (out_dtype != FFM_F32 && out_dtype != FFM_F64) return fail(FFM_E_INVALID, "out_dtype must be FFM_F32 or FFM_F64");
     cudaStream_t st = (cudaStream_t)stream;
     CU(cudaSetDevice(device));
+    {   // scratch comes from the stream-ordered pool; keep freed blocks cached so repeated calls do not hit the OS allocator
+        static bool pool_ready[64] = {};
+        if (device < 64 && !pool_ready[device]) {
+            cudaMemPool_t pool;
+            if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+                unsigned long long keep = ~0ULL;
+                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+            }
+            pool_ready[device] = true;
+        }
+    }
     const size_t HW = (size_t)H * W, total = HW * n_maps;
     const size_t osz = out_dtype == FFM_F64 ? 8 : 4;
     uint8_t* d_maps = nullptr; void* d_out = nullptr; float* d_dist = nullptr; uint8_t* d_dirty = nullptr;
@@ -916,17 +927,17 @@ int ffm_sff_generate(const uint8_t* maps, int32_t n_maps, int32_t H, int32_t W, 
     {
         const uint8_t* mp = maps;
         if (space == FFM_HOST) {
-            SFF_CU(cudaMalloc((void**)&d_maps, total));
+            SFF_CU(cudaMallocAsync((void**)&d_maps, total, st));
             SFF_CU(cudaMemcpyAsync(d_maps, maps, total, cudaMemcpyHostToDevice, st));
             mp = d_maps;
-            SFF_CU(cudaMalloc(&d_out, total * osz));
+            SFF_CU(cudaMallocAsync(&d_out, total * osz, st));
         } else {
             d_out = out;
         }
         const int bx = (int)((HW + 255) / 256 < 148 * 8 ? (HW + 255) / 256 : 148 * 8);
         if (mode <= FFM_SFF_LINF) {
-            SFF_CU(cudaMalloc((void**)&d_exits, (size_t)n_maps * ffm::SFF_MAX_EXITS * 2 * sizeof(int32_t)));
-            SFF_CU(cudaMalloc((void**)&d_counts, (size_t)n_maps * sizeof(int32_t)));
+            SFF_CU(cudaMallocAsync((void**)&d_exits, (size_t)n_maps * ffm::SFF_MAX_EXITS * 2 * sizeof(int32_t), st));
+            SFF_CU(cudaMallocAsync((void**)&d_counts, (size_t)n_maps * sizeof(int32_t), st));
             SFF_CU(cudaMemsetAsync(d_counts, 0, (size_t)n_maps * sizeof(int32_t), st));
             ffm::sff_collect_exits_kernel<<<dim3(bx, n_maps), 256, 0, st>>>(mp, d_exits, d_counts, H, W);
             if (out_dtype == FFM_F64)
@@ -943,9 +954,9 @@ int ffm_sff_generate(const uint8_t* maps, int32_t n_maps, int32_t H, int32_t W, 
             const int tiles_x = (W + ffm::SFF_TILE - 1) / ffm::SFF_TILE, tiles_y = (H + ffm::SFF_TILE - 1) / ffm::SFF_TILE;
             const size_t ntiles = (size_t)tiles_x * tiles_y * n_maps;
             if (tiles_y > 65535 || n_maps > 65535) { rc = fail(FFM_E_UNSUPPORTED, "too many tiles / maps for one launch"); goto done; }
-            SFF_CU(cudaMalloc((void**)&d_dist, total * sizeof(float)));
-            SFF_CU(cudaMalloc((void**)&d_dirty, 2 * ntiles));
-            SFF_CU(cudaMalloc((void**)&d_any, sizeof(int)));
+            SFF_CU(cudaMallocAsync((void**)&d_dist, total * sizeof(float), st));
+            SFF_CU(cudaMallocAsync((void**)&d_dirty, 2 * ntiles, st));
+            SFF_CU(cudaMallocAsync((void**)&d_any, sizeof(int), st));
             SFF_CU(cudaMemsetAsync(d_dirty, 0, 2 * ntiles, st));
             ffm::sff_relax_init_kernel<<<dim3(bx, n_maps), 256, 0, st>>>(mp, d_dist, d_dirty, H, W, tiles_x, tiles_y);
             const float INF = __builtin_huge_valf();
@@ -975,8 +986,12 @@ int ffm_sff_generate(const uint8_t* maps, int32_t n_maps, int32_t H, int32_t W, 
     }
 done:
 #undef SFF_CU
-    if (space == FFM_HOST) { cudaFree(d_maps); cudaFree(d_out); }
-    cudaFree(d_dist); cudaFree(d_dirty); cudaFree(d_exits); cudaFree(d_counts); cudaFree(d_any);
+    if (space == FFM_HOST) { if (d_maps) cudaFreeAsync(d_maps, st); if (d_out) cudaFreeAsync(d_out, st); }
+    if (d_dist) cudaFreeAsync(d_dist, st);
+    if (d_dirty) cudaFreeAsync(d_dirty, st);
+    if (d_exits) cudaFreeAsync(d_exits, st);
+    if (d_counts) cudaFreeAsync(d_counts, st);
+    if (d_any) cudaFreeAsync(d_any, st);
     if (rounds_out) *rounds_out = rounds;
     return rc;
 }
