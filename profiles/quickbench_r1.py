@@ -1,11 +1,11 @@
 import sys, time
 sys.path.insert(0, '.')
 import numpy as np, torch
-from oracle import assets
+from ffm_b200 import workloads
 from ffm_b200 import BatchSim
 B, N = int(sys.argv[1]) if len(sys.argv) > 1 else 1024, 1024
-m = assets.room_map(64, 64)
-sff = assets.sff_norm_min(m, "Linf", np.float32)
+m = workloads.room_map(64, 64)
+sff = workloads.sff_room(m, "moore")
 rng = np.random.RandomState(0)
 free = np.argwhere(m == 0)
 pos = np.stack([free[rng.permutation(len(free))[:N]] for _ in range(B)]).astype(np.int32)
