@@ -970,11 +970,11 @@ int ffm_sff_generate(const uint8_t* maps, int32_t n_maps, int32_t H, int32_t W, 
             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ffm::sff_relax_persistent_kernel, 256, 0);
             bool done_coop = false;
             if (coop && occ > 0 && !getenv("FFM_SFF_HOST_LOOP")) {
-                SFF_CU(cudaMallocAsync((void**)&d_any2, 4 * sizeof(int), st));
-                SFF_CU(cudaMemsetAsync(d_any2, 0, 4 * sizeof(int), st));
+                SFF_CU(cudaMallocAsync((void**)&d_any2, 3 * sizeof(int), st));
+                SFF_CU(cudaMemsetAsync(d_any2, 0, 3 * sizeof(int), st));
                 size_t want = ntiles < (size_t)occ * sms ? ntiles : (size_t)occ * sms;
                 int gridc = (int)(want < 1 ? 1 : want);
-                int* any_ptr = d_any2; int* rounds_ptr = d_any2 + 3;
+                int* any_ptr = d_any2; int* rounds_ptr = d_any2 + 2;
                 int Hh = H, Ww = W, txs = tiles_x, tys = tiles_y, nm = n_maps, mr = max_rounds;
                 float wa = w_axis, wd = w_diag;
                 void* args[] = {(void*)&mp, (void*)&d_dist, (void*)&d_dirty, (void*)&any_ptr, (void*)&rounds_ptr, &Hh, &Ww, &txs, &tys, &nm, &wa, &wd, &mr};

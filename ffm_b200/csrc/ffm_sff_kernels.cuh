@@ -188,7 +188,7 @@ sff_relax_tile_kernel(const uint8_t* __restrict__ maps, float* __restrict__ dist
 // grid-wide barriers separate the rounds, and the loop ends when a round wakes nobody -- no host round trips.
 __global__ void __launch_bounds__(256)
 sff_relax_persistent_kernel(const uint8_t* __restrict__ maps, float* __restrict__ dist, uint8_t* dirty /*[2][ntiles]*/,
-                            int* any /*[3]*/, int* rounds_out, int H, int W, int tiles_x, int tiles_y, int n_maps,
+                            int* any /*[2]*/, int* rounds_out, int H, int W, int tiles_x, int tiles_y, int n_maps,
                             float w_axis, float w_diag, int max_rounds) {
     cooperative_groups::grid_group grid = cooperative_groups::this_grid();
     const size_t ntiles = (size_t)tiles_x * tiles_y * n_maps;
@@ -197,22 +197,19 @@ sff_relax_persistent_kernel(const uint8_t* __restrict__ maps, float* __restrict_
     for (;;) {
         uint8_t* din = dirty + (size_t)cur * ntiles;
         uint8_t* dout = dirty + (size_t)(cur ^ 1) * ntiles;
-        // three rotating flags: round r raises any[r % 3] and clears any[(r + 1) % 3] for the next round; the flag
-        // everybody reads after the round is therefore not touched again until two barriers later
-        int* flag = &any[rounds % 3];
         for (size_t i = gtid; i < ntiles; i += gsize) dout[i] = 0;
-        if (gtid == 0) any[(rounds + 1) % 3] = 0;
+        if (gtid == 0) any[cur ^ 1] = 0;                 // the flag the NEXT round raises; any[cur] is this round's
         grid.sync();
         for (size_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             if (!__ldcg(&din[tile])) continue;            // block-uniform; L2 read: other CTAs wrote it last round
             const int mapi = (int)(tile / ((size_t)tiles_x * tiles_y));
             const int rem = (int)(tile - (size_t)mapi * tiles_x * tiles_y);
-            sff_relax_tile(maps, dist, dout, flag, H, W, tiles_x, tiles_y, rem % tiles_x, rem / tiles_x, mapi, w_axis, w_diag);
+            sff_relax_tile(maps, dist, dout, &any[cur], H, W, tiles_x, tiles_y, rem % tiles_x, rem / tiles_x, mapi, w_axis, w_diag);
         }
         __threadfence();
         grid.sync();
         ++rounds;
-        const int more = *((volatile int*)flag);
+        const int more = *((volatile int*)&any[cur]);
         if (!more || rounds >= max_rounds) break;
         cur ^= 1;
     }
