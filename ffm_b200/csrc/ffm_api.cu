@@ -917,7 +917,7 @@ int ffm_sff_generate(const uint8_t* maps, int32_t n_maps, int32_t H, int32_t W, 
     const size_t HW = (size_t)H * W, total = HW * n_maps;
     const size_t osz = out_dtype == FFM_F64 ? 8 : 4;
     uint8_t* d_maps = nullptr; void* d_out = nullptr; float* d_dist = nullptr; uint8_t* d_dirty = nullptr;
-    int32_t* d_exits = nullptr; int32_t* d_counts = nullptr; int* d_any = nullptr; int* d_any2 = nullptr;
+    int32_t* d_exits = nullptr; int32_t* d_counts = nullptr; int* d_any = nullptr;
     int rc = FFM_OK, rounds = 0;
 #define SFF_CU(call)                                                                        \
     do {                                                                                    \
@@ -962,34 +962,8 @@ int ffm_sff_generate(const uint8_t* maps, int32_t n_maps, int32_t H, int32_t W, 
             const float INF = __builtin_huge_valf();
             const float w_axis = 1.0f;
             const float w_diag = mode == FFM_SFF_BFS4 ? INF : (mode == FFM_SFF_BFS8 ? 1.0f : (float)1.4142135623730951);
-            const int max_rounds = 4 * (tiles_x + tiles_y) * ffm::SFF_TILE;
-            // preferred: all rounds in one cooperative launch (grid-wide barriers instead of host round trips)
-            int coop = 0, sms = 0, occ = 0;
-            cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device);
-            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ffm::sff_relax_persistent_kernel, 256, 0);
-            bool done_coop = false;
-            if (coop && occ > 0 && !getenv("FFM_SFF_HOST_LOOP")) {
-                SFF_CU(cudaMallocAsync((void**)&d_any2, 3 * sizeof(int), st));
-                SFF_CU(cudaMemsetAsync(d_any2, 0, 3 * sizeof(int), st));
-                size_t want = ntiles < (size_t)occ * sms ? ntiles : (size_t)occ * sms;
-                int gridc = (int)(want < 1 ? 1 : want);
-                int* any_ptr = d_any2; int* rounds_ptr = d_any2 + 2;
-                int Hh = H, Ww = W, txs = tiles_x, tys = tiles_y, nm = n_maps, mr = max_rounds;
-                float wa = w_axis, wd = w_diag;
-                void* args[] = {(void*)&mp, (void*)&d_dist, (void*)&d_dirty, (void*)&any_ptr, (void*)&rounds_ptr, &Hh, &Ww, &txs, &tys, &nm, &wa, &wd, &mr};
-                cudaError_t le = cudaLaunchCooperativeKernel((const void*)ffm::sff_relax_persistent_kernel, dim3(gridc), dim3(256), args, 0, st);
-                if (le == cudaSuccess) {
-                    SFF_CU(cudaMemcpyAsync(&rounds, rounds_ptr, sizeof(int), cudaMemcpyDeviceToHost, st));
-                    SFF_CU(cudaStreamSynchronize(st));
-                    if (rounds >= max_rounds) { rc = fail(FFM_E_CUDA, "SFF relaxation did not converge"); goto done; }
-                    done_coop = true;
-                } else {
-                    cudaGetLastError();     // clear; fall back to the host loop
-                }
-            }
             uint8_t* din = d_dirty; uint8_t* dout = d_dirty + ntiles;
-            while (!done_coop) {
+            for (;;) {
                 int any = 0;
                 SFF_CU(cudaMemsetAsync(d_any, 0, sizeof(int), st));
                 SFF_CU(cudaMemsetAsync(dout, 0, ntiles, st));
@@ -1000,7 +974,7 @@ int ffm_sff_generate(const uint8_t* maps, int32_t n_maps, int32_t H, int32_t W, 
                 SFF_CU(cudaStreamSynchronize(st));
                 if (!any) break;
                 uint8_t* t = din; din = dout; dout = t;
-                if (rounds > max_rounds) { rc = fail(FFM_E_CUDA, "SFF relaxation did not converge"); goto done; }
+                if (rounds > 4 * (tiles_x + tiles_y) * ffm::SFF_TILE) { rc = fail(FFM_E_CUDA, "SFF relaxation did not converge"); goto done; }
             }
             const int cb = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
             if (out_dtype == FFM_F64) ffm::sff_convert_kernel<double><<<cb, 256, 0, st>>>(d_dist, (double*)d_out, total);
@@ -1018,7 +992,6 @@ done:
     if (d_exits) cudaFreeAsync(d_exits, st);
     if (d_counts) cudaFreeAsync(d_counts, st);
     if (d_any) cudaFreeAsync(d_any, st);
-    if (d_any2) cudaFreeAsync(d_any2, st);
     if (rounds_out) *rounds_out = rounds;
     return rc;
 }
