@@ -80,7 +80,7 @@ struct RolloutParams {
 };
 
 struct SmemLayout {
-    uint32_t score, dffA, dffB, grid, claim, pos, tgt, list, alive, wpre, ctr, bar, nz, total;
+    uint32_t score, dffA, dffB, grid, claim, pos, tgt, list, alive, wpre, ctr, bar, total;
 };
 
 __host__ __device__ inline uint32_t align16(uint32_t x) { return (x + 15u) & ~15u; }
@@ -103,7 +103,6 @@ __host__ __device__ inline SmemLayout make_layout(int HW, int W, int n_max, int 
     L.wpre = o;  o = align16(o + nw * 4u);
     L.ctr = o;   o = align16(o + 8u * 4u);
     L.bar = o;   o = align16(o + 8u);
-    L.nz = o;    if (dff) o = align16(o + 2u * (uint32_t)((HW + 511) / 512 + 64));   // 2 x tile flags (16 x 32 tiles)
     L.total = o;
     return L;
 }
@@ -236,95 +235,6 @@ __device__ __forceinline__ void dff_decay_diffuse(const float* __restrict__ in, 
     }
 }
 
-// Sparse variant for maps whose width is a multiple of 32 and whose row bands are multiples of 16 rows: the field
-// is cut into 16-row x 32-column tiles with a "holds a non-zero" flag per tile and buffer.  A warp owns a column
-// block; a tile whose 3x3 tile neighbourhood is all-zero in the input can only produce zeros (every term is an exact
-// 0), so it is skipped -- it is zero-filled only if the output buffer still holds something there.  Flags are
-// conservative supersets (a flag may be set on an all-zero tile, never the reverse), so the result is bit-identical.
-constexpr int DFF_TR = 16;   // tile rows
-__device__ __forceinline__ bool dff_sparse_ok(int H, int W, int nthreads) {
-    if (W % 32 != 0 || nthreads % 32 != 0 || H % DFF_TR != 0) return false;
-    const int bands = W < nthreads ? nthreads / W : 1;
-    const int rpb = (H + bands - 1) / bands;
-    return rpb % DFF_TR == 0;
-}
-
-template <int NBR>
-__device__ __forceinline__ void dff_decay_diffuse_sparse(const float* __restrict__ in, float* __restrict__ out,
-                                                         const uint8_t* __restrict__ nz_in, uint8_t* __restrict__ nz_out,
-                                                         int H, int W, float c0, float c1, float thr, int tid, int nthreads) {
-    const int cw = W < nthreads ? W : nthreads;
-    const int bands = W < nthreads ? nthreads / W : 1;
-    const int rpb = (H + bands - 1) / bands;
-    const int band = tid / cw, colb = tid - band * cw;
-    if (band >= bands) return;                              // warp-uniform (cw is a multiple of 32)
-    const int r0 = band * rpb, r1 = min(H, r0 + rpb);
-    const int tiles_x = W / 32, tiles_y = H / DFF_TR;
-    const int lane = tid & 31;
-    for (int col = colb; col < W; col += cw) {
-        const int tx = col >> 5;
-        const bool hasl = col > 0, hasr = col + 1 < W;
-        for (int rt = r0; rt < r1; rt += DFF_TR) {
-            const int ty = rt / DFF_TR;
-            bool need = false;
-#pragma unroll
-            for (int dy = -1; dy <= 1; ++dy)
-#pragma unroll
-                for (int dx = -1; dx <= 1; ++dx) {
-                    const int yy = ty + dy, xx = tx + dx;
-                    if (yy >= 0 && yy < tiles_y && xx >= 0 && xx < tiles_x) need |= nz_in[yy * tiles_x + xx] != 0;
-                }
-            if (!need) {
-                if (nz_out[ty * tiles_x + tx]) {             // stale non-zeros in the buffer we are about to publish
-#pragma unroll 4
-                    for (int r = rt; r < rt + DFF_TR; ++r) out[(size_t)r * W + col] = 0.0f;
-                    __syncwarp();
-                    if (lane == 0) nz_out[ty * tiles_x + tx] = 0;
-                }
-                continue;
-            }
-            float up[3], uc[3], un[3], sc = 0.0f;
-            auto load_row = [&](int r, float (&u)[3], float& s_centre) {
-                float d0 = 0.0f, d1 = 0.0f, d2 = 0.0f;
-                if (r >= 0 && r < H) {
-                    const float* row = in + (size_t)r * W + col;
-                    d1 = row[0];
-                    if (hasl) d0 = row[-1];
-                    if (hasr) d2 = row[1];
-                }
-                const float s0 = __fmul_rn(c0, d0), s1 = __fmul_rn(c0, d1), s2 = __fmul_rn(c0, d2);   // (:109)
-                u[0] = __fmul_rn(c1, s0); u[1] = __fmul_rn(c1, s1); u[2] = __fmul_rn(c1, s2);         // (:113)
-                s_centre = s1;
-            };
-            float dummy;
-            load_row(rt - 1, up, dummy);
-            load_row(rt, uc, sc);
-            bool any = false;
-            for (int r = rt; r < rt + DFF_TR; ++r) {
-                float sn;
-                load_row(r + 1, un, sn);
-                float acc = sc;
-                if (NBR == 8) {
-                    acc = __fadd_rn(acc, up[0]); acc = __fadd_rn(acc, up[1]); acc = __fadd_rn(acc, up[2]);
-                    acc = __fadd_rn(acc, uc[0]); acc = __fadd_rn(acc, uc[2]);
-                    acc = __fadd_rn(acc, un[0]); acc = __fadd_rn(acc, un[1]); acc = __fadd_rn(acc, un[2]);
-                } else {
-                    acc = __fadd_rn(acc, up[1]); acc = __fadd_rn(acc, un[1]);
-                    acc = __fadd_rn(acc, uc[0]); acc = __fadd_rn(acc, uc[2]);
-                }
-                if (acc < thr) acc = 0.0f;                                                            // (:116-117)
-                out[(size_t)r * W + col] = acc;
-                any |= acc != 0.0f;
-#pragma unroll
-                for (int k = 0; k < 3; ++k) { up[k] = uc[k]; uc[k] = un[k]; }
-                sc = sn;
-            }
-            const bool tile_any = __any_sync(0xffffffffu, any);
-            if (lane == 0) nz_out[ty * tiles_x + tx] = tile_any ? 1 : 0;
-        }
-    }
-}
-
 template <typename S, typename PosT, int NBR, bool DFF, bool FIELDS_IN_SMEM, int THREADS>
 __global__ void __launch_bounds__(THREADS, (THREADS <= 256 && sizeof(S) == 4) ? 1536 / THREADS : 1)
 ffm_core_rollout_kernel(const RolloutParams P) {
@@ -346,11 +256,6 @@ ffm_core_rollout_kernel(const RolloutParams P) {
     uint32_t* alive = reinterpret_cast<uint32_t*>(smem_raw + L.alive);
     uint32_t* wpre = reinterpret_cast<uint32_t*>(smem_raw + L.wpre);
     uint32_t* ctr = reinterpret_cast<uint32_t*>(smem_raw + L.ctr);   // [parity][n_work, n_req, n_exit, -]
-    // DFF tile flags (sparse stencil): one byte per 16 x 32 tile and buffer
-    const bool sparse = DFF && dff_sparse_ok(H, W, THREADS);
-    const int nz_cap = (HW + 511) / 512 + 64, nz_tx = W / 32;
-    uint8_t* nzA = smem_raw + L.nz;
-    uint8_t* nzB = nzA + nz_cap;
     uint32_t* claim32 = reinterpret_cast<uint32_t*>(smem_raw + L.claim);
     const int claim_words = (HW + 7) / 8;
 
@@ -408,7 +313,6 @@ ffm_core_rollout_kernel(const RolloutParams P) {
     }
     if (tid < 8) ctr[tid] = 0u;
     for (int c = tid; c < claim_words; c += THREADS) claim32[c] = 0u;
-    if (DFF) for (int c = tid; c < 2 * nz_cap; c += THREADS) nzA[c] = 1;   // unknown contents: everything counts as non-zero
     mbar_wait(bar, 0);          // the bulk copies have landed (phase 0 of the barrier completed)
     __syncthreads();
     for (int i = tid; i < n; i += THREADS) grid[pos[i]] |= (uint16_t)(i + 1);
@@ -545,10 +449,7 @@ ffm_core_rollout_kernel(const RolloutParams P) {
                 }
             }
             if (moved) {
-                if (DFF) {
-                    dffA[c] = __fadd_rn(dffA[c], 1.0f);                       // footprint (:93,98)
-                    if (sparse) { const int rr = c / W; nzA[(rr / DFF_TR) * nz_tx + ((c - rr * W) >> 5)] = 1; }
-                }
+                if (DFF) dffA[c] = __fadd_rn(dffA[c], 1.0f);                  // footprint (:93,98)
                 if (T != (uint32_t)c) list[li] = (uint16_t)(s | 0x8000);      // to be applied in C
             }
         }
@@ -579,10 +480,7 @@ ffm_core_rollout_kernel(const RolloutParams P) {
         }
         for (int c = tid; c < claim_words; c += THREADS) claim32[c] = 0u;    // claim counters clean for the next step
         // DFF decay + diffusion reads the bumped field (phase B wrote it before the last barrier) -> other buffer
-        if (DFF) {
-            if (sparse) dff_decay_diffuse_sparse<NBR>(dffA, dffB, nzA, nzB, H, W, P.c0, P.c1, P.thr, tid, THREADS);
-            else dff_decay_diffuse<NBR>(dffA, dffB, H, W, P.c0, P.c1, P.thr, tid, THREADS);
-        }
+        if (DFF) dff_decay_diffuse<NBR>(dffA, dffB, H, W, P.c0, P.c1, P.thr, tid, THREADS);
         __syncthreads();
 
         const int n_exit = (int)cnt[2];
@@ -646,10 +544,7 @@ ffm_core_rollout_kernel(const RolloutParams P) {
             }
         }
 
-        if (DFF) {                                                       // phase D ran alongside C (above)
-            float* tmp = dffA; dffA = dffB; dffB = tmp;
-            uint8_t* tz = nzA; nzA = nzB; nzB = tz;
-        }
+        if (DFF) { float* tmp = dffA; dffA = dffB; dffB = tmp; }      // phase D ran alongside C (above)
 
         // trajectory row: positions after this step, alive-rank order (ffm_core.py:125)
         if (P.traj != nullptr && tl < P.traj_steps) {
