@@ -370,7 +370,7 @@ ffm_core_rollout_kernel(const RolloutParams P) {
                 tgt[s] = need_draw ? (PosT)m : (PosT)target;     // the mask rides in tgt[] until A2
             }
             warp_append<uint16_t>(need_draw, (uint16_t)s, list, &cnt[0], lane);
-            warp_append<uint16_t>(forced, (uint16_t)s, list, &cnt[1], lane, -1, list_last);
+            if (forced) list[list_last - (int)atomicAdd(&cnt[1], 1u)] = (uint16_t)s;   // rare (next to an exit): no warp aggregation
         }
         __syncthreads();
 
