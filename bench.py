@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Benchmark of the FFM hot path: pedestrian-steps/s of batched evacuation episodes (BASELINE.json).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c2dff|c3|c1] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c2dff|c3|c4|c1] [--impl ours|reference]
 
 A "step" is one pass of the hot path over one batch: B episodes placed, then rolled out by the
 persistent kernel until everybody has left (or the step cap).  Workload `c2` (the configuration the
@@ -39,6 +39,11 @@ UNIT = "ped-steps/s"
 # algorithmic bytes per pedestrian-step, SURVEY.md section 8(d): own position read 4 B + 9 cells x
 # (map/occupancy 1 B + SFF 4 B [+ DFF 4 B]) + position write 4 B + occupancy update 2 B
 BYTES_PER_PED_STEP = {False: 55, True: 91}
+# unified model (C4): 5 slots x (1 + 4 + 4) B + position 4 + 4 + occupancy 2 + 16 B of state-encoder cell reads + V[s], V[s'] read and
+# V[s] written (3 x 8 B)
+BYTES_PER_PED_STEP_UNIFIED = 95
+C4_PARAMS = dict(k_S=10, k_D=1, k_A=10, alpha_v=0.01, alpha_h=0.1, gamma=0.99, exit_reward=100.0, step_penalty=-1.0,
+                 collision_penalty=-1.0, neighborhood="neumann", block_size=1, diffuse=0.2, decay=0.2)   # run_unified_critic_training.py:40-50
 
 WORKLOADS = {
     # name: (H, W, peds/episode, episodes/GPU, step cap, neighbourhood, k_S, k_D, track_dff)
@@ -48,6 +53,9 @@ WORKLOADS = {
                   desc="C2 geometry with DFF on (k_D=1, diffuse=decay=0.2)"),
     "c3": dict(h=256, w=256, n=10000, episodes=148, cap=2048, nbh="moore", k_S=3, k_D=1, track_dff=True, plan="c3",
                desc="C3: 148 episodes/GPU, 256x256 floor plan (3x3 rooms, 4 exits), geodesic SFF, DFF on, Moore, 10000 peds/episode, cap 2048"),
+    "c4": dict(h=12, w=12, n=50, episodes=4096, cap=300, nbh="neumann", k_S=10, k_D=1, track_dff=True, model="unified", radius=15,
+               desc="C4: batched TD(0) critic learning (run_unified_critic_training.py MODEL_PARAMS), 12x12, N=50 within radius 15, "
+                    "4096 episodes/GPU per sync, all-reduce of the table deltas, cap 300"),
     "c1": dict(h=12, w=12, n=100, episodes=4096, cap=4096, nbh="neumann", k_S=3, k_D=1, track_dff=True,
                desc="C1 geometry batched: 12x12 room, neumann, N=100, DFF on"),
 }
@@ -149,6 +157,55 @@ def _cpu_worker(args):
     return ped, time.perf_counter() - t0, o.t
 
 
+def _cpu_worker_unified(args):
+    """Episodes of the NumPy port of model/ffm_unified.py (critic_only, sequential TD updates) for `budget` seconds."""
+    wl, placements, budget, seed = args
+    from oracle import unified_numpy
+
+    class MT:
+        rs = np.random.RandomState(seed)
+        def move(self, t, i, cdf=None): return self.rs.random_sample()
+        def winner(self, t, c, k): return self.rs.random_sample()
+        def eps_coin(self, t, i): return self.rs.random_sample()
+        def eps_pick(self, t, i, k): return self.rs.random_sample()
+
+    m, sff = wl["_fields"]
+    o = unified_numpy.UnifiedOracle(m, sff, placements[0], "critic_only", C4_PARAMS, MT())
+    t0 = time.perf_counter()
+    ped = steps = 0
+    for pos0 in placements:
+        o.positions, o.t = pos0.astype(np.int64), 0
+        o.dff[:] = 0
+        while o.positions.shape[0] > 0 and o.t < wl["cap"]:
+            ped += o.positions.shape[0]
+            o.step()
+            steps += 1
+        if time.perf_counter() - t0 > budget:
+            break
+    return ped, time.perf_counter() - t0, steps
+
+
+def cpu_numpy_port_unified(wl, budget_s, seed=1234, cores=None):
+    import multiprocessing as mp
+    cores = cores or os.cpu_count() or 1
+    m, _ = wl["_fields"]
+    free = np.argwhere(m == 0)
+    er, ec = np.argwhere(m == 3)[0]
+    near = free[np.abs(free[:, 0] - er) + np.abs(free[:, 1] - ec) <= wl["radius"]]
+    rng = np.random.RandomState(seed)
+    jobs = [(wl, [near[rng.choice(len(near), min(wl["n"], len(near)), replace=False)] for _ in range(64)], budget_s, seed + i)
+            for i in range(cores)]
+    with mp.get_context("fork").Pool(cores) as pool:
+        t0 = time.perf_counter()
+        res = pool.map(_cpu_worker_unified, jobs)
+        wall = time.perf_counter() - t0
+    ped = sum(r[0] for r in res)
+    return dict(value=ped / wall, unit=UNIT, cores=cores, kind="port",
+                sample=f"{cores} processes of the NumPy port of model/ffm_unified.py (oracle/unified_numpy.py, critic_only, the "
+                       f"reference's sequential TD updates), whole episodes for {budget_s:.0f} s each: {ped} ped-steps, "
+                       f"{sum(r[2] for r in res)} CA steps")
+
+
 def cpu_numpy_port(wl, budget_s, seed=1234, cores=None):
     import multiprocessing as mp
     cores = cores or os.cpu_count() or 1
@@ -205,7 +262,9 @@ def run_reference_arm(args, wl):
     times, vals, last = [], [], None
     for it in range(args.warmup + args.steps):
         t0 = time.perf_counter()
-        if have_c_oracle() and not args.numpy_port:
+        if wl.get("model") == "unified":
+            last = cpu_numpy_port_unified(wl, budget_s=args.cpu_budget, seed=1234 + it, cores=cores)
+        elif have_c_oracle() and not args.numpy_port:
             last = cpu_c_port(wl, episodes=CPU_C_EPISODES.get(args.workload, 64) * cores, seed=1234 + it, cores=cores)
         else:
             last = cpu_numpy_port(wl, budget_s=args.cpu_budget, seed=1234 + it, cores=cores)
@@ -277,9 +336,20 @@ def main():
     wl["_fields"] = (m, sff)
     params = {"k_S": wl["k_S"], "k_D": wl["k_D"], "diffuse": 0.2, "decay": 0.2, "neighborhood": wl["nbh"]}
     ep_base = rank * B                                   # global episode ids: results independent of N
-    pos_np = place(m, N, B, ep_base, args.seed)
     n_np = np.full((B,), N, dtype=np.int32)
-    sim = BatchSim(m, sff, B, N, params, seed=args.seed, episode_base=ep_base, track_dff=wl["track_dff"], device=local)
+    post_rollout = None
+    if wl.get("model") == "unified":
+        from ffm_b200 import UnifiedSim
+        from ffm_b200.sharding import BatchedLearner
+        sim = UnifiedSim(m, sff, B, N, mode="critic_only", learn="batched", params=C4_PARAMS, seed=args.seed,
+                         episode_base=ep_base, device=local)
+        exit_rc = tuple(int(v) for v in np.argwhere(m == 3)[0])
+        sim.place(n_np, exit_pos=exit_rc, radius=wl["radius"])          # initialize_agents(exit_pos, radius), keyed per episode
+        pos_np, n_np = sim.get_positions()
+        post_rollout = BatchedLearner(sim).sync                        # all-reduce of dV / dN / dH + flags, then fold in
+    else:
+        pos_np = place(m, N, B, ep_base, args.seed)
+        sim = BatchSim(m, sff, B, N, params, seed=args.seed, episode_base=ep_base, track_dff=wl["track_dff"], device=local)
     info = sim.kernel_info()
     pos_dev = torch.from_numpy(pos_np).cuda()
     n_dev = torch.from_numpy(n_np).cuda()
@@ -295,6 +365,7 @@ def main():
         if ev: ev[1].record()
         sim.rollout(cap)
         if ev: ev[2].record()
+        if post_rollout: post_rollout()
         sim.counters_into(steps_dev, ped_dev)
         if ev: ev[3].record()
 
@@ -321,7 +392,9 @@ def main():
     # ---- e2e: host buffers in, host counters out ------------------------------------------------
     e2e_evs = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(args.steps)]
     for _ in range(2):
-        sim.set_positions(pos_pin.numpy(), n_pin.numpy()); sim.rollout(cap); sim.counters()
+        sim.set_positions(pos_pin.numpy(), n_pin.numpy()); sim.rollout(cap)
+        if post_rollout: post_rollout()
+        sim.counters()
     barrier()
     e2e_ped = 0
     for k in range(args.steps):
@@ -329,6 +402,7 @@ def main():
         e2e_evs[k][0].record()
         sim.set_positions(pos_pin.numpy(), n_pin.numpy())       # H2D of this step's inputs
         sim.rollout(cap)
+        if post_rollout: post_rollout()
         st_h, ped_h = sim.counters()                             # D2H of the step's result (+ sync)
         e2e_evs[k][1].record()
         e2e_ped += int(ped_h.sum())
@@ -354,7 +428,7 @@ def main():
         except OSError:
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
-        alg_bytes = BYTES_PER_PED_STEP[wl["track_dff"]] * ped_per_pass
+        alg_bytes = (BYTES_PER_PED_STEP_UNIFIED if wl.get("model") == "unified" else BYTES_PER_PED_STEP[wl["track_dff"]]) * ped_per_pass
         if wl["track_dff"]:
             alg_bytes += 8 * wl["h"] * wl["w"] * int(steps_host.sum())      # DFF field read+write per episode-step
         achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
@@ -370,7 +444,7 @@ def main():
             "config": {"workload": wl["desc"], "episodes_per_gpu": B, "peds_per_episode": N, "map": f"{wl['h']}x{wl['w']}",
                        "step_cap": cap, "parallelism": f"episodes sharded over {world} GPU(s), no collective",
                        "l2": "256 MiB L2 flush between timed iterations (untimed)",
-                       "kernel": {"name": "ffm_core_rollout_kernel", **info},
+                       "kernel": {"name": "ffm_unified_rollout_kernel" if wl.get("model") == "unified" else "ffm_core_rollout_kernel", **info},
                        "mean_evacuation_steps": float(steps_host.mean()), "ped_steps_per_pass_per_gpu": ped_per_pass},
             "episodes_per_sec": B * world * args.steps / (total_ms * 1e-3),
             "clocks": clocks,
@@ -388,7 +462,9 @@ def main():
         }
         if not args.no_cpu and world == 1:
             try:
-                if have_c_oracle():
+                if wl.get("model") == "unified":
+                    line["cpu_baseline"] = cpu_numpy_port_unified(wl, budget_s=min(args.cpu_budget, 10.0))
+                elif have_c_oracle():
                     line["cpu_baseline"] = cpu_c_port(wl, episodes=CPU_C_EPISODES.get(args.workload, 64) * (os.cpu_count() or 1))
                     line["cpu_baseline_numpy"] = cpu_numpy_port(wl, budget_s=min(args.cpu_budget, 10.0))
                 else:
