@@ -2,22 +2,37 @@
 
 ``python -m ffm_b200.build`` or ``ffm_b200.build.build()``; the driver calls it through
 ``__graft_entry__.build()``.  nvcc cross-compiles without a GPU.
+
+Every ``csrc/*.cu`` is one translation unit (one kernel family each), compiled to an object in
+parallel and linked into the shared library.  An object is rebuilt when its source, ANY header under
+``csrc/`` or ``include/``, or this file is newer than it -- so an edit to any kernel header rebuilds
+what depends on it and a stale prebuilt library can never be loaded silently.
 """
+import glob
 import os
 import subprocess
 import sys
+from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 LIB = os.path.join(HERE, "libffm_b200.so")
-SOURCES = [os.path.join(HERE, "csrc", "ffm_api.cu")]
-HEADERS = [os.path.join(HERE, "csrc", f) for f in ("ffm_device.cuh", "ffm_core_kernel.cuh")] + [
-    os.path.join(ROOT, "include", "ffm_b200.h")]
+CSRC = os.path.join(HERE, "csrc")
+OBJDIR = os.path.join(HERE, "build")          # git-ignored
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-fmad=false",              # never contract a*b+c: the reference rounds the product first
-    "-shared", "-Xcompiler", "-fPIC",
+    "-Xcompiler", "-fPIC",
 ]
+
+
+def sources():
+    return sorted(glob.glob(os.path.join(CSRC, "*.cu")))
+
+
+def headers():
+    return sorted(glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(CSRC, "*.h")) +
+                  glob.glob(os.path.join(ROOT, "include", "*.h"))) + [os.path.abspath(__file__)]
 
 
 def _nvcc():
@@ -27,23 +42,55 @@ def _nvcc():
     return "nvcc"
 
 
+def _obj(src):
+    return os.path.join(OBJDIR, os.path.splitext(os.path.basename(src))[0] + ".o")
+
+
+def _newest(paths):
+    return max(os.path.getmtime(p) for p in paths)
+
+
+def stale_objects():
+    hdr_t = _newest(headers())
+    return [s for s in sources()
+            if not os.path.exists(_obj(s)) or os.path.getmtime(_obj(s)) < max(hdr_t, os.path.getmtime(s))]
+
+
 def is_stale():
-    if not os.path.exists(LIB):
+    if not os.path.exists(LIB) or stale_objects():
         return True
-    t = os.path.getmtime(LIB)
-    return any(os.path.getmtime(p) > t for p in SOURCES + HEADERS if os.path.exists(p))
+    objs = [_obj(s) for s in sources()]
+    stray = set(glob.glob(os.path.join(OBJDIR, "*.o"))) - set(objs)     # a deleted source leaves its object behind
+    return bool(stray) or os.path.getmtime(LIB) < _newest(objs)
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, jobs=None):
     if not force and not is_stale():
         return LIB
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + SOURCES
-    r = subprocess.run(cmd, capture_output=True, text=True)
+    os.makedirs(OBJDIR, exist_ok=True)
+    todo = sources() if force else stale_objects()
+    nvcc = _nvcc()
+
+    def compile_one(src):
+        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", _obj(src), src]
+        return src, subprocess.run(cmd, capture_output=True, text=True)
+
+    with ThreadPoolExecutor(max_workers=jobs or min(len(todo) or 1, os.cpu_count() or 1)) as pool:
+        results = list(pool.map(compile_one, todo))
+    for src, r in results:
+        if r.returncode != 0:
+            sys.stderr.write(r.stdout + r.stderr)
+            raise RuntimeError(f"nvcc failed on {os.path.basename(src)}")
+        if verbose:
+            sys.stderr.write(r.stderr)
+    objs = [_obj(s) for s in sources()]
+    for stray in set(glob.glob(os.path.join(OBJDIR, "*.o"))) - set(objs):
+        os.remove(stray)
+    r = subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB] + objs,
+                       capture_output=True, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)
-        raise RuntimeError("nvcc failed building libffm_b200.so")
-    if verbose:
-        sys.stderr.write(r.stderr)
+        raise RuntimeError("nvcc failed linking libffm_b200.so")
     return LIB
 
 

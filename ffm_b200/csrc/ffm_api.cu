@@ -14,6 +14,7 @@
 #include "ffm_sff_kernels.cuh"
 #include "ffm_unified_kernel.cuh"
 #include "ffm_mcq_kernel.cuh"
+#include "ffm_internal.h"
 
 namespace {
 
@@ -66,7 +67,8 @@ struct ffm_sim_s {
     // unified / trained models
     int S, A, nby;
     double* d_V; uint8_t* d_vseen; double* d_H; uint8_t* d_hseen;
-    double* d_dV; double* d_dN; double* d_dH;   // borrowed (caller-owned) delta tables
+    double* d_dV; double* d_dN; double* d_dH; double* d_dF;   // borrowed (caller-owned) delta tables
+    bool hstats_stale;   // H or its presence flags were replaced by the caller: extremes must be rescanned before the next rollout
     ffm::HStats* d_hstats;
     double* d_blk_lo; double* d_blk_hi; int* d_blk_any;
     double epsilon;
@@ -262,48 +264,8 @@ __global__ void unpack_positions_kernel(const uint32_t* pos, const int32_t* n, i
 
 namespace {
 
-template <typename S, typename PosT, int NBR, bool DFF, bool FS>
-const void* pick_threads(int threads) {
-    if (threads == 1024) return (const void*)ffm::ffm_core_rollout_kernel<S, PosT, NBR, DFF, FS, 1024>;
-    if (threads == 128) return (const void*)ffm::ffm_core_rollout_kernel<S, PosT, NBR, DFF, FS, 128>;
-    return (const void*)ffm::ffm_core_rollout_kernel<S, PosT, NBR, DFF, FS, 256>;
-}
-template <typename S, typename PosT, int NBR, bool DFF>
-const void* pick_fs(bool fs, int threads) {
-    return fs ? pick_threads<S, PosT, NBR, DFF, true>(threads) : pick_threads<S, PosT, NBR, DFF, false>(threads);
-}
-template <typename S, typename PosT, int NBR>
-const void* pick_dff(bool dff, bool fs, int threads) {
-    return dff ? pick_fs<S, PosT, NBR, true>(fs, threads) : pick_fs<S, PosT, NBR, false>(fs, threads);
-}
-template <typename S, typename PosT>
-const void* pick_nbr(int nbr, bool dff, bool fs, int threads) {
-    return nbr == 4 ? pick_dff<S, PosT, 4>(dff, fs, threads) : pick_dff<S, PosT, 8>(dff, fs, threads);
-}
-template <typename S>
-const void* pick_pos(bool small, int nbr, bool dff, bool fs, int threads) {
-    return small ? pick_nbr<S, uint16_t>(nbr, dff, fs, threads) : pick_nbr<S, uint32_t>(nbr, dff, fs, threads);
-}
 const void* pick_kernel(bool f64, bool small, int nbr, bool dff, bool fs, int threads) {
-    return f64 ? pick_pos<double>(small, nbr, dff, fs, threads) : pick_pos<float>(small, nbr, dff, fs, threads);
-}
-
-template <typename S, int NBR, bool FS>
-const void* upick_threads(int threads) {
-    if (threads >= 256) return (const void*)ffm::ffm_unified_rollout_kernel<S, NBR, FS, 256>;
-    return (const void*)ffm::ffm_unified_rollout_kernel<S, NBR, FS, 128>;
-}
-template <typename S, int NBR>
-const void* upick_fs(bool fs, int threads) { return fs ? upick_threads<S, NBR, true>(threads) : upick_threads<S, NBR, false>(threads); }
-template <typename S>
-const void* upick_nbr(int nbr, bool fs, int threads) { return nbr == 4 ? upick_fs<S, 4>(fs, threads) : upick_fs<S, 8>(fs, threads); }
-const void* upick_kernel(bool f64, int nbr, bool fs, int threads) {
-    return f64 ? upick_nbr<double>(nbr, fs, threads) : upick_nbr<float>(nbr, fs, threads);
-}
-
-template <typename S, int NBR>
-const void* probs_pick_dff(bool dff) {
-    return dff ? (const void*)ffm::core_move_probs_kernel<S, NBR, true> : (const void*)ffm::core_move_probs_kernel<S, NBR, false>;
+    return f64 ? ffm::pick_core_kernel_f64(small, nbr, dff, fs, threads) : ffm::pick_core_kernel_f32(small, nbr, dff, fs, threads);
 }
 
 int check_device_flag(ffm_sim_t s, cudaStream_t st) {
@@ -411,12 +373,8 @@ int ffm_create(const ffm_config_t* cfg, ffm_sim_t* out) {
     // global +10 %.  Rule: shared unless the global variant keeps at least 1.5x as many CTAs resident.
     if (mcq) s->threads = N <= 128 ? 128 : 256;
     auto kernel_for = [&](bool fs) {
-        if (mcq) {
-            const bool f64 = cfg->sff_dtype == FFM_F64;
-            if (s->threads == 128) return f64 ? (const void*)ffm::ffm_mcq_rollout_kernel<double, 128> : (const void*)ffm::ffm_mcq_rollout_kernel<float, 128>;
-            return f64 ? (const void*)ffm::ffm_mcq_rollout_kernel<double, 256> : (const void*)ffm::ffm_mcq_rollout_kernel<float, 256>;
-        }
-        return unified ? upick_kernel(cfg->sff_dtype == FFM_F64, cfg->neighborhood, fs, s->threads)
+        if (mcq) return ffm::pick_mcq_kernel(cfg->sff_dtype == FFM_F64, s->threads);
+        return unified ? ffm::pick_unified_kernel(cfg->sff_dtype == FFM_F64, cfg->neighborhood, fs, s->threads)
                        : pick_kernel(cfg->sff_dtype == FFM_F64, HW <= 65536, cfg->neighborhood, dff, fs, s->threads);
     };
     auto occupancy = [&](const void* k, int smem) {
@@ -576,8 +534,9 @@ int ffm_place(ffm_sim_t s, const int32_t* n, int32_t exit_row, int32_t exit_col,
     if (s->d_dff) CU(cudaMemsetAsync(s->d_dff, 0, (size_t)B * s->HW * 4, st));
     ffm::place_kernel<<<B, 256, smem, st>>>(s->d_free, s->d_free_count, s->d_n_req, s->d_pos, s->d_n, N, s->cfg.seed, s->cfg.episode_base, npad, s->d_err);
     CU(cudaGetLastError());
-    CU(cudaStreamSynchronize(st));      // n[] is a host buffer of the caller
     s->launches++;
+    int rcf = check_device_flag(s, st);  // synchronises (n[] is a host buffer of the caller) and surfaces a candidate-buffer overflow
+    if (rcf) return rcf;
     s->have_positions = true;
     return FFM_OK;
 }
@@ -692,7 +651,13 @@ int ffm_rollout(ffm_sim_t s, int32_t max_steps, const ffm_draws_t* draws, const 
         U.epsilon = s->epsilon; U.sff_min = s->cfg.sff_min; U.sff_max = s->cfg.sff_max;
         U.pos = s->d_pos; U.n_alive = s->d_n; U.t_done = s->d_t; U.ped_steps = s->d_ped_steps;
         U.dff = s->d_dff; U.dff_tmp = s->d_dff_tmp;
-        U.V = s->d_V; U.v_seen = s->d_vseen; U.Hm = s->d_H; U.h_seen = s->d_hseen; U.dV = s->d_dV; U.dN = s->d_dN; U.dH = s->d_dH;
+        U.V = s->d_V; U.v_seen = s->d_vseen; U.Hm = s->d_H; U.h_seen = s->d_hseen; U.dV = s->d_dV; U.dN = s->d_dN; U.dH = s->d_dH; U.dF = s->d_dF;
+        if (s->hstats_stale && s->cfg.model != FFM_MODEL_UNIFIED_CRITIC) {
+            // the caller replaced H: one small kernel recomputes its extremes before any CTA of the rollout looks at them
+            CU(ffm::launch_rescan_hstats(s->d_H, s->d_hseen, s->S, s->A, s->d_hstats, s->d_blk_lo, s->d_blk_hi, s->d_blk_any, 148, st));
+            s->launches += 2;
+        }
+        s->hstats_stale = false;
         U.hstats = s->d_hstats;
         U.seed = s->cfg.seed; U.episode_base = s->cfg.episode_base;
         if (draws) { U.move_draws = draws->move; U.conflict_draws = draws->conflict; U.draw_steps = draws->steps; U.draw_first = draws->first_step; }
@@ -752,8 +717,7 @@ int ffm_move_probs(ffm_sim_t s, double* probs, int32_t* kind, int space, void* s
     P.type_grid = s->d_type_grid; P.score = s->d_score; P.kd = (float)s->cfg.k_D;
     P.pos = s->d_pos; P.n_alive = s->d_n; P.dff = s->d_dff;
     const bool f64 = s->cfg.sff_dtype == FFM_F64, dff = s->d_dff != nullptr;
-    const void* k = f64 ? (s->cfg.neighborhood == 4 ? probs_pick_dff<double, 4>(dff) : probs_pick_dff<double, 8>(dff))
-                        : (s->cfg.neighborhood == 4 ? probs_pick_dff<float, 4>(dff) : probs_pick_dff<float, 8>(dff));
+    const void* k = ffm::pick_probs_kernel(f64, s->cfg.neighborhood, dff);
     const size_t smem = (size_t)(s->HW + 2 * (s->cfg.width + 1)) * 2 + 16;
     CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     void* args[] = {&P, &d_probs, &d_kind};
@@ -797,11 +761,8 @@ int ffm_tables_set(ffm_sim_t s, const double* V, const uint8_t* v_seen, const do
     if (v_seen && (rc = copy_in(s->d_vseen, v_seen, (size_t)s->S, space, st))) return rc;
     if (H && (rc = copy_in(s->d_H, H, (size_t)s->S * s->A * 8, space, st))) return rc;
     if (h_seen && (rc = copy_in(s->d_hseen, h_seen, (size_t)s->S, space, st))) return rc;
-    if (H || h_seen) {   // extremes of the H table must be rescanned before the next use
-        ffm::HStats hs; hs.hmin = 0; hs.hmax = 0; hs.dirty = 1; hs.any = 0;
-        CU(cudaMemcpyAsync(s->d_hstats, &hs, sizeof(hs), cudaMemcpyHostToDevice, st));
-    }
-    CU(cudaStreamSynchronize(st));
+    if (H || h_seen) s->hstats_stale = true;   // extremes of the H table are rescanned by the next ffm_rollout
+    if (space == FFM_HOST) CU(cudaStreamSynchronize(st));   // host buffers may be reused by the caller; device copies stay stream-ordered
     return FFM_OK;
 }
 
@@ -818,11 +779,12 @@ int ffm_tables_get(ffm_sim_t s, double* V, uint8_t* v_seen, double* H, uint8_t* 
     return FFM_OK;
 }
 
-int ffm_tables_bind_deltas(ffm_sim_t s, double* dV, double* dN, double* dH) {
-    if (!s || !dV || !dN) return fail(FFM_E_INVALID, "null argument");
-    if (s->cfg.model == FFM_MODEL_CORE) return fail(FFM_E_STATE, "the base model has no tables");
+int ffm_tables_bind_deltas(ffm_sim_t s, double* dV, double* dN, double* dF, double* dH) {
+    if (!s || !dV || !dN || !dF) return fail(FFM_E_INVALID, "null argument");
+    if (s->cfg.model == FFM_MODEL_CORE || s->cfg.model == FFM_MODEL_MCQ) return fail(FFM_E_STATE, "only the unified models take V/H delta tables");
     s->d_dV = dV;
     s->d_dN = dN;
+    s->d_dF = dF;
     s->d_dH = dH;
     return FFM_OK;
 }
@@ -834,12 +796,10 @@ int ffm_tables_apply_deltas(ffm_sim_t s, void* stream) {
     CU(cudaSetDevice(s->cfg.device));
     const bool has_h = s->cfg.model == FFM_MODEL_UNIFIED_ACTOR || s->cfg.model == FFM_MODEL_UNIFIED_BOTH;
     if (has_h && !s->d_dH) return fail(FFM_E_STATE, "actor learning needs a dH table");
-    const int blocks = 148;
-    ffm::unified_apply_deltas_kernel<<<blocks, 256, 0, st>>>(s->d_V, s->d_dV, s->d_dN, s->cfg.alpha_v, has_h ? s->d_H : nullptr, s->d_dH, s->d_hseen, s->S, s->A,
-                                                            s->d_hstats, s->d_blk_lo, s->d_blk_hi, s->d_blk_any);
-    if (has_h) ffm::unified_finish_stats_kernel<<<1, 32, 0, st>>>(s->d_hstats, s->d_blk_lo, s->d_blk_hi, s->d_blk_any, blocks);
-    CU(cudaGetLastError());
+    CU(ffm::launch_apply_deltas(s->d_V, s->d_dV, s->d_dN, s->d_dF, s->cfg.alpha_v, has_h ? s->d_H : nullptr, s->d_dH, s->d_hseen, s->d_vseen,
+                                s->S, s->A, s->d_hstats, s->d_blk_lo, s->d_blk_hi, s->d_blk_any, 148, st));
     s->launches += has_h ? 2 : 1;
+    if (has_h) s->hstats_stale = false;
     return FFM_OK;
 }
 
@@ -1001,10 +961,7 @@ int ffm_rollout_returns(const float* reward, const int32_t* len, int32_t B, int3
     if (!reward || !len || !returns) return fail(FFM_E_INVALID, "null argument");
     if (B < 1 || T < 1 || N < 1) return fail(FFM_E_INVALID, "bad shape");
     CU(cudaSetDevice(device));
-    const long long total = (long long)B * ((N + 3) / 4);
-    const int blocks = (int)((total + 255) / 256 < 148LL * 8 ? (total + 255) / 256 : 148LL * 8);
-    ffm::rollout_returns_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(reward, len, B, T, N, gamma, returns);
-    CU(cudaGetLastError());
+    CU(ffm::launch_rollout_returns(reward, len, B, T, N, gamma, returns, (cudaStream_t)stream));
     return FFM_OK;
 }
 

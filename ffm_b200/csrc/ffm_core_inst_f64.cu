@@ -1,0 +1,4 @@
+// Instantiations of the (round-1, pedestrian-centric) base-model rollout kernel for float64 scores.
+#include "ffm_core_kernel.cuh"
+#include "ffm_core_inst.inl"
+namespace ffm { const void* pick_core_kernel_f64(bool small, int nbr, bool dff, bool fs, int threads) { return pick_pos<double>(small, nbr, dff, fs, threads); } }

@@ -63,6 +63,7 @@ struct UnifiedParams {
     double* V; uint8_t* v_seen;  // [S]
     double* Hm; uint8_t* h_seen; // [S][A], [S]
     double* dV; double* dN; double* dH;   // batched mode: sum of TD errors, visit counts [S]; sum of alpha_h*delta [S][A]
+    double* dF;                           // batched mode: > 0 where a V key was touched (read or written) in this sync, or null
     HStats* hstats;
     unsigned long long seed; uint32_t episode_base;
     const double* move_draws; const double* conflict_draws; int draw_steps, draw_first;
@@ -215,9 +216,15 @@ ffm_unified_rollout_kernel(const UnifiedParams P) {
     const double* mv_draws = P.move_draws ? P.move_draws + (size_t)e * P.draw_steps * P.n_max : nullptr;
     const double* cf_draws = P.conflict_draws ? P.conflict_draws + (size_t)e * P.draw_steps * HW * 2 : nullptr;
     const bool actor = P.mode != UMODE_CRITIC;
-    const bool inserts_rows = (P.mode == UMODE_ACTOR || P.mode == UMODE_BOTH);   // H lookups insert zero rows (:405-410)
-    const bool learn_actor = inserts_rows && P.learn != ULEARN_NONE;
-    const bool track_stats = actor && P.learn != ULEARN_BATCHED;                 // batched: extremes frozen per launch
+    // The tables are written in place only by FFM_LEARN_EXACT (one episode = one CTA per handle).  With frozen tables
+    // (NONE) or batched learning many CTAs share them: rows are never inserted by lookups, the extremes of H are the
+    // ones found at launch (ffm_rollout refreshes them beforehand when they are stale) and every table write goes
+    // through the delta tables.
+    const bool exact = P.learn == ULEARN_EXACT;
+    const bool trains_h = (P.mode == UMODE_ACTOR || P.mode == UMODE_BOTH);
+    const bool inserts_rows = trains_h && exact;                                 // H lookups insert zero rows (:405-410)
+    const bool learn_actor = trains_h && P.learn != ULEARN_NONE;
+    const bool track_stats = actor && exact;
 
     unsigned long long ped_steps = 0;
     int tl = 0;
@@ -229,7 +236,11 @@ ffm_unified_rollout_kernel(const UnifiedParams P) {
 
         // ---- extremes of the H table at step start (rescan when an extreme value moved inwards) --
         if (actor) {
-            if (track_stats && P.hstats->dirty) {
+            if (track_stats) {                 // uniform across the CTA: tid 0 publishes the flag through shared memory
+                if (tid == 0) misc[1] = P.hstats->dirty;
+                __syncthreads();
+            }
+            if (track_stats && misc[1]) {
                 double lo = DINF, hi = -DINF;
                 int any = 0;
                 for (int s = tid; s < P.S; s += THREADS)
@@ -350,7 +361,7 @@ ffm_unified_rollout_kernel(const UnifiedParams P) {
                 // table extremes seen by this agent: step-start extremes plus the zero rows inserted by
                 // agents up to and including this one (:413-426)
                 double hmin = dmisc[0], hmax = dmisc[1];
-                if (first_new <= i) { hmin = fmin(hmin, 0.0); hmax = fmax(hmax, 0.0); }
+                if (first_new <= i || (!exact && !have)) { hmin = fmin(hmin, 0.0); hmax = fmax(hmax, 0.0); }
                 if (hmax - hmin > 1e-6) {                               // :434
                     const double den = hmax - hmin, rng = P.sff_max - P.sff_min;
 #pragma unroll
@@ -472,10 +483,10 @@ ffm_unified_rollout_kernel(const UnifiedParams P) {
                     const int c = (int)posB[i];
                     const int r = c / W, col = c - r * W;
                     ns = encode_state(grid, c, r, col, H, W, P.block_size, P.nby);
-                    P.v_seen[ns] = 1;
+                    if (exact) P.v_seen[ns] = 1; else if (P.dF) P.dF[ns] = 1.0;
                 }
                 nst[i] = ns;
-                P.v_seen[st[i]] = 1;
+                if (exact) P.v_seen[st[i]] = 1; else if (P.dF) P.dF[st[i]] = 1.0;
             }
             __syncthreads();
             if (P.learn == ULEARN_EXACT) {
@@ -534,8 +545,7 @@ ffm_unified_rollout_kernel(const UnifiedParams P) {
                     const double td = __dadd_rn(__dadd_rn(agent_reward(P, w), __dmul_rn(P.gamma, v_next)), -P.V[sid]);
                     atomicAdd(&P.dV[sid], td);
                     atomicAdd(&P.dN[sid], 1.0);
-                    if (learn_actor) {
-                        P.h_seen[sid] = 1;
+                    if (learn_actor) {                                   // the row becomes present when the deltas are applied
                         const uint32_t a = w & INFO_SLOT_MASK;
                         if ((w >> (INFO_VALID_SHIFT + a)) & 1u) atomicAdd(&P.dH[(size_t)sid * A + a], __dmul_rn(P.alpha_h, td));
                     }
@@ -608,7 +618,7 @@ ffm_unified_rollout_kernel(const UnifiedParams P) {
 // (ffm_learning_core.py:262-278, 350-355: `G = r + self.gamma * G`, float64).  HBM-bound streaming kernel:
 // one thread owns 4 adjacent pedestrians of an episode, reads float4 reward rows and writes 2 x double2
 // return rows walking the time axis backwards; rows are contiguous over pedestrians -> fully coalesced.
-__global__ void __launch_bounds__(256)
+static __global__ void __launch_bounds__(256)
 rollout_returns_kernel(const float* __restrict__ reward, const int32_t* __restrict__ len, int B, int T, int N, double gamma,
                        double* __restrict__ G) {
     const int groups = (N + 3) / 4;
@@ -657,26 +667,39 @@ rollout_returns_kernel(const float* __restrict__ reward, const int32_t* __restri
 // Batched learning, between launches.  A state visited n times in the sync with TD errors d_1..d_n against
 // the frozen table receives V += (1 - (1 - alpha_v)^n) * mean(d): what n sequential updates towards the same
 // targets would give (a plain sum would multiply the step size by n and diverge for well-visited states).
-// H accumulates alpha_h * delta like the reference (:777).  Deltas zeroed, extremes of H recomputed.
-__global__ void unified_apply_deltas_kernel(double* V, double* dV, double* dN, double alpha_v, double* Hm, double* dH,
-                                            const uint8_t* h_seen, int S, int A,
-                                            HStats* hstats, double* block_lo, double* block_hi, int* block_any) {
+// H accumulates alpha_h * delta like the reference (:777).  Keys touched in the sync (dF > 0) become present in V,
+// visited states (dN > 0) get their H row when the actor learns.  Deltas zeroed, extremes of H recomputed.
+// With dV == nullptr only the extremes are recomputed (tables loaded by the caller: ffm_tables_set).
+static __global__ void unified_apply_deltas_kernel(double* V, double* dV, double* dN, double* dF, double alpha_v, double* Hm, double* dH,
+                                            uint8_t* h_seen, uint8_t* v_seen, int S, int A,
+                                            double* block_lo, double* block_hi, int* block_any) {
     const double DINF = __longlong_as_double(0x7ff0000000000000LL);
     double lo = DINF, hi = -DINF;
     int any = 0;
     for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < S; s += gridDim.x * blockDim.x) {
-        const double cnt = dN[s];
-        if (cnt > 0.0) V[s] += (1.0 - pow(1.0 - alpha_v, cnt)) * (dV[s] / cnt);
-        dV[s] = 0.0;
-        dN[s] = 0.0;
-        if (Hm != nullptr) {
-            for (int a = 0; a < A; ++a) {
-                const double v = Hm[(size_t)s * A + a] + dH[(size_t)s * A + a];
-                Hm[(size_t)s * A + a] = v;
-                dH[(size_t)s * A + a] = 0.0;
-                if (h_seen[s]) { lo = fmin(lo, v); hi = fmax(hi, v); }
+        bool visited = false;
+        if (dV != nullptr) {
+            const double cnt = dN[s];
+            visited = cnt > 0.0;
+            if (visited) {
+                V[s] += (1.0 - pow(1.0 - alpha_v, cnt)) * (dV[s] / cnt);
+                dV[s] = 0.0;
+                dN[s] = 0.0;
             }
-            if (h_seen[s]) any = 1;
+            if (dF != nullptr && dF[s] != 0.0) { v_seen[s] = 1; dF[s] = 0.0; }
+        }
+        if (Hm != nullptr) {
+            if (visited && dH != nullptr) {
+                h_seen[s] = 1;
+                for (int a = 0; a < A; ++a) {
+                    Hm[(size_t)s * A + a] += dH[(size_t)s * A + a];
+                    dH[(size_t)s * A + a] = 0.0;
+                }
+            }
+            if (h_seen[s]) {
+                any = 1;
+                for (int a = 0; a < A; ++a) { const double v = Hm[(size_t)s * A + a]; lo = fmin(lo, v); hi = fmax(hi, v); }
+            }
         }
     }
     __shared__ double slo[32], shi[32];
@@ -693,10 +716,9 @@ __global__ void unified_apply_deltas_kernel(double* V, double* dV, double* dN, d
         for (int w = 1; w < (int)blockDim.x / 32; ++w) { lo = fmin(lo, slo[w]); hi = fmax(hi, shi[w]); any |= sany[w]; }
         block_lo[blockIdx.x] = lo; block_hi[blockIdx.x] = hi; block_any[blockIdx.x] = any;
     }
-    (void)hstats;
 }
 
-__global__ void unified_finish_stats_kernel(HStats* hstats, const double* block_lo, const double* block_hi, const int* block_any, int nblocks) {
+static __global__ void unified_finish_stats_kernel(HStats* hstats, const double* block_lo, const double* block_hi, const int* block_any, int nblocks) {
     if (threadIdx.x == 0 && blockIdx.x == 0) {
         const double DINF = __longlong_as_double(0x7ff0000000000000LL);
         double lo = DINF, hi = -DINF;

@@ -1,5 +1,5 @@
 """Multi-GPU plumbing: episodes shard over ranks with no data-path collective; the learning
-configurations add ONE exchange step per sync -- the all-reduce of the table deltas.
+configurations add ONE exchange step per sync -- a single all-reduce of the flat delta buffer.
 
 One process per GPU (torch.distributed, NCCL over NVLink); every function also works on CPU tensors
 with the gloo backend, which is how tests/test_sharding_cpu.py exercises the logic without GPUs.
@@ -24,48 +24,66 @@ def shard_range(total, rank=None, world_size=None):
     return first, base + (1 if rank < rem else 0)
 
 
-def allreduce_deltas(deltas, seen_flags=()):
-    """Sum the delta tables (dV [S], dH [S, A]) and OR the key-present flags (uint8) over all ranks,
-    in place.  No-op on a single rank.  The flags ride along as one MAX all-reduce."""
+def allreduce_flat(flat, async_op=False):
+    """Sum ONE flat delta buffer ([dV | dN | dF | dH], float64) over all ranks, in place.  The key-touched marks dF
+    ride along as numbers (> 0 = touched on some rank), so the whole exchange is a single collective.
+    Returns the work handle when async_op (None on a single rank)."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
-        return
-    handles = [dist.all_reduce(t, op=dist.ReduceOp.SUM, async_op=True) for t in deltas if t is not None]
-    handles += [dist.all_reduce(f, op=dist.ReduceOp.MAX, async_op=True) for f in seen_flags if f is not None]
-    for h in handles:
-        h.wait()
+        return None
+    return dist.all_reduce(flat, op=dist.ReduceOp.SUM, async_op=async_op)
 
 
 class BatchedLearner:
     """Synchronous batched TD learning of the unified model (BASELINE config 4).
 
-    Each sync: every rank rolls out its B episodes against the frozen tables (kernel mode
-    FFM_LEARN_BATCHED accumulates TD errors, visit counts and alpha_h*delta into dV / dN / dH with atomics), the deltas and key flags are
-    all-reduced over ranks, and every rank applies the same update -- so all ranks hold identical
-    tables without ever broadcasting them.  This is a different algorithm from the reference's
-    sequential per-agent updates ("sequential learning semantics"); it is judged
-    statistically, while FFM_LEARN_EXACT reproduces the reference bit for bit on one episode.
+    Each sync: every rank rolls out its B episodes against the frozen tables (kernel mode FFM_LEARN_BATCHED
+    accumulates TD errors, visit counts, key marks and alpha_h*delta into the flat delta buffer), the buffer is
+    all-reduced over ranks -- ONE collective -- and every rank applies the same update, so all ranks hold identical
+    tables without ever broadcasting them.  This is a different algorithm from the reference's sequential per-agent
+    updates ("sequential learning semantics"); it is judged statistically, while FFM_LEARN_EXACT
+    reproduces the reference bit for bit on one episode.
+
+    overlap=True pipelines the exchange: the all-reduce of chunk k runs on NCCL's stream while chunk k+1 rolls out
+    into a second buffer; chunk k's deltas are applied right after rollout k+1 (tables lag by one chunk --
+    stale-synchronous with staleness 1, deterministic and identical on every rank).  Call flush() at the end.
     """
 
-    def __init__(self, sim, distributed=True):
+    def __init__(self, sim, distributed=True, overlap=False):
         assert sim.learn == "batched"
         self.sim = sim
         self.distributed = distributed      # False: never touch the process group (single-rank reference runs)
-        dev = sim.dV.device
-        self._vseen = torch.zeros(sim.S, dtype=torch.uint8, device=dev)
-        self._hseen = torch.zeros(sim.S, dtype=torch.uint8, device=dev)
+        self.overlap = overlap
+        self.bufs = [sim.delta, sim.new_delta_buffer()] if overlap else [sim.delta]
+        self._cur = 0
+        self._pending = None                # (work handle or None, buffer index) of the exchange in flight
+
+    def _apply(self, idx):
+        self.sim.bind_deltas(self.bufs[idx])
+        self.sim.apply_deltas()
 
     def sync(self):
-        """All-reduce deltas + flags, apply.  Call after rollout()."""
-        import ctypes as C
-        from . import _abi
-        from .sim import _ptr, _stream
-        s = self.sim
-        rank, ws = world() if self.distributed else (0, 1)
-        if ws > 1:
-            _abi.check(s._lib.ffm_tables_get(s._h, None, _ptr(self._vseen), None, _ptr(self._hseen), _abi.FFM_DEVICE, _stream()))
-            allreduce_deltas([s.dV, s.dN, s.dH], [self._vseen, self._hseen])
-            _abi.check(s._lib.ffm_tables_set(s._h, None, _ptr(self._vseen), None, _ptr(self._hseen), _abi.FFM_DEVICE, _stream()))
-        s.apply_deltas()
+        """Exchange + fold in.  Call after rollout().  No host synchronisation: everything is stream-ordered."""
+        if not self.overlap:
+            if self.distributed:
+                allreduce_flat(self.sim.delta)
+            self.sim.apply_deltas()
+            return
+        cur = self._cur
+        work = allreduce_flat(self.bufs[cur], async_op=True) if self.distributed else None
+        self.flush()                                   # the previous chunk's deltas: reduced while this chunk rolled out
+        self._pending = (work, cur)
+        self._cur = 1 - cur
+        self.sim.bind_deltas(self.bufs[self._cur])     # zeroed by its last apply
+
+    def flush(self):
+        """Apply the exchange still in flight (overlap mode)."""
+        if self._pending is not None:
+            work, idx = self._pending
+            if work is not None:
+                work.wait()                            # makes the current stream wait; the host does not block
+            self._apply(idx)
+            self._pending = None
+            self.sim.bind_deltas(self.bufs[self._cur])
 
     def round(self, pos_rc, n, max_steps, sync_every=None):
         """One batch of episodes.  sync_every = K folds the deltas in every K CA steps (value information then
@@ -76,7 +94,12 @@ class BatchedLearner:
             self.sim.rollout(max_steps)
             self.sync()
         else:
-            for _ in range(0, max_steps, sync_every):
-                self.sim.rollout(min(sync_every, max_steps))
+            done = 0
+            while done < max_steps:
+                k = min(sync_every, max_steps - done)
+                self.sim.rollout(k)
                 self.sync()
+                done += k
+        if self.overlap:
+            self.flush()
         return self.sim.counters()

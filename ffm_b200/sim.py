@@ -127,8 +127,7 @@ class BatchSim:
         keyed by the global episode id.  Resets DFF and counters."""
         n = np.ascontiguousarray(np.broadcast_to(np.asarray(n, dtype=np.int32), (self.B,)))
         er, ec, rad = (-1, -1, -1) if exit_pos is None or radius is None else (int(exit_pos[0]), int(exit_pos[1]), int(radius))
-        _abi.check(self._lib.ffm_place(self._h, _ptr(n), er, ec, rad, _stream()))
-        self._lib.ffm_get_positions(self._h, None, None, _abi.FFM_HOST, _stream())   # surfaces device-side errors
+        _abi.check(self._lib.ffm_place(self._h, _ptr(n), er, ec, rad, _stream()))   # synchronous; reports device-side errors
 
     def get_positions(self):
         """-> (pos_rc int32 [B, n_max, 2] with -1 padding, n int32 [B]) as NumPy arrays."""
@@ -274,13 +273,9 @@ class UnifiedSim(BatchSim):
         self.S, self.A = S.value, A.value
         self.bs = int(self.params["block_size"])
         self.nby = -(-self.W // self.bs)
-        self.dV = self.dN = self.dH = None
+        self.delta = self.dV = self.dN = self.dF = self.dH = None
         if learn == "batched":
-            dev = f"cuda:{self.device}"
-            self.dV = torch.zeros(self.S, dtype=torch.float64, device=dev)
-            self.dN = torch.zeros(self.S, dtype=torch.float64, device=dev)
-            self.dH = torch.zeros((self.S, self.A), dtype=torch.float64, device=dev)
-            _abi.check(self._lib.ffm_tables_bind_deltas(self._h, _ptr(self.dV), _ptr(self.dN), _ptr(self.dH)))
+            self.bind_deltas(self.new_delta_buffer())
 
     def _score_field(self, sff):
         if self.mode == "critic_only":
@@ -350,8 +345,22 @@ class UnifiedSim(BatchSim):
     def set_epsilon(self, epsilon):
         _abi.check(self._lib.ffm_set_epsilon(self._h, float(epsilon)))
 
+    # -- batched learning: ONE flat float64 buffer [dV | dN | dF | dH] per sync, so that the cross-GPU exchange is a
+    #    single all-reduce(sum) -----------------------------------------------------------------------
+    def new_delta_buffer(self):
+        return torch.zeros((3 + self.A) * self.S, dtype=torch.float64, device=f"cuda:{self.device}")
+
+    def bind_deltas(self, flat):
+        """Make ``flat`` (from new_delta_buffer) the buffer the following rollouts accumulate into."""
+        S = self.S
+        assert flat.is_cuda and flat.dtype == torch.float64 and flat.is_contiguous() and flat.numel() == (3 + self.A) * S
+        self.delta = flat
+        self.dV, self.dN, self.dF, self.dH = flat[:S], flat[S:2 * S], flat[2 * S:3 * S], flat[3 * S:].view(S, self.A)
+        _abi.check(self._lib.ffm_tables_bind_deltas(self._h, _ptr(self.dV), _ptr(self.dN), _ptr(self.dF), _ptr(self.dH)))
+
     def apply_deltas(self):
-        """V += dV, H += dH, deltas zeroed, H extremes refreshed (call after all-reducing dV / dH)."""
+        """Fold the bound delta buffer in (call after all-reducing it): V += (1-(1-alpha_v)^n) * mean TD error,
+        H += dH, touched keys marked present, deltas zeroed, H extremes refreshed.  Stream-ordered."""
         _abi.check(self._lib.ffm_tables_apply_deltas(self._h, _stream()))
 
 

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define FFM_ABI_VERSION 3
+#define FFM_ABI_VERSION 4
 
 enum {
     FFM_OK = 0,
@@ -194,12 +194,14 @@ int ffm_tables_set(ffm_sim_t sim, const double *V, const uint8_t *v_seen, const 
                    int space, void *stream);   /* set_v_table() :823-830, pretrained_v_path :84-110, h_table_path */
 int ffm_tables_get(ffm_sim_t sim, double *V, uint8_t *v_seen, double *H, uint8_t *h_seen, int space,
                    void *stream);              /* get_v_table() :814-821, get_h_table() :847-857 */
-/* FFM_LEARN_BATCHED: caller-owned device buffers the rollouts accumulate into with atomics and the caller
- * all-reduces (sum) across GPUs: dV double [S] sum of TD errors, dN double [S] visit counts,
- * dH double [S][A] sum of alpha_h*delta.  ffm_tables_apply_deltas then does, per state visited n times,
- * V += (1-(1-alpha_v)^n) * dV/n (n sequential updates towards the same targets), H += dH, zeroes the
- * deltas and refreshes the extremes of H. */
-int ffm_tables_bind_deltas(ffm_sim_t sim, double *dV, double *dN, double *dH);
+/* FFM_LEARN_BATCHED: caller-owned device buffers the rollouts accumulate into and the caller all-reduces (sum)
+ * across GPUs -- normally four slices of ONE flat buffer, so that the exchange is a single collective:
+ * dV double [S] sum of TD errors, dN double [S] visit counts, dF double [S] > 0 where a key of V was touched
+ * (the defaultdict reads of ffm_unified.py:658,661 insert keys), dH double [S][A] sum of alpha_h*delta (may be NULL
+ * for critic_only).  ffm_tables_apply_deltas then does, per state visited n times, V += (1-(1-alpha_v)^n) * dV/n
+ * (n sequential updates towards the same targets), H += dH, marks the touched keys / visited rows present, zeroes
+ * the deltas and refreshes the extremes of H.  Stream-ordered, no host synchronisation. */
+int ffm_tables_bind_deltas(ffm_sim_t sim, double *dV, double *dN, double *dF, double *dH);
 int ffm_tables_apply_deltas(ffm_sim_t sim, void *stream);
 int ffm_set_epsilon(ffm_sim_t sim, double epsilon);   /* set_epsilon() :859-867 */
 /* global id of episode 0 for the following rollouts (a drop-in object advances it on every reset()) */

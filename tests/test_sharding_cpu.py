@@ -28,12 +28,14 @@ def _worker(rank, ws, port, out):
         first, count = sharding.shard_range(10, None, None)
         S, A = 64, 5
         g = torch.Generator().manual_seed(100 + rank)
-        dV = torch.rand(S, dtype=torch.float64, generator=g)
-        dH = torch.rand(S, A, dtype=torch.float64, generator=g)
-        seen = torch.zeros(S, dtype=torch.uint8)
-        seen[rank::3] = 1
-        sharding.allreduce_deltas([dV, dH], [seen])
-        out.put((rank, first, count, dV.numpy().copy(), dH.numpy().copy(), seen.numpy().copy()))
+        flat = torch.zeros((3 + A) * S, dtype=torch.float64)          # [dV | dN | dF | dH], one collective
+        flat[:S] = torch.rand(S, dtype=torch.float64, generator=g)
+        flat[3 * S:] = torch.rand(S * A, dtype=torch.float64, generator=g)
+        flat[2 * S + rank:3 * S:3] = 1.0                               # key-touched marks of this rank
+        work = sharding.allreduce_flat(flat, async_op=True)
+        work.wait()
+        out.put((rank, first, count, flat[:S].numpy().copy(), flat[3 * S:].numpy().copy(),
+                 (flat[2 * S:3 * S] > 0).numpy().astype(np.uint8)))
         dist.barrier()
     finally:
         dist.destroy_process_group()
