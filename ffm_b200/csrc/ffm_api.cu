@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "ffm_core_kernel.cuh"
+#include "ffm_cell_kernel.cuh"
 #include "ffm_sff_kernels.cuh"
 #include "ffm_unified_kernel.cuh"
 #include "ffm_mcq_kernel.cuh"
@@ -64,6 +65,10 @@ struct ffm_sim_s {
     uint32_t* d_free; int* d_free_count; int32_t* d_n_req;   // placement: eligible cells, their number, requested counts
     int place_er, place_ec, place_radius, place_count;       // what d_free currently holds (-2: nothing)
     const void* kernel;  // selected rollout kernel
+    bool cell_kernel;    // base model: the cell-centric kernel (ffm_cell_kernel.cuh); false = round-1 pedestrian-centric kernel
+    int cluster;         // CTAs per episode (thread-block cluster, row bands in distributed shared memory); 1 = one CTA
+    int RW, RB;          // bitboard words per row, rows per band
+    uint32_t* d_wall_bits;
     // unified / trained models
     int S, A, nby;
     double* d_V; uint8_t* d_vseen; double* d_H; uint8_t* d_hseen;
@@ -115,6 +120,26 @@ __global__ void prep_fields_kernel(const uint8_t* map, const S* sff, uint16_t* t
             score[c] = mul_rn(neg_ks, sff[c]);
         }
         type_grid[x] = (uint16_t)cell;
+    }
+}
+
+// static bitboard of the cell-centric kernel: row br = r + 1, word bw = col / 32 + 1 (one guard row / word on every
+// side), bit set = not passable or outside the map
+__global__ void prep_wall_bits_kernel(const uint16_t* type_grid, uint32_t* wall_bits, int H, int W, int RW) {
+    const int G = W + 1, total = (H + 2) * RW;
+    for (int x = blockIdx.x * blockDim.x + threadIdx.x; x < total; x += gridDim.x * blockDim.x) {
+        const int br = x / RW, bw = x - br * RW;
+        const int r = br - 1;
+        uint32_t v = 0xffffffffu;
+        if (r >= 0 && r < H && bw >= 1 && bw <= RW - 2) {
+            v = 0u;
+            for (int b = 0; b < 32; ++b) {
+                const int col = (bw - 1) * 32 + b;
+                const bool blocked = col >= W || ((type_grid[r * W + col + G] >> TYPE_SHIFT) == TYPE_WALL);
+                if (blocked) v |= 1u << b;
+            }
+        }
+        wall_bits[x] = v;
     }
 }
 
@@ -346,16 +371,31 @@ int ffm_create(const ffm_config_t* cfg, ffm_sim_t* out) {
     const int ssz = cfg->sff_dtype == FFM_F64 ? 8 : 4;
     const bool dff = cfg->track_dff != 0;
 
-    // kernel variant: fields in shared memory when they fit, and as many threads as pedestrians
+    // kernel variant: fields in shared memory when they fit, and as many threads as there is work per step
     // (rounded to a supported CTA size) without starving co-resident CTAs
-    const int tot_in = mcq ? (1 << 30) : unified ? (int)ffm::make_ulayout(HW, W, N, ssz, true).total : (int)ffm::make_layout(HW, W, N, ssz, dff, true).total;
-    const int tot_out = mcq ? (int)ffm::make_mlayout(HW, W, N).total
-                            : unified ? (int)ffm::make_ulayout(HW, W, N, ssz, false).total : (int)ffm::make_layout(HW, W, N, ssz, dff, false).total;
+    const bool core = !mcq && !unified;
+    const int WW = (W + 31) / 32;
+    s->RW = WW + 2;
+    s->RB = cfg->height;
+    s->cluster = 1;
+    s->cell_kernel = core;
+    if (const char* ev = getenv("FFM_KERNEL")) s->cell_kernel = core && strcmp(ev, "ped") != 0;   // A/B switch: the round-1 kernel
+    const int esz = HW <= 65536 ? 2 : 4;
+    auto layout_total = [&](bool fs) -> long long {
+        if (mcq) return fs ? (1LL << 30) : (long long)ffm::make_mlayout(HW, W, N).total;
+        if (unified) return ffm::make_ulayout(HW, W, N, ssz, fs).total;
+        if (s->cell_kernel) return ffm::make_cell_layout(s->RB, W, s->RW, N, ssz, esz, dff, fs).total;
+        return ffm::make_layout(HW, W, N, ssz, dff, fs).total;
+    };
+    if (s->cell_kernel && layout_total(false) > MAX_SMEM_OPTIN) s->cell_kernel = false;   // TODO cluster variants
+    if (s->cell_kernel && (long long)HW * W >= (1LL << 32)) s->cell_kernel = false;       // row = umulhi(cell, magic) needs cell * W < 2^32
+    const long long tot_in = layout_total(true), tot_out = layout_total(false);
     if (tot_out > MAX_SMEM_OPTIN) {
         delete s;
-        return fail(FFM_E_UNSUPPORTED, "episode state (%d B) does not fit the 227 KB of shared memory of one SM", tot_out);
+        return fail(FFM_E_UNSUPPORTED, "episode state (%lld B) does not fit the 227 KB of shared memory of one SM", tot_out);
     }
-    const int work = N > HW / 8 ? N : HW / 8;
+    int work = N > HW / 8 ? N : HW / 8;
+    if (s->cell_kernel) work = cfg->height * 2 * WW;      // 16-cell bitboard chunks per step
     s->threads = work <= 128 ? 128 : (work <= 2048 ? 256 : 1024);
     if (const char* ev = getenv("FFM_THREADS")) {   // tuning override: 128 | 256 | 1024
         const int v = atoi(ev);
@@ -373,9 +413,11 @@ int ffm_create(const ffm_config_t* cfg, ffm_sim_t* out) {
     // global +10 %.  Rule: shared unless the global variant keeps at least 1.5x as many CTAs resident.
     if (mcq) s->threads = N <= 128 ? 128 : 256;
     auto kernel_for = [&](bool fs) {
-        if (mcq) return ffm::pick_mcq_kernel(cfg->sff_dtype == FFM_F64, s->threads);
-        return unified ? ffm::pick_unified_kernel(cfg->sff_dtype == FFM_F64, cfg->neighborhood, fs, s->threads)
-                       : pick_kernel(cfg->sff_dtype == FFM_F64, HW <= 65536, cfg->neighborhood, dff, fs, s->threads);
+        const bool f64 = cfg->sff_dtype == FFM_F64;
+        if (mcq) return ffm::pick_mcq_kernel(f64, s->threads);
+        if (unified) return ffm::pick_unified_kernel(f64, cfg->neighborhood, fs, s->threads);
+        if (s->cell_kernel) return ffm::pick_cell_kernel(f64, HW <= 65536, cfg->neighborhood, dff, fs, s->threads, s->cluster);
+        return pick_kernel(f64, HW <= 65536, cfg->neighborhood, dff, fs, s->threads);
     };
     auto occupancy = [&](const void* k, int smem) {
         int occ = 0;
@@ -383,12 +425,12 @@ int ffm_create(const ffm_config_t* cfg, ffm_sim_t* out) {
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, s->threads, smem) != cudaSuccess) return 0;
         return occ;
     };
-    const int occ_out = occupancy(kernel_for(false), tot_out);
-    const int occ_in = tot_in <= MAX_SMEM_OPTIN ? occupancy(kernel_for(true), tot_in) : 0;
+    const int occ_out = occupancy(kernel_for(false), (int)tot_out);
+    const int occ_in = tot_in <= MAX_SMEM_OPTIN ? occupancy(kernel_for(true), (int)tot_in) : 0;
     s->fields_in_smem = occ_in > 0 && 2 * occ_out < 3 * occ_in;
     if (getenv("FFM_FIELDS_GLOBAL")) s->fields_in_smem = false;          // tuning overrides
     if (getenv("FFM_FIELDS_SMEM") && occ_in > 0) s->fields_in_smem = true;
-    s->smem_bytes = s->fields_in_smem ? tot_in : tot_out;
+    s->smem_bytes = (int)(s->fields_in_smem ? tot_in : tot_out);
     s->kernel = kernel_for(s->fields_in_smem);
     cudaError_t ce = cudaFuncSetAttribute(s->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, s->smem_bytes);
     if (ce != cudaSuccess) { delete s; return fail(FFM_E_CUDA, "cudaFuncSetAttribute(smem=%d): %s", s->smem_bytes, cudaGetErrorString(ce)); }
@@ -404,6 +446,7 @@ int ffm_create(const ffm_config_t* cfg, ffm_sim_t* out) {
     } while (0)
     ALLOC(s->d_map, (size_t)HW);
     ALLOC(s->d_type_grid, (size_t)(HW + 2 * (W + 1)) * 2 + 16);   // padded: the rollout kernel bulk-copies it in 16-byte units
+    ALLOC(s->d_wall_bits, (size_t)(cfg->height + 2) * s->RW * 4);
     ALLOC(s->d_sff, (size_t)HW * ssz);
     ALLOC(s->d_score, (size_t)HW * ssz);
     ALLOC(s->d_pos, (size_t)B * N * 4);
@@ -418,7 +461,7 @@ int ffm_create(const ffm_config_t* cfg, ffm_sim_t* out) {
     s->place_radius = -2;
     if (dff) {
         // both DFF buffers in one allocation
-        const bool two = !s->fields_in_smem || mcq;
+        const bool two = !s->fields_in_smem || mcq;   // the cluster variants keep the ping-pong buffer on chip too
         ALLOC(s->d_dff, (size_t)B * HW * 4 * (two ? 2 : 1));
         if (two) s->d_dff_tmp = s->d_dff + (size_t)B * HW;
     }
@@ -465,7 +508,7 @@ int ffm_create(const ffm_config_t* cfg, ffm_sim_t* out) {
 int ffm_destroy(ffm_sim_t s) {
     if (!s) return FFM_OK;
     cudaSetDevice(s->cfg.device);
-    cudaFree(s->d_map); cudaFree(s->d_type_grid); cudaFree(s->d_sff); cudaFree(s->d_score);
+    cudaFree(s->d_map); cudaFree(s->d_type_grid); cudaFree(s->d_wall_bits); cudaFree(s->d_sff); cudaFree(s->d_score);
     cudaFree(s->d_pos); cudaFree(s->d_pos_rc); cudaFree(s->d_n); cudaFree(s->d_t);
     cudaFree(s->d_ped_steps); cudaFree(s->d_err); cudaFree(s->d_dff);
     cudaFree(s->d_free); cudaFree(s->d_free_count); cudaFree(s->d_n_req);
@@ -491,7 +534,9 @@ int ffm_set_fields(ffm_sim_t s, const uint8_t* map, const void* sff, int space, 
     else
         ffm::prep_fields_kernel<float><<<blocks, 256, 0, st>>>(s->d_map, (const float*)s->d_sff, s->d_type_grid, (float*)s->d_score, H, W, s->cfg.neighborhood, (float)(-s->cfg.k_S), s->d_err);
     CU(cudaGetLastError());
-    s->launches++;
+    ffm::prep_wall_bits_kernel<<<((H + 2) * s->RW + 255) / 256, 256, 0, st>>>(s->d_type_grid, s->d_wall_bits, H, W, s->RW);
+    CU(cudaGetLastError());
+    s->launches += 2;
     if ((rc = check_device_flag(s, st))) return rc;
     s->have_fields = true;
     s->place_radius = -2;
@@ -671,6 +716,44 @@ int ffm_rollout(ffm_sim_t s, int32_t max_steps, const ffm_draws_t* draws, const 
         }
         void* uargs[] = {&U};
         CU(cudaLaunchKernel(s->kernel, dim3(s->cfg.n_episodes), dim3(s->threads), uargs, (size_t)s->smem_bytes, st));
+        s->launches++;
+        return FFM_OK;
+    }
+    if (s->cell_kernel) {
+        ffm::CellParams C;
+        memset(&C, 0, sizeof(C));
+        C.H = s->cfg.height; C.W = s->cfg.width; C.HW = s->HW; C.n_max = s->cfg.n_max; C.B = s->cfg.n_episodes;
+        C.max_steps = max_steps;
+        C.RW = s->RW; C.RB = s->RB;
+        C.magic_w = (uint32_t)(((1ULL << 32) + (uint64_t)C.W - 1) / (uint64_t)C.W);
+        const uint64_t cpr = 2ULL * (uint64_t)(s->RW - 2);
+        C.magic_cpr = (uint32_t)(((1ULL << 32) + cpr - 1) / cpr);
+        C.type_grid = s->d_type_grid; C.wall_bits = s->d_wall_bits; C.score = s->d_score;
+        C.kd = (float)s->cfg.k_D; C.c0 = s->cfg.dff_c0; C.c1 = s->cfg.dff_c1; C.thr = s->cfg.dff_threshold;
+        C.pos = s->d_pos; C.n_alive = s->d_n; C.t_done = s->d_t; C.ped_steps = s->d_ped_steps;
+        C.dff = s->d_dff; C.dff_tmp = s->d_dff_tmp;
+        C.seed = s->cfg.seed; C.episode_base = s->cfg.episode_base;
+        if (draws) { C.move_draws = draws->move; C.conflict_draws = draws->conflict; C.draw_steps = draws->steps; C.draw_first = draws->first_step; }
+        if (out && out->traj_cells) {
+            if (!out->traj_n) return fail(FFM_E_INVALID, "traj_cells without traj_n");
+            C.traj = out->traj_cells; C.traj_n = out->traj_n; C.traj_steps = out->traj_steps;
+        }
+        void* cargs[] = {&C};
+        if (s->cluster == 1) {
+            CU(cudaLaunchKernel(s->kernel, dim3(s->cfg.n_episodes), dim3(s->threads), cargs, (size_t)s->smem_bytes, st));
+        } else {
+            cudaLaunchConfig_t lc;
+            memset(&lc, 0, sizeof(lc));
+            lc.gridDim = dim3((unsigned)s->cfg.n_episodes * (unsigned)s->cluster);
+            lc.blockDim = dim3(s->threads);
+            lc.dynamicSmemBytes = (size_t)s->smem_bytes;
+            lc.stream = st;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = (unsigned)s->cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+            lc.attrs = at; lc.numAttrs = 1;
+            CU(cudaLaunchKernelExC(&lc, s->kernel, cargs));
+        }
         s->launches++;
         return FFM_OK;
     }

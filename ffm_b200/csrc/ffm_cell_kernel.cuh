@@ -1,0 +1,758 @@
+// Persistent rollout kernel of the base floor-field CA, cell-centric formulation: one CTA per episode -- or one
+// thread-block CLUSTER per episode, the map split into row bands held in distributed shared memory -- all steps
+// in-kernel.
+//
+// Reproduces, per step, FloorFieldModel.step() + update_dff() of the reference (model/ffm_core.py:36-117) and,
+// around it, the loop of run() (ffm_core.py:119-126).
+//
+// The reference walks the pedestrians one by one and rebuilds each one's candidate list with np.isin (:48-60).
+// Here the crowd is a BITBOARD (one bit per cell: blocked = wall or occupied) and a step is three block-wide phases
+// separated by one barrier each:
+//
+//   1 (cells -> movers)   every thread owns 16 cells of a bitboard row: the 8 (4) shifted copies of the "free" rows
+//                         give, bit-parallel, which occupied cells have a free neighbour at all (:57-63 -- a
+//                         pedestrian with no candidate makes no request and draws nothing) and, through a carry-save
+//                         adder over the shifted words, HOW MANY free neighbours each has.  Movers are appended to
+//                         three work lists by candidate count (2 / 3 / more candidates incl. "stay"), so that phase 2
+//                         runs with uniform trip counts.  Blocked pedestrians (55 % of all pedestrian-steps in a
+//                         packed crowd) cost nothing beyond these bit operations.
+//                         The same phase sweeps the claim masks, refreshes the alive-rank prefix after exits and runs
+//                         the DFF decay/diffusion of the PREVIOUS step (:106-117).
+//   2 (movers -> requests) per list entry: candidate mask from the bitboard windows, forced exit (:66-72) or
+//                         score = -k_S*sff + k_D*dff, exp(score - max), keyed uniform, CDF search (:74-88) -> target;
+//                         the request is one atomicOr of the direction bit into the target cell's CLAIM MASK (a byte
+//                         per cell: bit k = "the occupant of neighbour k wants this cell"); the requester that finds
+//                         the mask empty becomes the cell's resolver.  "Stay" decisions leave their footprint here.
+//   3 (resolve + apply)   one thread per requested cell: a lone claimant moves (:91-93); k >= 2 claimants -> coin,
+//                         then the floor(u*k)-th claimant in ascending agent index (:94-98), found from the claim
+//                         mask (no neighbourhood scan per claimant).  The move is applied at once: owner grid,
+//                         bitboard, DFF footprint, exit removal (:101-102).  Concurrent resolvers never touch the
+//                         same cells: a pedestrian claims exactly one cell, and a cell has exactly one resolver.
+//
+// A pedestrian's identity is a stable id (its index at launch); the reference's array index -- the key of its move
+// draw -- is the id's alive rank (prefix popcount over the alive bitmap), because the reference compacts the
+// position array stably (:101-102).  There are no per-pedestrian arrays at all: the owner grid maps cell -> id.
+//
+// Cluster mode (CL > 1): CTA b of the cluster owns rows [b*RB, (b+1)*RB) of every per-cell array.  Phase 1 reads
+// the bitboard row above / below its band from the neighbour CTA, moves / claims / DFF reads that cross a band
+// boundary go through distributed shared memory (cluster.map_shared_rank), the alive bitmap is replicated and exits
+// are broadcast; the three barriers become cluster barriers.  This keeps maps that do not fit one SM's shared memory
+// (BASELINE C3: 256x256 with DFF) entirely on chip.
+#pragma once
+#include <cooperative_groups.h>
+
+#include <type_traits>
+
+#include "ffm_core_kernel.cuh"
+
+namespace ffm {
+
+namespace cg = cooperative_groups;
+
+struct CellParams {
+    int H, W, HW, n_max, B;
+    int max_steps;
+    int RW;                      // bitboard words per row: ceil(W/32) + 2 guard words
+    int RB;                      // rows per band (H when one CTA holds the whole map)
+    uint32_t magic_w;            // ceil(2^32 / W): row = umulhi(cell, magic_w) for cell * W < 2^32
+    uint32_t magic_cpr;          // ceil(2^32 / chunks per row), chunks per row = 2 * ceil(W/32)
+    const uint16_t* type_grid;   // [HW + 2*(W+1)] type bits only, guard band included
+    const uint32_t* wall_bits;   // [(H+2) * RW] 1 = not passable / outside the map
+    const void* score;           // [HW] S
+    float kd, c0, c1, thr;
+    uint32_t* pos;               // [B][n_max] linear cells, alive-rank order
+    int32_t* n_alive;            // [B]
+    int32_t* t_done;             // [B]
+    unsigned long long* ped_steps;  // [B]
+    float* dff;                  // [B][HW]
+    float* dff_tmp;              // [B][HW]   second buffer when the fields stay in global memory
+    unsigned long long seed;
+    uint32_t episode_base;
+    const double* move_draws;    // [B][draw_steps][n_max] or null
+    const double* conflict_draws;  // [B][draw_steps][HW][2] or null
+    int draw_steps, draw_first;
+    uint32_t* traj;              // [B][traj_steps][n_max] or null
+    int32_t* traj_n;             // [B][traj_steps]
+    int traj_steps;
+    // compact trajectory record (what run() collects, ffm_core.py:125 / main.py:44-52): per episode a stream of
+    // (row, col) int16 pairs, the rows of consecutive steps back to back, each padded to a multiple of 4 entries
+    short2* ctraj;               // [B][ctraj_cap]
+    int32_t* ctraj_off;          // [B][traj_steps + 1]: entry offset of each step's row (CSR); [steps] = end
+    int ctraj_cap;
+};
+
+struct CellLayout {
+    uint32_t score, dffA, dffB, grid, cmask, blk, wall, listA, listB, alive, wpre, ctr, bar, total;
+    uint32_t cap;   // capacity of each work list (entries)
+};
+
+__host__ __device__ inline CellLayout make_cell_layout(int RB, int W, int RW, int n_max, int sizeof_score, int sizeof_ent, bool dff,
+                                                       bool fields_in_smem) {
+    const uint32_t cells = (uint32_t)RB * W;
+    const uint32_t nw = (uint32_t)(n_max + 31) / 32 + 1;
+    CellLayout L;
+    L.cap = (uint32_t)n_max < cells ? (uint32_t)n_max : cells;
+    uint32_t o = 0;
+    L.score = o; if (fields_in_smem) o = align16(o + cells * sizeof_score);
+    L.dffA = o;  if (fields_in_smem && dff) o = align16(o + cells * 4u);
+    L.dffB = o;  if (fields_in_smem && dff) o = align16(o + cells * 4u);
+    L.grid = o;  o = align16(o + (cells + 2u * (W + 1)) * 2u);
+    L.cmask = o; o = align16(o + cells);
+    L.blk = o;   o = align16(o + (uint32_t)(RB + 2) * RW * 4u);
+    L.wall = o;  o = align16(o + (uint32_t)(RB + 2) * RW * 4u);
+    L.listA = o; o = align16(o + L.cap * sizeof_ent);
+    L.listB = o; o = align16(o + L.cap * sizeof_ent);
+    L.alive = o; o = align16(o + nw * 4u);
+    L.wpre = o;  o = align16(o + nw * 4u);
+    L.ctr = o;   o = align16(o + 16u * 4u);
+    L.bar = o;   o = align16(o + 8u);
+    L.total = o;
+    return L;
+}
+
+// row / column offset of a neighbour index only known at run time (the tables of nbr_off_rt)
+template <int NBR> __device__ __forceinline__ int nbr_dr_rt(int k) { return (int)(((NBR == 8 ? 0xA940u : 0x58u) >> (2 * k)) & 3u) - 1; }
+template <int NBR> __device__ __forceinline__ int nbr_dc_rt(int k) { return (int)(((NBR == 8 ? 0x9224u : 0x85u) >> (2 * k)) & 3u) - 1; }
+
+// index of the neighbour opposite to k (the direction from the target back to the claimant)
+template <int NBR> __device__ __forceinline__ int nbr_opp(int k) { return NBR == 8 ? 7 - k : (k ^ 1); }
+
+// Compare-exchange network: ascending sort of the NBR keys (invalid entries hold 0xFFFFFFFF and end up last).
+template <int NBR>
+__device__ __forceinline__ void sort_keys(uint32_t (&v)[NBR]) {
+#define FFM_CX(a, b) { const uint32_t lo_ = min(v[a], v[b]), hi_ = max(v[a], v[b]); v[a] = lo_; v[b] = hi_; }
+    if (NBR == 4) {
+        FFM_CX(0, 1) FFM_CX(2, 3) FFM_CX(0, 2) FFM_CX(1, 3) FFM_CX(1, 2)
+    } else {
+        FFM_CX(0, 1) FFM_CX(2, 3) FFM_CX(4, 5) FFM_CX(6, 7)
+        FFM_CX(0, 2) FFM_CX(1, 3) FFM_CX(4, 6) FFM_CX(5, 7)
+        FFM_CX(1, 2) FFM_CX(5, 6) FFM_CX(0, 4) FFM_CX(3, 7)
+        FFM_CX(1, 5) FFM_CX(2, 6)
+        FFM_CX(1, 4) FFM_CX(3, 6)
+        FFM_CX(2, 4) FFM_CX(3, 5)
+        FFM_CX(3, 4)
+    }
+#undef FFM_CX
+}
+
+// update_dff (ffm_core.py:106-117) over the rows [r0, r1) of a field whose rows are reached through in_row(r)
+// (nullptr outside the map: np.pad of the scaled field, :111) -- same arithmetic as dff_decay_diffuse.
+template <int NBR, typename RowIn, typename RowOut>
+__device__ __forceinline__ void dff_stencil_rows(RowIn in_row, RowOut out_row, int r0, int r1, int W, float c0, float c1, float thr,
+                                                 int tid, int nthreads) {
+    const int Hb = r1 - r0;
+    const int cw = W < nthreads ? W : nthreads;
+    const int bands = W < nthreads ? nthreads / W : 1;
+    const int rpb = (Hb + bands - 1) / bands;
+    const int band = tid / cw, colb = tid - band * cw;
+    if (band >= bands) return;
+    const int a0 = r0 + band * rpb, a1 = min(r1, a0 + rpb);
+    if (a0 >= a1) return;
+    for (int col = colb; col < W; col += cw) {
+        const bool hasl = col > 0, hasr = col + 1 < W;
+        float up[3], uc[3], un[3], sc = 0.0f;
+        auto load_row = [&](int r, float (&u)[3], float& s_centre) {
+            float d0 = 0.0f, d1 = 0.0f, d2 = 0.0f;
+            const float* row = in_row(r);
+            if (row != nullptr) {
+                d1 = row[col];
+                if (hasl) d0 = row[col - 1];
+                if (hasr) d2 = row[col + 1];
+            }
+            const float s0 = __fmul_rn(c0, d0), s1 = __fmul_rn(c0, d1), s2 = __fmul_rn(c0, d2);   // (:109)
+            u[0] = __fmul_rn(c1, s0); u[1] = __fmul_rn(c1, s1); u[2] = __fmul_rn(c1, s2);         // (:113)
+            s_centre = s1;
+        };
+        float dummy;
+        load_row(a0 - 1, up, dummy);
+        load_row(a0, uc, sc);
+        for (int r = a0; r < a1; ++r) {
+            float sn;
+            load_row(r + 1, un, sn);
+            float acc = sc;
+            if (NBR == 8) {   // (-1,-1) (-1,0) (-1,1) (0,-1) (0,1) (1,-1) (1,0) (1,1)
+                acc = __fadd_rn(acc, up[0]); acc = __fadd_rn(acc, up[1]); acc = __fadd_rn(acc, up[2]);
+                acc = __fadd_rn(acc, uc[0]); acc = __fadd_rn(acc, uc[2]);
+                acc = __fadd_rn(acc, un[0]); acc = __fadd_rn(acc, un[1]); acc = __fadd_rn(acc, un[2]);
+            } else {          // (-1,0) (1,0) (0,-1) (0,1)
+                acc = __fadd_rn(acc, up[1]); acc = __fadd_rn(acc, un[1]);
+                acc = __fadd_rn(acc, uc[0]); acc = __fadd_rn(acc, uc[2]);
+            }
+            if (acc < thr) acc = 0.0f;                                                            // (:116-117)
+            out_row(r)[col] = acc;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { up[k] = uc[k]; uc[k] = un[k]; }
+            sc = sn;
+        }
+    }
+}
+
+template <typename S, typename EntT, int NBR, bool DFF, bool FIELDS_IN_SMEM, int THREADS, int CL>
+__global__ void __launch_bounds__(THREADS, (CL == 1 && THREADS <= 256 && sizeof(S) == 4) ? 1536 / THREADS : 1)
+ffm_cell_rollout_kernel(const CellParams P) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int NW = THREADS / 32;
+    constexpr uint32_t EXIT_EMPTY = TYPE_EXIT << TYPE_SHIFT;
+    constexpr uint32_t FULL = 0xffffffffu;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int W = P.W, HW = P.HW, H = P.H, RW = P.RW, G = W + 1;
+    const int WW = RW - 2;
+
+    // ---- band geometry ------------------------------------------------------------------------------
+    unsigned band = 0;
+    int e = blockIdx.x;
+    if (CL > 1) {
+        band = cg::this_cluster().block_rank();
+        e = blockIdx.x / CL;
+    }
+    const int RB = P.RB;
+    const int r0 = (int)band * RB;                       // first row of this band
+    const int r1 = min(H, r0 + RB);                      // one past its last row (an empty band has r1 <= r0)
+    const int RBl = max(0, r1 - r0);
+    const int lo = r0 * W, hi = lo + RBl * W;            // cells owned: [lo, hi)
+    const bool top = (CL == 1) || band == 0, bottom = (CL == 1) || r1 >= H;
+    // cells addressable in this CTA's arrays: the owned ones plus the guard bands at the map's top / bottom edge
+    const int lo_acc = lo - (top ? G : 0);
+    const uint32_t span_acc = (uint32_t)(hi - lo_acc + (bottom ? G : 0));
+
+    const CellLayout L = make_cell_layout(RB, W, RW, P.n_max, (int)sizeof(S), (int)sizeof(EntT), DFF, FIELDS_IN_SMEM);
+    uint16_t* grid_l = reinterpret_cast<uint16_t*>(smem_raw + L.grid) + G;     // grid_l[c - lo]
+    uint32_t* cmask_l = reinterpret_cast<uint32_t*>(smem_raw + L.cmask);       // byte (c - lo) of this array
+    uint32_t* blk_l = reinterpret_cast<uint32_t*>(smem_raw + L.blk);           // row (r - r0 + 1), word (col/32 + 1)
+    uint32_t* wall_l = reinterpret_cast<uint32_t*>(smem_raw + L.wall);
+    EntT* listA = reinterpret_cast<EntT*>(smem_raw + L.listA);
+    EntT* listB = reinterpret_cast<EntT*>(smem_raw + L.listB);
+    const int cap1 = (int)L.cap - 1;
+    uint32_t* alive = reinterpret_cast<uint32_t*>(smem_raw + L.alive);
+    uint32_t* wpre = reinterpret_cast<uint32_t*>(smem_raw + L.wpre);
+    uint32_t* ctr = reinterpret_cast<uint32_t*>(smem_raw + L.ctr);             // [parity][n2, n3, nbig, n_exit, ...]
+    unsigned long long* bar = reinterpret_cast<unsigned long long*>(smem_raw + L.bar);
+    S* score_l = reinterpret_cast<S*>(smem_raw + L.score);
+    float* dffA_l = reinterpret_cast<float*>(smem_raw + L.dffA);
+    float* dffB_l = reinterpret_cast<float*>(smem_raw + L.dffB);
+    const S* score_g = reinterpret_cast<const S*>(P.score);
+    float* dff_home = DFF ? P.dff + (size_t)e * HW : nullptr;
+    float* dffA_g = dff_home;
+    float* dffB_g = DFF ? P.dff_tmp + (size_t)e * HW : nullptr;
+
+    // ---- accessors: a cell of this band is local shared memory, a cell of a neighbouring band is reached through
+    //      distributed shared memory (same offset in the neighbour CTA's window) --------------------------------
+    auto is_local = [&](int c) -> bool { return CL == 1 || (uint32_t)(c - lo_acc) < span_acc; };
+    auto nb_rank = [&](int c) -> unsigned { return c < lo ? band - 1 : band + 1; };
+    auto grid_ptr = [&](int c) -> uint16_t* {
+        if (is_local(c)) return grid_l + (c - lo);
+        const unsigned rk = nb_rank(c);
+        return cg::this_cluster().map_shared_rank(grid_l, rk) + (c - (int)rk * RB * W);
+    };
+    auto cmask_word = [&](int c, uint32_t& shift) -> uint32_t* {          // the 32-bit word holding cell c's claim byte
+        uint32_t* base = cmask_l;
+        int lc = c - lo;
+        if (!is_local(c)) {
+            const unsigned rk = nb_rank(c);
+            base = cg::this_cluster().map_shared_rank(cmask_l, rk);
+            lc = c - (int)rk * RB * W;
+        }
+        shift = 8u * ((uint32_t)lc & 3u);
+        return base + (lc >> 2);
+    };
+    auto blk_word = [&](int r, int col, uint32_t& bit) -> uint32_t* {     // bitboard word of cell (r, col)
+        bit = 1u << (col & 31);
+        if (CL == 1 || (r >= r0 && r < r1)) return blk_l + (r - r0 + 1) * RW + 1 + (col >> 5);
+        const unsigned rk = r < r0 ? band - 1 : band + 1;
+        return cg::this_cluster().map_shared_rank(blk_l, rk) + (r - (int)rk * RB + 1) * RW + 1 + (col >> 5);
+    };
+    int dpar = 0;   // which physical DFF buffer currently holds the field ("A"); flips once per step in every CTA alike
+    auto dff_cur = [&](int c) -> float* {                                 // current DFF value of cell c
+        if (!FIELDS_IN_SMEM) return (dpar ? dffB_g : dffA_g) + c;
+        float* base = dpar ? dffB_l : dffA_l;
+        if (is_local(c) && (CL == 1 || (c >= lo && c < hi))) return base + (c - lo);
+        const unsigned rk = nb_rank(c);
+        return cg::this_cluster().map_shared_rank(base, rk) + (c - (int)rk * RB * W);
+    };
+    auto score_at = [&](int c) -> S {
+        if (!FIELDS_IN_SMEM) return score_g[c];
+        if (CL == 1 || (c >= lo && c < hi)) return score_l[c - lo];
+        const unsigned rk = nb_rank(c);
+        return cg::this_cluster().map_shared_rank(score_l, rk)[c - (int)rk * RB * W];
+    };
+    auto sync_all = [&]() {
+        if (CL == 1) __syncthreads(); else cg::this_cluster().sync();
+    };
+
+    // ---- prologue: stage the band's fields (TMA bulk copies + mbarrier when 16-byte aligned) -----------------
+    const uint32_t cells = (uint32_t)RBl * W;
+    const uint32_t grid_elems = cells + 2u * G;
+    const uint32_t grid_bytes = align16(grid_elems * 2u), score_bytes = cells * (uint32_t)sizeof(S), dff_bytes = cells * 4u;
+    // the band slices start at element lo of their arrays (type_grid: index = cell + G, and local index 0 <-> cell lo - G)
+    const bool tma_grid = RBl > 0 && (((size_t)lo * 2u) % 16u == 0u);   // d_type_grid is padded to a multiple of 16 bytes
+    const bool tma_fields = FIELDS_IN_SMEM && RBl > 0 && (score_bytes % 16u == 0u) && (dff_bytes % 16u == 0u) &&
+                            (((size_t)lo * sizeof(S)) % 16u == 0u) && (((size_t)lo * 4u) % 16u == 0u) && (((size_t)HW * 4u) % 16u == 0u);
+    if (tid == 0) mbar_init(bar, 1);
+    __syncthreads();
+    if (tid == 0) {
+        uint32_t bytes = 0;
+        if (tma_grid) bytes += grid_bytes;
+        if (tma_fields) bytes += score_bytes + (DFF ? dff_bytes : 0u);
+        mbar_arrive_expect_tx(bar, bytes);
+        if (tma_grid) bulk_copy_g2s(smem_raw + L.grid, P.type_grid + lo, grid_bytes, bar);
+        if (tma_fields) {
+            bulk_copy_g2s(score_l, score_g + lo, score_bytes, bar);
+            if (DFF) bulk_copy_g2s(dffA_l, dff_home + lo, dff_bytes, bar);
+        }
+    }
+    if (!tma_grid) for (uint32_t x = tid; x < grid_elems; x += THREADS) grid_l[(int)x - G] = P.type_grid[lo + x];
+    if (FIELDS_IN_SMEM && !tma_fields) {
+        for (uint32_t x = tid; x < cells; x += THREADS) score_l[x] = score_g[lo + x];
+        if (DFF) for (uint32_t x = tid; x < cells; x += THREADS) dffA_l[x] = dff_home[lo + x];
+    }
+    // bitboards: rows r0-1 .. r1 of the static wall board (the halo rows matter only at the map's edge)
+    for (int x = tid; x < (RB + 2) * RW; x += THREADS) {
+        const int lr = x / RW;
+        const int gr = r0 + lr;                           // row index in the global board (which has its own +1 offset)
+        const uint32_t wv = (gr <= H + 1 && lr <= RBl + 1) ? P.wall_bits[(size_t)gr * RW + (x - lr * RW)] : FULL;
+        wall_l[x] = wv;
+        blk_l[x] = wv;
+    }
+    int n = P.n_alive[e];                                 // pedestrians still inside (whole episode)
+    const int n_ids = n;                                  // ids 0 .. n_ids-1 (= index at launch)
+    const int nwords = (n_ids + 31) >> 5;
+    const int t0 = P.t_done[e];
+    uint32_t* gpos = P.pos + (size_t)e * P.n_max;
+    for (int w = tid; w <= nwords; w += THREADS) {
+        const int b0 = w * 32;
+        alive[w] = (b0 + 32 <= n) ? FULL : (b0 < n ? ((1u << (n - b0)) - 1u) : 0u);
+        wpre[w] = (uint32_t)(b0 < n ? b0 : n);
+    }
+    if (tid < 16) ctr[tid] = 0u;
+    for (uint32_t x = tid; x < (cells + 3u) / 4u; x += THREADS) cmask_l[x] = 0u;
+    mbar_wait(bar, 0);
+    __syncthreads();
+    for (int i = tid; i < n; i += THREADS) {
+        const int c = (int)gpos[i];
+        if (c >= lo && c < hi) {
+            grid_l[c - lo] |= (uint16_t)(i + 1);
+            const int r = (int)__umulhi((uint32_t)c, P.magic_w), col = c - r * W;
+            atomicOr(&blk_l[(r - r0 + 1) * RW + 1 + (col >> 5)], 1u << (col & 31));
+        }
+    }
+    sync_all();
+
+    const uint32_t episode = P.episode_base + (uint32_t)e;
+    const double* mv_draws = P.move_draws ? P.move_draws + (size_t)e * P.draw_steps * P.n_max : nullptr;
+    const double* cf_draws = P.conflict_draws ? P.conflict_draws + (size_t)e * P.draw_steps * HW * 2 : nullptr;
+    const int cpr = 2 * WW;                               // 16-cell chunks per bitboard row
+    const int nchunks = RBl * cpr;
+
+    // alive-rank prefix (exclusive popcount prefix over the alive words), one warp
+    auto refresh_prefix = [&]() {
+        uint32_t carry = 0;
+        for (int w0 = 0; w0 < nwords; w0 += 32) {
+            const int w = w0 + lane;
+            const uint32_t x = (w < nwords) ? (uint32_t)__popc(alive[w]) : 0u;
+            uint32_t inc = x;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t y = __shfl_up_sync(FULL, inc, d);
+                if (lane >= d) inc += y;
+            }
+            if (w < nwords) wpre[w] = carry + inc - x;
+            carry += __shfl_sync(FULL, inc, 31);
+        }
+    };
+    auto rank_of = [&](uint32_t id) -> uint32_t {
+        return wpre[id >> 5] + (uint32_t)__popc(alive[id >> 5] & ((1u << (id & 31u)) - 1u));
+    };
+    // 18-bit window of a bitboard row around a 16-cell chunk: bit i <-> column 32*j + 16*h - 1 + i
+    auto window18 = [&](const uint32_t* wp, int h) -> uint32_t {
+        const uint32_t w = wp[0];
+        return h == 0 ? (((w << 1) | (wp[-1] >> 31)) & 0x3FFFFu) : (((w >> 15) | (wp[1] << 17)) & 0x3FFFFu);
+    };
+    // pointer to word (j+1) of the bitboard row above / below local row lr (a neighbour CTA's row at a band boundary)
+    auto blk_row_word = [&](int lr_abs /* local row index incl. the +1 offset */, int jw) -> const uint32_t* {
+        if (CL > 1) {
+            if (lr_abs == 0 && !top) return cg::this_cluster().map_shared_rank(blk_l, band - 1) + RB * RW + jw;
+            if (lr_abs == RBl + 1 && !bottom) return cg::this_cluster().map_shared_rank(blk_l, band + 1) + 1 * RW + jw;
+        }
+        return blk_l + lr_abs * RW + jw;
+    };
+    // 3x3 candidate mask of cell c = (r, col) from the bitboard: bit k set <-> neighbour k passable and unoccupied
+    auto cand_mask = [&](int r, int col) -> uint32_t {
+        const int lr = r - r0 + 1, cm = col - 1;          // window starts at column col-1 (>= 0: border cells hold no pedestrians)
+        const int jw = (cm >> 5) + 1, sh = cm & 31;
+        const uint32_t* pu = blk_row_word(lr - 1, jw);
+        const uint32_t* pm = blk_l + lr * RW + jw;
+        const uint32_t* pd = blk_row_word(lr + 1, jw);
+        const uint32_t fu = ~__funnelshift_r(pu[0], pu[1], sh) & 7u;
+        const uint32_t fm = ~__funnelshift_r(pm[0], pm[1], sh) & 7u;
+        const uint32_t fd = ~__funnelshift_r(pd[0], pd[1], sh) & 7u;
+        if (NBR == 8) return fu | ((fm & 1u) << 3) | ((fm & 4u) << 2) | (fd << 5);
+        return ((fu >> 1) & 1u) | (((fd >> 1) & 1u) << 1) | ((fm & 1u) << 2) | ((fm & 4u) << 1);
+    };
+    // positions in alive-rank order -> dst[rank] (epilogue / dense trajectory rows)
+    auto emit_positions = [&](uint32_t* dst) {
+        for (int ch = tid; ch < nchunks; ch += THREADS) {
+            const int lr = (int)__umulhi((uint32_t)ch, P.magic_cpr), rem = ch - lr * cpr;
+            const int idx = (lr + 1) * RW + 1 + (rem >> 1);
+            uint32_t occ = ((blk_l[idx] & ~wall_l[idx]) >> (16 * (rem & 1))) & 0xFFFFu;
+            const int cbase = (r0 + lr) * W + 32 * (rem >> 1) + 16 * (rem & 1);
+            while (occ) {
+                const int b = __ffs(occ) - 1;
+                occ &= occ - 1u;
+                const int c = cbase + b;
+                const uint32_t id = (grid_l[c - lo] & OCC_MASK) - 1u;
+                dst[rank_of(id)] = (uint32_t)c;
+            }
+        }
+    };
+
+    unsigned long long ped_steps = 0;
+    bool need_prefix = false;      // somebody left since the prefix was last computed
+    bool dff_pending = false;      // the DFF update of the previous step has not run yet
+    int tl = 0;
+    for (; tl < P.max_steps && n > 0; ++tl) {
+        const uint32_t t = (uint32_t)(t0 + tl);
+        ped_steps += (unsigned long long)n;
+        const int di = (int)t - P.draw_first;
+        const bool inj = di >= 0 && di < P.draw_steps;
+        uint32_t* cnt = ctr + ((tl & 1) << 3);
+
+        // ================= phase 1: cells -> movers, by candidate count =================================
+        {
+            uint4* cm4 = reinterpret_cast<uint4*>(cmask_l);                   // claim masks: clean for this step
+            for (uint32_t x = tid; x < (cells + 15u) / 16u; x += THREADS) cm4[x] = make_uint4(0u, 0u, 0u, 0u);
+        }
+        if (need_prefix && warp == NW - 1) refresh_prefix();
+        for (int ch0 = 0; ch0 < nchunks; ch0 += THREADS) {
+            const int ch = ch0 + tid;
+            uint32_t mov = 0, m2 = 0, m3 = 0;
+            int cbase = 0;
+            if (ch < nchunks) {
+                const int lr = (int)__umulhi((uint32_t)ch, P.magic_cpr), rem = ch - lr * cpr;
+                const int j = rem >> 1, h = rem & 1;
+                const int idx = (lr + 1) * RW + 1 + j;
+                const uint32_t occ16 = ((blk_l[idx] & ~wall_l[idx]) >> (16 * h)) & 0xFFFFu;
+                if (occ16 != 0u) {
+                    cbase = (r0 + lr) * W + 32 * j + 16 * h - 1;               // cell of window bit 0
+                    const uint32_t fu = ~window18(blk_row_word(lr, j + 1), h) & 0x3FFFFu;       // free cells, row above
+                    const uint32_t fm = ~window18(blk_l + idx, h) & 0x3FFFFu;
+                    const uint32_t fd = ~window18(blk_row_word(lr + 2, j + 1), h) & 0x3FFFFu;   // row below
+                    // number of free neighbours of every cell, bit-sliced (ones / twos / fours / eights)
+                    uint32_t ones, twos, more;
+                    if (NBR == 8) {
+                        const uint32_t x0 = fu << 1, x1 = fu, x2 = fu >> 1, x3 = fm << 1, x4 = fm >> 1, x5 = fd << 1, x6 = fd, x7 = fd >> 1;
+                        const uint32_t sa = x0 ^ x1 ^ x2, ca = (x0 & x1) | (x2 & (x0 ^ x1));
+                        const uint32_t sb = x3 ^ x4 ^ x5, cb = (x3 & x4) | (x5 & (x3 ^ x4));
+                        const uint32_t sc = x6 ^ x7, cc = x6 & x7;
+                        ones = sa ^ sb ^ sc;
+                        const uint32_t cd = (sa & sb) | (sc & (sa ^ sb));
+                        const uint32_t ts = ca ^ cb ^ cc, tc = (ca & cb) | (cc & (ca ^ cb));
+                        twos = ts ^ cd;
+                        more = tc | (ts & cd);                                 // fours or eights
+                    } else {
+                        const uint32_t x0 = fu, x1 = fd, x2 = fm << 1, x3 = fm >> 1;
+                        const uint32_t sa = x0 ^ x1 ^ x2, ca = (x0 & x1) | (x2 & (x0 ^ x1));
+                        ones = sa ^ x3;
+                        const uint32_t c2 = sa & x3;
+                        twos = ca ^ c2;
+                        more = ca & c2;
+                    }
+                    const uint32_t occw = occ16 << 1;                          // aligned with the window bits 1..16
+                    mov = occw & (ones | twos | more);                         // at least one candidate (:57-63)
+                    m2 = mov & ones & ~(twos | more);                          // exactly one free neighbour (+ stay)
+                    m3 = mov & twos & ~(ones | more);                          // exactly two
+                }
+            }
+            if (__ballot_sync(FULL, mov != 0u) == 0u) continue;
+            // list offsets: one packed inclusive scan over the warp (10 bits per class), one atomic per class per warp
+            const uint32_t mb = mov & ~(m2 | m3);
+            const uint32_t mine = (uint32_t)__popc(m2) | ((uint32_t)__popc(m3) << 10) | ((uint32_t)__popc(mb) << 20);
+            uint32_t inc = mine;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t y = __shfl_up_sync(FULL, inc, d);
+                if (lane >= d) inc += y;
+            }
+            const uint32_t tot = __shfl_sync(FULL, inc, 31);
+            uint32_t base = 0;
+            if (lane < 3) {
+                const uint32_t k = (tot >> (10 * lane)) & 0x3FFu;
+                if (k) base = atomicAdd(&cnt[lane], k);
+            }
+            const uint32_t ex = inc - mine;
+            int o2 = (int)(__shfl_sync(FULL, base, 0) + (ex & 0x3FFu));
+            int o3 = (int)(__shfl_sync(FULL, base, 1) + ((ex >> 10) & 0x3FFu));
+            int ob = (int)(__shfl_sync(FULL, base, 2) + (ex >> 20));
+            uint32_t m = mov;
+            while (m) {
+                const int i = __ffs(m) - 1;
+                const uint32_t bit = 1u << i;
+                m &= m - 1u;
+                const EntT ent = (EntT)(cbase + i);
+                if (m2 & bit) listA[o2++] = ent;
+                else if (m3 & bit) listA[cap1 - (o3++)] = ent;
+                else listB[ob++] = ent;
+            }
+        }
+        // DFF decay + diffusion of the previous step (reads the field with that step's footprints) -> other buffer
+        if (DFF && dff_pending) {
+            if (FIELDS_IN_SMEM) {
+                const float* inb = dpar ? dffB_l : dffA_l;
+                float* outb = dpar ? dffA_l : dffB_l;
+                const float* in_up = (CL > 1 && !top) ? cg::this_cluster().map_shared_rank(const_cast<float*>(inb), band - 1) : nullptr;
+                const float* in_dn = (CL > 1 && !bottom) ? cg::this_cluster().map_shared_rank(const_cast<float*>(inb), band + 1) : nullptr;
+                dff_stencil_rows<NBR>(
+                    [&](int r) -> const float* {
+                        if (r < 0 || r >= H) return nullptr;
+                        if (r < r0) return in_up + (size_t)(RB - 1) * W;
+                        if (r >= r1) return in_dn;
+                        return inb + (size_t)(r - r0) * W;
+                    },
+                    [&](int r) -> float* { return outb + (size_t)(r - r0) * W; }, r0, r1, W, P.c0, P.c1, P.thr, tid, THREADS);
+            } else {
+                const float* inb = dpar ? dffB_g : dffA_g;
+                float* outb = dpar ? dffA_g : dffB_g;
+                dff_stencil_rows<NBR>([&](int r) -> const float* { return (r < 0 || r >= H) ? nullptr : inb + (size_t)r * W; },
+                                      [&](int r) -> float* { return outb + (size_t)r * W; }, r0, r1, W, P.c0, P.c1, P.thr, tid, THREADS);
+            }
+        }
+        if (DFF && !FIELDS_IN_SMEM && CL > 1 && dff_pending) __threadfence();   // global DFF rows are read by the neighbour CTAs
+        sync_all();
+        if (DFF && dff_pending) dpar ^= 1;
+        dff_pending = false;
+        need_prefix = false;
+        if (tid == 0) {                                   // the other parity's counters: last read right after the previous
+            uint32_t* nx = ctr + (((tl + 1) & 1) << 3);   // step's final barrier, next written in the next step's phase 1
+            nx[0] = 0u; nx[1] = 0u; nx[2] = 0u; nx[3] = 0u;
+        }
+
+        // ================= phase 2: movers -> requests ==================================================
+        const int n2 = (int)cnt[0], n3 = (int)cnt[1], nb = (int)cnt[2];
+        // One mover: candidates in neighbour order then "stay" (the order of the reference's neighbor_coords array,
+        // :54,60,64); NC = compile-time candidate count (0: read it from the mask).
+        auto decide = [&](EntT* slot_ptr, auto nc_tag) {
+            constexpr int NC = decltype(nc_tag)::value;
+            const int c = (int)*slot_ptr;
+            const int r = (int)__umulhi((uint32_t)c, P.magic_w), col = c - r * W;
+            uint32_t mm = cand_mask(r, col);
+            const uint32_t g = grid_l[c - lo];
+            const uint32_t id = (g & OCC_MASK) - 1u;
+            uint32_t target = (uint32_t)c;
+            int kdir = NBR;                                                   // NBR = stay / no request
+            bool request = false, footprint = false;
+            if ((g >> TYPE_SHIFT) >= TYPE_EXIT) {
+                // on an exit, or a free cell next to one: an exit among the candidates forces the request, no draw (:66-72)
+                uint32_t exm = 0;
+#pragma unroll
+                for (int k = 0; k < NBR; ++k)
+                    if (((mm >> k) & 1u) && *grid_ptr(c + nbr_off<NBR>(k, W)) == EXIT_EMPTY) exm |= 1u << k;
+                if ((g >> TYPE_SHIFT) == TYPE_EXIT && exm == 0u) { footprint = true; mm = 0u; }    // "stay" is the first exit (:64)
+                else if (exm != 0u) { kdir = __ffs(exm) - 1; request = true; mm = 0u; }
+            }
+            if (mm != 0u) {
+                const int ncand = NC > 0 ? NC : __popc(mm) + 1;
+                int kk[NBR + 1];
+                S p[NBR + 1];
+                S mx = neg_inf<S>();
+                uint32_t m = mm;
+#pragma unroll
+                for (int j = 0; j <= NBR; ++j)
+                    if (NC > 0 ? j < NC : j < ncand) {
+                        int cc = c;
+                        kk[j] = NBR;
+                        if (j < ncand - 1) {
+                            kk[j] = __ffs(m) - 1;
+                            m &= m - 1u;
+                            cc = c + nbr_off_rt<NBR>(kk[j], W);
+                        }
+                        S sc = score_at(cc);                                       // -k_S * sff
+                        if (DFF) sc = add_rn(sc, (S)mul_rn(P.kd, *dff_cur(cc)));   // + k_D * dff   (:77)
+                        p[j] = sc;
+                        mx = max_t(mx, sc);
+                    }
+                double tot = 0.0;
+#pragma unroll
+                for (int j = 0; j <= NBR; ++j)
+                    if (NC > 0 ? j < NC : j < ncand) {
+                        p[j] = exp_t(add_rn(p[j], -mx));                           // exp(score - max) (:80)
+                        tot += (double)p[j];
+                    }
+                if (isfinite(tot) && tot != 0.0) {                                // (:82)
+                    const uint32_t rank = rank_of(id);                            // the reference's array index
+                    const double u = (inj && mv_draws) ? mv_draws[(size_t)di * P.n_max + rank]
+                                                       : draw_u0(P.seed, episode, t, STREAM_MOVE, rank);
+                    const double thresh = u * tot;
+                    double run = 0.0;
+                    bool done = false;
+                    footprint = true;                                             // E_n > u * E_n always: "stay" is last
+#pragma unroll
+                    for (int j = 0; j < NBR; ++j)
+                        if ((NC > 0 ? j < NC - 1 : j < ncand - 1) && !done) {
+                            run += (double)p[j];
+                            if (run > thresh) { kdir = kk[j]; done = true; request = true; footprint = false; }
+                        }
+                }
+            }
+            EntT out = (EntT)0;                                                   // cell 0 is a border cell: "no request"
+            if (request) {
+                target = (uint32_t)(c + nbr_off_rt<NBR>(kdir, W));
+                uint32_t sh;
+                uint32_t* wp = cmask_word((int)target, sh);
+                const uint32_t old = atomicOr(wp, (1u << nbr_opp<NBR>(kdir)) << sh);
+                if (((old >> sh) & 0xFFu) == 0u) out = (EntT)target;              // first claimant: this entry resolves the cell
+            }
+            if (DFF && footprint) { float* d = dff_cur(c); *d = __fadd_rn(*d, 1.0f); }   // a granted "stay" (:91-93)
+            *slot_ptr = out;
+        };
+        // the three lists start at different warps so that a short list does not always land on warp 0
+        for (int i = tid; i < n2; i += THREADS) decide(&listA[i], std::integral_constant<int, 2>());
+        for (int i = THREADS - 1 - tid; i < n3; i += THREADS) decide(&listA[cap1 - i], std::integral_constant<int, 3>());
+        for (int i = (tid + THREADS / 2) % THREADS; i < nb; i += THREADS) decide(&listB[i], std::integral_constant<int, 0>());
+        sync_all();
+
+        // ================= phase 3: one resolver per requested cell; moves applied at once ===============
+        const int ntot = n2 + n3 + nb;
+        for (int x0 = 0; x0 < ntot; x0 += THREADS) {
+            const int x = x0 + tid;
+            bool leaves = false;
+            if (x < ntot) {
+                const uint32_t T = (uint32_t)(x < n2 ? listA[x] : (x < n2 + n3 ? listA[cap1 - (x - n2)] : listB[x - n2 - n3]));
+                if (T != 0u) {
+                    uint32_t sh;
+                    const uint32_t cm = (*cmask_word((int)T, sh) >> sh) & 0xFFu;  // bit k: the occupant of neighbour k wants T
+                    const int k = __popc(cm);
+                    int from = __ffs(cm) - 1;                                     // lone claimant: moves (:91-93)
+                    bool moved = true;
+                    if (k > 1) {
+                        Draw2 d;
+                        if (inj && cf_draws) {
+                            d.u0 = cf_draws[((size_t)di * HW + T) * 2];
+                            d.u1 = cf_draws[((size_t)di * HW + T) * 2 + 1];
+                        } else {
+                            d = draw2(P.seed, episode, t, STREAM_CONFLICT, T);
+                        }
+                        moved = d.u0 < 0.5;                                       // coin (:95)
+                        if (moved) {
+                            // agents[int(u * k)] in ascending agent index (:96): sort (id, direction) keys
+                            uint32_t key[NBR];
+#pragma unroll
+                            for (int q = 0; q < NBR; ++q) {
+                                key[q] = FULL;
+                                if ((cm >> q) & 1u) key[q] = (((uint32_t)*grid_ptr((int)T + nbr_off<NBR>(q, W)) & OCC_MASK) << 3) | (uint32_t)q;
+                            }
+                            sort_keys<NBR>(key);
+                            const int w = (int)(d.u1 * (double)k);
+                            uint32_t sel = key[0];
+#pragma unroll
+                            for (int q = 1; q < NBR; ++q) if (q == w) sel = key[q];
+                            from = (int)(sel & 7u);
+                        }
+                    }
+                    if (moved) {
+                        const int q = (int)T + nbr_off_rt<NBR>(from, W);          // the winner's cell
+                        uint16_t* gq = grid_ptr(q);
+                        uint16_t* gT = grid_ptr((int)T);
+                        const uint32_t vq = *gq, vT = *gT;
+                        const int rT = (int)__umulhi(T, P.magic_w), cT = (int)T - rT * W;
+                        const int rq = rT + nbr_dr_rt<NBR>(from), cq = cT + nbr_dc_rt<NBR>(from);
+                        uint32_t bit;
+                        uint32_t* bw = blk_word(rq, cq, bit);
+                        atomicAnd(bw, ~bit);
+                        *gq = (uint16_t)(vq & TYPE_BITS);
+                        if (vT == EXIT_EMPTY) {                                   // reached an exit: removed (:101-102)
+                            leaves = true;
+                            const uint32_t id = (vq & OCC_MASK) - 1u;
+                            if (CL == 1) {
+                                atomicAnd(&alive[id >> 5], ~(1u << (id & 31u)));
+                            } else {
+#pragma unroll
+                                for (int rk = 0; rk < CL; ++rk)
+                                    atomicAnd(cg::this_cluster().map_shared_rank(alive, rk) + (id >> 5), ~(1u << (id & 31u)));
+                            }
+                        } else {
+                            *gT = (uint16_t)(vT | (vq & OCC_MASK));
+                            bw = blk_word(rT, cT, bit);
+                            atomicOr(bw, bit);
+                        }
+                        if (DFF) { float* dq = dff_cur(q); *dq = __fadd_rn(*dq, 1.0f); }   // footprint (:93,98)
+                    }
+                }
+            }
+            const uint32_t bal = __ballot_sync(FULL, leaves);
+            if (bal != 0u && lane == 0) {
+                if (CL == 1) {
+                    atomicAdd(&cnt[3], (uint32_t)__popc(bal));
+                } else {
+#pragma unroll
+                    for (int rk = 0; rk < CL; ++rk) atomicAdd(cg::this_cluster().map_shared_rank(cnt, rk) + 3, (uint32_t)__popc(bal));
+                }
+            }
+        }
+        sync_all();
+
+        const int n_exit = (int)cnt[3];
+        if (n_exit > 0) { n -= n_exit; need_prefix = true; }
+        dff_pending = DFF;
+
+        // trajectory row: positions after this step, alive-rank order (ffm_core.py:125)
+        if (P.traj != nullptr && tl < P.traj_steps) {
+            if (need_prefix) {
+                if (warp == 0) refresh_prefix();
+                __syncthreads();
+                need_prefix = false;
+            }
+            emit_positions(P.traj + ((size_t)e * P.traj_steps + tl) * P.n_max);
+            if (tid == 0 && band == 0) P.traj_n[(size_t)e * P.traj_steps + tl] = n;
+        }
+    }
+
+    // ---- the last step's DFF update ------------------------------------------------------------------------
+    if (DFF && dff_pending) {
+        if (FIELDS_IN_SMEM) {
+            const float* inb = dpar ? dffB_l : dffA_l;
+            float* outb = dpar ? dffA_l : dffB_l;
+            const float* in_up = (CL > 1 && !top) ? cg::this_cluster().map_shared_rank(const_cast<float*>(inb), band - 1) : nullptr;
+            const float* in_dn = (CL > 1 && !bottom) ? cg::this_cluster().map_shared_rank(const_cast<float*>(inb), band + 1) : nullptr;
+            dff_stencil_rows<NBR>(
+                [&](int r) -> const float* {
+                    if (r < 0 || r >= H) return nullptr;
+                    if (r < r0) return in_up + (size_t)(RB - 1) * W;
+                    if (r >= r1) return in_dn;
+                    return inb + (size_t)(r - r0) * W;
+                },
+                [&](int r) -> float* { return outb + (size_t)(r - r0) * W; }, r0, r1, W, P.c0, P.c1, P.thr, tid, THREADS);
+        } else {
+            const float* inb = dpar ? dffB_g : dffA_g;
+            float* outb = dpar ? dffA_g : dffB_g;
+            dff_stencil_rows<NBR>([&](int r) -> const float* { return (r < 0 || r >= H) ? nullptr : inb + (size_t)r * W; },
+                                  [&](int r) -> float* { return outb + (size_t)r * W; }, r0, r1, W, P.c0, P.c1, P.thr, tid, THREADS);
+        }
+        dpar ^= 1;
+    }
+    if (need_prefix && warp == 0) refresh_prefix();
+    sync_all();
+
+    // ---- epilogue: state back to HBM, alive-rank order ---------------------------------------------------------
+    emit_positions(gpos);
+    if (DFF) {
+        if (FIELDS_IN_SMEM) {
+            float* cur = dpar ? dffB_l : dffA_l;
+            if (tma_fields) {               // shared -> global bulk store of the band's final DFF
+                fence_proxy_async_smem();
+                __syncthreads();
+                if (tid == 0) { bulk_copy_s2g(dff_home + lo, cur, dff_bytes); bulk_commit_wait_all(); }
+            } else {
+                for (uint32_t x = tid; x < cells; x += THREADS) dff_home[lo + x] = cur[x];
+            }
+        } else if (dpar) {
+            for (int c = lo + tid; c < hi; c += THREADS) dffA_g[c] = dffB_g[c];
+        }
+    }
+    if (tid == 0 && band == 0) {
+        P.n_alive[e] = n;
+        P.t_done[e] = t0 + tl;
+        P.ped_steps[e] += ped_steps;
+    }
+    if (CL > 1) cg::this_cluster().sync();     // nobody leaves while a neighbour may still read its shared memory
+}
+
+}  // namespace ffm

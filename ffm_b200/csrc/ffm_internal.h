@@ -11,7 +11,7 @@ struct HStats;
 
 // ---- base CA model (ffm_cell_kernel.cuh) ----------------------------------------------------------
 // cluster = CTAs per episode (1, 2, 4, 8): the map is split into row bands held in distributed shared memory
-const void* pick_cell_kernel(bool f64, int nbr, bool dff, bool fields_in_smem, int threads, int cluster);
+const void* pick_cell_kernel(bool f64, bool small, int nbr, bool dff, bool fields_in_smem, int threads, int cluster);
 const void* pick_probs_kernel(bool f64, int nbr, bool dff);
 // round-1 pedestrian-centric kernel (ffm_core_kernel.cuh), kept selectable for A/B measurements: FFM_KERNEL=ped
 const void* pick_core_kernel_f32(bool small, int nbr, bool dff, bool fields_in_smem, int threads);
