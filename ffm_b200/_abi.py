@@ -77,6 +77,7 @@ SIGNATURES = {
                                    C.c_int32, C.c_void_p, C.POINTER(C.c_int32)]),
     "ffm_rollout_returns": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_double, C.c_void_p,
                                       C.c_int32, C.c_void_p]),
+    "ffm_measure_smem_bandwidth": (C.c_int, [C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "ffm_launch_count": (C.c_int64, [C.c_void_p]),
     "ffm_kernel_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32),
                                   C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),

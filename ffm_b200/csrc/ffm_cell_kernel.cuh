@@ -82,7 +82,7 @@ struct CellParams {
 };
 
 struct CellLayout {
-    uint32_t score, dffA, dffB, grid, cmask, blk, wall, listA, listB, alive, wpre, ctr, bar, total;
+    uint32_t score, dffA, dffB, grid, cmask, blk, wall, listA, listB, clist, alive, wpre, ctr, bar, total;
     uint32_t cap;   // capacity of each work list (entries)
 };
 
@@ -102,6 +102,7 @@ __host__ __device__ inline CellLayout make_cell_layout(int RB, int W, int RW, in
     L.wall = o;  o = align16(o + (uint32_t)(RB + 2) * RW * 4u);
     L.listA = o; o = align16(o + L.cap * sizeof_ent);
     L.listB = o; o = align16(o + L.cap * sizeof_ent);
+    L.clist = o; o = align16(o + (L.cap / 2u + 1u) * sizeof_ent);   // contested cells: at least two claimants each
     L.alive = o; o = align16(o + nw * 4u);
     L.wpre = o;  o = align16(o + nw * 4u);
     L.ctr = o;   o = align16(o + 16u * 4u);
@@ -113,6 +114,13 @@ __host__ __device__ inline CellLayout make_cell_layout(int RB, int W, int RW, in
 // row / column offset of a neighbour index only known at run time (the tables of nbr_off_rt)
 template <int NBR> __device__ __forceinline__ int nbr_dr_rt(int k) { return (int)(((NBR == 8 ? 0xA940u : 0x58u) >> (2 * k)) & 3u) - 1; }
 template <int NBR> __device__ __forceinline__ int nbr_dc_rt(int k) { return (int)(((NBR == 8 ? 0x9224u : 0x85u) >> (2 * k)) & 3u) - 1; }
+
+// Candidate masks.  Moore: bit b = 4*(dr+1) + (dc+1) of the 3x3 window (bits 0,1,2, 4,6, 8,9,10 -- ascending bit order
+// is the reference's neighbour order, ffm_core.py:32-34), so that the cell offset is linear in the bit index.
+// von Neumann: bit k of the reference's list [(-1,0),(1,0),(0,-1),(0,1)] (:30).
+template <int NBR> __device__ __forceinline__ int cand_off(int b, int W) { return NBR == 8 ? (b >> 2) * W + (b & 3) - (W + 1) : nbr_off_rt<4>(b, W); }
+template <int NBR> __device__ __forceinline__ int cand_dir(int b) { return NBR == 8 ? 3 * (b >> 2) + (b & 3) - (b > 5 ? 1 : 0) : b; }
+template <int NBR> __device__ __forceinline__ constexpr int cand_bit(int k) { return NBR == 8 ? k + (k >= 3 ? 1 : 0) + (k >= 4 ? 1 : 0) + (k >= 5 ? 1 : 0) : k; }
 
 // index of the neighbour opposite to k (the direction from the target back to the claimant)
 template <int NBR> __device__ __forceinline__ int nbr_opp(int k) { return NBR == 8 ? 7 - k : (k ^ 1); }
@@ -187,6 +195,25 @@ __device__ __forceinline__ void dff_stencil_rows(RowIn in_row, RowOut out_row, i
     }
 }
 
+// alive-rank prefix: exclusive popcount prefix over the alive words, by one warp (kept out of line: it runs only in
+// steps where somebody left, and the hot loop should stay small for the instruction cache)
+static __device__ __noinline__ void refresh_alive_prefix(const uint32_t* alive, uint32_t* wpre, int nwords, int lane) {
+    uint32_t carry = 0;
+#pragma unroll 1
+    for (int w0 = 0; w0 < nwords; w0 += 32) {
+        const int w = w0 + lane;
+        const uint32_t x = (w < nwords) ? (uint32_t)__popc(alive[w]) : 0u;
+        uint32_t inc = x;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, inc, d);
+            if (lane >= d) inc += y;
+        }
+        if (w < nwords) wpre[w] = carry + inc - x;
+        carry += __shfl_sync(0xffffffffu, inc, 31);
+    }
+}
+
 template <typename S, typename EntT, int NBR, bool DFF, bool FIELDS_IN_SMEM, int THREADS, int CL>
 __global__ void __launch_bounds__(THREADS, (CL == 1 && THREADS <= 256 && sizeof(S) == 4) ? 1536 / THREADS : 1)
 ffm_cell_rollout_kernel(const CellParams P) {
@@ -222,10 +249,11 @@ ffm_cell_rollout_kernel(const CellParams P) {
     uint32_t* wall_l = reinterpret_cast<uint32_t*>(smem_raw + L.wall);
     EntT* listA = reinterpret_cast<EntT*>(smem_raw + L.listA);
     EntT* listB = reinterpret_cast<EntT*>(smem_raw + L.listB);
+    EntT* clist = reinterpret_cast<EntT*>(smem_raw + L.clist);
     const int cap1 = (int)L.cap - 1;
     uint32_t* alive = reinterpret_cast<uint32_t*>(smem_raw + L.alive);
     uint32_t* wpre = reinterpret_cast<uint32_t*>(smem_raw + L.wpre);
-    uint32_t* ctr = reinterpret_cast<uint32_t*>(smem_raw + L.ctr);             // [parity][n2, n3, nbig, n_exit, ...]
+    uint32_t* ctr = reinterpret_cast<uint32_t*>(smem_raw + L.ctr);             // [parity][n2, n3, nbig, n_exit, n_contested, warps done, ..]
     unsigned long long* bar = reinterpret_cast<unsigned long long*>(smem_raw + L.bar);
     S* score_l = reinterpret_cast<S*>(smem_raw + L.score);
     float* dffA_l = reinterpret_cast<float*>(smem_raw + L.dffA);
@@ -300,12 +328,18 @@ ffm_cell_rollout_kernel(const CellParams P) {
             if (DFF) bulk_copy_g2s(dffA_l, dff_home + lo, dff_bytes, bar);
         }
     }
-    if (!tma_grid) for (uint32_t x = tid; x < grid_elems; x += THREADS) grid_l[(int)x - G] = P.type_grid[lo + x];
+    if (!tma_grid)
+#pragma unroll 1
+        for (uint32_t x = tid; x < grid_elems; x += THREADS) grid_l[(int)x - G] = P.type_grid[lo + x];
     if (FIELDS_IN_SMEM && !tma_fields) {
+#pragma unroll 1
         for (uint32_t x = tid; x < cells; x += THREADS) score_l[x] = score_g[lo + x];
-        if (DFF) for (uint32_t x = tid; x < cells; x += THREADS) dffA_l[x] = dff_home[lo + x];
+        if (DFF)
+#pragma unroll 1
+            for (uint32_t x = tid; x < cells; x += THREADS) dffA_l[x] = dff_home[lo + x];
     }
     // bitboards: rows r0-1 .. r1 of the static wall board (the halo rows matter only at the map's edge)
+#pragma unroll 1
     for (int x = tid; x < (RB + 2) * RW; x += THREADS) {
         const int lr = x / RW;
         const int gr = r0 + lr;                           // row index in the global board (which has its own +1 offset)
@@ -318,15 +352,18 @@ ffm_cell_rollout_kernel(const CellParams P) {
     const int nwords = (n_ids + 31) >> 5;
     const int t0 = P.t_done[e];
     uint32_t* gpos = P.pos + (size_t)e * P.n_max;
+#pragma unroll 1
     for (int w = tid; w <= nwords; w += THREADS) {
         const int b0 = w * 32;
         alive[w] = (b0 + 32 <= n) ? FULL : (b0 < n ? ((1u << (n - b0)) - 1u) : 0u);
         wpre[w] = (uint32_t)(b0 < n ? b0 : n);
     }
     if (tid < 16) ctr[tid] = 0u;
+#pragma unroll 1
     for (uint32_t x = tid; x < (cells + 3u) / 4u; x += THREADS) cmask_l[x] = 0u;
     mbar_wait(bar, 0);
     __syncthreads();
+#pragma unroll 1
     for (int i = tid; i < n; i += THREADS) {
         const int c = (int)gpos[i];
         if (c >= lo && c < hi) {
@@ -343,22 +380,7 @@ ffm_cell_rollout_kernel(const CellParams P) {
     const int cpr = 2 * WW;                               // 16-cell chunks per bitboard row
     const int nchunks = RBl * cpr;
 
-    // alive-rank prefix (exclusive popcount prefix over the alive words), one warp
-    auto refresh_prefix = [&]() {
-        uint32_t carry = 0;
-        for (int w0 = 0; w0 < nwords; w0 += 32) {
-            const int w = w0 + lane;
-            const uint32_t x = (w < nwords) ? (uint32_t)__popc(alive[w]) : 0u;
-            uint32_t inc = x;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const uint32_t y = __shfl_up_sync(FULL, inc, d);
-                if (lane >= d) inc += y;
-            }
-            if (w < nwords) wpre[w] = carry + inc - x;
-            carry += __shfl_sync(FULL, inc, 31);
-        }
-    };
+    auto refresh_prefix = [&]() { refresh_alive_prefix(alive, wpre, nwords, lane); };
     auto rank_of = [&](uint32_t id) -> uint32_t {
         return wpre[id >> 5] + (uint32_t)__popc(alive[id >> 5] & ((1u << (id & 31u)) - 1u));
     };
@@ -385,11 +407,12 @@ ffm_cell_rollout_kernel(const CellParams P) {
         const uint32_t fu = ~__funnelshift_r(pu[0], pu[1], sh) & 7u;
         const uint32_t fm = ~__funnelshift_r(pm[0], pm[1], sh) & 7u;
         const uint32_t fd = ~__funnelshift_r(pd[0], pd[1], sh) & 7u;
-        if (NBR == 8) return fu | ((fm & 1u) << 3) | ((fm & 4u) << 2) | (fd << 5);
+        if (NBR == 8) return fu | ((fm & 5u) << 4) | (fd << 8);           // window bit space (see cand_off)
         return ((fu >> 1) & 1u) | (((fd >> 1) & 1u) << 1) | ((fm & 1u) << 2) | ((fm & 4u) << 1);
     };
     // positions in alive-rank order -> dst[rank] (epilogue / dense trajectory rows)
     auto emit_positions = [&](uint32_t* dst) {
+#pragma unroll 1
         for (int ch = tid; ch < nchunks; ch += THREADS) {
             const int lr = (int)__umulhi((uint32_t)ch, P.magic_cpr), rem = ch - lr * cpr;
             const int idx = (lr + 1) * RW + 1 + (rem >> 1);
@@ -419,7 +442,9 @@ ffm_cell_rollout_kernel(const CellParams P) {
         // ================= phase 1: cells -> movers, by candidate count =================================
         {
             uint4* cm4 = reinterpret_cast<uint4*>(cmask_l);                   // claim masks: clean for this step
-            for (uint32_t x = tid; x < (cells + 15u) / 16u; x += THREADS) cm4[x] = make_uint4(0u, 0u, 0u, 0u);
+            const uint32_t n16 = (cells + 15u) / 16u;
+            if ((uint32_t)tid < n16) cm4[tid] = make_uint4(0u, 0u, 0u, 0u);
+            for (uint32_t x = tid + THREADS; x < n16; x += THREADS) cm4[x] = make_uint4(0u, 0u, 0u, 0u);
         }
         if (need_prefix && warp == NW - 1) refresh_prefix();
         for (int ch0 = 0; ch0 < nchunks; ch0 += THREADS) {
@@ -482,16 +507,9 @@ ffm_cell_rollout_kernel(const CellParams P) {
             int o2 = (int)(__shfl_sync(FULL, base, 0) + (ex & 0x3FFu));
             int o3 = (int)(__shfl_sync(FULL, base, 1) + ((ex >> 10) & 0x3FFu));
             int ob = (int)(__shfl_sync(FULL, base, 2) + (ex >> 20));
-            uint32_t m = mov;
-            while (m) {
-                const int i = __ffs(m) - 1;
-                const uint32_t bit = 1u << i;
-                m &= m - 1u;
-                const EntT ent = (EntT)(cbase + i);
-                if (m2 & bit) listA[o2++] = ent;
-                else if (m3 & bit) listA[cap1 - (o3++)] = ent;
-                else listB[ob++] = ent;
-            }
+            for (uint32_t m = m2; m; m &= m - 1u) listA[o2++] = (EntT)(cbase + __ffs(m) - 1);
+            for (uint32_t m = m3; m; m &= m - 1u) listA[cap1 - (o3++)] = (EntT)(cbase + __ffs(m) - 1);
+            for (uint32_t m = mb; m; m &= m - 1u) listB[ob++] = (EntT)(cbase + __ffs(m) - 1);
         }
         // DFF decay + diffusion of the previous step (reads the field with that step's footprints) -> other buffer
         if (DFF && dff_pending) {
@@ -522,47 +540,45 @@ ffm_cell_rollout_kernel(const CellParams P) {
         need_prefix = false;
         if (tid == 0) {                                   // the other parity's counters: last read right after the previous
             uint32_t* nx = ctr + (((tl + 1) & 1) << 3);   // step's final barrier, next written in the next step's phase 1
-            nx[0] = 0u; nx[1] = 0u; nx[2] = 0u; nx[3] = 0u;
+            nx[0] = 0u; nx[1] = 0u; nx[2] = 0u; nx[3] = 0u; nx[4] = 0u; nx[5] = 0u;
         }
 
         // ================= phase 2: movers -> requests ==================================================
         const int n2 = (int)cnt[0], n3 = (int)cnt[1], nb = (int)cnt[2];
         // One mover: candidates in neighbour order then "stay" (the order of the reference's neighbor_coords array,
-        // :54,60,64); NC = compile-time candidate count (0: read it from the mask).
-        auto decide = [&](EntT* slot_ptr, auto nc_tag) {
-            constexpr int NC = decltype(nc_tag)::value;
+        // :54,60,64).  The lists are sorted by candidate count, so the trip counts below are warp-uniform.
+        auto decide = [&](EntT* slot_ptr) {
             const int c = (int)*slot_ptr;
             const int r = (int)__umulhi((uint32_t)c, P.magic_w), col = c - r * W;
             uint32_t mm = cand_mask(r, col);
             const uint32_t g = grid_l[c - lo];
             const uint32_t id = (g & OCC_MASK) - 1u;
-            uint32_t target = (uint32_t)c;
-            int kdir = NBR;                                                   // NBR = stay / no request
-            bool request = false, footprint = false;
+            int kdir = -1;                                                    // neighbour index of the request
+            bool footprint = false;
             if ((g >> TYPE_SHIFT) >= TYPE_EXIT) {
                 // on an exit, or a free cell next to one: an exit among the candidates forces the request, no draw (:66-72)
                 uint32_t exm = 0;
 #pragma unroll
                 for (int k = 0; k < NBR; ++k)
-                    if (((mm >> k) & 1u) && *grid_ptr(c + nbr_off<NBR>(k, W)) == EXIT_EMPTY) exm |= 1u << k;
+                    if (((mm >> cand_bit<NBR>(k)) & 1u) && *grid_ptr(c + nbr_off<NBR>(k, W)) == EXIT_EMPTY) exm |= 1u << k;
                 if ((g >> TYPE_SHIFT) == TYPE_EXIT && exm == 0u) { footprint = true; mm = 0u; }    // "stay" is the first exit (:64)
-                else if (exm != 0u) { kdir = __ffs(exm) - 1; request = true; mm = 0u; }
+                else if (exm != 0u) { kdir = __ffs(exm) - 1; mm = 0u; }
             }
             if (mm != 0u) {
-                const int ncand = NC > 0 ? NC : __popc(mm) + 1;
-                int kk[NBR + 1];
+                const int ncand = __popc(mm) + 1;
+                int kb[NBR + 1];
                 S p[NBR + 1];
                 S mx = neg_inf<S>();
                 uint32_t m = mm;
 #pragma unroll
                 for (int j = 0; j <= NBR; ++j)
-                    if (NC > 0 ? j < NC : j < ncand) {
+                    if (j < ncand) {
                         int cc = c;
-                        kk[j] = NBR;
+                        kb[j] = 0;
                         if (j < ncand - 1) {
-                            kk[j] = __ffs(m) - 1;
+                            kb[j] = __ffs(m) - 1;
                             m &= m - 1u;
-                            cc = c + nbr_off_rt<NBR>(kk[j], W);
+                            cc = c + cand_off<NBR>(kb[j], W);
                         }
                         S sc = score_at(cc);                                       // -k_S * sff
                         if (DFF) sc = add_rn(sc, (S)mul_rn(P.kd, *dff_cur(cc)));   // + k_D * dff   (:77)
@@ -572,7 +588,7 @@ ffm_cell_rollout_kernel(const CellParams P) {
                 double tot = 0.0;
 #pragma unroll
                 for (int j = 0; j <= NBR; ++j)
-                    if (NC > 0 ? j < NC : j < ncand) {
+                    if (j < ncand) {
                         p[j] = exp_t(add_rn(p[j], -mx));                           // exp(score - max) (:80)
                         tot += (double)p[j];
                     }
@@ -582,19 +598,18 @@ ffm_cell_rollout_kernel(const CellParams P) {
                                                        : draw_u0(P.seed, episode, t, STREAM_MOVE, rank);
                     const double thresh = u * tot;
                     double run = 0.0;
-                    bool done = false;
                     footprint = true;                                             // E_n > u * E_n always: "stay" is last
 #pragma unroll
                     for (int j = 0; j < NBR; ++j)
-                        if ((NC > 0 ? j < NC - 1 : j < ncand - 1) && !done) {
+                        if (j < ncand - 1 && footprint) {
                             run += (double)p[j];
-                            if (run > thresh) { kdir = kk[j]; done = true; request = true; footprint = false; }
+                            if (run > thresh) { kdir = cand_dir<NBR>(kb[j]); footprint = false; }
                         }
                 }
             }
             EntT out = (EntT)0;                                                   // cell 0 is a border cell: "no request"
-            if (request) {
-                target = (uint32_t)(c + nbr_off_rt<NBR>(kdir, W));
+            if (kdir >= 0) {
+                const uint32_t target = (uint32_t)(c + nbr_off_rt<NBR>(kdir, W));
                 uint32_t sh;
                 uint32_t* wp = cmask_word((int)target, sh);
                 const uint32_t old = atomicOr(wp, (1u << nbr_opp<NBR>(kdir)) << sh);
@@ -603,26 +618,102 @@ ffm_cell_rollout_kernel(const CellParams P) {
             if (DFF && footprint) { float* d = dff_cur(c); *d = __fadd_rn(*d, 1.0f); }   // a granted "stay" (:91-93)
             *slot_ptr = out;
         };
-        // the three lists start at different warps so that a short list does not always land on warp 0
-        for (int i = tid; i < n2; i += THREADS) decide(&listA[i], std::integral_constant<int, 2>());
-        for (int i = THREADS - 1 - tid; i < n3; i += THREADS) decide(&listA[cap1 - i], std::integral_constant<int, 3>());
-        for (int i = (tid + THREADS / 2) % THREADS; i < nb; i += THREADS) decide(&listB[i], std::integral_constant<int, 0>());
+        {
+            // warp tasks of 32 entries, the long ones (most candidates) first; warp w takes tasks w, w + NW, ...
+            const int tb = (nb + 31) >> 5, t3 = (n3 + 31) >> 5, t2 = (n2 + 31) >> 5;
+            for (int task = warp; task < tb + t3 + t2; task += NW) {
+                EntT* ptr;
+                bool valid;
+                if (task < tb) { const int i = task * 32 + lane; valid = i < nb; ptr = &listB[i]; }
+                else if (task < tb + t3) { const int i = (task - tb) * 32 + lane; valid = i < n3; ptr = &listA[cap1 - i]; }
+                else { const int i = (task - tb - t3) * 32 + lane; valid = i < n2; ptr = &listA[i]; }
+                if (valid) decide(ptr);
+            }
+        }
         sync_all();
 
         // ================= phase 3: one resolver per requested cell; moves applied at once ===============
+        // apply the move of the occupant of T's neighbour `from` into T
+        auto apply_move = [&](uint32_t T, int from) -> bool {
+            const int q = (int)T + nbr_off_rt<NBR>(from, W);                      // the winner's cell
+            uint16_t* gq = grid_ptr(q);
+            uint16_t* gT = grid_ptr((int)T);
+            const uint32_t vq = *gq, vT = *gT;
+            const int rT = (int)__umulhi(T, P.magic_w), cT = (int)T - rT * W;
+            const int rq = rT + nbr_dr_rt<NBR>(from), cq = cT + nbr_dc_rt<NBR>(from);
+            uint32_t bit;
+            uint32_t* bw = blk_word(rq, cq, bit);
+            atomicAnd(bw, ~bit);
+            *gq = (uint16_t)(vq & TYPE_BITS);
+            bool leaves = false;
+            if (vT == EXIT_EMPTY) {                                               // reached an exit: removed (:101-102)
+                leaves = true;
+                const uint32_t id = (vq & OCC_MASK) - 1u;
+                if (CL == 1) {
+                    atomicAnd(&alive[id >> 5], ~(1u << (id & 31u)));
+                } else {
+#pragma unroll
+                    for (int rk = 0; rk < CL; ++rk)
+                        atomicAnd(cg::this_cluster().map_shared_rank(alive, rk) + (id >> 5), ~(1u << (id & 31u)));
+                }
+            } else {
+                *gT = (uint16_t)(vT | (vq & OCC_MASK));
+                bw = blk_word(rT, cT, bit);
+                atomicOr(bw, bit);
+            }
+            if (DFF) { float* dq = dff_cur(q); *dq = __fadd_rn(*dq, 1.0f); }      // footprint (:93,98)
+            return leaves;
+        };
+        auto count_exits = [&](bool leaves) {
+            const uint32_t bal = __ballot_sync(FULL, leaves);
+            if (bal != 0u && lane == 0) {
+                if (CL == 1) {
+                    atomicAdd(&cnt[3], (uint32_t)__popc(bal));
+                } else {
+#pragma unroll
+                    for (int rk = 0; rk < CL; ++rk) atomicAdd(cg::this_cluster().map_shared_rank(cnt, rk) + 3, (uint32_t)__popc(bal));
+                }
+            }
+        };
         const int ntot = n2 + n3 + nb;
         for (int x0 = 0; x0 < ntot; x0 += THREADS) {
             const int x = x0 + tid;
-            bool leaves = false;
+            bool leaves = false, contested = false;
+            uint32_t T = 0;
             if (x < ntot) {
-                const uint32_t T = (uint32_t)(x < n2 ? listA[x] : (x < n2 + n3 ? listA[cap1 - (x - n2)] : listB[x - n2 - n3]));
+                T = (uint32_t)(x < n2 ? listA[x] : (x < n2 + n3 ? listA[cap1 - (x - n2)] : listB[x - n2 - n3]));
                 if (T != 0u) {
                     uint32_t sh;
                     const uint32_t cm = (*cmask_word((int)T, sh) >> sh) & 0xFFu;  // bit k: the occupant of neighbour k wants T
-                    const int k = __popc(cm);
-                    int from = __ffs(cm) - 1;                                     // lone claimant: moves (:91-93)
-                    bool moved = true;
-                    if (k > 1) {
+                    if (cm & (cm - 1u)) contested = true;                         // two or more claimants: resolved below
+                    else leaves = apply_move(T, __ffs(cm) - 1);                   // lone claimant: moves (:91-93)
+                }
+            }
+            count_exits(leaves);
+            // contested cells are rare per warp: they are collected and resolved with full lanes by the last warp to finish
+            const uint32_t cb = __ballot_sync(FULL, contested);
+            if (cb != 0u) {
+                uint32_t base = 0;
+                if (lane == 0) base = atomicAdd(&cnt[4], (uint32_t)__popc(cb));
+                base = __shfl_sync(FULL, base, 0);
+                if (contested) clist[base + __popc(cb & lanemask_lt())] = (EntT)T;
+            }
+        }
+        {
+            __syncwarp();
+            uint32_t done = 0;
+            if (lane == 0) { __threadfence_block(); done = atomicAdd(&cnt[5], 1u); __threadfence_block(); }
+            done = __shfl_sync(FULL, done, 0);
+            if (done == NW - 1) {
+                const int ncont = (int)*((volatile uint32_t*)&cnt[4]);
+                for (int i0 = 0; i0 < ncont; i0 += 32) {
+                    const int i = i0 + lane;
+                    bool leaves = false;
+                    if (i < ncont) {
+                        const uint32_t T = (uint32_t)((volatile EntT*)clist)[i];
+                        uint32_t sh;
+                        const uint32_t cm = (*cmask_word((int)T, sh) >> sh) & 0xFFu;
+                        const int k = __popc(cm);
                         Draw2 d;
                         if (inj && cf_draws) {
                             d.u0 = cf_draws[((size_t)di * HW + T) * 2];
@@ -630,8 +721,7 @@ ffm_cell_rollout_kernel(const CellParams P) {
                         } else {
                             d = draw2(P.seed, episode, t, STREAM_CONFLICT, T);
                         }
-                        moved = d.u0 < 0.5;                                       // coin (:95)
-                        if (moved) {
+                        if (d.u0 < 0.5) {                                         // coin (:95): somebody moves
                             // agents[int(u * k)] in ascending agent index (:96): sort (id, direction) keys
                             uint32_t key[NBR];
 #pragma unroll
@@ -644,46 +734,10 @@ ffm_cell_rollout_kernel(const CellParams P) {
                             uint32_t sel = key[0];
 #pragma unroll
                             for (int q = 1; q < NBR; ++q) if (q == w) sel = key[q];
-                            from = (int)(sel & 7u);
+                            leaves = apply_move(T, (int)(sel & 7u));
                         }
                     }
-                    if (moved) {
-                        const int q = (int)T + nbr_off_rt<NBR>(from, W);          // the winner's cell
-                        uint16_t* gq = grid_ptr(q);
-                        uint16_t* gT = grid_ptr((int)T);
-                        const uint32_t vq = *gq, vT = *gT;
-                        const int rT = (int)__umulhi(T, P.magic_w), cT = (int)T - rT * W;
-                        const int rq = rT + nbr_dr_rt<NBR>(from), cq = cT + nbr_dc_rt<NBR>(from);
-                        uint32_t bit;
-                        uint32_t* bw = blk_word(rq, cq, bit);
-                        atomicAnd(bw, ~bit);
-                        *gq = (uint16_t)(vq & TYPE_BITS);
-                        if (vT == EXIT_EMPTY) {                                   // reached an exit: removed (:101-102)
-                            leaves = true;
-                            const uint32_t id = (vq & OCC_MASK) - 1u;
-                            if (CL == 1) {
-                                atomicAnd(&alive[id >> 5], ~(1u << (id & 31u)));
-                            } else {
-#pragma unroll
-                                for (int rk = 0; rk < CL; ++rk)
-                                    atomicAnd(cg::this_cluster().map_shared_rank(alive, rk) + (id >> 5), ~(1u << (id & 31u)));
-                            }
-                        } else {
-                            *gT = (uint16_t)(vT | (vq & OCC_MASK));
-                            bw = blk_word(rT, cT, bit);
-                            atomicOr(bw, bit);
-                        }
-                        if (DFF) { float* dq = dff_cur(q); *dq = __fadd_rn(*dq, 1.0f); }   // footprint (:93,98)
-                    }
-                }
-            }
-            const uint32_t bal = __ballot_sync(FULL, leaves);
-            if (bal != 0u && lane == 0) {
-                if (CL == 1) {
-                    atomicAdd(&cnt[3], (uint32_t)__popc(bal));
-                } else {
-#pragma unroll
-                    for (int rk = 0; rk < CL; ++rk) atomicAdd(cg::this_cluster().map_shared_rank(cnt, rk) + 3, (uint32_t)__popc(bal));
+                    count_exits(leaves);
                 }
             }
         }

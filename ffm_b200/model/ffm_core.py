@@ -14,7 +14,7 @@ reference's placement draw, from the global NumPy generator at construction -- s
 """
 import numpy as np
 
-from ..sim import BatchSim, CORE_DEFAULTS, MOORE, NEUMANN
+from ..sim import seed_from_numpy_state, BatchSim, CORE_DEFAULTS, MOORE, NEUMANN
 
 
 class FloorFieldModel:
@@ -26,8 +26,7 @@ class FloorFieldModel:
         self.neighbors = self.get_neighbors()
         self._episode = 0
         seed = self.params.get("seed")
-        self._seed = int(np.random.randint(0, 2**31 - 1)) * 2**31 + int(np.random.randint(0, 2**31 - 1)) \
-            if seed is None else int(seed)
+        self._seed = seed_from_numpy_state() if seed is None else int(seed)
         positions = self.initialize_agents()                                                   # ffm_core.py:20
         self._cap = max(int(N), 1)
         self._sim = BatchSim(self.map_array, np.asarray(self.sff), 1, self._cap, self.params,

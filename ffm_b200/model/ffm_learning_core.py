@@ -16,7 +16,7 @@ import pickle
 
 import numpy as np
 
-from ..sim import MCQ_DEFAULTS, McqSim
+from ..sim import seed_from_numpy_state, MCQ_DEFAULTS, McqSim
 from .ffm_unified import MAX_CAPACITY
 
 
@@ -33,8 +33,7 @@ class FloorFieldModel:
         self.action_size = 5
         self.max_steps = int(self.params["max_steps"])
         seed = self.params.get("seed")
-        self._seed = int(np.random.randint(0, 2**31 - 1)) * 2**31 + int(np.random.randint(0, 2**31 - 1)) \
-            if seed is None else int(seed)
+        self._seed = seed_from_numpy_state() if seed is None else int(seed)
         self._episode = int(self.params.get("episode", 0))
         self._sim = None
         self._made_with = None

@@ -9,7 +9,7 @@ import pickle
 
 import numpy as np
 
-from ..sim import MOORE, NEUMANN, TRAINED_DEFAULTS, UnifiedSim
+from ..sim import seed_from_numpy_state, MOORE, NEUMANN, TRAINED_DEFAULTS, UnifiedSim
 from .ffm_unified import MAX_CAPACITY
 
 
@@ -31,8 +31,7 @@ class FloorFieldModel:
             self.H[(tuple(int(r) for r in k[0]), (int(k[1][0]), int(k[1][1])))] = v
         print(f"✓ 学習済みHテーブルを読み込みました: {len(self.H)}状態")
         seed = self.params.get("seed")
-        self._seed = int(np.random.randint(0, 2**31 - 1)) * 2**31 + int(np.random.randint(0, 2**31 - 1)) \
-            if seed is None else int(seed)
+        self._seed = seed_from_numpy_state() if seed is None else int(seed)
         self._episode = 0
         self._cap = min(max(int((self.map_array == 0).sum()), int(N), 1), MAX_CAPACITY)
         self._sim = UnifiedSim(self.map_array, np.asarray(sff_loaded), 1, self._cap, mode="trained", learn="none",

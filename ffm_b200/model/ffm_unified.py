@@ -20,7 +20,7 @@ from collections import defaultdict
 
 import numpy as np
 
-from ..sim import MOORE, NEUMANN, UNIFIED_DEFAULTS, UnifiedSim
+from ..sim import seed_from_numpy_state, MOORE, NEUMANN, UNIFIED_DEFAULTS, UnifiedSim
 
 MAX_CAPACITY = 16380
 
@@ -47,8 +47,7 @@ class FloorFieldModelUnified:
         self.alpha_h = self.params["alpha_h"] if actor else None
         self.epsilon = self.params.get("epsilon", 0.0) if actor else None
         seed = self.params.get("seed")
-        self._seed = int(np.random.randint(0, 2**31 - 1)) * 2**31 + int(np.random.randint(0, 2**31 - 1)) \
-            if seed is None else int(seed)
+        self._seed = seed_from_numpy_state() if seed is None else int(seed)
         self._episode = 0
         cap = min(max(int((self.map_array == 0).sum()), int(N), 1), MAX_CAPACITY)
         self._cap = cap

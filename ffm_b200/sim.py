@@ -15,6 +15,16 @@ MOORE = [(-1, -1), (-1, 0), (-1, 1), (0, -1), (0, 1), (1, -1), (1, 0), (1, 1)]  
 CORE_DEFAULTS = {"k_S": 3, "k_D": 1, "diffuse": 0.2, "decay": 0.2, "neighborhood": "moore"}  # ffm_core.py:8-14
 
 
+def seed_from_numpy_state():
+    """Philox seed of a drop-in object whose params carry no "seed": a hash of the process-global NumPy generator's
+    state, taken WITHOUT advancing it -- after ``np.random.seed(s)`` the run is reproducible and the placement draw
+    that follows (initialize_agents, ffm_core.py:25) sees exactly the stream the reference would see."""
+    import hashlib
+    st = np.random.get_state()
+    h = hashlib.blake2b(st[1].tobytes() + int(st[2]).to_bytes(4, "little"), digest_size=8).digest()
+    return int.from_bytes(h, "little") >> 2
+
+
 def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 

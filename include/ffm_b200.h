@@ -237,6 +237,10 @@ int ffm_sff_generate(const uint8_t *maps, int32_t n_maps, int32_t height, int32_
 int ffm_rollout_returns(const float *reward, const int32_t *len, int32_t n_episodes, int32_t steps, int32_t n_max,
                         double gamma, double *returns, int32_t device, void *stream);
 
+/* Roofline denominator of the shared-memory-resident kernels, measured on `device`: conflict-free 16-byte shared
+ * loads from every SM (GB/s; nominal 128 B/clk/SM), and the SM clock the driver reports (MHz).  Synchronous. */
+int ffm_measure_smem_bandwidth(int32_t device, double *gb_per_s, double *sm_clock_mhz);
+
 /* number of kernels this handle has launched so far (bench.py "gpu_launches") */
 int64_t ffm_launch_count(ffm_sim_t sim);
 

@@ -241,7 +241,16 @@ def shipped():
 
 
 def main():
+    import sys
     os.makedirs(OUT, exist_ok=True)
+    only = [a for a in sys.argv[1:] if not a.startswith("-")]
+    if only:                      # python -m oracle.make_golden core_50x50_moore_f64 ...: regenerate the named core fixtures
+        for name in only:
+            if name == "core_50x50_moore_f64":
+                core_case(name, 50, 50, 100, "moore", "L2", np.float64, 13, 5, dff_every=20)
+            else:
+                raise SystemExit(f"no single-fixture recipe for {name}; run without arguments")
+        return
     core_case("core_12x12_neumann_f32", 12, 12, 50, "neumann", "L1", np.float32, 11, 3)
     core_case("core_12x12_moore_f32_full", 12, 12, 100, "moore", "L1", np.float32, 12, 0)
     core_case("core_50x50_moore_f64", 50, 50, 100, "moore", "L2", np.float64, 13, 5, dff_every=20)

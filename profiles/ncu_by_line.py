@@ -5,10 +5,12 @@ import collections, csv, io, os, re, subprocess, sys, tempfile
 rep, lib, kname = sys.argv[1:4]
 tmp = tempfile.mkdtemp()
 subprocess.run(['cuobjdump', '-xelf', 'all', os.path.abspath(lib)], cwd=tmp, capture_output=True)
-cub = [os.path.join(tmp, f) for f in os.listdir(tmp) if f.endswith('.cubin')][0]
-dis = subprocess.run(['nvdisasm', '-g', '-c', cub], capture_output=True, text=True).stdout.splitlines()
-# locate function
-start = next(i for i, l in enumerate(dis) if l.startswith('.text.') and kname in l)
+# locate function (the library holds one cubin per translation unit)
+for cub in [os.path.join(tmp, f) for f in os.listdir(tmp) if f.endswith('.cubin')]:
+    dis = subprocess.run(['nvdisasm', '-g', '-c', cub], capture_output=True, text=True).stdout.splitlines()
+    start = next((i for i, l in enumerate(dis) if l.startswith('.text.') and kname in l), None)
+    if start is not None:
+        break
 lines = {}   # offset -> (file line)
 cur = None
 for l in dis[start + 1:]:
