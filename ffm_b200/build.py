@@ -16,7 +16,7 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
-LIB = os.path.join(HERE, "libffm_b200.so")
+LIB = os.environ.get("FFM_B200_LIB") or os.path.join(HERE, "libffm_b200.so")   # FFM_B200_LIB: load a prebuilt experiment build
 CSRC = os.path.join(HERE, "csrc")
 OBJDIR = os.path.join(HERE, "build")          # git-ignored
 NVCC_FLAGS = [

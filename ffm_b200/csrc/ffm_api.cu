@@ -3,6 +3,7 @@
 // launches a kernel on the configured device or fails with FFM_E_CUDA.
 #include "../../include/ffm_b200.h"
 
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -68,6 +69,7 @@ struct ffm_sim_s {
     bool cell_kernel;    // base model: the cell-centric kernel (ffm_cell_kernel.cuh); false = round-1 pedestrian-centric kernel
     int cluster;         // CTAs per episode (thread-block cluster, row bands in distributed shared memory); 1 = one CTA
     int RW, RB;          // bitboard words per row, rows per band
+    bool wall_in_smem;   // static wall bitboard staged in shared memory
     uint32_t* d_wall_bits;
     // unified / trained models
     int S, A, nby;
@@ -387,51 +389,83 @@ int ffm_create(const ffm_config_t* cfg, ffm_sim_t* out) {
         if (s->cell_kernel) return ffm::make_cell_layout(s->RB, W, s->RW, N, ssz, esz, dff, fs).total;
         return ffm::make_layout(HW, W, N, ssz, dff, fs).total;
     };
-    if (s->cell_kernel && layout_total(false) > MAX_SMEM_OPTIN) s->cell_kernel = false;   // TODO cluster variants
+    s->wall_in_smem = true;
     if (s->cell_kernel && (long long)HW * W >= (1LL << 32)) s->cell_kernel = false;       // row = umulhi(cell, magic) needs cell * W < 2^32
-    const long long tot_in = layout_total(true), tot_out = layout_total(false);
-    if (tot_out > MAX_SMEM_OPTIN) {
-        delete s;
-        return fail(FFM_E_UNSUPPORTED, "episode state (%lld B) does not fit the 227 KB of shared memory of one SM", tot_out);
-    }
-    int work = N > HW / 8 ? N : HW / 8;
-    if (s->cell_kernel) work = cfg->height * 2 * WW;      // 16-cell bitboard chunks per step
-    s->threads = work <= 128 ? 128 : (work <= 2048 ? 256 : 1024);
-    if (const char* ev = getenv("FFM_THREADS")) {   // tuning override: 128 | 256 | 1024
-        const int v = atoi(ev);
-        if (v == 128 || v == 256 || v == 1024) s->threads = v;
+    if (s->cell_kernel && ffm::make_cell_layout(s->RB, W, s->RW, N, ssz, esz, dff, false, false).total > (unsigned)MAX_SMEM_OPTIN)
+        s->cell_kernel = false;   // TODO cluster variants
+    auto occupancy = [&](const void* k, int threads, int smem) {
+        int occ = 0;
+        if (!k) return 0;
+        if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, threads, smem) != cudaSuccess) return 0;
+        return occ;
+    };
+    const bool f64 = cfg->sff_dtype == FFM_F64;
+    if (s->cell_kernel) {
+        // Cell-centric kernel: the rollout is bound by its three barriers per step, so what counts is how many CTAs
+        // (independent barrier domains) an SM holds, then how many threads each has.  Measured on C2 (one B200):
+        // 6 CTAs x 256 threads, fields in shared memory 73.2 ms; the same with fields read through L1 74.4 ms; 5 and 4 CTAs
+        // (more registers) 77.8 / 86.1 ms; 10 CTAs x 128 threads, fields through L1, 68.1 ms.  Rule: maximise
+        // CTAs/SM x sqrt(threads), with a small preference for shared-memory-resident fields.
+        const int chunks = cfg->height * 2 * WW;          // 16-cell bitboard chunks per step
+        const int tlist[3] = {128, 256, 1024};
+        const int force_threads = getenv("FFM_THREADS") ? atoi(getenv("FFM_THREADS")) : 0;
+        double best = -1.0;
+        for (int ti = 0; ti < 3; ++ti) {
+            const int th = tlist[ti];
+            if (force_threads ? th != force_threads : ((th == 256 && chunks <= 128) || (th == 1024 && chunks <= 2048))) continue;
+            for (int fsi = 1; fsi >= 0; --fsi)
+                for (int wi = 1; wi >= 0; --wi) {
+                    if (fsi == 1 && getenv("FFM_FIELDS_GLOBAL")) continue;
+                    if (fsi == 0 && getenv("FFM_FIELDS_SMEM")) continue;
+                    if (wi == 1 && getenv("FFM_WALL_GLOBAL")) continue;
+                    const long long tot = ffm::make_cell_layout(s->RB, W, s->RW, N, ssz, esz, dff, fsi != 0, wi != 0).total;
+                    if (tot > MAX_SMEM_OPTIN) continue;
+                    const void* k = ffm::pick_cell_kernel(f64, HW <= 65536, cfg->neighborhood, dff, fsi != 0, th, 1);
+                    const int occ = occupancy(k, th, (int)tot);
+                    const double score = occ * sqrt((double)th) * (fsi ? 1.0 : 0.95) * (wi ? 1.0 : 0.99);
+                    if (occ > 0 && score > best) {
+                        best = score;
+                        s->threads = th; s->fields_in_smem = fsi != 0; s->wall_in_smem = wi != 0;
+                        s->smem_bytes = (int)tot; s->kernel = k; s->ctas_per_sm = occ;
+                    }
+                }
+        }
+        if (best < 0.0) { delete s; return fail(FFM_E_UNSUPPORTED, "no resident configuration of the rollout kernel for this map / capacity"); }
+    } else {
+        const long long tot_in = layout_total(true), tot_out = layout_total(false);
+        if (tot_out > MAX_SMEM_OPTIN) {
+            delete s;
+            return fail(FFM_E_UNSUPPORTED, "episode state (%lld B) does not fit the 227 KB of shared memory of one SM", tot_out);
+        }
+        const int work = N > HW / 8 ? N : HW / 8;
+        s->threads = work <= 128 ? 128 : (work <= 2048 ? 256 : 1024);
+        if (const char* ev = getenv("FFM_THREADS")) {   // tuning override: 128 | 256 | 1024
+            const int v = atoi(ev);
+            if (v == 128 || v == 256 || v == 1024) s->threads = v;
+        }
+        if (unified || mcq) s->threads = N <= 128 ? 128 : 256;
+        // Fields (score, DFF) in shared memory or left in global memory (L1/L2)?  Shared memory is faster per access
+        // but costs residency.  Rule: shared unless the global variant keeps at least 1.5x as many CTAs resident.
+        auto kernel_for = [&](bool fs) {
+            if (mcq) return ffm::pick_mcq_kernel(f64, s->threads);
+            if (unified) return ffm::pick_unified_kernel(f64, cfg->neighborhood, fs, s->threads);
+            return pick_kernel(f64, HW <= 65536, cfg->neighborhood, dff, fs, s->threads);
+        };
+        const int occ_out = occupancy(kernel_for(false), s->threads, (int)tot_out);
+        const int occ_in = tot_in <= MAX_SMEM_OPTIN ? occupancy(kernel_for(true), s->threads, (int)tot_in) : 0;
+        s->fields_in_smem = occ_in > 0 && 2 * occ_out < 3 * occ_in;
+        if (getenv("FFM_FIELDS_GLOBAL")) s->fields_in_smem = false;          // tuning overrides
+        if (getenv("FFM_FIELDS_SMEM") && occ_in > 0) s->fields_in_smem = true;
+        s->smem_bytes = (int)(s->fields_in_smem ? tot_in : tot_out);
+        s->kernel = kernel_for(s->fields_in_smem);
     }
     if (unified) {
-        s->threads = N <= 128 ? 128 : 256;
         s->A = cfg->neighborhood + 1;
         s->nby = (W + cfg->block_size - 1) / cfg->block_size;
         s->S = ((cfg->height + cfg->block_size - 1) / cfg->block_size) * s->nby * 256;
         s->epsilon = cfg->epsilon;
     }
-    // Fields (score, DFF) in shared memory or left in global memory (L1/L2)?  Shared memory is faster per access
-    // but costs residency; measured on C2: SFF-only 6 vs 6 CTAs/SM -> shared +8 %, DFF-on 3 vs 6 CTAs/SM ->
-    // global +10 %.  Rule: shared unless the global variant keeps at least 1.5x as many CTAs resident.
-    if (mcq) s->threads = N <= 128 ? 128 : 256;
-    auto kernel_for = [&](bool fs) {
-        const bool f64 = cfg->sff_dtype == FFM_F64;
-        if (mcq) return ffm::pick_mcq_kernel(f64, s->threads);
-        if (unified) return ffm::pick_unified_kernel(f64, cfg->neighborhood, fs, s->threads);
-        if (s->cell_kernel) return ffm::pick_cell_kernel(f64, HW <= 65536, cfg->neighborhood, dff, fs, s->threads, s->cluster);
-        return pick_kernel(f64, HW <= 65536, cfg->neighborhood, dff, fs, s->threads);
-    };
-    auto occupancy = [&](const void* k, int smem) {
-        int occ = 0;
-        if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, s->threads, smem) != cudaSuccess) return 0;
-        return occ;
-    };
-    const int occ_out = occupancy(kernel_for(false), (int)tot_out);
-    const int occ_in = tot_in <= MAX_SMEM_OPTIN ? occupancy(kernel_for(true), (int)tot_in) : 0;
-    s->fields_in_smem = occ_in > 0 && 2 * occ_out < 3 * occ_in;
-    if (getenv("FFM_FIELDS_GLOBAL")) s->fields_in_smem = false;          // tuning overrides
-    if (getenv("FFM_FIELDS_SMEM") && occ_in > 0) s->fields_in_smem = true;
-    s->smem_bytes = (int)(s->fields_in_smem ? tot_in : tot_out);
-    s->kernel = kernel_for(s->fields_in_smem);
     cudaError_t ce = cudaFuncSetAttribute(s->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, s->smem_bytes);
     if (ce != cudaSuccess) { delete s; return fail(FFM_E_CUDA, "cudaFuncSetAttribute(smem=%d): %s", s->smem_bytes, cudaGetErrorString(ce)); }
     int occ = 0;
@@ -724,7 +758,8 @@ int ffm_rollout(ffm_sim_t s, int32_t max_steps, const ffm_draws_t* draws, const 
         memset(&C, 0, sizeof(C));
         C.H = s->cfg.height; C.W = s->cfg.width; C.HW = s->HW; C.n_max = s->cfg.n_max; C.B = s->cfg.n_episodes;
         C.max_steps = max_steps;
-        C.RW = s->RW; C.RB = s->RB;
+        C.RW = s->RW; C.RB = s->RB; C.wall_in_smem = s->wall_in_smem ? 1 : 0;
+        C.L = ffm::make_cell_layout(s->RB, C.W, s->RW, C.n_max, s->cfg.sff_dtype == FFM_F64 ? 8 : 4, s->HW <= 65536 ? 2 : 4, s->d_dff != nullptr, s->fields_in_smem, s->wall_in_smem);
         C.magic_w = (uint32_t)(((1ULL << 32) + (uint64_t)C.W - 1) / (uint64_t)C.W);
         const uint64_t cpr = 2ULL * (uint64_t)(s->RW - 2);
         C.magic_cpr = (uint32_t)(((1ULL << 32) + cpr - 1) / cpr);

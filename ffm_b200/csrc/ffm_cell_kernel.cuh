@@ -49,11 +49,18 @@ namespace ffm {
 
 namespace cg = cooperative_groups;
 
+struct CellLayout {
+    uint32_t score, dffA, dffB, grid, cmask, blk, wall, listA, listB, clist, alive, wpre, ctr, bar, total;
+    uint32_t cap;   // capacity of each work list (entries)
+};
+
 struct CellParams {
+    CellLayout L;                // shared-memory layout of one CTA (make_cell_layout, computed by the host)
     int H, W, HW, n_max, B;
     int max_steps;
     int RW;                      // bitboard words per row: ceil(W/32) + 2 guard words
     int RB;                      // rows per band (H when one CTA holds the whole map)
+    int wall_in_smem;            // static wall bitboard staged in shared memory (else read through L1 from wall_bits)
     uint32_t magic_w;            // ceil(2^32 / W): row = umulhi(cell, magic_w) for cell * W < 2^32
     uint32_t magic_cpr;          // ceil(2^32 / chunks per row), chunks per row = 2 * ceil(W/32)
     const uint16_t* type_grid;   // [HW + 2*(W+1)] type bits only, guard band included
@@ -81,13 +88,8 @@ struct CellParams {
     int ctraj_cap;
 };
 
-struct CellLayout {
-    uint32_t score, dffA, dffB, grid, cmask, blk, wall, listA, listB, clist, alive, wpre, ctr, bar, total;
-    uint32_t cap;   // capacity of each work list (entries)
-};
-
 __host__ __device__ inline CellLayout make_cell_layout(int RB, int W, int RW, int n_max, int sizeof_score, int sizeof_ent, bool dff,
-                                                       bool fields_in_smem) {
+                                                       bool fields_in_smem, bool wall_in_smem = true) {
     const uint32_t cells = (uint32_t)RB * W;
     const uint32_t nw = (uint32_t)(n_max + 31) / 32 + 1;
     CellLayout L;
@@ -99,10 +101,10 @@ __host__ __device__ inline CellLayout make_cell_layout(int RB, int W, int RW, in
     L.grid = o;  o = align16(o + (cells + 2u * (W + 1)) * 2u);
     L.cmask = o; o = align16(o + cells);
     L.blk = o;   o = align16(o + (uint32_t)(RB + 2) * RW * 4u);
-    L.wall = o;  o = align16(o + (uint32_t)(RB + 2) * RW * 4u);
+    L.wall = o;  if (wall_in_smem) o = align16(o + (uint32_t)(RB + 2) * RW * 4u);
     L.listA = o; o = align16(o + L.cap * sizeof_ent);
     L.listB = o; o = align16(o + L.cap * sizeof_ent);
-    L.clist = o; o = align16(o + (L.cap / 2u + 1u) * sizeof_ent);   // contested cells: at least two claimants each
+    L.clist = o;   // (the contested-cell list lives in the larger free part of the two work lists)
     L.alive = o; o = align16(o + nw * 4u);
     L.wpre = o;  o = align16(o + nw * 4u);
     L.ctr = o;   o = align16(o + 16u * 4u);
@@ -214,8 +216,11 @@ static __device__ __noinline__ void refresh_alive_prefix(const uint32_t* alive, 
     }
 }
 
+#ifndef FFM_CELL_MINB256
+#define FFM_CELL_MINB256 6      // resident CTAs per SM the 256-thread float32 variant is compiled for (register cap)
+#endif
 template <typename S, typename EntT, int NBR, bool DFF, bool FIELDS_IN_SMEM, int THREADS, int CL>
-__global__ void __launch_bounds__(THREADS, (CL == 1 && THREADS <= 256 && sizeof(S) == 4) ? 1536 / THREADS : 1)
+__global__ void __launch_bounds__(THREADS, (CL == 1 && THREADS <= 256 && sizeof(S) == 4) ? (FFM_CELL_MINB256 * 256) / THREADS : 1)
 ffm_cell_rollout_kernel(const CellParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int NW = THREADS / 32;
@@ -242,14 +247,13 @@ ffm_cell_rollout_kernel(const CellParams P) {
     const int lo_acc = lo - (top ? G : 0);
     const uint32_t span_acc = (uint32_t)(hi - lo_acc + (bottom ? G : 0));
 
-    const CellLayout L = make_cell_layout(RB, W, RW, P.n_max, (int)sizeof(S), (int)sizeof(EntT), DFF, FIELDS_IN_SMEM);
+    const CellLayout& L = P.L;
     uint16_t* grid_l = reinterpret_cast<uint16_t*>(smem_raw + L.grid) + G;     // grid_l[c - lo]
     uint32_t* cmask_l = reinterpret_cast<uint32_t*>(smem_raw + L.cmask);       // byte (c - lo) of this array
     uint32_t* blk_l = reinterpret_cast<uint32_t*>(smem_raw + L.blk);           // row (r - r0 + 1), word (col/32 + 1)
     uint32_t* wall_l = reinterpret_cast<uint32_t*>(smem_raw + L.wall);
     EntT* listA = reinterpret_cast<EntT*>(smem_raw + L.listA);
     EntT* listB = reinterpret_cast<EntT*>(smem_raw + L.listB);
-    EntT* clist = reinterpret_cast<EntT*>(smem_raw + L.clist);
     const int cap1 = (int)L.cap - 1;
     uint32_t* alive = reinterpret_cast<uint32_t*>(smem_raw + L.alive);
     uint32_t* wpre = reinterpret_cast<uint32_t*>(smem_raw + L.wpre);
@@ -344,7 +348,7 @@ ffm_cell_rollout_kernel(const CellParams P) {
         const int lr = x / RW;
         const int gr = r0 + lr;                           // row index in the global board (which has its own +1 offset)
         const uint32_t wv = (gr <= H + 1 && lr <= RBl + 1) ? P.wall_bits[(size_t)gr * RW + (x - lr * RW)] : FULL;
-        wall_l[x] = wv;
+        if (P.wall_in_smem) wall_l[x] = wv;
         blk_l[x] = wv;
     }
     int n = P.n_alive[e];                                 // pedestrians still inside (whole episode)
@@ -384,6 +388,10 @@ ffm_cell_rollout_kernel(const CellParams P) {
     auto rank_of = [&](uint32_t id) -> uint32_t {
         return wpre[id >> 5] + (uint32_t)__popc(alive[id >> 5] & ((1u << (id & 31u)) - 1u));
     };
+    // static wall word at local bitboard index idx (row lr + 1 of this band)
+    auto wall_word = [&](int idx) -> uint32_t {
+        return P.wall_in_smem ? wall_l[idx] : __ldg(P.wall_bits + (size_t)r0 * RW + idx);
+    };
     // 18-bit window of a bitboard row around a 16-cell chunk: bit i <-> column 32*j + 16*h - 1 + i
     auto window18 = [&](const uint32_t* wp, int h) -> uint32_t {
         const uint32_t w = wp[0];
@@ -416,7 +424,7 @@ ffm_cell_rollout_kernel(const CellParams P) {
         for (int ch = tid; ch < nchunks; ch += THREADS) {
             const int lr = (int)__umulhi((uint32_t)ch, P.magic_cpr), rem = ch - lr * cpr;
             const int idx = (lr + 1) * RW + 1 + (rem >> 1);
-            uint32_t occ = ((blk_l[idx] & ~wall_l[idx]) >> (16 * (rem & 1))) & 0xFFFFu;
+            uint32_t occ = ((blk_l[idx] & ~wall_word(idx)) >> (16 * (rem & 1))) & 0xFFFFu;
             const int cbase = (r0 + lr) * W + 32 * (rem >> 1) + 16 * (rem & 1);
             while (occ) {
                 const int b = __ffs(occ) - 1;
@@ -455,7 +463,7 @@ ffm_cell_rollout_kernel(const CellParams P) {
                 const int lr = (int)__umulhi((uint32_t)ch, P.magic_cpr), rem = ch - lr * cpr;
                 const int j = rem >> 1, h = rem & 1;
                 const int idx = (lr + 1) * RW + 1 + j;
-                const uint32_t occ16 = ((blk_l[idx] & ~wall_l[idx]) >> (16 * h)) & 0xFFFFu;
+                const uint32_t occ16 = ((blk_l[idx] & ~wall_word(idx)) >> (16 * h)) & 0xFFFFu;
                 if (occ16 != 0u) {
                     cbase = (r0 + lr) * W + 32 * j + 16 * h - 1;               // cell of window bit 0
                     const uint32_t fu = ~window18(blk_row_word(lr, j + 1), h) & 0x3FFFFu;       // free cells, row above
@@ -498,15 +506,17 @@ ffm_cell_rollout_kernel(const CellParams P) {
                 if (lane >= d) inc += y;
             }
             const uint32_t tot = __shfl_sync(FULL, inc, 31);
-            uint32_t base = 0;
-            if (lane < 3) {
-                const uint32_t k = (tot >> (10 * lane)) & 0x3FFu;
-                if (k) base = atomicAdd(&cnt[lane], k);
+            uint32_t b23 = 0, bb = 0;
+            if (lane == 0) {     // classes 2 and 3 share one packed counter (16 bits each: at most 16380 pedestrians)
+                b23 = atomicAdd(&cnt[0], (tot & 0x3FFu) | (((tot >> 10) & 0x3FFu) << 16));
+                if (tot >> 20) bb = atomicAdd(&cnt[2], tot >> 20);
             }
+            b23 = __shfl_sync(FULL, b23, 0);
+            bb = __shfl_sync(FULL, bb, 0);
             const uint32_t ex = inc - mine;
-            int o2 = (int)(__shfl_sync(FULL, base, 0) + (ex & 0x3FFu));
-            int o3 = (int)(__shfl_sync(FULL, base, 1) + ((ex >> 10) & 0x3FFu));
-            int ob = (int)(__shfl_sync(FULL, base, 2) + (ex >> 20));
+            int o2 = (int)((b23 & 0xFFFFu) + (ex & 0x3FFu));
+            int o3 = (int)((b23 >> 16) + ((ex >> 10) & 0x3FFu));
+            int ob = (int)(bb + (ex >> 20));
             for (uint32_t m = m2; m; m &= m - 1u) listA[o2++] = (EntT)(cbase + __ffs(m) - 1);
             for (uint32_t m = m3; m; m &= m - 1u) listA[cap1 - (o3++)] = (EntT)(cbase + __ffs(m) - 1);
             for (uint32_t m = mb; m; m &= m - 1u) listB[ob++] = (EntT)(cbase + __ffs(m) - 1);
@@ -544,7 +554,7 @@ ffm_cell_rollout_kernel(const CellParams P) {
         }
 
         // ================= phase 2: movers -> requests ==================================================
-        const int n2 = (int)cnt[0], n3 = (int)cnt[1], nb = (int)cnt[2];
+        const int n2 = (int)(cnt[0] & 0xFFFFu), n3 = (int)(cnt[0] >> 16), nb = (int)cnt[2];
         // One mover: candidates in neighbour order then "stay" (the order of the reference's neighbor_coords array,
         // :54,60,64).  The lists are sorted by candidate count, so the trip counts below are warp-uniform.
         auto decide = [&](EntT* slot_ptr) {
@@ -676,6 +686,9 @@ ffm_cell_rollout_kernel(const CellParams P) {
             }
         };
         const int ntot = n2 + n3 + nb;
+        // contested cells (at most ntot / 2) are listed in the larger free part of the two work lists: the middle of
+        // listA has cap - n2 - n3 free entries, the tail of listB cap - nb, together at least cap >= ntot
+        EntT* clist = ((int)L.cap - n2 - n3 >= (int)L.cap - nb) ? listA + n2 : listB + nb;
         for (int x0 = 0; x0 < ntot; x0 += THREADS) {
             const int x = x0 + tid;
             bool leaves = false, contested = false;
