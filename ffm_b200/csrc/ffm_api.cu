@@ -380,8 +380,11 @@ int ffm_create(const ffm_config_t* cfg, ffm_sim_t* out) {
     s->RW = WW + 2;
     s->RB = cfg->height;
     s->cluster = 1;
-    s->cell_kernel = core;
-    if (const char* ev = getenv("FFM_KERNEL")) s->cell_kernel = core && strcmp(ev, "ped") != 0;   // A/B switch: the round-1 kernel
+    // Two kernels implement the base model.  The cell-centric one (bitboard movers, ffm_cell_kernel.cuh) wins on maps with
+    // enough bitboard words to keep a CTA busy (C2: 5.4e10 vs 4.3e10 ped-steps/s); on small maps (12x12 .. 32x32: a
+    // dozen words) the pedestrian-centric one (ffm_core_kernel.cuh) has less fixed work per step (C1: 1.5e10 vs 1.2e10).
+    s->cell_kernel = core && cfg->height * WW >= 64;
+    if (const char* ev = getenv("FFM_KERNEL")) s->cell_kernel = core && strcmp(ev, "ped") != 0;   // test / tuning override: cell | ped
     const int esz = HW <= 65536 ? 2 : 4;
     auto layout_total = [&](bool fs) -> long long {
         if (mcq) return fs ? (1LL << 30) : (long long)ffm::make_mlayout(HW, W, N).total;
@@ -407,7 +410,7 @@ int ffm_create(const ffm_config_t* cfg, ffm_sim_t* out) {
         // 6 CTAs x 256 threads, fields in shared memory 73.2 ms; the same with fields read through L1 74.4 ms; 5 and 4 CTAs
         // (more registers) 77.8 / 86.1 ms; 10 CTAs x 128 threads, fields through L1, 68.1 ms.  Rule: maximise
         // CTAs/SM x sqrt(threads), with a small preference for shared-memory-resident fields.
-        const int chunks = cfg->height * 2 * WW;          // 16-cell bitboard chunks per step
+        const int chunks = cfg->height * WW;              // 32-cell bitboard chunks per step
         const int tlist[3] = {128, 256, 1024};
         const int force_threads = getenv("FFM_THREADS") ? atoi(getenv("FFM_THREADS")) : 0;
         double best = -1.0;
@@ -761,8 +764,8 @@ int ffm_rollout(ffm_sim_t s, int32_t max_steps, const ffm_draws_t* draws, const 
         C.RW = s->RW; C.RB = s->RB; C.wall_in_smem = s->wall_in_smem ? 1 : 0;
         C.L = ffm::make_cell_layout(s->RB, C.W, s->RW, C.n_max, s->cfg.sff_dtype == FFM_F64 ? 8 : 4, s->HW <= 65536 ? 2 : 4, s->d_dff != nullptr, s->fields_in_smem, s->wall_in_smem);
         C.magic_w = (uint32_t)(((1ULL << 32) + (uint64_t)C.W - 1) / (uint64_t)C.W);
-        const uint64_t cpr = 2ULL * (uint64_t)(s->RW - 2);
-        C.magic_cpr = (uint32_t)(((1ULL << 32) + cpr - 1) / cpr);
+        const uint64_t cpr = (uint64_t)(s->RW - 2);      // chunks (bitboard words) per row; the kernel skips the division when it is 1
+        C.magic_cpr = cpr > 1 ? (uint32_t)(((1ULL << 32) + cpr - 1) / cpr) : 0u;
         C.type_grid = s->d_type_grid; C.wall_bits = s->d_wall_bits; C.score = s->d_score;
         C.kd = (float)s->cfg.k_D; C.c0 = s->cfg.dff_c0; C.c1 = s->cfg.dff_c1; C.thr = s->cfg.dff_threshold;
         C.pos = s->d_pos; C.n_alive = s->d_n; C.t_done = s->d_t; C.ped_steps = s->d_ped_steps;

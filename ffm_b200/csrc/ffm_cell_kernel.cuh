@@ -62,7 +62,7 @@ struct CellParams {
     int RB;                      // rows per band (H when one CTA holds the whole map)
     int wall_in_smem;            // static wall bitboard staged in shared memory (else read through L1 from wall_bits)
     uint32_t magic_w;            // ceil(2^32 / W): row = umulhi(cell, magic_w) for cell * W < 2^32
-    uint32_t magic_cpr;          // ceil(2^32 / chunks per row), chunks per row = 2 * ceil(W/32)
+    uint32_t magic_cpr;          // ceil(2^32 / chunks per row), chunks per row = ceil(W/32) (one bitboard word each)
     const uint16_t* type_grid;   // [HW + 2*(W+1)] type bits only, guard band included
     const uint32_t* wall_bits;   // [(H+2) * RW] 1 = not passable / outside the map
     const void* score;           // [HW] S
@@ -195,6 +195,14 @@ __device__ __forceinline__ void dff_stencil_rows(RowIn in_row, RowOut out_row, i
             sc = sn;
         }
     }
+}
+
+// atomicAdd on a CTA-local shared-memory word issued by ONE lane: the plain instruction, without the warp-aggregation
+// sequence (vote / popc / shuffle) the compiler wraps around atomicAdd() on a possibly uniform address
+__device__ __forceinline__ uint32_t smem_atomic_add(uint32_t* p, uint32_t v) {
+    uint32_t old;
+    asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(smem_u32(p)), "r"(v) : "memory");
+    return old;
 }
 
 // alive-rank prefix: exclusive popcount prefix over the alive words, by one warp (kept out of line: it runs only in
@@ -381,7 +389,7 @@ ffm_cell_rollout_kernel(const CellParams P) {
     const uint32_t episode = P.episode_base + (uint32_t)e;
     const double* mv_draws = P.move_draws ? P.move_draws + (size_t)e * P.draw_steps * P.n_max : nullptr;
     const double* cf_draws = P.conflict_draws ? P.conflict_draws + (size_t)e * P.draw_steps * HW * 2 : nullptr;
-    const int cpr = 2 * WW;                               // 16-cell chunks per bitboard row
+    const int cpr = WW;                                   // 32-cell chunks (one bitboard word) per row
     const int nchunks = RBl * cpr;
 
     auto refresh_prefix = [&]() { refresh_alive_prefix(alive, wpre, nwords, lane); };
@@ -391,11 +399,6 @@ ffm_cell_rollout_kernel(const CellParams P) {
     // static wall word at local bitboard index idx (row lr + 1 of this band)
     auto wall_word = [&](int idx) -> uint32_t {
         return P.wall_in_smem ? wall_l[idx] : __ldg(P.wall_bits + (size_t)r0 * RW + idx);
-    };
-    // 18-bit window of a bitboard row around a 16-cell chunk: bit i <-> column 32*j + 16*h - 1 + i
-    auto window18 = [&](const uint32_t* wp, int h) -> uint32_t {
-        const uint32_t w = wp[0];
-        return h == 0 ? (((w << 1) | (wp[-1] >> 31)) & 0x3FFFFu) : (((w >> 15) | (wp[1] << 17)) & 0x3FFFFu);
     };
     // pointer to word (j+1) of the bitboard row above / below local row lr (a neighbour CTA's row at a band boundary)
     auto blk_row_word = [&](int lr_abs /* local row index incl. the +1 offset */, int jw) -> const uint32_t* {
@@ -422,10 +425,10 @@ ffm_cell_rollout_kernel(const CellParams P) {
     auto emit_positions = [&](uint32_t* dst) {
 #pragma unroll 1
         for (int ch = tid; ch < nchunks; ch += THREADS) {
-            const int lr = (int)__umulhi((uint32_t)ch, P.magic_cpr), rem = ch - lr * cpr;
-            const int idx = (lr + 1) * RW + 1 + (rem >> 1);
-            uint32_t occ = ((blk_l[idx] & ~wall_word(idx)) >> (16 * (rem & 1))) & 0xFFFFu;
-            const int cbase = (r0 + lr) * W + 32 * (rem >> 1) + 16 * (rem & 1);
+            const int lr = cpr == 1 ? ch : (int)__umulhi((uint32_t)ch, P.magic_cpr), j = ch - lr * cpr;
+            const int idx = (lr + 1) * RW + 1 + j;
+            uint32_t occ = blk_l[idx] & ~wall_word(idx);
+            const int cbase = (r0 + lr) * W + 32 * j;
             while (occ) {
                 const int b = __ffs(occ) - 1;
                 occ &= occ - 1u;
@@ -460,19 +463,24 @@ ffm_cell_rollout_kernel(const CellParams P) {
             uint32_t mov = 0, m2 = 0, m3 = 0;
             int cbase = 0;
             if (ch < nchunks) {
-                const int lr = (int)__umulhi((uint32_t)ch, P.magic_cpr), rem = ch - lr * cpr;
-                const int j = rem >> 1, h = rem & 1;
+                const int lr = cpr == 1 ? ch : (int)__umulhi((uint32_t)ch, P.magic_cpr), j = ch - lr * cpr;
                 const int idx = (lr + 1) * RW + 1 + j;
-                const uint32_t occ16 = ((blk_l[idx] & ~wall_word(idx)) >> (16 * h)) & 0xFFFFu;
-                if (occ16 != 0u) {
-                    cbase = (r0 + lr) * W + 32 * j + 16 * h - 1;               // cell of window bit 0
-                    const uint32_t fu = ~window18(blk_row_word(lr, j + 1), h) & 0x3FFFFu;       // free cells, row above
-                    const uint32_t fm = ~window18(blk_l + idx, h) & 0x3FFFFu;
-                    const uint32_t fd = ~window18(blk_row_word(lr + 2, j + 1), h) & 0x3FFFFu;   // row below
+                const uint32_t occw = blk_l[idx] & ~wall_word(idx);            // pedestrians of this word
+                if (occw != 0u) {
+                    cbase = (r0 + lr) * W + 32 * j;                            // cell of bit 0
+                    // free cells of the three rows, and the same shifted by one column either way (bit i <-> column 32j + i;
+                    // the bit shifted in comes from the neighbouring word)
+                    const uint32_t* pu = blk_row_word(lr, j + 1);
+                    const uint32_t* pm = blk_l + idx;
+                    const uint32_t* pd = blk_row_word(lr + 2, j + 1);
+                    const uint32_t fu = ~pu[0], fm = ~pm[0], fd = ~pd[0];
+                    const uint32_t ful = __funnelshift_l(~pu[-1], fu, 1), fur = __funnelshift_r(fu, ~pu[1], 1);   // column - 1 / + 1
+                    const uint32_t fml = __funnelshift_l(~pm[-1], fm, 1), fmr = __funnelshift_r(fm, ~pm[1], 1);
+                    const uint32_t fdl = __funnelshift_l(~pd[-1], fd, 1), fdr = __funnelshift_r(fd, ~pd[1], 1);
                     // number of free neighbours of every cell, bit-sliced (ones / twos / fours / eights)
                     uint32_t ones, twos, more;
                     if (NBR == 8) {
-                        const uint32_t x0 = fu << 1, x1 = fu, x2 = fu >> 1, x3 = fm << 1, x4 = fm >> 1, x5 = fd << 1, x6 = fd, x7 = fd >> 1;
+                        const uint32_t x0 = ful, x1 = fu, x2 = fur, x3 = fml, x4 = fmr, x5 = fdl, x6 = fd, x7 = fdr;
                         const uint32_t sa = x0 ^ x1 ^ x2, ca = (x0 & x1) | (x2 & (x0 ^ x1));
                         const uint32_t sb = x3 ^ x4 ^ x5, cb = (x3 & x4) | (x5 & (x3 ^ x4));
                         const uint32_t sc = x6 ^ x7, cc = x6 & x7;
@@ -482,14 +490,13 @@ ffm_cell_rollout_kernel(const CellParams P) {
                         twos = ts ^ cd;
                         more = tc | (ts & cd);                                 // fours or eights
                     } else {
-                        const uint32_t x0 = fu, x1 = fd, x2 = fm << 1, x3 = fm >> 1;
+                        const uint32_t x0 = fu, x1 = fd, x2 = fml, x3 = fmr;
                         const uint32_t sa = x0 ^ x1 ^ x2, ca = (x0 & x1) | (x2 & (x0 ^ x1));
                         ones = sa ^ x3;
                         const uint32_t c2 = sa & x3;
                         twos = ca ^ c2;
                         more = ca & c2;
                     }
-                    const uint32_t occw = occ16 << 1;                          // aligned with the window bits 1..16
                     mov = occw & (ones | twos | more);                         // at least one candidate (:57-63)
                     m2 = mov & ones & ~(twos | more);                          // exactly one free neighbour (+ stay)
                     m3 = mov & twos & ~(ones | more);                          // exactly two
@@ -508,8 +515,8 @@ ffm_cell_rollout_kernel(const CellParams P) {
             const uint32_t tot = __shfl_sync(FULL, inc, 31);
             uint32_t b23 = 0, bb = 0;
             if (lane == 0) {     // classes 2 and 3 share one packed counter (16 bits each: at most 16380 pedestrians)
-                b23 = atomicAdd(&cnt[0], (tot & 0x3FFu) | (((tot >> 10) & 0x3FFu) << 16));
-                if (tot >> 20) bb = atomicAdd(&cnt[2], tot >> 20);
+                b23 = smem_atomic_add(&cnt[0], (tot & 0x3FFu) | (((tot >> 10) & 0x3FFu) << 16));
+                if (tot >> 20) bb = smem_atomic_add(&cnt[2], tot >> 20);
             }
             b23 = __shfl_sync(FULL, b23, 0);
             bb = __shfl_sync(FULL, bb, 0);
@@ -578,30 +585,44 @@ ffm_cell_rollout_kernel(const CellParams P) {
                 const int ncand = __popc(mm) + 1;
                 int kb[NBR + 1];
                 S p[NBR + 1];
-                S mx = neg_inf<S>();
-                uint32_t m = mm;
-#pragma unroll
-                for (int j = 0; j <= NBR; ++j)
-                    if (j < ncand) {
-                        int cc = c;
-                        kb[j] = 0;
-                        if (j < ncand - 1) {
-                            kb[j] = __ffs(m) - 1;
-                            m &= m - 1u;
-                            cc = c + cand_off<NBR>(kb[j], W);
-                        }
-                        S sc = score_at(cc);                                       // -k_S * sff
-                        if (DFF) sc = add_rn(sc, (S)mul_rn(P.kd, *dff_cur(cc)));   // + k_D * dff   (:77)
-                        p[j] = sc;
-                        mx = max_t(mx, sc);
-                    }
                 double tot = 0.0;
+                if (ncand == 2) {
+                    // one free neighbour + "stay" (half of all movers in a packed crowd): the larger score gives exp(0) = 1
+                    // and the other one exp(-|difference|) -- the same two values as the general path, one exp
+                    kb[0] = __ffs(mm) - 1;
+                    const int cc = c + cand_off<NBR>(kb[0], W);
+                    S s0 = score_at(cc), s1 = score_at(c);
+                    if (DFF) { s0 = add_rn(s0, (S)mul_rn(P.kd, *dff_cur(cc))); s1 = add_rn(s1, (S)mul_rn(P.kd, *dff_cur(c))); }
+                    const S d = add_rn(s0, -s1);
+                    const S ex = exp_t(d >= (S)0 ? -d : d);                        // NaN (inf - inf) falls through to "no request"
+                    p[0] = d >= (S)0 ? (S)1 : ex;
+                    p[1] = d >= (S)0 ? ex : (S)1;
+                    tot = (double)p[0] + (double)p[1];
+                } else {
+                    S mx = neg_inf<S>();
+                    uint32_t m = mm;
 #pragma unroll
-                for (int j = 0; j <= NBR; ++j)
-                    if (j < ncand) {
-                        p[j] = exp_t(add_rn(p[j], -mx));                           // exp(score - max) (:80)
-                        tot += (double)p[j];
-                    }
+                    for (int j = 0; j <= NBR; ++j)
+                        if (j < ncand) {
+                            int cc = c;
+                            kb[j] = 0;
+                            if (j < ncand - 1) {
+                                kb[j] = __ffs(m) - 1;
+                                m &= m - 1u;
+                                cc = c + cand_off<NBR>(kb[j], W);
+                            }
+                            S sc = score_at(cc);                                       // -k_S * sff
+                            if (DFF) sc = add_rn(sc, (S)mul_rn(P.kd, *dff_cur(cc)));   // + k_D * dff   (:77)
+                            p[j] = sc;
+                            mx = max_t(mx, sc);
+                        }
+#pragma unroll
+                    for (int j = 0; j <= NBR; ++j)
+                        if (j < ncand) {
+                            p[j] = exp_t(add_rn(p[j], -mx));                           // exp(score - max) (:80)
+                            tot += (double)p[j];
+                        }
+                }
                 if (isfinite(tot) && tot != 0.0) {                                // (:82)
                     const uint32_t rank = rank_of(id);                            // the reference's array index
                     const double u = (inj && mv_draws) ? mv_draws[(size_t)di * P.n_max + rank]
@@ -678,7 +699,7 @@ ffm_cell_rollout_kernel(const CellParams P) {
             const uint32_t bal = __ballot_sync(FULL, leaves);
             if (bal != 0u && lane == 0) {
                 if (CL == 1) {
-                    atomicAdd(&cnt[3], (uint32_t)__popc(bal));
+                    smem_atomic_add(&cnt[3], (uint32_t)__popc(bal));
                 } else {
 #pragma unroll
                     for (int rk = 0; rk < CL; ++rk) atomicAdd(cg::this_cluster().map_shared_rank(cnt, rk) + 3, (uint32_t)__popc(bal));
@@ -707,7 +728,7 @@ ffm_cell_rollout_kernel(const CellParams P) {
             const uint32_t cb = __ballot_sync(FULL, contested);
             if (cb != 0u) {
                 uint32_t base = 0;
-                if (lane == 0) base = atomicAdd(&cnt[4], (uint32_t)__popc(cb));
+                if (lane == 0) base = smem_atomic_add(&cnt[4], (uint32_t)__popc(cb));
                 base = __shfl_sync(FULL, base, 0);
                 if (contested) clist[base + __popc(cb & lanemask_lt())] = (EntT)T;
             }
@@ -715,7 +736,7 @@ ffm_cell_rollout_kernel(const CellParams P) {
         {
             __syncwarp();
             uint32_t done = 0;
-            if (lane == 0) { __threadfence_block(); done = atomicAdd(&cnt[5], 1u); __threadfence_block(); }
+            if (lane == 0) { __threadfence_block(); done = smem_atomic_add(&cnt[5], 1u); __threadfence_block(); }
             done = __shfl_sync(FULL, done, 0);
             if (done == NW - 1) {
                 const int ncont = (int)*((volatile uint32_t*)&cnt[4]);

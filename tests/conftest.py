@@ -27,3 +27,11 @@ def cuda_device(ffm_lib):
         pytest.skip("no CUDA device")
     torch.cuda.set_device(0)
     return 0
+
+
+@pytest.fixture(params=["cell", "ped"])
+def core_kernel(request, monkeypatch):
+    """Runs a test once per base-model kernel: "cell" = cell-centric (csrc/ffm_cell_kernel.cuh), "ped" =
+    pedestrian-centric (csrc/ffm_core_kernel.cuh); libffm_b200 reads FFM_KERNEL in ffm_create."""
+    monkeypatch.setenv("FFM_KERNEL", request.param)
+    return request.param

@@ -22,7 +22,7 @@ CASES = [
 
 
 @pytest.mark.parametrize("h,w,N,nbh,metric,dtype,extra", CASES)
-def test_rollout_matches_oracle(cuda_device, h, w, N, nbh, metric, dtype, extra):
+def test_rollout_matches_oracle(cuda_device, core_kernel, h, w, N, nbh, metric, dtype, extra):
     import torch
     from ffm_b200 import BatchSim
 
@@ -62,7 +62,7 @@ def test_rollout_matches_oracle(cuda_device, h, w, N, nbh, metric, dtype, extra)
     sim.close()
 
 
-def test_stepwise_equals_single_launch(cuda_device):
+def test_stepwise_equals_single_launch(cuda_device, core_kernel):
     """step() x T through separate launches (state round-trips through HBM) == one persistent launch."""
     import torch
     from ffm_b200 import BatchSim

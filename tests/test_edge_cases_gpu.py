@@ -29,7 +29,7 @@ def _check_recorded(sim, ref, T, W):
         assert np.array_equal(cells[e, :s][mask], ref["traj"][e, :s][mask]), e
 
 
-def test_empty_single_and_ragged_episodes(cuda_device):
+def test_empty_single_and_ragged_episodes(cuda_device, core_kernel):
     from ffm_b200 import BatchSim
     m = assets.room_map(16, 20)
     sff = assets.sff_norm_min_fast(m, "L2", np.float32)
@@ -45,7 +45,7 @@ def test_empty_single_and_ragged_episodes(cuda_device):
     assert np.array_equal(sim.get_dff().view(np.uint32), ref["final_dff"].view(np.uint32))
 
 
-def test_32bit_cell_ids_above_65536_cells(cuda_device):
+def test_32bit_cell_ids_above_65536_cells(cuda_device, core_kernel):
     """300 x 260 = 78 000 cells: PosT = uint32 variant, fields in global memory."""
     from ffm_b200 import BatchSim
     m = assets.obstacle_map_c5(300, 260, index=1, n_exits=4)
@@ -62,7 +62,7 @@ def test_32bit_cell_ids_above_65536_cells(cuda_device):
     assert np.array_equal(sim.get_dff().view(np.uint32), ref["final_dff"].view(np.uint32))
 
 
-def test_maximum_capacity(cuda_device):
+def test_maximum_capacity(cuda_device, core_kernel):
     """n_max = 16 380 pedestrians (the owner grid's 14-bit id space) in a 130 x 130 room: 96.9 % of the cells
     occupied at t = 0.  (256 x 256 maps hold at most ~10 100 pedestrians: one SM's shared memory.)"""
     from ffm_b200 import BatchSim
@@ -86,7 +86,7 @@ def test_maximum_capacity(cuda_device):
 
 
 @pytest.mark.parametrize("nbh", ["neumann", "moore"])
-def test_obstacles_and_several_exits_full_episodes(cuda_device, nbh):
+def test_obstacles_and_several_exits_full_episodes(cuda_device, core_kernel, nbh):
     from ffm_b200 import BatchSim
     m = assets.obstacle_map_c5(96, 80, index=3, n_exits=8)
     sff = c_oracle.geodesic(m, "bfs4" if nbh == "neumann" else "dijkstra8").astype(np.float64)

@@ -12,7 +12,7 @@ pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("name", CORE_FIXTURES)
-def test_reference_fixture(cuda_device, name):
+def test_reference_fixture(cuda_device, core_kernel, name):
     import torch
     from ffm_b200 import BatchSim
 
@@ -39,7 +39,7 @@ def test_reference_fixture(cuda_device, name):
     assert steps[0] == T and sim.get_positions()[1][0] == 0
 
 
-def test_stock_main_seed42_replay(cuda_device):
+def test_stock_main_seed42_replay(cuda_device, core_kernel):
     """The reference's stock run (main.py, config/default_config.yaml, seed 42: 272 steps,
     14 079 pedestrian-steps) replayed from its recorded MT19937 draws through the draw buffers."""
     import torch
