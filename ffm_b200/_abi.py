@@ -81,6 +81,8 @@ SIGNATURES = {
     "ffm_launch_count": (C.c_int64, [C.c_void_p]),
     "ffm_kernel_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32),
                                   C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "ffm_cluster_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32),
+                                   C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
 }
 
 _lib = None

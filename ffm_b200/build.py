@@ -18,7 +18,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 LIB = os.environ.get("FFM_B200_LIB") or os.path.join(HERE, "libffm_b200.so")   # FFM_B200_LIB: load a prebuilt experiment build
 CSRC = os.path.join(HERE, "csrc")
-OBJDIR = os.path.join(HERE, "build")          # git-ignored
+OBJDIR = os.environ.get("FFM_B200_OBJDIR") or os.path.join(HERE, "build")          # git-ignored
+EXTRA_FLAGS = os.environ.get("FFM_B200_NVCC_FLAGS", "").split()     # experiment builds (e.g. -DFFM_PHASE_TIMING), with FFM_B200_LIB / FFM_B200_OBJDIR
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-fmad=false",              # never contract a*b+c: the reference rounds the product first
@@ -32,6 +33,7 @@ def sources():
 
 def headers():
     return sorted(glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(CSRC, "*.h")) +
+                  glob.glob(os.path.join(CSRC, "*.inl")) +
                   glob.glob(os.path.join(ROOT, "include", "*.h"))) + [os.path.abspath(__file__)]
 
 
@@ -72,7 +74,7 @@ def build(force=False, verbose=False, jobs=None):
     nvcc = _nvcc()
 
     def compile_one(src):
-        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", _obj(src), src]
+        cmd = [nvcc] + NVCC_FLAGS + EXTRA_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", _obj(src), src]
         return src, subprocess.run(cmd, capture_output=True, text=True)
 
     with ThreadPoolExecutor(max_workers=jobs or min(len(todo) or 1, os.cpu_count() or 1)) as pool:

@@ -68,8 +68,10 @@ struct ffm_sim_s {
     const void* kernel;  // selected rollout kernel
     bool cell_kernel;    // base model: the cell-centric kernel (ffm_cell_kernel.cuh); false = round-1 pedestrian-centric kernel
     int cluster;         // CTAs per episode (thread-block cluster, row bands in distributed shared memory); 1 = one CTA
+    int max_clusters;    // clusters the device holds at once (cudaOccupancyMaxActiveClusters)
     int RW, RB;          // bitboard words per row, rows per band
     bool wall_in_smem;   // static wall bitboard staged in shared memory
+    bool score_in_smem;  // score field staged in shared memory (cluster variants may leave it to L1/L2)
     uint32_t* d_wall_bits;
     // unified / trained models
     int S, A, nby;
@@ -393,9 +395,31 @@ int ffm_create(const ffm_config_t* cfg, ffm_sim_t* out) {
         return ffm::make_layout(HW, W, N, ssz, dff, fs).total;
     };
     s->wall_in_smem = true;
+    s->score_in_smem = true;
     if (s->cell_kernel && (long long)HW * W >= (1LL << 32)) s->cell_kernel = false;       // row = umulhi(cell, magic) needs cell * W < 2^32
-    if (s->cell_kernel && ffm::make_cell_layout(s->RB, W, s->RW, N, ssz, esz, dff, false, false).total > (unsigned)MAX_SMEM_OPTIN)
-        s->cell_kernel = false;   // TODO cluster variants
+    // A map whose per-cell state does not fit one SM's shared memory runs as a thread-block cluster: CL CTAs per episode,
+    // each holding a band of rows (distributed shared memory).  FFM_CLUSTER=n forces a cluster size (tests, tuning).
+    int force_cluster = 0;
+    if (const char* ev = getenv("FFM_CLUSTER")) force_cluster = atoi(ev);
+    if (s->cell_kernel && (force_cluster > 1 ||
+                           ffm::make_cell_layout(s->RB, W, s->RW, N, ssz, esz, dff, false, false).total > (unsigned)MAX_SMEM_OPTIN)) {
+        const int cls[3] = {2, 4, 8};
+        bool found = false;
+        for (int ci = 0; ci < 3 && !found; ++ci) {
+            const int cl = cls[ci];
+            if (force_cluster > 1 && cl != force_cluster) continue;
+            const int rb = (cfg->height + cl - 1) / cl;
+            for (int si = 1; si >= 0 && !found; --si) {
+                if (si == 1 && getenv("FFM_SCORE_GLOBAL")) continue;
+                for (int wi = 1; wi >= 0 && !found; --wi) {
+                    if (ffm::make_cell_layout(rb, W, s->RW, N, ssz, esz, dff, true, wi != 0, si != 0).total > (unsigned)MAX_SMEM_OPTIN) continue;
+                    s->cluster = cl; s->RB = rb; s->score_in_smem = si != 0; s->wall_in_smem = wi != 0;
+                    found = true;
+                }
+            }
+        }
+        if (!found) s->cell_kernel = false;
+    }
     auto occupancy = [&](const void* k, int threads, int smem) {
         int occ = 0;
         if (!k) return 0;
@@ -404,7 +428,16 @@ int ffm_create(const ffm_config_t* cfg, ffm_sim_t* out) {
         return occ;
     };
     const bool f64 = cfg->sff_dtype == FFM_F64;
-    if (s->cell_kernel) {
+    if (s->cell_kernel && s->cluster > 1) {
+        // one cluster per episode, one CTA per SM; 1024 threads when a band has enough 32-cell chunks to feed them
+        const int chunks_band = s->RB * WW;
+        s->threads = chunks_band >= 1024 ? 1024 : 512;
+        if (const char* ev = getenv("FFM_THREADS")) { const int v = atoi(ev); if (v == 512 || v == 1024) s->threads = v; }
+        s->fields_in_smem = true;
+        s->smem_bytes = (int)ffm::make_cell_layout(s->RB, W, s->RW, N, ssz, esz, dff, true, s->wall_in_smem, s->score_in_smem).total;
+        s->kernel = ffm::pick_cell_kernel(f64, HW <= 65536, cfg->neighborhood, dff, true, s->threads, s->cluster);
+        if (!s->kernel) { delete s; return fail(FFM_E_UNSUPPORTED, "no cluster variant of the rollout kernel for this configuration"); }
+    } else if (s->cell_kernel) {
         // Cell-centric kernel: the rollout is bound by its three barriers per step, so what counts is how many CTAs
         // (independent barrier domains) an SM holds, then how many threads each has.  Measured on C2 (one B200):
         // 6 CTAs x 256 threads, fields in shared memory 73.2 ms; the same with fields read through L1 74.4 ms; 5 and 4 CTAs
@@ -475,6 +508,19 @@ int ffm_create(const ffm_config_t* cfg, ffm_sim_t* out) {
     ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, s->kernel, s->threads, s->smem_bytes);
     if (ce != cudaSuccess || occ < 1) { delete s; return fail(FFM_E_CUDA, "rollout kernel cannot be resident (smem=%d, threads=%d): %s", s->smem_bytes, s->threads, cudaGetErrorString(ce)); }
     s->ctas_per_sm = occ;
+    if (s->cluster > 1) {
+        cudaLaunchConfig_t lc;
+        memset(&lc, 0, sizeof(lc));
+        lc.gridDim = dim3((unsigned)s->cluster); lc.blockDim = dim3(s->threads); lc.dynamicSmemBytes = (size_t)s->smem_bytes;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = (unsigned)s->cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        lc.attrs = at; lc.numAttrs = 1;
+        int ncl = 0;
+        ce = cudaOccupancyMaxActiveClusters(&ncl, s->kernel, &lc);
+        if (ce != cudaSuccess || ncl < 1) { delete s; return fail(FFM_E_CUDA, "no cluster of %d CTAs can be resident (smem=%d, threads=%d): %s", s->cluster, s->smem_bytes, s->threads, cudaGetErrorString(ce)); }
+        s->max_clusters = ncl;
+    }
 
 #define ALLOC(ptr, bytes)                                                                     \
     do {                                                                                      \
@@ -762,7 +808,8 @@ int ffm_rollout(ffm_sim_t s, int32_t max_steps, const ffm_draws_t* draws, const 
         C.H = s->cfg.height; C.W = s->cfg.width; C.HW = s->HW; C.n_max = s->cfg.n_max; C.B = s->cfg.n_episodes;
         C.max_steps = max_steps;
         C.RW = s->RW; C.RB = s->RB; C.wall_in_smem = s->wall_in_smem ? 1 : 0;
-        C.L = ffm::make_cell_layout(s->RB, C.W, s->RW, C.n_max, s->cfg.sff_dtype == FFM_F64 ? 8 : 4, s->HW <= 65536 ? 2 : 4, s->d_dff != nullptr, s->fields_in_smem, s->wall_in_smem);
+        C.L = ffm::make_cell_layout(s->RB, C.W, s->RW, C.n_max, s->cfg.sff_dtype == FFM_F64 ? 8 : 4, s->HW <= 65536 ? 2 : 4, s->d_dff != nullptr, s->fields_in_smem, s->wall_in_smem, s->score_in_smem);
+        C.score_in_smem = s->score_in_smem ? 1 : 0;
         C.magic_w = (uint32_t)(((1ULL << 32) + (uint64_t)C.W - 1) / (uint64_t)C.W);
         const uint64_t cpr = (uint64_t)(s->RW - 2);      // chunks (bitboard words) per row; the kernel skips the division when it is 1
         C.magic_cpr = cpr > 1 ? (uint32_t)(((1ULL << 32) + cpr - 1) / cpr) : 0u;
@@ -776,6 +823,11 @@ int ffm_rollout(ffm_sim_t s, int32_t max_steps, const ffm_draws_t* draws, const 
             if (!out->traj_n) return fail(FFM_E_INVALID, "traj_cells without traj_n");
             C.traj = out->traj_cells; C.traj_n = out->traj_n; C.traj_steps = out->traj_steps;
         }
+#ifdef FFM_PHASE_TIMING
+        static unsigned long long* d_dbg = nullptr;
+        if (!d_dbg) { cudaMalloc((void**)&d_dbg, 64); cudaMemset(d_dbg, 0, 64); }
+        C.dbg = d_dbg;
+#endif
         void* cargs[] = {&C};
         if (s->cluster == 1) {
             CU(cudaLaunchKernel(s->kernel, dim3(s->cfg.n_episodes), dim3(s->threads), cargs, (size_t)s->smem_bytes, st));
@@ -793,6 +845,17 @@ int ffm_rollout(ffm_sim_t s, int32_t max_steps, const ffm_draws_t* draws, const 
             CU(cudaLaunchKernelExC(&lc, s->kernel, cargs));
         }
         s->launches++;
+#ifdef FFM_PHASE_TIMING
+        {
+            unsigned long long h[8];
+            cudaStreamSynchronize(st);
+            cudaMemcpy(h, d_dbg, 64, cudaMemcpyDeviceToHost);
+            cudaMemset(d_dbg, 0, 64);
+            double tot = 0; for (int i = 0; i < 7; ++i) tot += (double)h[i];
+            fprintf(stderr, "[phase cycles, share over warps] p1 %.3f dff %.3f wait1 %.3f p2 %.3f wait2 %.3f p3 %.3f wait3 %.3f  (total %.3e warp-cycles)\n",
+                    h[0] / tot, h[1] / tot, h[2] / tot, h[3] / tot, h[4] / tot, h[5] / tot, h[6] / tot, tot);
+        }
+#endif
         return FFM_OK;
     }
     ffm::RolloutParams P;
@@ -1094,6 +1157,15 @@ int ffm_kernel_info(ffm_sim_t s, int32_t* smem_bytes, int32_t* threads, int32_t*
     if (threads) *threads = s->threads;
     if (ctas_per_sm) *ctas_per_sm = s->ctas_per_sm;
     if (fields_in_smem) *fields_in_smem = s->fields_in_smem ? 1 : 0;
+    return FFM_OK;
+}
+
+int ffm_cluster_info(ffm_sim_t s, int32_t* cluster, int32_t* max_clusters, int32_t* score_in_smem, int32_t* cell_kernel) {
+    if (!s) return fail(FFM_E_INVALID, "null argument");
+    if (cluster) *cluster = s->cluster;
+    if (max_clusters) *max_clusters = s->cluster > 1 ? s->max_clusters : 0;
+    if (score_in_smem) *score_in_smem = (s->fields_in_smem && s->score_in_smem) ? 1 : 0;
+    if (cell_kernel) *cell_kernel = s->cfg.model == FFM_MODEL_CORE ? (s->cell_kernel ? 1 : 0) : -1;
     return FFM_OK;
 }
 

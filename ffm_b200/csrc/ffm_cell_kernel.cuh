@@ -44,6 +44,7 @@
 #include <type_traits>
 
 #include "ffm_core_kernel.cuh"
+#include "ffm_dff_stencil.cuh"
 
 namespace ffm {
 
@@ -61,6 +62,8 @@ struct CellParams {
     int RW;                      // bitboard words per row: ceil(W/32) + 2 guard words
     int RB;                      // rows per band (H when one CTA holds the whole map)
     int wall_in_smem;            // static wall bitboard staged in shared memory (else read through L1 from wall_bits)
+    int score_in_smem;           // score field staged in shared memory (else read through L1/L2: it is read-only and shared by all
+                                 // episodes of the handle); only meaningful when the fields are shared-memory resident
     uint32_t magic_w;            // ceil(2^32 / W): row = umulhi(cell, magic_w) for cell * W < 2^32
     uint32_t magic_cpr;          // ceil(2^32 / chunks per row), chunks per row = ceil(W/32) (one bitboard word each)
     const uint16_t* type_grid;   // [HW + 2*(W+1)] type bits only, guard band included
@@ -83,19 +86,20 @@ struct CellParams {
     int traj_steps;
     // compact trajectory record (what run() collects, ffm_core.py:125 / main.py:44-52): per episode a stream of
     // (row, col) int16 pairs, the rows of consecutive steps back to back, each padded to a multiple of 4 entries
+    unsigned long long* dbg;     // FFM_PHASE_TIMING builds: [8] accumulated cycles (work / wait per phase), else unused
     short2* ctraj;               // [B][ctraj_cap]
     int32_t* ctraj_off;          // [B][traj_steps + 1]: entry offset of each step's row (CSR); [steps] = end
     int ctraj_cap;
 };
 
 __host__ __device__ inline CellLayout make_cell_layout(int RB, int W, int RW, int n_max, int sizeof_score, int sizeof_ent, bool dff,
-                                                       bool fields_in_smem, bool wall_in_smem = true) {
+                                                       bool fields_in_smem, bool wall_in_smem = true, bool score_in_smem = true) {
     const uint32_t cells = (uint32_t)RB * W;
     const uint32_t nw = (uint32_t)(n_max + 31) / 32 + 1;
     CellLayout L;
     L.cap = (uint32_t)n_max < cells ? (uint32_t)n_max : cells;
     uint32_t o = 0;
-    L.score = o; if (fields_in_smem) o = align16(o + cells * sizeof_score);
+    L.score = o; if (fields_in_smem && score_in_smem) o = align16(o + cells * sizeof_score);
     L.dffA = o;  if (fields_in_smem && dff) o = align16(o + cells * 4u);
     L.dffB = o;  if (fields_in_smem && dff) o = align16(o + cells * 4u);
     L.grid = o;  o = align16(o + (cells + 2u * (W + 1)) * 2u);
@@ -227,8 +231,11 @@ static __device__ __noinline__ void refresh_alive_prefix(const uint32_t* alive, 
 #ifndef FFM_CELL_MINB256
 #define FFM_CELL_MINB256 6      // resident CTAs per SM the 256-thread float32 variant is compiled for (register cap)
 #endif
+#ifndef FFM_CELL_MINB256_DFF
+#define FFM_CELL_MINB256_DFF 4  // the same with the DFF tracked: the stencil's register window needs 64 registers (no spills)
+#endif
 template <typename S, typename EntT, int NBR, bool DFF, bool FIELDS_IN_SMEM, int THREADS, int CL>
-__global__ void __launch_bounds__(THREADS, (CL == 1 && THREADS <= 256 && sizeof(S) == 4) ? (FFM_CELL_MINB256 * 256) / THREADS : 1)
+__global__ void __launch_bounds__(THREADS, (CL == 1 && THREADS <= 256 && sizeof(S) == 4) ? ((DFF ? FFM_CELL_MINB256_DFF : FFM_CELL_MINB256) * 256) / THREADS : 1)
 ffm_cell_rollout_kernel(const CellParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int NW = THREADS / 32;
@@ -309,8 +316,10 @@ ffm_cell_rollout_kernel(const CellParams P) {
         const unsigned rk = nb_rank(c);
         return cg::this_cluster().map_shared_rank(base, rk) + (c - (int)rk * RB * W);
     };
+    const bool score_smem = FIELDS_IN_SMEM && P.score_in_smem;
     auto score_at = [&](int c) -> S {
         if (!FIELDS_IN_SMEM) return score_g[c];
+        if (!score_smem) return __ldg(score_g + c);
         if (CL == 1 || (c >= lo && c < hi)) return score_l[c - lo];
         const unsigned rk = nb_rank(c);
         return cg::this_cluster().map_shared_rank(score_l, rk)[c - (int)rk * RB * W];
@@ -325,18 +334,18 @@ ffm_cell_rollout_kernel(const CellParams P) {
     const uint32_t grid_bytes = align16(grid_elems * 2u), score_bytes = cells * (uint32_t)sizeof(S), dff_bytes = cells * 4u;
     // the band slices start at element lo of their arrays (type_grid: index = cell + G, and local index 0 <-> cell lo - G)
     const bool tma_grid = RBl > 0 && (((size_t)lo * 2u) % 16u == 0u);   // d_type_grid is padded to a multiple of 16 bytes
-    const bool tma_fields = FIELDS_IN_SMEM && RBl > 0 && (score_bytes % 16u == 0u) && (dff_bytes % 16u == 0u) &&
+    const bool tma_fields = FIELDS_IN_SMEM && RBl > 0 && (score_bytes % 16u == 0u || !score_smem) && (dff_bytes % 16u == 0u) &&
                             (((size_t)lo * sizeof(S)) % 16u == 0u) && (((size_t)lo * 4u) % 16u == 0u) && (((size_t)HW * 4u) % 16u == 0u);
     if (tid == 0) mbar_init(bar, 1);
     __syncthreads();
     if (tid == 0) {
         uint32_t bytes = 0;
         if (tma_grid) bytes += grid_bytes;
-        if (tma_fields) bytes += score_bytes + (DFF ? dff_bytes : 0u);
+        if (tma_fields) bytes += (score_smem ? score_bytes : 0u) + (DFF ? dff_bytes : 0u);
         mbar_arrive_expect_tx(bar, bytes);
         if (tma_grid) bulk_copy_g2s(smem_raw + L.grid, P.type_grid + lo, grid_bytes, bar);
         if (tma_fields) {
-            bulk_copy_g2s(score_l, score_g + lo, score_bytes, bar);
+            if (score_smem) bulk_copy_g2s(score_l, score_g + lo, score_bytes, bar);
             if (DFF) bulk_copy_g2s(dffA_l, dff_home + lo, dff_bytes, bar);
         }
     }
@@ -345,7 +354,7 @@ ffm_cell_rollout_kernel(const CellParams P) {
         for (uint32_t x = tid; x < grid_elems; x += THREADS) grid_l[(int)x - G] = P.type_grid[lo + x];
     if (FIELDS_IN_SMEM && !tma_fields) {
 #pragma unroll 1
-        for (uint32_t x = tid; x < cells; x += THREADS) score_l[x] = score_g[lo + x];
+        for (uint32_t x = tid; x < (score_smem ? cells : 0u); x += THREADS) score_l[x] = score_g[lo + x];
         if (DFF)
 #pragma unroll 1
             for (uint32_t x = tid; x < cells; x += THREADS) dffA_l[x] = dff_home[lo + x];
@@ -439,6 +448,40 @@ ffm_cell_rollout_kernel(const CellParams P) {
         }
     };
 
+    // update_dff (:106-117) of this CTA's rows: current buffer -> the other one.  Width a multiple of 4: the vectorised
+    // stencil; rows of a neighbouring band (cluster) come through distributed shared memory.
+    auto dff_update = [&]() {
+        if (FIELDS_IN_SMEM) {
+            const float* inb = dpar ? dffB_l : dffA_l;
+            float* outb = dpar ? dffA_l : dffB_l;
+            const float* in_up = (CL > 1 && !top) ? cg::this_cluster().map_shared_rank(const_cast<float*>(inb), band - 1) + (RB - 1) * W : nullptr;
+            const float* in_dn = (CL > 1 && !bottom) ? cg::this_cluster().map_shared_rank(const_cast<float*>(inb), band + 1) : nullptr;
+            auto edge = [&](int r) -> const float* { return r < r0 ? in_up : in_dn; };   // nullptr outside the map
+            if ((W & 3) == 0)
+                dff_stencil_v4<NBR>([&](int r) -> const float* { return inb + (r - r0) * W; }, edge,
+                                    [&](int r) -> float* { return outb + (r - r0) * W; }, r0, r1, W, P.c0, P.c1, P.thr, tid, THREADS);
+            else
+                dff_stencil_rows<NBR>([&](int r) -> const float* { return (r >= r0 && r < r1) ? inb + (r - r0) * W : edge(r); },
+                                      [&](int r) -> float* { return outb + (r - r0) * W; }, r0, r1, W, P.c0, P.c1, P.thr, tid, THREADS);
+        } else {
+            const float* inb = dpar ? dffB_g : dffA_g;
+            float* outb = dpar ? dffA_g : dffB_g;
+            auto edge = [&](int r) -> const float* { return (r < 0 || r >= H) ? nullptr : inb + (size_t)r * W; };
+            if ((W & 3) == 0)
+                dff_stencil_v4<NBR>([&](int r) -> const float* { return inb + (size_t)r * W; }, edge,
+                                    [&](int r) -> float* { return outb + (size_t)r * W; }, r0, r1, W, P.c0, P.c1, P.thr, tid, THREADS);
+            else
+                dff_stencil_rows<NBR>(edge, [&](int r) -> float* { return outb + (size_t)r * W; }, r0, r1, W, P.c0, P.c1, P.thr, tid, THREADS);
+        }
+    };
+
+#ifdef FFM_PHASE_TIMING
+    long long tw[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long tc = clock64();
+#define FFM_TICK(i) { const long long now_ = clock64(); tw[i] += now_ - tc; tc = now_; }
+#else
+#define FFM_TICK(i)
+#endif
     unsigned long long ped_steps = 0;
     bool need_prefix = false;      // somebody left since the prefix was last computed
     bool dff_pending = false;      // the DFF update of the previous step has not run yet
@@ -528,30 +571,13 @@ ffm_cell_rollout_kernel(const CellParams P) {
             for (uint32_t m = m3; m; m &= m - 1u) listA[cap1 - (o3++)] = (EntT)(cbase + __ffs(m) - 1);
             for (uint32_t m = mb; m; m &= m - 1u) listB[ob++] = (EntT)(cbase + __ffs(m) - 1);
         }
+        FFM_TICK(0)
         // DFF decay + diffusion of the previous step (reads the field with that step's footprints) -> other buffer
-        if (DFF && dff_pending) {
-            if (FIELDS_IN_SMEM) {
-                const float* inb = dpar ? dffB_l : dffA_l;
-                float* outb = dpar ? dffA_l : dffB_l;
-                const float* in_up = (CL > 1 && !top) ? cg::this_cluster().map_shared_rank(const_cast<float*>(inb), band - 1) : nullptr;
-                const float* in_dn = (CL > 1 && !bottom) ? cg::this_cluster().map_shared_rank(const_cast<float*>(inb), band + 1) : nullptr;
-                dff_stencil_rows<NBR>(
-                    [&](int r) -> const float* {
-                        if (r < 0 || r >= H) return nullptr;
-                        if (r < r0) return in_up + (size_t)(RB - 1) * W;
-                        if (r >= r1) return in_dn;
-                        return inb + (size_t)(r - r0) * W;
-                    },
-                    [&](int r) -> float* { return outb + (size_t)(r - r0) * W; }, r0, r1, W, P.c0, P.c1, P.thr, tid, THREADS);
-            } else {
-                const float* inb = dpar ? dffB_g : dffA_g;
-                float* outb = dpar ? dffA_g : dffB_g;
-                dff_stencil_rows<NBR>([&](int r) -> const float* { return (r < 0 || r >= H) ? nullptr : inb + (size_t)r * W; },
-                                      [&](int r) -> float* { return outb + (size_t)r * W; }, r0, r1, W, P.c0, P.c1, P.thr, tid, THREADS);
-            }
-        }
+        if (DFF && dff_pending) dff_update();
         if (DFF && !FIELDS_IN_SMEM && CL > 1 && dff_pending) __threadfence();   // global DFF rows are read by the neighbour CTAs
+        FFM_TICK(1)
         sync_all();
+        FFM_TICK(2)
         if (DFF && dff_pending) dpar ^= 1;
         dff_pending = false;
         need_prefix = false;
@@ -661,7 +687,9 @@ ffm_cell_rollout_kernel(const CellParams P) {
                 if (valid) decide(ptr);
             }
         }
+        FFM_TICK(3)
         sync_all();
+        FFM_TICK(4)
 
         // ================= phase 3: one resolver per requested cell; moves applied at once ===============
         // apply the move of the occupant of T's neighbour `from` into T
@@ -724,7 +752,7 @@ ffm_cell_rollout_kernel(const CellParams P) {
                 }
             }
             count_exits(leaves);
-            // contested cells are rare per warp: they are collected and resolved with full lanes by the last warp to finish
+            // contested cells are collected and resolved below
             const uint32_t cb = __ballot_sync(FULL, contested);
             if (cb != 0u) {
                 uint32_t base = 0;
@@ -733,49 +761,58 @@ ffm_cell_rollout_kernel(const CellParams P) {
                 if (contested) clist[base + __popc(cb & lanemask_lt())] = (EntT)T;
             }
         }
-        {
+        // k >= 2 claimants of cell clist[i]: coin, then the floor(u*k)-th claimant in ascending agent index (:94-98)
+        auto resolve_contested = [&](int i, int ncont) {
+            bool leaves = false;
+            if (i < ncont) {
+                const uint32_t T = (uint32_t)((volatile EntT*)clist)[i];
+                uint32_t sh;
+                const uint32_t cm = (*cmask_word((int)T, sh) >> sh) & 0xFFu;
+                const int k = __popc(cm);
+                Draw2 d;
+                if (inj && cf_draws) {
+                    d.u0 = cf_draws[((size_t)di * HW + T) * 2];
+                    d.u1 = cf_draws[((size_t)di * HW + T) * 2 + 1];
+                } else {
+                    d = draw2(P.seed, episode, t, STREAM_CONFLICT, T);
+                }
+                if (d.u0 < 0.5) {                                         // coin (:95): somebody moves
+                    // agents[int(u * k)] in ascending agent index (:96): sort (id, direction) keys
+                    uint32_t key[NBR];
+#pragma unroll
+                    for (int q = 0; q < NBR; ++q) {
+                        key[q] = FULL;
+                        if ((cm >> q) & 1u) key[q] = (((uint32_t)*grid_ptr((int)T + nbr_off<NBR>(q, W)) & OCC_MASK) << 3) | (uint32_t)q;
+                    }
+                    sort_keys<NBR>(key);
+                    const int w = (int)(d.u1 * (double)k);
+                    uint32_t sel = key[0];
+#pragma unroll
+                    for (int q = 1; q < NBR; ++q) if (q == w) sel = key[q];
+                    leaves = apply_move(T, (int)(sel & 7u));
+                }
+            }
+            count_exits(leaves);
+        };
+        if (THREADS >= 512) {
+            // a large CTA: every warp takes its share of the contested cells once the list is complete
+            __syncthreads();
+            const int ncont = (int)cnt[4];
+            for (int i0 = warp * 32; i0 < ncont; i0 += THREADS) resolve_contested(i0 + lane, ncont);
+        } else {
+            // contested cells are rare per warp: the last warp to finish the loop above resolves them with full lanes
             __syncwarp();
             uint32_t done = 0;
             if (lane == 0) { __threadfence_block(); done = smem_atomic_add(&cnt[5], 1u); __threadfence_block(); }
             done = __shfl_sync(FULL, done, 0);
             if (done == NW - 1) {
                 const int ncont = (int)*((volatile uint32_t*)&cnt[4]);
-                for (int i0 = 0; i0 < ncont; i0 += 32) {
-                    const int i = i0 + lane;
-                    bool leaves = false;
-                    if (i < ncont) {
-                        const uint32_t T = (uint32_t)((volatile EntT*)clist)[i];
-                        uint32_t sh;
-                        const uint32_t cm = (*cmask_word((int)T, sh) >> sh) & 0xFFu;
-                        const int k = __popc(cm);
-                        Draw2 d;
-                        if (inj && cf_draws) {
-                            d.u0 = cf_draws[((size_t)di * HW + T) * 2];
-                            d.u1 = cf_draws[((size_t)di * HW + T) * 2 + 1];
-                        } else {
-                            d = draw2(P.seed, episode, t, STREAM_CONFLICT, T);
-                        }
-                        if (d.u0 < 0.5) {                                         // coin (:95): somebody moves
-                            // agents[int(u * k)] in ascending agent index (:96): sort (id, direction) keys
-                            uint32_t key[NBR];
-#pragma unroll
-                            for (int q = 0; q < NBR; ++q) {
-                                key[q] = FULL;
-                                if ((cm >> q) & 1u) key[q] = (((uint32_t)*grid_ptr((int)T + nbr_off<NBR>(q, W)) & OCC_MASK) << 3) | (uint32_t)q;
-                            }
-                            sort_keys<NBR>(key);
-                            const int w = (int)(d.u1 * (double)k);
-                            uint32_t sel = key[0];
-#pragma unroll
-                            for (int q = 1; q < NBR; ++q) if (q == w) sel = key[q];
-                            leaves = apply_move(T, (int)(sel & 7u));
-                        }
-                    }
-                    count_exits(leaves);
-                }
+                for (int i0 = 0; i0 < ncont; i0 += 32) resolve_contested(i0 + lane, ncont);
             }
         }
+        FFM_TICK(5)
         sync_all();
+        FFM_TICK(6)
 
         const int n_exit = (int)cnt[3];
         if (n_exit > 0) { n -= n_exit; need_prefix = true; }
@@ -795,25 +832,7 @@ ffm_cell_rollout_kernel(const CellParams P) {
 
     // ---- the last step's DFF update ------------------------------------------------------------------------
     if (DFF && dff_pending) {
-        if (FIELDS_IN_SMEM) {
-            const float* inb = dpar ? dffB_l : dffA_l;
-            float* outb = dpar ? dffA_l : dffB_l;
-            const float* in_up = (CL > 1 && !top) ? cg::this_cluster().map_shared_rank(const_cast<float*>(inb), band - 1) : nullptr;
-            const float* in_dn = (CL > 1 && !bottom) ? cg::this_cluster().map_shared_rank(const_cast<float*>(inb), band + 1) : nullptr;
-            dff_stencil_rows<NBR>(
-                [&](int r) -> const float* {
-                    if (r < 0 || r >= H) return nullptr;
-                    if (r < r0) return in_up + (size_t)(RB - 1) * W;
-                    if (r >= r1) return in_dn;
-                    return inb + (size_t)(r - r0) * W;
-                },
-                [&](int r) -> float* { return outb + (size_t)(r - r0) * W; }, r0, r1, W, P.c0, P.c1, P.thr, tid, THREADS);
-        } else {
-            const float* inb = dpar ? dffB_g : dffA_g;
-            float* outb = dpar ? dffA_g : dffB_g;
-            dff_stencil_rows<NBR>([&](int r) -> const float* { return (r < 0 || r >= H) ? nullptr : inb + (size_t)r * W; },
-                                  [&](int r) -> float* { return outb + (size_t)r * W; }, r0, r1, W, P.c0, P.c1, P.thr, tid, THREADS);
-        }
+        dff_update();
         dpar ^= 1;
     }
     if (need_prefix && warp == 0) refresh_prefix();
@@ -835,6 +854,10 @@ ffm_cell_rollout_kernel(const CellParams P) {
             for (int c = lo + tid; c < hi; c += THREADS) dffA_g[c] = dffB_g[c];
         }
     }
+#ifdef FFM_PHASE_TIMING
+    if (P.dbg != nullptr && lane == 0)
+        for (int i = 0; i < 8; ++i) atomicAdd(P.dbg + i, (unsigned long long)tw[i]);
+#endif
     if (tid == 0 && band == 0) {
         P.n_alive[e] = n;
         P.t_done[e] = t0 + tl;

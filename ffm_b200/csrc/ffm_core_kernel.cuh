@@ -47,6 +47,7 @@
 //   alive u32[n_max/32+1]    alive bitmap;  wpre u32[n_max/32+1] exclusive prefix popcounts
 #pragma once
 #include "ffm_device.cuh"
+#include "ffm_dff_stencil.cuh"
 
 namespace ffm {
 
@@ -190,6 +191,11 @@ __device__ __forceinline__ double move_weights(uint32_t mm, int ncand, int c, in
 template <int NBR>
 __device__ __forceinline__ void dff_decay_diffuse(const float* __restrict__ in, float* __restrict__ out, int H, int W,
                                                   float c0, float c1, float thr, int tid, int nthreads) {
+    if ((W & 3) == 0) {   // rows are 16-byte aligned: the vectorised walk (ffm_dff_stencil.cuh), same arithmetic
+        dff_stencil_v4<NBR>([&](int r) -> const float* { return in + (size_t)r * W; }, [](int) -> const float* { return nullptr; },
+                            [&](int r) -> float* { return out + (size_t)r * W; }, 0, H, W, c0, c1, thr, tid, nthreads);
+        return;
+    }
     const int cw = W < nthreads ? W : nthreads;          // columns handled per sweep
     const int bands = W < nthreads ? nthreads / W : 1;   // row bands working in parallel on one column sweep
     const int rpb = (H + bands - 1) / bands;

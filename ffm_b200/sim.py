@@ -241,7 +241,12 @@ class BatchSim:
     def kernel_info(self):
         a, b, c, d = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32()
         _abi.check(self._lib.ffm_kernel_info(self._h, C.byref(a), C.byref(b), C.byref(c), C.byref(d)))
-        return dict(smem_bytes=a.value, threads=b.value, ctas_per_sm=c.value, fields_in_smem=bool(d.value))
+        info = dict(smem_bytes=a.value, threads=b.value, ctas_per_sm=c.value, fields_in_smem=bool(d.value))
+        _abi.check(self._lib.ffm_cluster_info(self._h, C.byref(a), C.byref(b), C.byref(c), C.byref(d)))
+        info.update(cluster=a.value, max_clusters=b.value, score_in_smem=bool(c.value),
+                    name={1: "ffm_cell_rollout_kernel", 0: "ffm_core_rollout_kernel"}.get(
+                        d.value, "ffm_mcq_rollout_kernel" if isinstance(self, McqSim) else "ffm_unified_rollout_kernel"))
+        return info
 
 
 UNIFIED_DEFAULTS = {                      # ffm_unified.py:36-53

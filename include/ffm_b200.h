@@ -248,6 +248,11 @@ int64_t ffm_launch_count(ffm_sim_t sim);
 int ffm_kernel_info(ffm_sim_t sim, int32_t *smem_bytes, int32_t *threads, int32_t *ctas_per_sm,
                     int32_t *fields_in_smem);
 
+/* thread-block-cluster geometry of the rollout kernel: CTAs per episode (1 = no cluster; the map is split into row
+ * bands held in distributed shared memory otherwise), clusters the device keeps resident at once, whether the score
+ * field is staged on chip, and which kernel runs (0 = pedestrian-centric, 1 = cell-centric; -1 for the other models) */
+int ffm_cluster_info(ffm_sim_t sim, int32_t *cluster, int32_t *max_clusters, int32_t *score_in_smem, int32_t *cell_kernel);
+
 #ifdef __cplusplus
 }
 #endif

@@ -29,9 +29,15 @@ def cuda_device(ffm_lib):
     return 0
 
 
-@pytest.fixture(params=["cell", "ped"])
+@pytest.fixture(params=["cell", "ped", "cl2", "cl4", "cl8"])
 def core_kernel(request, monkeypatch):
     """Runs a test once per base-model kernel: "cell" = cell-centric (csrc/ffm_cell_kernel.cuh), "ped" =
-    pedestrian-centric (csrc/ffm_core_kernel.cuh); libffm_b200 reads FFM_KERNEL in ffm_create."""
-    monkeypatch.setenv("FFM_KERNEL", request.param)
+    pedestrian-centric (csrc/ffm_core_kernel.cuh), "clN" = the cell-centric kernel as a thread-block cluster of N CTAs
+    per episode (row bands in distributed shared memory); libffm_b200 reads FFM_KERNEL / FFM_CLUSTER in ffm_create."""
+    if request.param.startswith("cl"):
+        monkeypatch.setenv("FFM_KERNEL", "cell")
+        monkeypatch.setenv("FFM_CLUSTER", request.param[2:])
+    else:
+        monkeypatch.setenv("FFM_KERNEL", request.param)
+        monkeypatch.delenv("FFM_CLUSTER", raising=False)
     return request.param

@@ -21,29 +21,50 @@ def _ks(a, b):
     return float(stats.ks_2samp(a, b).statistic)
 
 
+# (seed, first global episode id) of the four 512-episode batches pooled on either side.  Calibration with the C oracle
+# alone (profiles/exp_ks_c2dff.py): single 2048-episode batches under different seeds differ by up to KS = 0.076
+# (batch means scatter by ~2 steps around 1720, sigma 42), pooled batches agree to 0.028 (DFF) / 0.018 (SFF only).
+GPU_BATCHES = [(0xA11CE, 0), (0xC0C, 100000), (0xD0D, 200000), (0xE0E, 300000)]
+REF_BATCHES = [(0xB0B, 50000), (0xF0F, 150000), (0x101, 250000), (0x202, 350000)]
+
+
 @pytest.mark.parametrize("k_D,track", [(0, False), (1, True)], ids=["c2_sff_only", "c2_dff"])
 def test_c2_evacuation_time_distribution(cuda_device, k_D, track):
-    """C2 geometry (64x64 single-exit room, 1024 pedestrians, Moore), to evacuation: n = m = 2048 episodes."""
+    """C2 geometry (64x64 single-exit room, 1024 pedestrians, Moore), to evacuation: n = m = 2048 episodes, each side
+    pooled over four (seed, episode range) batches.  Two statements: (1) independent seeds -- KS <= 0.06, mean within
+    1 %; (2) the SAME seeds -- the CUDA path and the oracle agree episode by episode except where a draw fell on a
+    knife edge of the CDF (exp differs by <= 2 ulp between libm and CUDA): >= 99 % identical evacuation times."""
     import bench
     from ffm_b200 import BatchSim
     from oracle import c_oracle
 
     m = bench.room_map(64, 64)
     sff = bench.sff_room(m, "moore")
-    n_ep, N = 2048, 1024
+    n_ep, N = 512, 1024
     params = {"k_S": 3, "k_D": k_D, "neighborhood": "moore"}
     n = np.full((n_ep,), N, np.int32)
-    sim = BatchSim(m, sff, n_ep, N, params, seed=0xA11CE, episode_base=0, track_dff=track)
-    sim.set_positions(bench.place(m, N, n_ep, 0, 0xA11CE), n)
-    sim.rollout(4096)
-    gpu_steps, _ = sim.counters()
-    assert (sim.get_positions()[1] == 0).all()
-    ref_steps, _ = c_oracle.run_core_batch(m, sff, bench.place(m, N, n_ep, 50_000, 0xB0B), n, params, seed=0xB0B, episode_base=50_000,
-                                           max_steps=4096, threads=os.cpu_count() or 1, track_dff=track)
+
+    def gpu(seed, base):
+        sim = BatchSim(m, sff, n_ep, N, params, seed=seed, episode_base=base, track_dff=track)
+        sim.set_positions(bench.place(m, N, n_ep, base, seed), n)
+        sim.rollout(4096)
+        steps, _ = sim.counters()
+        assert (sim.get_positions()[1] == 0).all()
+        sim.close()
+        return steps
+
+    def ref(seed, base):
+        return c_oracle.run_core_batch(m, sff, bench.place(m, N, n_ep, base, seed), n, params, seed=seed, episode_base=base,
+                                       max_steps=4096, threads=os.cpu_count() or 1, track_dff=track)[0]
+
+    gpu_steps = np.concatenate([gpu(*b) for b in GPU_BATCHES])
+    ref_steps = np.concatenate([ref(*b) for b in REF_BATCHES])
     ks = _ks(gpu_steps, ref_steps)
     assert ks <= KS_BOUND, ks
     assert abs(gpu_steps.mean() - ref_steps.mean()) <= 0.01 * ref_steps.mean()
     assert abs(gpu_steps.std() - ref_steps.std()) <= 0.15 * ref_steps.std()
+    same = np.concatenate([gpu(*b) for b in REF_BATCHES])
+    assert (same == ref_steps).mean() >= 0.99, (same == ref_steps).mean()
 
 
 def test_c3_plan_evacuated_count_distribution(cuda_device):

@@ -117,26 +117,38 @@ def test_properties_at_full_size(cuda_device):
     assert np.array_equal(b.get_dff().view(np.uint32), a.get_dff()[B // 2:].view(np.uint32))
 
 
-def test_c3_floor_plan_matches_c_oracle(cuda_device):
+@pytest.mark.parametrize("variant,B,T", [("auto", 2, 200), ("ped", 2, 200), ("cl8", 2, 200), ("auto", 8, 1000)])
+def test_c3_floor_plan_matches_c_oracle(cuda_device, monkeypatch, variant, B, T):
     """BASELINE configs[2] geometry: 256x256 rooms-and-doors plan, geodesic SFF (generated on the GPU), DFF on,
-    10 000 pedestrians; fields stay in global memory (L2) at this size.  Recorded-draw protocol, 200 steps."""
+    10 000 pedestrians.  "auto" = what ffm_create picks: the cell-centric kernel as a cluster of 4 CTAs per episode,
+    DFF + owner grid in distributed shared memory; "cl8" forces 8 CTAs; "ped" = the round-1 kernel (one CTA, fields
+    in L2).  Recorded-draw protocol; the long case covers 8 episodes x 1000 steps."""
     import torch
     from ffm_b200 import BatchSim
     from ffm_b200.sff import generate_sff
     from ffm_b200.workloads import place, rooms_map_c3
     from oracle import c_oracle
 
+    if variant == "ped":
+        monkeypatch.setenv("FFM_KERNEL", "ped")
+    elif variant.startswith("cl"):
+        monkeypatch.setenv("FFM_CLUSTER", variant[2:])
     m = rooms_map_c3()
     sff = generate_sff(m, "bfs8", np.float32)
     assert np.array_equal(sff, c_oracle.geodesic(m, "bfs8"))
-    B, N, seed, T = 2, 10000, 0x5EED0003, 200
+    N, seed = 10000, 0x5EED0003
     params = {"k_S": 3, "k_D": 1, "neighborhood": "moore"}
     pos = place(m, N, B, 0, seed)
     n = np.full((B,), N, np.int32)
-    ref = c_oracle.run_core_batch(m, sff, pos, n, params, seed=seed, max_steps=T, threads=2, traj_steps=T, want_state=True,
+    ref = c_oracle.run_core_batch(m, sff, pos, n, params, seed=seed, max_steps=T, threads=min(B, 8), traj_steps=T, want_state=True,
                                   guard=1e-5, record_moves=T)
     sim = BatchSim(m, sff, B, N, params, seed=seed)
-    assert not sim.kernel_info()["fields_in_smem"]
+    info = sim.kernel_info()
+    if variant == "ped":
+        assert info["name"] == "ffm_core_rollout_kernel" and not info["fields_in_smem"]
+    else:
+        assert info["name"] == "ffm_cell_rollout_kernel" and info["fields_in_smem"]
+        assert info["cluster"] == (8 if variant == "cl8" else 4), info
     sim.set_positions(pos, n)
     cells, cnt = sim.rollout(T, draws=dict(move=torch.from_numpy(ref["move_draws"]).cuda()), record=T)
     torch.cuda.synchronize()
@@ -145,7 +157,7 @@ def test_c3_floor_plan_matches_c_oracle(cuda_device):
     cells, cnt = cells.cpu().numpy(), cnt.cpu().numpy()
     assert np.array_equal(cnt, ref["traj_n"])
     for e in range(B):
-        for t in (0, 1, 50, T - 1):
+        for t in (0, 1, 50, T // 2, T - 1):
             k = cnt[e, t]
             assert np.array_equal(cells[e, t, :k], ref["traj"][e, t, :k]), (e, t)
     p_gpu, n_gpu = sim.get_positions()
