@@ -7,7 +7,7 @@ import os
 
 from . import build as _build
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 FFM_HOST, FFM_DEVICE = 0, 1
 FFM_NEUMANN, FFM_MOORE = 4, 8
 FFM_F32, FFM_F64 = 0, 1
@@ -43,7 +43,8 @@ class Draws(C.Structure):
 class RolloutOut(C.Structure):
     _fields_ = [("traj_cells", C.c_void_p), ("traj_n", C.c_void_p), ("traj_steps", C.c_int32),
                 ("reserved", C.c_int32), ("rec_state", C.c_void_p), ("rec_action", C.c_void_p),
-                ("rec_reward", C.c_void_p), ("rec_len", C.c_void_p)]
+                ("rec_reward", C.c_void_p), ("rec_len", C.c_void_p),
+                ("ctraj", C.c_void_p), ("ctraj_off", C.c_void_p), ("ctraj_cap", C.c_int64)]
 
 
 # name -> (restype, argtypes); tests/test_abi.py checks this table against the header

@@ -403,21 +403,33 @@ int ffm_create(const ffm_config_t* cfg, ffm_sim_t* out) {
     if (const char* ev = getenv("FFM_CLUSTER")) force_cluster = atoi(ev);
     if (s->cell_kernel && (force_cluster > 1 ||
                            ffm::make_cell_layout(s->RB, W, s->RW, N, ssz, esz, dff, false, false).total > (unsigned)MAX_SMEM_OPTIN)) {
+        // Measured on BASELINE C3 (256x256, 10 000 pedestrians, DFF on; profiles/r2j_*): the pedestrian-centric kernel with
+        // one CTA of 1024 threads per SM and the fields in L2 does 1.83e10 ped-steps/s, the 4-CTA cluster with everything
+        // on chip 1.31e10 (33 clusters resident, three cluster barriers per step, 16 warps per SM to hide the latency of
+        // the decide chains).  So a map that still fits the pedestrian-centric layout runs there unless a cluster is asked for.
+        const bool ped_fits = ffm::make_layout(HW, W, N, ssz, dff, false).total <= (unsigned)MAX_SMEM_OPTIN;
+        if (force_cluster <= 1 && ped_fits && !getenv("FFM_KERNEL")) s->cell_kernel = false;
+    }
+    if (s->cell_kernel && (force_cluster > 1 ||
+                           ffm::make_cell_layout(s->RB, W, s->RW, N, ssz, esz, dff, false, false).total > (unsigned)MAX_SMEM_OPTIN)) {
         const int cls[3] = {2, 4, 8};
         bool found = false;
-        for (int ci = 0; ci < 3 && !found; ++ci) {
-            const int cl = cls[ci];
-            if (force_cluster > 1 && cl != force_cluster) continue;
-            const int rb = (cfg->height + cl - 1) / cl;
-            for (int si = 1; si >= 0 && !found; --si) {
-                if (si == 1 && getenv("FFM_SCORE_GLOBAL")) continue;
-                for (int wi = 1; wi >= 0 && !found; --wi) {
-                    if (ffm::make_cell_layout(rb, W, s->RW, N, ssz, esz, dff, true, wi != 0, si != 0).total > (unsigned)MAX_SMEM_OPTIN) continue;
-                    s->cluster = cl; s->RB = rb; s->score_in_smem = si != 0; s->wall_in_smem = wi != 0;
-                    found = true;
+        for (int fsi = 1; fsi >= 0 && !found; --fsi)           // fields on chip first; else DFF + score stay in L2 (any map size)
+            for (int ci = 0; ci < 3 && !found; ++ci) {
+                const int cl = cls[ci];
+                if (force_cluster > 1 && cl != force_cluster) continue;
+                if (fsi == 1 && getenv("FFM_FIELDS_GLOBAL")) continue;
+                const int rb = (cfg->height + cl - 1) / cl;
+                for (int si = fsi; si >= 0 && !found; --si) {
+                    if (si == 1 && getenv("FFM_SCORE_GLOBAL")) continue;
+                    for (int wi = 1; wi >= 0 && !found; --wi) {
+                        if (ffm::make_cell_layout(rb, W, s->RW, N, ssz, esz, dff, fsi != 0, wi != 0, si != 0).total > (unsigned)MAX_SMEM_OPTIN) continue;
+                        s->cluster = cl; s->RB = rb; s->score_in_smem = si != 0; s->wall_in_smem = wi != 0;
+                        s->fields_in_smem = fsi != 0;
+                        found = true;
+                    }
                 }
             }
-        }
         if (!found) s->cell_kernel = false;
     }
     auto occupancy = [&](const void* k, int threads, int smem) {
@@ -429,13 +441,10 @@ int ffm_create(const ffm_config_t* cfg, ffm_sim_t* out) {
     };
     const bool f64 = cfg->sff_dtype == FFM_F64;
     if (s->cell_kernel && s->cluster > 1) {
-        // one cluster per episode, one CTA per SM; 1024 threads when a band has enough 32-cell chunks to feed them
-        const int chunks_band = s->RB * WW;
-        s->threads = chunks_band >= 1024 ? 1024 : 512;
-        if (const char* ev = getenv("FFM_THREADS")) { const int v = atoi(ev); if (v == 512 || v == 1024) s->threads = v; }
-        s->fields_in_smem = true;
-        s->smem_bytes = (int)ffm::make_cell_layout(s->RB, W, s->RW, N, ssz, esz, dff, true, s->wall_in_smem, s->score_in_smem).total;
-        s->kernel = ffm::pick_cell_kernel(f64, HW <= 65536, cfg->neighborhood, dff, true, s->threads, s->cluster);
+        // one cluster per episode, one CTA of 512 threads per SM (1024 threads measured slower on C3: 64 registers, spills)
+        s->threads = 512;
+        s->smem_bytes = (int)ffm::make_cell_layout(s->RB, W, s->RW, N, ssz, esz, dff, s->fields_in_smem, s->wall_in_smem, s->score_in_smem).total;
+        s->kernel = ffm::pick_cell_kernel(f64, HW <= 65536, cfg->neighborhood, dff, s->fields_in_smem, s->threads, s->cluster);
         if (!s->kernel) { delete s; return fail(FFM_E_UNSUPPORTED, "no cluster variant of the rollout kernel for this configuration"); }
     } else if (s->cell_kernel) {
         // Cell-centric kernel: the rollout is bound by its three barriers per step, so what counts is how many CTAs
@@ -734,6 +743,8 @@ int ffm_rollout(ffm_sim_t s, int32_t max_steps, const ffm_draws_t* draws, const 
     if (!s->have_fields || !s->have_positions) return fail(FFM_E_STATE, "fields and positions must be set before ffm_rollout");
     if (max_steps < 0 && !(max_steps == -1 && s->cfg.model == FFM_MODEL_MCQ)) return fail(FFM_E_INVALID, "max_steps < 0");
     if (draws && draws->space != FFM_DEVICE) return fail(FFM_E_INVALID, "recorded draws must live in device memory");
+    if (out && out->ctraj && !(s->cfg.model == FFM_MODEL_CORE && s->cell_kernel))
+        return fail(FFM_E_UNSUPPORTED, "the compact trajectory record is written by the cell-centric base-model kernel (ffm_cluster_info: cell_kernel == 1)");
     cudaStream_t st = (cudaStream_t)stream;
     CU(cudaSetDevice(s->cfg.device));
     // the opt-in shared-memory size is per-function state shared by all handles: re-assert ours before launching
@@ -822,6 +833,14 @@ int ffm_rollout(ffm_sim_t s, int32_t max_steps, const ffm_draws_t* draws, const 
         if (out && out->traj_cells) {
             if (!out->traj_n) return fail(FFM_E_INVALID, "traj_cells without traj_n");
             C.traj = out->traj_cells; C.traj_n = out->traj_n; C.traj_steps = out->traj_steps;
+        }
+        if (out && out->ctraj) {
+            if (!out->traj_n || !out->ctraj_off) return fail(FFM_E_INVALID, "ctraj needs ctraj_off and traj_n");
+            if (out->ctraj_cap < 4 || (out->ctraj_cap & 3) || out->ctraj_cap > 0x7FFFFFF0LL)
+                return fail(FFM_E_INVALID, "ctraj_cap must be a multiple of 4 in [4, 2^31)");
+            if (out->traj_steps < 1) return fail(FFM_E_INVALID, "traj_steps < 1");
+            C.ctraj = reinterpret_cast<uint32_t*>(out->ctraj); C.ctraj_off = out->ctraj_off; C.ctraj_cap = out->ctraj_cap;
+            C.traj_n = out->traj_n; C.traj_steps = out->traj_steps;
         }
 #ifdef FFM_PHASE_TIMING
         static unsigned long long* d_dbg = nullptr;
@@ -1060,8 +1079,8 @@ int ffm_sff_generate(const uint8_t* maps, int32_t n_maps, int32_t H, int32_t W, 
     }
     const size_t HW = (size_t)H * W, total = HW * n_maps;
     const size_t osz = out_dtype == FFM_F64 ? 8 : 4;
-    uint8_t* d_maps = nullptr; void* d_out = nullptr; float* d_dist = nullptr; uint8_t* d_dirty = nullptr;
-    int32_t* d_exits = nullptr; int32_t* d_counts = nullptr; int* d_any = nullptr;
+    uint8_t* d_maps = nullptr; void* d_out = nullptr; float* d_dist = nullptr;
+    int32_t* d_exits = nullptr; int32_t* d_counts = nullptr; int* d_queue = nullptr;
     int rc = FFM_OK, rounds = 0;
 #define SFF_CU(call)                                                                        \
     do {                                                                                    \
@@ -1098,44 +1117,50 @@ int ffm_sff_generate(const uint8_t* maps, int32_t n_maps, int32_t H, int32_t W, 
             const int tiles_x = (W + ffm::SFF_TILE - 1) / ffm::SFF_TILE, tiles_y = (H + ffm::SFF_TILE - 1) / ffm::SFF_TILE;
             const size_t ntiles = (size_t)tiles_x * tiles_y * n_maps;
             if (tiles_y > 65535 || n_maps > 65535) { rc = fail(FFM_E_UNSUPPORTED, "too many tiles / maps for one launch"); goto done; }
+            if (ntiles > 0x3FFFFFFFULL) { rc = fail(FFM_E_UNSUPPORTED, "too many tiles for one call"); goto done; }
             SFF_CU(cudaMallocAsync((void**)&d_dist, total * sizeof(float), st));
-            SFF_CU(cudaMallocAsync((void**)&d_dirty, 2 * ntiles, st));
-            SFF_CU(cudaMallocAsync((void**)&d_any, sizeof(int), st));
-            SFF_CU(cudaMemsetAsync(d_dirty, 0, 2 * ntiles, st));
-            ffm::sff_relax_init_kernel<<<dim3(bx, n_maps), 256, 0, st>>>(mp, d_dist, d_dirty, H, W, tiles_x, tiles_y);
+            // queue scratch in ONE allocation: ring [2 * tiles] | flags [tiles] | 4 counters
+            const size_t qwords = 3 * ntiles + 4;
+            SFF_CU(cudaMallocAsync((void**)&d_queue, qwords * sizeof(int), st));
+            ffm::SffQueue q;
+            q.ring = d_queue; q.flag = d_queue + 2 * ntiles; q.ctrl = reinterpret_cast<unsigned int*>(d_queue + 3 * ntiles);
+            q.cap = (unsigned int)(2 * ntiles);
+            SFF_CU(cudaMemsetAsync(q.ring, 0xFF, 2 * ntiles * sizeof(int), st));        // -1 = empty slot
+            SFF_CU(cudaMemsetAsync(q.flag, 0, (ntiles + 4) * sizeof(int), st));
+            ffm::sff_relax_init_kernel<<<dim3(bx, n_maps), 256, 0, st>>>(mp, d_dist, q, H, W, tiles_x, tiles_y);
             const float INF = __builtin_huge_valf();
             const float w_axis = 1.0f;
             const float w_diag = mode == FFM_SFF_BFS4 ? INF : (mode == FFM_SFF_BFS8 ? 1.0f : (float)1.4142135623730951);
-            uint8_t* din = d_dirty; uint8_t* dout = d_dirty + ntiles;
-            for (;;) {
-                int any = 0;
-                SFF_CU(cudaMemsetAsync(d_any, 0, sizeof(int), st));
-                SFF_CU(cudaMemsetAsync(dout, 0, ntiles, st));
-                ffm::sff_relax_tile_kernel<<<dim3(tiles_x, tiles_y, n_maps), 256, 0, st>>>(mp, d_dist, din, dout, d_any, H, W, tiles_x, tiles_y, w_axis, w_diag);
-                SFF_CU(cudaGetLastError());
-                ++rounds;
-                SFF_CU(cudaMemcpyAsync(&any, d_any, sizeof(int), cudaMemcpyDeviceToHost, st));
+            int per_sm = 0, sms = 0;
+            SFF_CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ffm::sff_relax_queue_kernel, 256, 0));
+            SFF_CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+            const size_t resident = (size_t)per_sm * sms;      // persistent CTAs: spinning consumers must all be resident
+            const int grid = (int)(ntiles < resident ? ntiles : resident);
+            ffm::sff_relax_queue_kernel<<<grid, 256, 0, st>>>(mp, d_dist, q, H, W, tiles_x, tiles_y, w_axis, w_diag);
+            SFF_CU(cudaGetLastError());
+            if (rounds_out) {                                  // tile visits, for the caller that asks (one 4-byte read-back)
+                unsigned int visits = 0;
+                SFF_CU(cudaMemcpyAsync(&visits, q.ctrl + 3, sizeof(visits), cudaMemcpyDeviceToHost, st));
                 SFF_CU(cudaStreamSynchronize(st));
-                if (!any) break;
-                uint8_t* t = din; din = dout; dout = t;
-                if (rounds > 4 * (tiles_x + tiles_y) * ffm::SFF_TILE) { rc = fail(FFM_E_CUDA, "SFF relaxation did not converge"); goto done; }
+                rounds = (int)visits;
             }
             const int cb = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
             if (out_dtype == FFM_F64) ffm::sff_convert_kernel<double><<<cb, 256, 0, st>>>(d_dist, (double*)d_out, total);
             else ffm::sff_convert_kernel<float><<<cb, 256, 0, st>>>(d_dist, (float*)d_out, total);
             SFF_CU(cudaGetLastError());
         }
-        if (space == FFM_HOST) SFF_CU(cudaMemcpyAsync(out, d_out, total * osz, cudaMemcpyDeviceToHost, st));
-        SFF_CU(cudaStreamSynchronize(st));
+        if (space == FFM_HOST) {     // device-space calls stay stream-ordered: no host synchronisation at all in the geodesic modes
+            SFF_CU(cudaMemcpyAsync(out, d_out, total * osz, cudaMemcpyDeviceToHost, st));
+            SFF_CU(cudaStreamSynchronize(st));
+        }
     }
 done:
 #undef SFF_CU
     if (space == FFM_HOST) { if (d_maps) cudaFreeAsync(d_maps, st); if (d_out) cudaFreeAsync(d_out, st); }
     if (d_dist) cudaFreeAsync(d_dist, st);
-    if (d_dirty) cudaFreeAsync(d_dirty, st);
     if (d_exits) cudaFreeAsync(d_exits, st);
     if (d_counts) cudaFreeAsync(d_counts, st);
-    if (d_any) cudaFreeAsync(d_any, st);
+    if (d_queue) cudaFreeAsync(d_queue, st);
     if (rounds_out) *rounds_out = rounds;
     return rc;
 }

@@ -3,10 +3,8 @@
 namespace ffm { namespace {
 template <typename S, typename EntT, int NBR, bool DFF, bool FS, int CL>
 const void* cpick_threads(int threads) {
-    if constexpr (CL > 1) {   // cluster variants exist with the fields on chip only (that is what they are for)
-        if (!FS) return nullptr;
-        if (threads == 1024) return (const void*)ffm_cell_rollout_kernel<S, EntT, NBR, DFF, true, 1024, CL>;
-        return (const void*)ffm_cell_rollout_kernel<S, EntT, NBR, DFF, true, 512, CL>;
+    if constexpr (CL > 1) {   // cluster variants: 512 threads per CTA (1024 measured slower: 64 registers, spills)
+        return (const void*)ffm_cell_rollout_kernel<S, EntT, NBR, DFF, FS, 512, CL>;
     } else {
         if (threads == 1024) return (const void*)ffm_cell_rollout_kernel<S, EntT, NBR, DFF, FS, 1024, 1>;
         if (threads == 128) return (const void*)ffm_cell_rollout_kernel<S, EntT, NBR, DFF, FS, 128, 1>;

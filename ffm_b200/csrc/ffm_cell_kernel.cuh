@@ -87,9 +87,9 @@ struct CellParams {
     // compact trajectory record (what run() collects, ffm_core.py:125 / main.py:44-52): per episode a stream of
     // (row, col) int16 pairs, the rows of consecutive steps back to back, each padded to a multiple of 4 entries
     unsigned long long* dbg;     // FFM_PHASE_TIMING builds: [8] accumulated cycles (work / wait per phase), else unused
-    short2* ctraj;               // [B][ctraj_cap]
+    uint32_t* ctraj;             // [B][ctraj_cap]  low half = row, high half = col (an int16 pair in memory)
     int32_t* ctraj_off;          // [B][traj_steps + 1]: entry offset of each step's row (CSR); [steps] = end
-    int ctraj_cap;
+    long long ctraj_cap;
 };
 
 __host__ __device__ inline CellLayout make_cell_layout(int RB, int W, int RW, int n_max, int sizeof_score, int sizeof_ent, bool dff,
@@ -431,7 +431,7 @@ ffm_cell_rollout_kernel(const CellParams P) {
         return ((fu >> 1) & 1u) | (((fd >> 1) & 1u) << 1) | ((fm & 1u) << 2) | ((fm & 4u) << 1);
     };
     // positions in alive-rank order -> dst[rank] (epilogue / dense trajectory rows)
-    auto emit_positions = [&](uint32_t* dst) {
+    auto emit_positions = [&](uint32_t* dst, bool as_row_col = false) {
 #pragma unroll 1
         for (int ch = tid; ch < nchunks; ch += THREADS) {
             const int lr = cpr == 1 ? ch : (int)__umulhi((uint32_t)ch, P.magic_cpr), j = ch - lr * cpr;
@@ -443,7 +443,7 @@ ffm_cell_rollout_kernel(const CellParams P) {
                 occ &= occ - 1u;
                 const int c = cbase + b;
                 const uint32_t id = (grid_l[c - lo] & OCC_MASK) - 1u;
-                dst[rank_of(id)] = (uint32_t)c;
+                dst[rank_of(id)] = as_row_col ? ((uint32_t)(r0 + lr) | ((uint32_t)(32 * j + b) << 16)) : (uint32_t)c;
             }
         }
     };
@@ -483,6 +483,8 @@ ffm_cell_rollout_kernel(const CellParams P) {
 #define FFM_TICK(i)
 #endif
     unsigned long long ped_steps = 0;
+    int coff = 0;                  // compact trajectory record: entries of this episode's stream written so far (-1: overflowed)
+    if (P.ctraj != nullptr && tid == 0 && band == 0) P.ctraj_off[(size_t)e * (P.traj_steps + 1)] = 0;
     bool need_prefix = false;      // somebody left since the prefix was last computed
     bool dff_pending = false;      // the DFF update of the previous step has not run yet
     int tl = 0;
@@ -827,6 +829,40 @@ ffm_cell_rollout_kernel(const CellParams P) {
             }
             emit_positions(P.traj + ((size_t)e * P.traj_steps + tl) * P.n_max);
             if (tid == 0 && band == 0) P.traj_n[(size_t)e * P.traj_steps + tl] = n;
+        }
+        // compact record: (row, col) int16 pairs of this step's row appended to the episode's stream (CSR offsets)
+        if (P.ctraj != nullptr && tl < P.traj_steps) {
+            if (need_prefix) {
+                if (warp == 0) refresh_prefix();
+                __syncthreads();
+                need_prefix = false;
+            }
+            const uint32_t npad = ((uint32_t)n + 3u) & ~3u;
+            const bool fits = coff >= 0 && (long long)coff + npad <= P.ctraj_cap;
+            if (fits) {
+                uint32_t* dst = P.ctraj + (size_t)e * P.ctraj_cap + coff;
+                uint32_t* stage = reinterpret_cast<uint32_t*>(smem_raw + L.listA);   // the work lists are idle until the next phase 1
+                if (CL == 1 && npad * 4u <= L.alive - L.listA) {
+                    // rank-order scatter into shared memory, then 16-byte coalesced stores
+                    emit_positions(stage, true);
+                    if ((uint32_t)tid < npad - (uint32_t)n) stage[n + tid] = 0xFFFFFFFFu;
+                    __syncthreads();
+                    uint4* d4 = reinterpret_cast<uint4*>(dst);
+                    const uint4* s4 = reinterpret_cast<const uint4*>(stage);
+                    for (uint32_t x = tid; x < npad / 4u; x += THREADS) __stcs(d4 + x, s4[x]);
+                    __syncthreads();
+                } else {
+                    emit_positions(dst, true);
+                    if (band == 0 && (uint32_t)tid < npad - (uint32_t)n) dst[n + tid] = 0xFFFFFFFFu;
+                }
+                coff += (int)npad;
+            } else {
+                coff = -1;
+            }
+            if (tid == 0 && band == 0) {
+                P.ctraj_off[(size_t)e * (P.traj_steps + 1) + tl + 1] = coff;
+                if (P.traj == nullptr) P.traj_n[(size_t)e * P.traj_steps + tl] = n;
+            }
         }
     }
 

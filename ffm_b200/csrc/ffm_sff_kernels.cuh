@@ -3,14 +3,15 @@
 //  * sff_norm_min_kernel      obstacle-blind min-over-exits norm distance -- exact counterpart of the
 //                             reference generators (Create_SFF.py:14-33: L1 / np.hypot / Linf, float64,
 //                             inf on non-walkable cells; create_12x12_map_and_sff.py:36-50: L1, float32)
-//  * sff_relax_tile_kernel    geodesic (obstacle-aware) distance from the exits, 4-/8-connected unit
+//  * sff_relax_queue_kernel   geodesic (obstacle-aware) distance from the exits, 4-/8-connected unit
 //                             steps (= wavefront BFS levels) or (1, sqrt 2)-weighted 8-connected steps
 //                             (= Dijkstra), computed as the least fixpoint of
 //                                 d[c] = min(d[c], min_nb fl32(d[nb] + w))
-//                             by block-asynchronous relaxation: a CTA owns a 32x32 tile in shared
-//                             memory, relaxes it to local convergence, writes it back and marks the
-//                             neighbouring tiles dirty if its rim changed; rounds repeat over dirty
-//                             tiles until none is left.  Any relaxation order reaches the same fixpoint
+//                             by block-asynchronous relaxation: persistent CTAs pop 32x32 tiles from a
+//                             device-side work queue, relax a tile in shared memory to local convergence,
+//                             fold it back with atomicMin and queue the neighbouring tiles whose halo
+//                             changed, until the queue is empty and nothing is in flight -- one launch, no
+//                             host round trips.  Any relaxation order reaches the same fixpoint
 //                             (fl32(d + w) is monotone in d), so the result is bit-identical to a
 //                             float32 Dijkstra (which is what the CPU checker of the test-suite runs).
 //                             North-star item 2 (the reference has no obstacle-aware generator).
@@ -68,8 +69,28 @@ __global__ void sff_norm_min_kernel(const uint8_t* __restrict__ maps, const int3
     }
 }
 
-// initial field: 0 on exits, +inf elsewhere; every tile that holds an exit starts dirty
-__global__ void sff_relax_init_kernel(const uint8_t* __restrict__ maps, float* __restrict__ dist, uint8_t* __restrict__ dirty,
+// ---- geodesic fields: asynchronous tile relaxation driven by a device-side work queue ---------------------------------
+// Scratch of one ffm_sff_generate call: a ring of tile ids (capacity 2 x tiles), a "queued" flag per tile (so a tile is
+// in the ring at most once) and three counters.  No host round trip: the persistent CTAs of sff_relax_queue_kernel pop
+// tiles until the ring is empty and nothing is in flight.
+struct SffQueue {
+    int* ring;                 // [cap] tile id or -1 (empty slot)
+    int* flag;                 // [tiles] 1 = queued and not yet popped
+    unsigned int* ctrl;        // [0] head (tickets claimed), [1] tail (tickets issued), [2] pending (queued + in flight), [3] tile visits
+    unsigned int cap;
+};
+
+__device__ __forceinline__ void sff_push(const SffQueue& q, int tile) {
+    if (atomicExch(&q.flag[tile], 1) != 0) return;             // already queued: whoever pops it reads our data
+    atomicAdd(&q.ctrl[2], 1u);
+    const unsigned int t = atomicAdd(&q.ctrl[1], 1u);
+    volatile int* slot = q.ring + (t % q.cap);
+    while (*slot != -1) __nanosleep(32);                        // the ticket one lap behind has been claimed, not yet taken
+    *slot = tile;
+}
+
+// initial field: 0 on exits, +inf elsewhere; every tile that holds an exit is queued
+__global__ void sff_relax_init_kernel(const uint8_t* __restrict__ maps, float* __restrict__ dist, SffQueue q,
                                       int H, int W, int tiles_x, int tiles_y) {
     const int mapi = blockIdx.y;
     const size_t HW = (size_t)H * W;
@@ -78,101 +99,129 @@ __global__ void sff_relax_init_kernel(const uint8_t* __restrict__ maps, float* _
         dist[mapi * HW + c] = ex ? 0.0f : __int_as_float(0x7f800000);
         if (ex) {
             const int r = (int)(c / W), col = (int)(c - (size_t)r * W);
-            dirty[((size_t)mapi * tiles_y + r / SFF_TILE) * tiles_x + col / SFF_TILE] = 1;
+            sff_push(q, (int)(((size_t)mapi * tiles_y + r / SFF_TILE) * tiles_x + col / SFF_TILE));
         }
     }
 }
 
-// One relaxation round: CTA (x, y, map) = tile.  dirty_in says which tiles must run; dirty_out collects
-// the tiles to run next round; *any_out is set when something is left to do.
+// Persistent CTAs: pop a tile, relax it in shared memory to local convergence against the halo it sees, fold the result
+// into the global field with atomicMin (two CTAs may hold the same tile: values only ever decrease), wake the neighbours
+// whose halo changed.  A tile's "queued" flag is cleared BEFORE its data is read, so an improvement that arrives later
+// re-queues it.  Distances are non-negative floats: their bit patterns order like the values, which is what atomicMin
+// on the int view relies on.
 __global__ void __launch_bounds__(256)
-sff_relax_tile_kernel(const uint8_t* __restrict__ maps, float* __restrict__ dist, const uint8_t* __restrict__ dirty_in,
-                      uint8_t* __restrict__ dirty_out, int* __restrict__ any_out, int H, int W, int tiles_x, int tiles_y,
-                      float w_axis, float w_diag) {
-    const int tx = blockIdx.x, ty = blockIdx.y, mapi = blockIdx.z;
-    const size_t tile_id = ((size_t)mapi * tiles_y + ty) * tiles_x + tx;
-    if (!dirty_in[tile_id]) return;
+sff_relax_queue_kernel(const uint8_t* __restrict__ maps, float* dist, SffQueue q, int H, int W, int tiles_x, int tiles_y,
+                       float w_axis, float w_diag) {
     constexpr int T = SFF_TILE, P = SFF_TILE + 2;
     __shared__ float d[P][P + 1];
     __shared__ uint8_t pass[T][T];
     __shared__ int rim_changed[4];   // top, bottom, left, right
-    const size_t HW = (size_t)H * W;
-    const uint8_t* map = maps + mapi * HW;
-    float* g = dist + mapi * HW;
-    const int r0 = ty * T, c0 = tx * T;
+    __shared__ int s_tile;
     const float INF = __int_as_float(0x7f800000);
-    if (threadIdx.x < 4) rim_changed[threadIdx.x] = 0;
-    for (int x = threadIdx.x; x < P * P; x += blockDim.x) {
-        const int lr = x / P, lc = x - lr * P;
-        const int r = r0 + lr - 1, c = c0 + lc - 1;
-        float v = INF;
-        if (r >= 0 && r < H && c >= 0 && c < W) v = g[(size_t)r * W + c];
-        d[lr][lc] = v;
-        if (lr >= 1 && lr <= T && lc >= 1 && lc <= T) {
-            uint8_t p = 0;
-            if (r < H && c < W) { const uint8_t m = map[(size_t)r * W + c]; p = (m == 0 || m == 3) ? 1 : 0; }
-            pass[lr - 1][lc - 1] = p;
+    const size_t HW = (size_t)H * W;
+    const int tiles_per_map = tiles_x * tiles_y;
+    for (;;) {
+        if (threadIdx.x == 0) {
+            int tile = -1;
+            volatile unsigned int* ctrl = q.ctrl;
+            for (;;) {
+                const unsigned int h = ctrl[0], t = ctrl[1];
+                if ((int)(t - h) > 0) {
+                    if (atomicCAS(&q.ctrl[0], h, h + 1u) != h) continue;
+                    volatile int* slot = q.ring + (h % q.cap);
+                    while ((tile = *slot) == -1) __nanosleep(32);
+                    *slot = -1;
+                    __threadfence();
+                    atomicExch(&q.flag[tile], 0);                  // from here on an improved neighbour re-queues this tile
+                    __threadfence();
+                    atomicAdd(&q.ctrl[3], 1u);
+                    break;
+                }
+                if (ctrl[2] == 0u) break;                          // ring empty and nothing in flight: done
+                __nanosleep(200);
+            }
+            s_tile = tile;
+            rim_changed[0] = rim_changed[1] = rim_changed[2] = rim_changed[3] = 0;
         }
-    }
-    __syncthreads();
-    // 256 threads x 4 cells; in-place (Gauss-Seidel style) min-relaxation: a concurrently updated
-    // neighbour is read as either its old or its new value, both valid upper bounds of the fixpoint
-    volatile float (*vd)[P + 1] = d;
-    for (int it = 0; it < 4 * T * T; ++it) {
-        bool ch = false;
+        __syncthreads();
+        const int tile = s_tile;
+        if (tile < 0) return;
+        const int mapi = tile / tiles_per_map, trem = tile - mapi * tiles_per_map;
+        const int ty = trem / tiles_x, tx = trem - ty * tiles_x;
+        const uint8_t* map = maps + mapi * HW;
+        float* g = dist + mapi * HW;
+        const int r0 = ty * T, c0 = tx * T;
+        for (int x = threadIdx.x; x < P * P; x += blockDim.x) {
+            const int lr = x / P, lc = x - lr * P;
+            const int r = r0 + lr - 1, c = c0 + lc - 1;
+            float v = INF;
+            if (r >= 0 && r < H && c >= 0 && c < W) v = __ldcg(g + (size_t)r * W + c);     // L2: other SMs update the field
+            d[lr][lc] = v;
+            if (lr >= 1 && lr <= T && lc >= 1 && lc <= T) {
+                uint8_t p = 0;
+                if (r < H && c < W) { const uint8_t m = map[(size_t)r * W + c]; p = (m == 0 || m == 3) ? 1 : 0; }
+                pass[lr - 1][lc - 1] = p;
+            }
+        }
+        __syncthreads();
+        // 256 threads x 4 cells; in-place (Gauss-Seidel style) min-relaxation: a concurrently updated
+        // neighbour is read as either its old or its new value, both valid upper bounds of the fixpoint
+        volatile float (*vd)[P + 1] = d;
+        for (int it = 0; it < 4 * T * T; ++it) {
+            bool ch = false;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const int x = threadIdx.x + q * 256;
+            for (int qd = 0; qd < 4; ++qd) {
+                const int x = threadIdx.x + qd * 256;
+                const int lr = x / T, lc = x - lr * T;
+                if (!pass[lr][lc]) continue;
+                const int a = lr + 1, b = lc + 1;
+                float best = vd[a][b];
+                const float old = best;
+                best = fminf(best, __fadd_rn(vd[a - 1][b], w_axis));
+                best = fminf(best, __fadd_rn(vd[a + 1][b], w_axis));
+                best = fminf(best, __fadd_rn(vd[a][b - 1], w_axis));
+                best = fminf(best, __fadd_rn(vd[a][b + 1], w_axis));
+                if (w_diag < INF) {
+                    best = fminf(best, __fadd_rn(vd[a - 1][b - 1], w_diag));
+                    best = fminf(best, __fadd_rn(vd[a - 1][b + 1], w_diag));
+                    best = fminf(best, __fadd_rn(vd[a + 1][b - 1], w_diag));
+                    best = fminf(best, __fadd_rn(vd[a + 1][b + 1], w_diag));
+                }
+                if (best < old) { vd[a][b] = best; ch = true; }
+            }
+            if (!__syncthreads_or(ch ? 1 : 0)) break;
+        }
+        // fold into the global field; detect rim changes to wake the neighbours
+        for (int x = threadIdx.x; x < T * T; x += blockDim.x) {
             const int lr = x / T, lc = x - lr * T;
-            if (!pass[lr][lc]) continue;
-            const int a = lr + 1, b = lc + 1;
-            float best = vd[a][b];
-            const float old = best;
-            best = fminf(best, __fadd_rn(vd[a - 1][b], w_axis));
-            best = fminf(best, __fadd_rn(vd[a + 1][b], w_axis));
-            best = fminf(best, __fadd_rn(vd[a][b - 1], w_axis));
-            best = fminf(best, __fadd_rn(vd[a][b + 1], w_axis));
-            if (w_diag < INF) {
-                best = fminf(best, __fadd_rn(vd[a - 1][b - 1], w_diag));
-                best = fminf(best, __fadd_rn(vd[a - 1][b + 1], w_diag));
-                best = fminf(best, __fadd_rn(vd[a + 1][b - 1], w_diag));
-                best = fminf(best, __fadd_rn(vd[a + 1][b + 1], w_diag));
-            }
-            if (best < old) { vd[a][b] = best; ch = true; }
-        }
-        if (!__syncthreads_or(ch ? 1 : 0)) break;
-    }
-    // write back; detect rim changes to wake the neighbours
-    for (int x = threadIdx.x; x < T * T; x += blockDim.x) {
-        const int lr = x / T, lc = x - lr * T;
-        const int r = r0 + lr, c = c0 + lc;
-        if (r < H && c < W) {
-            const float v = d[lr + 1][lc + 1];
-            const size_t gi = (size_t)r * W + c;
-            if (v < g[gi]) {
-                g[gi] = v;
-                if (lr == 0) rim_changed[0] = 1;
-                if (lr == T - 1) rim_changed[1] = 1;
-                if (lc == 0) rim_changed[2] = 1;
-                if (lc == T - 1) rim_changed[3] = 1;
+            const int r = r0 + lr, c = c0 + lc;
+            if (r < H && c < W && pass[lr][lc]) {
+                const float v = d[lr + 1][lc + 1];
+                if (v < INF) {
+                    const int vi = __float_as_int(v);
+                    const int oldi = atomicMin(reinterpret_cast<int*>(g + (size_t)r * W + c), vi);
+                    if (vi < oldi) {
+                        if (lr == 0) rim_changed[0] = 1;
+                        if (lr == T - 1) rim_changed[1] = 1;
+                        if (lc == 0) rim_changed[2] = 1;
+                        if (lc == T - 1) rim_changed[3] = 1;
+                    }
+                }
             }
         }
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        // a changed rim wakes the three tiles on that side (safe superset: corners included)
-        bool any = false;
-        auto mark = [&](int ny, int nx) {
-            if (ny >= 0 && ny < tiles_y && nx >= 0 && nx < tiles_x) {
-                dirty_out[((size_t)mapi * tiles_y + ny) * tiles_x + nx] = 1;
-                any = true;
+        __threadfence();
+        __syncthreads();
+        // a changed rim wakes the three tiles on that side (safe superset: corners included); lanes 0..11 take one each
+        if (threadIdx.x < 12) {
+            const int side = threadIdx.x / 3, k = threadIdx.x - side * 3 - 1;
+            if (rim_changed[side]) {
+                const int ny = side == 0 ? ty - 1 : (side == 1 ? ty + 1 : ty + k);
+                const int nx = side == 2 ? tx - 1 : (side == 3 ? tx + 1 : tx + k);
+                if (ny >= 0 && ny < tiles_y && nx >= 0 && nx < tiles_x) sff_push(q, (mapi * tiles_y + ny) * tiles_x + nx);
             }
-        };
-        if (rim_changed[0]) for (int dx = -1; dx <= 1; ++dx) mark(ty - 1, tx + dx);
-        if (rim_changed[1]) for (int dx = -1; dx <= 1; ++dx) mark(ty + 1, tx + dx);
-        if (rim_changed[2]) for (int dy = -1; dy <= 1; ++dy) mark(ty + dy, tx - 1);
-        if (rim_changed[3]) for (int dy = -1; dy <= 1; ++dy) mark(ty + dy, tx + 1);
-        if (any) *any_out = 1;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) { __threadfence(); atomicSub(&q.ctrl[2], 1u); }
     }
 }
 

@@ -37,7 +37,7 @@ def generate_sff(maps, metric="L1", dtype=np.float64, device=None, return_rounds
         H, W = shape[-2:]
         out = torch.empty(shape, dtype=torch.float32 if code == _abi.FFM_F32 else torch.float64, device=maps.device)
         _abi.check(_abi.lib().ffm_sff_generate(C.c_void_p(maps.data_ptr()), n, H, W, MODES[metric], code,
-                                               C.c_void_p(out.data_ptr()), _abi.FFM_DEVICE, device, stream, C.byref(rounds)))
+                                               C.c_void_p(out.data_ptr()), _abi.FFM_DEVICE, device, stream, C.byref(rounds) if return_rounds else None))
     else:
         m = np.ascontiguousarray(np.asarray(maps).astype(np.uint8))
         single = m.ndim == 2
@@ -45,5 +45,5 @@ def generate_sff(maps, metric="L1", dtype=np.float64, device=None, return_rounds
         H, W = m.shape[-2:]
         out = np.empty(m.shape, dtype=dt)
         _abi.check(_abi.lib().ffm_sff_generate(C.c_void_p(m.ctypes.data), n, H, W, MODES[metric], code,
-                                               C.c_void_p(out.ctypes.data), _abi.FFM_HOST, device, stream, C.byref(rounds)))
+                                               C.c_void_p(out.ctypes.data), _abi.FFM_HOST, device, stream, C.byref(rounds) if return_rounds else None))
     return (out, rounds.value) if return_rounds else out

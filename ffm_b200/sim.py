@@ -178,13 +178,17 @@ class BatchSim:
         _abi.check(self._lib.ffm_get_counters(self._h, _ptr(steps_t), _ptr(ped_steps_t), _abi.FFM_DEVICE, _stream()))
 
     # -- stepping ------------------------------------------------------------------------------
-    def rollout(self, max_steps, draws=None, record=0, record_buffer=False):
+    def rollout(self, max_steps, draws=None, record=0, record_buffer=False, compact_cap=None):
         """Run up to ``max_steps`` CA steps per episode (asynchronous on the current stream).
 
         draws   optional dict(move=float64 [B, T, n_max], conflict=float64 [B, T, H*W, 2],
                 first_step=int) of recorded uniforms (CUDA tensors) overriding the Philox streams
         record  > 0: also return (traj_cells uint32-as-int32 [B, record, n_max], traj_n int32
                 [B, record]) CUDA tensors with the positions after each step
+        compact_cap  with record > 0: return the COMPACT record instead -- dict(ctraj=int16 [B, compact_cap, 2] (row, col)
+                pairs, the rows of consecutive steps back to back (each padded with -1 to a multiple of 4 entries),
+                off=int32 [B, record + 1] CSR offsets, n=int32 [B, record] row lengths): 4 bytes per pedestrian-step
+                (see unpack_trajectory)
         """
         dptr = None
         if draws is not None:
@@ -220,6 +224,13 @@ class BatchSim:
                 rl = torch.zeros((self.B, self.n_max), dtype=torch.int32, device=dev)
                 o.rec_state, o.rec_action, o.rec_reward, o.rec_len = rs.data_ptr(), ra.data_ptr(), rr.data_ptr(), rl.data_ptr()
                 ret = dict(state=rs, action=ra, reward=rr, length=rl)
+            elif compact_cap:
+                cap = (int(compact_cap) + 3) & ~3
+                ct = torch.empty((self.B, cap, 2), dtype=torch.int16, device=dev)
+                off = torch.full((self.B, record + 1), -1, dtype=torch.int32, device=dev)
+                cnt = torch.zeros((self.B, record), dtype=torch.int32, device=dev)
+                o.ctraj, o.ctraj_off, o.ctraj_cap, o.traj_n = ct.data_ptr(), off.data_ptr(), cap, cnt.data_ptr()
+                ret = dict(ctraj=ct, off=off, n=cnt)
             else:
                 cells = torch.zeros((self.B, record, self.n_max), dtype=torch.int32, device=dev)
                 cnt = torch.zeros((self.B, record), dtype=torch.int32, device=dev)
@@ -247,6 +258,19 @@ class BatchSim:
                     name={1: "ffm_cell_rollout_kernel", 0: "ffm_core_rollout_kernel"}.get(
                         d.value, "ffm_mcq_rollout_kernel" if isinstance(self, McqSim) else "ffm_unified_rollout_kernel"))
         return info
+
+
+def unpack_trajectory(ctraj, off, n, steps=None):
+    """One episode of a compact record (NumPy: ctraj int16 [cap, 2], off int32 [T + 1], n int32 [T]) -> the list run()
+    collects: one int64 [n_t, 2] array of (row, col) per step (ffm_core.py:125; `np.array(buffer, dtype=object)` of it is
+    main.py:52's positions.npy)."""
+    T = len(n) if steps is None else int(steps)
+    out = []
+    for t in range(T):
+        if off[t] < 0 or off[t + 1] < 0:
+            raise ValueError(f"trajectory record overflowed at step {t}: raise compact_cap")
+        out.append(ctraj[off[t]:off[t] + n[t]].astype(np.int64))
+    return out
 
 
 UNIFIED_DEFAULTS = {                      # ffm_unified.py:36-53

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define FFM_ABI_VERSION 4
+#define FFM_ABI_VERSION 5
 
 enum {
     FFM_OK = 0,
@@ -134,6 +134,17 @@ typedef struct ffm_rollout_out {
     uint8_t *rec_action;
     float *rec_reward;
     int32_t *rec_len;
+    /* Compact trajectory record -- what run() collects (`buffer.append(copy(positions))`, ffm_core.py:125, main.py:44-52)
+     * at 4 bytes per pedestrian-step instead of a dense [T][n_max] slab:
+     *   ctraj      int16 [B][ctraj_cap][2]  (row, col) pairs, alive-rank order; the rows of consecutive steps of this launch
+     *              back to back, each padded with (-1, -1) to a multiple of 4 entries (16-byte vector stores)
+     *   ctraj_off  int32 [B][traj_steps + 1] entry offset of each step's row within the episode's stream (CSR); element
+     *              [steps run] = end.  A step whose row would not fit is not recorded and its offset is -1 from there on.
+     *   traj_n     (above) the number of valid entries of each row
+     * Base model only. */
+    int16_t *ctraj;
+    int32_t *ctraj_off;
+    int64_t ctraj_cap;
 } ffm_rollout_out_t;
 
 int ffm_abi_version(void);
@@ -224,7 +235,8 @@ int ffm_mcq_finalize_timeouts(ffm_sim_t sim, void *stream);   /* finalize_timeou
  *                            create_12x12_map_and_sff.py:36-50
  *   FFM_SFF_BFS4 / BFS8      geodesic distance in 4-/8-connected unit steps (wavefront BFS levels)
  *   FFM_SFF_DIJKSTRA8        geodesic distance with step costs (1, float32(sqrt 2)), float32 sums
- * `rounds` (may be NULL) receives the number of relaxation rounds the geodesic modes needed.
+ * `rounds` (may be NULL; non-NULL costs one 4-byte read-back + synchronisation) receives the number of tile visits of the
+ * geodesic modes' work queue.
  * Synchronous with respect to the host on return. */
 enum { FFM_SFF_L1 = 0, FFM_SFF_L2 = 1, FFM_SFF_LINF = 2, FFM_SFF_BFS4 = 3, FFM_SFF_BFS8 = 4, FFM_SFF_DIJKSTRA8 = 5 };
 int ffm_sff_generate(const uint8_t *maps, int32_t n_maps, int32_t height, int32_t width, int32_t mode, int32_t out_dtype,

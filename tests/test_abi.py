@@ -29,7 +29,7 @@ def test_abi_version_and_struct_sizes(ffm_lib):
     from ffm_b200 import _abi
     assert ffm_lib.ffm_abi_version() == _abi.ABI_VERSION
     assert ctypes.sizeof(_abi.Config) == 88 + 16 + 10 * 8 + 24   # core block + 4 x int32 + 10 x double + MCQ block
-    assert ctypes.sizeof(_abi.Draws) == 32 and ctypes.sizeof(_abi.RolloutOut) == 56
+    assert ctypes.sizeof(_abi.Draws) == 32 and ctypes.sizeof(_abi.RolloutOut) == 80
 
 
 def test_no_cpu_fallback_without_gpu():

@@ -66,7 +66,7 @@ def test_maximum_capacity(cuda_device, core_kernel):
     """n_max = 16 380 pedestrians (the owner grid's 14-bit id space) in a 130 x 130 room: 96.9 % of the cells
     occupied at t = 0.  (256 x 256 maps hold at most ~10 100 pedestrians: one SM's shared memory.)"""
     from ffm_b200 import BatchSim
-    from ffm_b200.workloads import place, rooms_map_c3
+    from ffm_b200.workloads import place
     m = assets.room_map(130, 130)
     sff = assets.sff_norm_min_fast(m, "Linf", np.float32)
     N = 16380
@@ -80,9 +80,80 @@ def test_maximum_capacity(cuda_device, core_kernel):
     assert np.array_equal(sim.get_dff().view(np.uint32), ref["final_dff"].view(np.uint32))
     with pytest.raises(Exception):
         BatchSim(m, sff, 1, N + 1, params)
-    m3 = rooms_map_c3()
-    with pytest.raises(Exception, match="shared memory"):
-        BatchSim(m3, np.zeros(m3.shape, np.float32), 1, N, params)
+
+
+def test_maps_beyond_one_sm_run_as_clusters(cuda_device):
+    """520 x 400 = 208 000 cells with 12 000 pedestrians, DFF on: neither kernel's per-episode state fits one SM's
+    227 KB, so ffm_create picks the cell-centric kernel as a thread-block cluster (owner grid + claim masks in
+    distributed shared memory, DFF and score left in L2 at this size).  Recorded-draw parity, 120 steps."""
+    from ffm_b200 import BatchSim
+    m = assets.obstacle_map_c5(520, 400, index=2, n_exits=8)
+    sff = c_oracle.geodesic(m, "dijkstra8")
+    rng = np.random.RandomState(4)
+    reach = np.argwhere((m == 0) & np.isfinite(sff))
+    N = 12000
+    pos0 = [reach[rng.choice(len(reach), N - 1000 * e, replace=False)] for e in range(2)]
+    pos, n = pack_positions(pos0, N)
+    params = {"neighborhood": "moore", "k_S": 1.5, "k_D": 1.0}
+    ref = _recorded(m, sff, pos, n, params, 11, 120)
+    sim = BatchSim(m, sff, 2, N, params, seed=11)
+    info = sim.kernel_info()
+    assert info["name"] == "ffm_cell_rollout_kernel" and info["cluster"] >= 2, info
+    sim.set_positions(pos, n)
+    _check_recorded(sim, ref, 120, 400)
+    assert np.array_equal(sim.get_dff().view(np.uint32), ref["final_dff"].view(np.uint32))
+
+
+@pytest.mark.parametrize("variant", ["cell", "cl2", "cl4"])
+def test_compact_trajectory_record(cuda_device, monkeypatch, variant):
+    """The compact record (int16 (row, col) pairs, CSR offsets per step, 4 bytes per pedestrian-step) holds exactly
+    what run() collects (ffm_core.py:125): compared with the dense record of the same run and with the oracle;
+    ragged batch incl. an empty episode; an undersized buffer reports the overflow instead of writing past it."""
+    import torch
+    from ffm_b200 import BatchSim
+    from ffm_b200.sim import unpack_trajectory
+    monkeypatch.setenv("FFM_KERNEL", "cell")
+    if variant.startswith("cl"):
+        monkeypatch.setenv("FFM_CLUSTER", variant[2:])
+    m = assets.room_map(40, 72)
+    sff = assets.sff_norm_min_fast(m, "Linf", np.float32)
+    rng = np.random.RandomState(7)
+    counts = [0, 1, 37, 300, 513]
+    pos0 = [random_positions(m, k, rng) if k else np.zeros((0, 2), np.int64) for k in counts]
+    pos, n = pack_positions(pos0, 513)
+    params = {"neighborhood": "moore"}
+    T = 500
+    ref = _recorded(m, sff, pos, n, params, 21, T)
+    sim = BatchSim(m, sff, len(counts), 513, params, seed=21)
+    sim.set_positions(pos, n)
+    cap = int(ref["ped_steps"].max()) + 4 * T
+    rec = sim.rollout(T, draws=dict(move=torch.from_numpy(ref["move_draws"]).cuda()), record=T, compact_cap=cap)
+    torch.cuda.synchronize()
+    steps, ped = sim.counters()
+    assert np.array_equal(ped, ref["ped_steps"])
+    ct, off, cnt = rec["ctraj"].cpu().numpy(), rec["off"].cpu().numpy(), rec["n"].cpu().numpy()
+    for e in range(len(counts)):
+        s = int(steps[e])
+        assert np.array_equal(cnt[e, :s], ref["traj_n"][e, :s])
+        assert off[e, 0] == 0 and np.array_equal(np.diff(off[e, :s + 1]), (cnt[e, :s] + 3) // 4 * 4)
+        rows = unpack_trajectory(ct[e], off[e], cnt[e], steps=s)
+        for t in range(s):
+            assert rows[t].dtype == np.int64 and rows[t].shape == (cnt[e, t], 2)
+            assert np.array_equal(rows[t][:, 0] * 72 + rows[t][:, 1], ref["traj"][e, t, :cnt[e, t]]), (e, t)
+        # padding entries are (-1, -1)
+        if s:
+            pad = ct[e, off[e, 0] + cnt[e, 0]:off[e, 1]]
+            assert (pad == -1).all()
+    # bytes: 4 per (padded) pedestrian-step
+    assert int(off[np.arange(len(counts)), steps].sum()) * 4 <= 4 * int(ped.sum()) + 16 * int(steps.sum())
+    # overflow: a buffer of half the size stops recording and says so
+    sim.set_positions(pos, n)
+    rec = sim.rollout(T, draws=dict(move=torch.from_numpy(ref["move_draws"]).cuda()), record=T, compact_cap=cap // 2)
+    torch.cuda.synchronize()
+    off2 = rec["off"].cpu().numpy()
+    assert (off2[4] == -1).any() and off2[4, 1] > 0 and np.array_equal(sim.counters()[1], ref["ped_steps"])
+    with pytest.raises(Exception):
+        unpack_trajectory(rec["ctraj"][4].cpu().numpy(), off2[4], rec["n"][4].cpu().numpy(), steps=int(steps[4]))
 
 
 @pytest.mark.parametrize("nbh", ["neumann", "moore"])
