@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """Benchmark of the FFM hot path: pedestrian-steps/s of batched evacuation episodes (BASELINE.json).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c2dff|c3|c4|c1] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c2dff|c3|c4|c1|c2traj|sff] [--impl ours|reference]
+                    [--no-secondary]
 
 A "step" is one pass of the hot path over one batch: B episodes placed, then rolled out by the
 persistent kernel until everybody has left (or the step cap).  Workload `c2` (the configuration the
@@ -12,9 +13,15 @@ episode id, sharded over ranks with no data-path collective (weak scaling).
 `value`     ped-steps/s with the initial positions already resident in HBM (CUDA events, max over ranks)
 `e2e`       same metric through the public API with HOST buffers: pinned-host positions -> H2D ->
             rollout -> D2H of the per-episode counters, all inside the timed region
-`roofline`  dominant kernel (ffm_core_rollout_kernel): algorithmic bytes / CUDA-event duration vs the
-            measured HBM copy peak (MEASURED_PEAKS.json)
+`roofline`  dominant kernel: algorithmic bytes / CUDA-event duration.  For the shared-memory-resident rollouts (C1, C2)
+            the bound is the SHARED-MEMORY bandwidth, measured live by a micro-benchmark (ffm_measure_smem_bandwidth);
+            the HBM view of the same bytes is kept under roofline.hbm.  C3 (fields in L2), the trajectory record and
+            the SFF sweep are reported against the measured HBM copy peak (MEASURED_PEAKS.json).
 `cpu_baseline` the oracle port timed on this box's host cores on a bounded sample (rank 0, N = 1)
+`secondary` (default C2 run only) the other configurations of BASELINE.json, each measured the same way with its own
+            clocks / e2e / roofline: c3 (256x256 plan, DFF), c4 (batched TD learning, the NCCL all-reduce of the table
+            deltas inside the timed region), c2traj (C2 with the compact trajectory record, D2H of the record in e2e),
+            sff (64-map 1024x1024 geodesic sweep)
 
 `--impl reference` times the CPU implementation (oracle port; the Python reference cannot travel to
 the GPU box) on all host threads on the same workload and prints the same line with impl=reference.
@@ -58,7 +65,15 @@ WORKLOADS = {
                     "4096 episodes/GPU per sync, all-reduce of the table deltas, cap 300"),
     "c1": dict(h=12, w=12, n=100, episodes=4096, cap=4096, nbh="neumann", k_S=3, k_D=1, track_dff=True,
                desc="C1 geometry batched: 12x12 room, neumann, N=100, DFF on"),
+    "c2traj": dict(h=64, w=64, n=1024, episodes=256, cap=4096, nbh="moore", k_S=3, k_D=0, track_dff=False, record=True,
+                   desc="C2 geometry, 256 episodes/GPU, with the compact trajectory record (int16 row/col pairs, 4 B per "
+                        "pedestrian-step; what run() collects, ffm_core.py:125 / main.py:44-52)"),
+    "sff": dict(h=1024, w=1024, maps=64, sff=True,
+                desc="C5: static-floor-field sweep, 64 maps/GPU of 1024x1024 with 20 % random rectangular obstacles and 8 exits: "
+                     "geodesic BFS-4, BFS-8, (1, sqrt2)-Dijkstra fields + the obstacle-blind L1 field of Create_SFF.py"),
 }
+SECONDARY = ("c3", "c4", "c2traj", "sff")
+C4_ROUNDS = 16          # rollout + exchange rounds per timed step of the c4 workload (>= 50 syncs over the default 5 steps)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -285,6 +300,329 @@ def run_reference_arm(args, wl):
 # ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
+class Ctx:
+    """Process-wide state of the GPU arm: torch / distributed handles, the L2-flush buffer, measured peaks."""
+
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist, self.args = torch, dist, args
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device: the FFM kernels have no CPU fallback")
+        torch.cuda.set_device(self.local)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=torch.device(f"cuda:{self.local}"))
+        self.flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")   # > 126 MB L2
+        self.peaks = {}
+        try:
+            self.peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except OSError:
+            pass
+        self.hbm_peak = float(self.peaks.get("hbm_gbs", 6650.0))
+        self.hbm_peak_source = "measured (MEASURED_PEAKS.json hbm_gbs)" if self.peaks else "fallback 6650 GB/s"
+        self._smem = None
+        try:
+            self.profile = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))
+        except OSError:
+            self.profile = {}
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def reduce(self, maxed, summed):
+        """max over ranks of the timings, sum over ranks of the unit counts"""
+        torch = self.torch
+        tm = torch.tensor(maxed, dtype=torch.float64, device="cuda")
+        ts = torch.tensor(summed, dtype=torch.float64, device="cuda")
+        if self.world > 1:
+            self.dist.all_reduce(tm, op=self.dist.ReduceOp.MAX)
+            self.dist.all_reduce(ts, op=self.dist.ReduceOp.SUM)
+        return tm.tolist(), ts.tolist()
+
+    def smem_peak(self):
+        """(GB/s, SM MHz) of the shared-memory read micro-benchmark (conflict-free 16-byte loads on every SM)."""
+        if self._smem is None:
+            import ctypes as C
+            from ffm_b200 import _abi
+            g, mhz = C.c_double(), C.c_double()
+            _abi.check(_abi.lib().ffm_measure_smem_bandwidth(self.local, C.byref(g), C.byref(mhz)))
+            self._smem = (g.value, mhz.value)
+        return self._smem
+
+
+def event_pairs(torch, k, n):
+    return [[torch.cuda.Event(enable_timing=True) for _ in range(n)] for _ in range(k)]
+
+
+def run_rollout_workload(ctx, name, wl):
+    """One rollout workload: W warm-up passes, K timed passes with the inputs resident in HBM (CUDA events), K timed
+    passes through host buffers (e2e), clocks sampled over both.  Returns the fields of a bench line."""
+    torch, args = ctx.torch, ctx.args
+    from ffm_b200 import BatchSim
+    world, rank, local = ctx.world, ctx.rank, ctx.local
+    B, N, cap = wl["episodes"], wl["n"], wl["cap"]
+    m, sff = build_fields(wl)
+    wl["_fields"] = (m, sff)
+    params = {"k_S": wl["k_S"], "k_D": wl["k_D"], "diffuse": 0.2, "decay": 0.2, "neighborhood": wl["nbh"]}
+    ep_base = rank * B                                   # global episode ids: results independent of N
+    n_np = np.full((B,), N, dtype=np.int32)
+    unified = wl.get("model") == "unified"
+    record = bool(wl.get("record"))
+    rounds = C4_ROUNDS if unified else 1
+    learner = None
+    if unified:
+        from ffm_b200 import UnifiedSim
+        from ffm_b200.sharding import BatchedLearner
+        sim = UnifiedSim(m, sff, B, N, mode="critic_only", learn="batched", params=C4_PARAMS, seed=args.seed,
+                         episode_base=ep_base, device=local)
+        exit_rc = tuple(int(v) for v in np.argwhere(m == 3)[0])
+        sim.place(n_np, exit_pos=exit_rc, radius=wl["radius"])          # initialize_agents(exit_pos, radius), keyed per episode
+        pos_np, n_np = sim.get_positions()
+        learner = BatchedLearner(sim, overlap=world > 1)                # one all-reduce of the flat delta buffer per sync
+    else:
+        pos_np = place(m, N, B, ep_base, args.seed)
+        sim = BatchSim(m, sff, B, N, params, seed=args.seed, episode_base=ep_base, track_dff=wl["track_dff"], device=local)
+    info = sim.kernel_info()
+    pos_dev = torch.from_numpy(pos_np).cuda()
+    n_dev = torch.from_numpy(n_np).cuda()
+    pos_pin = torch.from_numpy(pos_np).pin_memory()
+    n_pin = torch.from_numpy(n_np).pin_memory()
+    steps_dev = torch.zeros(B, dtype=torch.int32, device="cuda")
+    ped_dev = torch.zeros(B, dtype=torch.int64, device="cuda")
+    rec_cap, rec_host, rec = 0, None, {}
+    if record:
+        rec_cap = 1 << 20                                              # entries per episode (C2: ~8.9e5 pedestrian-steps + padding)
+        rec_host = torch.empty((B, rec_cap, 2), dtype=torch.int16).pin_memory()
+
+    def roll():
+        if record:
+            rec["r"] = sim.rollout(cap, record=cap, compact_cap=rec_cap)
+        else:
+            sim.rollout(cap)
+
+    def one_pass_resident(ev=None):
+        if ev: ev[0].record()
+        kern = 0.0
+        for r in range(rounds):
+            sim.set_positions(pos_dev, n_dev)
+            if ev and r == 0: ev[1].record()
+            roll()
+            if ev and r == 0: ev[2].record()
+            if learner: learner.sync()
+        if learner: learner.flush()
+        sim.counters_into(steps_dev, ped_dev)
+        if ev: ev[3].record()
+
+    def one_pass_e2e():
+        ped = 0
+        for r in range(rounds):
+            sim.set_positions(pos_pin.numpy(), n_pin.numpy())       # H2D of this round's inputs
+            roll()
+            if learner: learner.sync()
+            if r == rounds - 1 and learner: learner.flush()
+            if record:                                              # D2H of the trajectory record (+ its CSR offsets / counts)
+                rec_host.copy_(rec["r"]["ctraj"], non_blocking=True)
+                rec["off_h"] = rec["r"]["off"].cpu(); rec["n_h"] = rec["r"]["n"].cpu()
+            st_h, ped_h = sim.counters()                             # D2H of the round's result (+ sync)
+            ped += int(ped_h.sum())
+        return ped
+
+    for _ in range(args.warmup):
+        ctx.flush.fill_(1)
+        one_pass_resident()
+    ctx.barrier()
+    ped_per_round = int(ped_dev.sum().item())
+    ped_per_pass = ped_per_round * rounds
+    steps_host = steps_dev.cpu().numpy()
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    evs = event_pairs(torch, args.steps, 4)
+    l0 = sim.launch_count
+    ctx.barrier()
+    for k in range(args.steps):
+        ctx.flush.fill_(k & 0xFF)                 # L2 flush between timed iterations (not timed)
+        one_pass_resident(evs[k])
+    ctx.barrier()
+    launches = sim.launch_count - l0
+    total_ms = sum(e[0].elapsed_time(e[3]) for e in evs)
+    kern_ms = sum(e[1].elapsed_time(e[2]) for e in evs) / args.steps
+
+    sync_ms = None
+    if learner:                                   # the exchange alone: all-reduce + fold-in on the critical path (blocking form)
+        from ffm_b200.sharding import BatchedLearner
+        plain = BatchedLearner(sim, overlap=False)
+        sim.set_positions(pos_dev, n_dev); sim.rollout(cap); plain.sync()
+        ctx.barrier()
+        se = event_pairs(torch, 20, 2)
+        for k in range(20):
+            se[k][0].record(); plain.sync(); se[k][1].record()
+        ctx.barrier()
+        sync_ms = float(np.median([e[0].elapsed_time(e[1]) for e in se]))
+        sim.bind_deltas(learner.bufs[learner._cur])
+
+    # ---- e2e: host buffers in, host counters (and the trajectory record) out ------------------------
+    e2e_evs = event_pairs(torch, args.steps, 2)
+    for _ in range(2):
+        one_pass_e2e()
+    ctx.barrier()
+    e2e_ped = 0
+    for k in range(args.steps):
+        ctx.flush.fill_(k & 0xFF)
+        e2e_evs[k][0].record()
+        e2e_ped += one_pass_e2e()
+        e2e_evs[k][1].record()
+    ctx.barrier()
+    clocks = sampler.stop()
+    e2e_ms = sum(e[0].elapsed_time(e[1]) for e in e2e_evs)
+
+    (total_ms, e2e_ms, kern_ms), (ped_all, e2e_ped_all) = ctx.reduce([total_ms, e2e_ms, kern_ms], [float(ped_per_pass), float(e2e_ped)])
+    out = None
+    if rank == 0:
+        value = ped_all * args.steps / (total_ms * 1e-3)
+        e2e_value = e2e_ped_all / (e2e_ms * 1e-3)
+        alg_bytes = (BYTES_PER_PED_STEP_UNIFIED if unified else BYTES_PER_PED_STEP[wl["track_dff"]]) * ped_per_round
+        if wl["track_dff"]:
+            alg_bytes += 8 * wl["h"] * wl["w"] * int(steps_host.sum())      # DFF field read+write per episode-step
+        if record:
+            alg_bytes += 4 * ped_per_round                                  # the record itself: 4 B per pedestrian-step to HBM
+        achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
+        prof = ctx.profile.get(name, {})
+        on_chip = bool(info["fields_in_smem"]) or not wl["track_dff"]      # SFF-only runs keep the bitboards / owner grid on chip either way
+        hbm = {"achieved": achieved, "peak": ctx.hbm_peak, "unit": "GB/s", "frac": achieved / ctx.hbm_peak, "peak_source": ctx.hbm_peak_source}
+        if on_chip and not record:
+            smem_gbs, mhz = ctx.smem_peak()
+            roof = {"bound": "smem", "achieved": achieved, "peak": smem_gbs, "unit": "GB/s", "frac": achieved / smem_gbs,
+                    "peak_source": f"measured live: ffm_measure_smem_bandwidth (conflict-free 16-byte shared loads on all SMs, {mhz:.0f} MHz)",
+                    "hbm": hbm,
+                    "note": "the episode state is shared-memory resident: DRAM traffic is the prologue/epilogue only (see traffic); the "
+                            "kernel is issue-bound, see issue_active_pct / smem wavefronts from the committed ncu capture"}
+        else:
+            roof = {"bound": "hbm", **hbm,
+                    "note": ("record stores stream to HBM; " if record else "") +
+                            ("score/DFF fields live in L2/HBM at this map size" if not info["fields_in_smem"] else "")}
+        roof.update({"traffic": prof.get("dram_bytes_per_launch") if B == prof.get("episodes") else None,
+                     "kernel_ms": kern_ms, "algorithmic_bytes_per_launch": alg_bytes,
+                     "ncu": {k: prof.get(k) for k in ("smem_wavefronts_pct_of_peak", "smem_bank_conflict_share", "issue_active_pct",
+                                                       "lanes_active_per_instruction", "warps_active_pct", "source") if k in prof}})
+        par = f"episodes sharded over {world} GPU(s)" + (
+            f"; one NCCL all-reduce of the flat table-delta buffer ({(3 + sim.A) * sim.S * 8} B) per sync, "
+            f"{'overlapped with the next rollout (staleness 1)' if learner.overlap else 'blocking'}" if learner else ", no collective")
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": wl["desc"], "episodes_per_gpu": B, "peds_per_episode": N, "map": f"{wl['h']}x{wl['w']}",
+                       "step_cap": cap, "parallelism": par,
+                       "l2": "256 MiB L2 flush between timed iterations (untimed)",
+                       "kernel": info,
+                       "mean_evacuation_steps": float(steps_host.mean()), "ped_steps_per_pass_per_gpu": ped_per_pass},
+            "episodes_per_sec": B * rounds * world * args.steps / (total_ms * 1e-3),
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT,
+                    "h2d_bytes_per_step": int(pos_np.nbytes + n_np.nbytes) * rounds,
+                    "d2h_bytes_per_step": (int(B * 4 + B * 8) + (int(rec_host.numel() * 2 + B * (2 * cap + 1) * 4) if record else 0)) * rounds,
+                    "ms_per_step": e2e_ms / args.steps},
+            "gpu_launches": int(launches),
+            "roofline": roof,
+        }
+        if learner:
+            out["config"]["rounds_per_step"] = rounds
+            out["config"]["syncs_timed"] = rounds * args.steps
+            out["sync_ms_blocking"] = sync_ms
+        if record:
+            off_h = rec["off_h"].numpy(); st = np.minimum(steps_host, cap)
+            used = int(off_h[np.arange(B), st].sum())
+            out["record"] = {"bytes_written_per_pass_per_gpu": used * 4, "ped_steps_per_pass_per_gpu": ped_per_pass,
+                             "bytes_per_ped_step": used * 4 / ped_per_pass, "overflowed": bool((off_h[np.arange(B), st] < 0).any())}
+    sim.close()
+    del sim
+    torch.cuda.empty_cache()
+    return out
+
+
+def run_sff_workload(ctx, name, wl):
+    """C5: SFF sweep.  A step = all fields of all maps of this rank.  value = cells/s over the geodesic modes."""
+    torch, args = ctx.torch, ctx.args
+    from ffm_b200.sff import generate_sff
+    from ffm_b200.workloads import obstacle_map_c5
+    world, rank = ctx.world, ctx.rank
+    M, H, W = wl["maps"], wl["h"], wl["w"]
+    maps = np.stack([obstacle_map_c5(H, W, index=rank * M + i) for i in range(M)])
+    dm = torch.from_numpy(maps).cuda()
+    pin = torch.from_numpy(maps).pin_memory()
+    modes = ("bfs4", "bfs8", "dijkstra8", "L1")
+    host_out = torch.empty((M, H, W), dtype=torch.float32).pin_memory()
+
+    def sweep(ev=None):
+        for i, mode in enumerate(modes):
+            if ev: ev[i].record()
+            out = generate_sff(dm, mode, np.float32)
+        if ev: ev[len(modes)].record()
+        return out
+
+    for _ in range(args.warmup):
+        sweep()
+    ctx.barrier()
+    sampler = ClockSampler(ctx.local)
+    sampler.start()
+    evs = event_pairs(torch, args.steps, len(modes) + 1)
+    ctx.barrier()
+    for k in range(args.steps):
+        ctx.flush.fill_(k & 0xFF)
+        sweep(evs[k])
+    ctx.barrier()
+    total_ms = sum(e[0].elapsed_time(e[-1]) for e in evs)
+    mode_ms = [sum(e[i].elapsed_time(e[i + 1]) for e in evs) / args.steps for i in range(len(modes))]
+    # e2e: maps from pinned host memory, fields back to pinned host memory
+    e2 = event_pairs(torch, args.steps, 2)
+    ctx.barrier()
+    for k in range(args.steps):
+        e2[k][0].record()
+        dmk = pin.cuda(non_blocking=True)
+        for mode in modes:
+            host_out.copy_(generate_sff(dmk, mode, np.float32), non_blocking=True)
+        torch.cuda.synchronize()
+        e2[k][1].record()
+    ctx.barrier()
+    clocks = sampler.stop()
+    e2e_ms = sum(e[0].elapsed_time(e[1]) for e in e2)
+    cells = float(M * H * W * len(modes))
+    (total_ms, e2e_ms, *mode_ms), (cells_all,) = ctx.reduce([total_ms, e2e_ms] + mode_ms, [cells])
+    if rank != 0:
+        return None
+    geo_ms = sum(mode_ms[:3])
+    alg = 5.0 * M * H * W            # SURVEY 8(d): >= 5 B per cell (1 B map read + 4 B field write) per field
+    return {
+        "metric": "sff_cells_per_sec", "value": cells_all * args.steps / (total_ms * 1e-3), "unit": "cells/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": wl["desc"], "maps_per_gpu": M, "map": f"{H}x{W}", "fields_per_step": list(modes),
+                   "parallelism": f"maps sharded over {world} GPU(s), no collective", "l2": "256 MiB L2 flush between timed iterations (untimed)"},
+        "maps_per_sec": M * len(modes) * world * args.steps / (total_ms * 1e-3),
+        "per_mode_ms": dict(zip(modes, mode_ms)),
+        "geodesic_cells_per_sec": 3.0 * M * H * W * world / (geo_ms * 1e-3),
+        "clocks": clocks,
+        "e2e": {"value": cells_all * args.steps / (e2e_ms * 1e-3), "unit": "cells/s", "h2d_bytes_per_step": int(maps.nbytes),
+                "d2h_bytes_per_step": int(host_out.numel() * 4 * len(modes)), "ms_per_step": e2e_ms / args.steps},
+        "gpu_launches": args.steps * (3 * 3 + 2),
+        "roofline": {"bound": "hbm", "achieved": alg * 3 / (geo_ms * 1e-3) / 1e9, "peak": ctx.hbm_peak, "unit": "GB/s",
+                     "frac": alg * 3 / (geo_ms * 1e-3) / 1e9 / ctx.hbm_peak, "traffic": None, "peak_source": ctx.hbm_peak_source,
+                     "kernel_ms": geo_ms / 3, "algorithmic_bytes_per_launch": alg,
+                     "note": "geodesic modes (sff_relax_queue_kernel): wavefront propagation is latency-bound, not bandwidth-bound; "
+                             "cells/s and maps/s are the meaningful figures (SURVEY 8(d))"},
+    }
+
+
+def run_workload(ctx, name, wl):
+    return run_sff_workload(ctx, name, wl) if wl.get("sff") else run_rollout_workload(ctx, name, wl)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -296,12 +634,15 @@ def main():
     ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU work for the cpu_baseline sample")
     ap.add_argument("--numpy-port", action="store_true", help="reference arm: force the NumPy port")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the secondary workloads of the default C2 run")
     ap.add_argument("--seed", type=lambda s: int(s, 0), default=0x5EED0002)
     args = ap.parse_args()
     wl = dict(WORKLOADS[args.workload])
     if args.episodes:
         wl["episodes"] = args.episodes
     if args.impl == "reference":
+        if wl.get("sff") or wl.get("record"):
+            raise SystemExit("the reference arm covers the rollout workloads")
         run_reference_arm(args, wl)
         return
 
@@ -311,156 +652,21 @@ def main():
     json_fd = os.dup(1)
     os.dup2(2, 1)
 
-    import torch
-    import torch.distributed as dist
-    from ffm_b200 import BatchSim
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: the FFM kernels have no CPU fallback")
-    torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    ctx = Ctx(args)
     if args.warmup < 3:
         args.warmup = 3
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    B, N, cap = wl["episodes"], wl["n"], wl["cap"]
-    m, sff = build_fields(wl)
-    wl["_fields"] = (m, sff)
-    params = {"k_S": wl["k_S"], "k_D": wl["k_D"], "diffuse": 0.2, "decay": 0.2, "neighborhood": wl["nbh"]}
-    ep_base = rank * B                                   # global episode ids: results independent of N
-    n_np = np.full((B,), N, dtype=np.int32)
-    post_rollout = None
-    if wl.get("model") == "unified":
-        from ffm_b200 import UnifiedSim
-        from ffm_b200.sharding import BatchedLearner
-        sim = UnifiedSim(m, sff, B, N, mode="critic_only", learn="batched", params=C4_PARAMS, seed=args.seed,
-                         episode_base=ep_base, device=local)
-        exit_rc = tuple(int(v) for v in np.argwhere(m == 3)[0])
-        sim.place(n_np, exit_pos=exit_rc, radius=wl["radius"])          # initialize_agents(exit_pos, radius), keyed per episode
-        pos_np, n_np = sim.get_positions()
-        post_rollout = BatchedLearner(sim).sync                        # all-reduce of dV / dN / dH + flags, then fold in
-    else:
-        pos_np = place(m, N, B, ep_base, args.seed)
-        sim = BatchSim(m, sff, B, N, params, seed=args.seed, episode_base=ep_base, track_dff=wl["track_dff"], device=local)
-    info = sim.kernel_info()
-    pos_dev = torch.from_numpy(pos_np).cuda()
-    n_dev = torch.from_numpy(n_np).cuda()
-    pos_pin = torch.from_numpy(pos_np).pin_memory()
-    n_pin = torch.from_numpy(n_np).pin_memory()
-    steps_dev = torch.zeros(B, dtype=torch.int32, device="cuda")
-    ped_dev = torch.zeros(B, dtype=torch.int64, device="cuda")
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")   # > 126 MB L2
-
-    def one_pass_resident(ev=None):
-        if ev: ev[0].record()
-        sim.set_positions(pos_dev, n_dev)
-        if ev: ev[1].record()
-        sim.rollout(cap)
-        if ev: ev[2].record()
-        if post_rollout: post_rollout()
-        sim.counters_into(steps_dev, ped_dev)
-        if ev: ev[3].record()
-
-    for _ in range(args.warmup):
-        flush.fill_(1)
-        one_pass_resident()
-    barrier()
-    ped_per_pass = int(ped_dev.sum().item())
-    steps_host = steps_dev.cpu().numpy()
-
-    sampler = ClockSampler(local)
-    sampler.start()
-    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
-    l0 = sim.launch_count
-    barrier()
-    for k in range(args.steps):
-        flush.fill_(k & 0xFF)                 # L2 flush between timed iterations (not timed)
-        one_pass_resident(evs[k])
-    barrier()
-    launches = sim.launch_count - l0
-    total_ms = sum(e[0].elapsed_time(e[3]) for e in evs)
-    kern_ms = sum(e[1].elapsed_time(e[2]) for e in evs) / args.steps
-
-    # ---- e2e: host buffers in, host counters out ------------------------------------------------
-    e2e_evs = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(args.steps)]
-    for _ in range(2):
-        sim.set_positions(pos_pin.numpy(), n_pin.numpy()); sim.rollout(cap)
-        if post_rollout: post_rollout()
-        sim.counters()
-    barrier()
-    e2e_ped = 0
-    for k in range(args.steps):
-        flush.fill_(k & 0xFF)
-        e2e_evs[k][0].record()
-        sim.set_positions(pos_pin.numpy(), n_pin.numpy())       # H2D of this step's inputs
-        sim.rollout(cap)
-        if post_rollout: post_rollout()
-        st_h, ped_h = sim.counters()                             # D2H of the step's result (+ sync)
-        e2e_evs[k][1].record()
-        e2e_ped += int(ped_h.sum())
-    barrier()
-    clocks = sampler.stop()
-    e2e_ms = sum(e[0].elapsed_time(e[1]) for e in e2e_evs)
-
-    t = torch.tensor([total_ms, e2e_ms, kern_ms, float(ped_per_pass), float(e2e_ped)], dtype=torch.float64, device="cuda")
-    if world > 1:
-        tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
-        total_ms, e2e_ms, kern_ms = tmax[0].item(), tmax[1].item(), tmax[2].item()
-        ped_all, e2e_ped_all = tsum[3].item(), tsum[4].item()
-    else:
-        ped_all, e2e_ped_all = float(ped_per_pass), float(e2e_ped)
-
-    if rank == 0:
-        value = ped_all * args.steps / (total_ms * 1e-3)
-        e2e_value = e2e_ped_all / (e2e_ms * 1e-3)
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except OSError:
-            pass
-        peak = float(peaks.get("hbm_gbs", 6650.0))
-        alg_bytes = (BYTES_PER_PED_STEP_UNIFIED if wl.get("model") == "unified" else BYTES_PER_PED_STEP[wl["track_dff"]]) * ped_per_pass
-        if wl["track_dff"]:
-            alg_bytes += 8 * wl["h"] * wl["w"] * int(steps_host.sum())      # DFF field read+write per episode-step
-        achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
-        prof = {}
-        try:
-            prof = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json"))).get(args.workload, {})
-        except OSError:
-            pass
-        line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
-            "config": {"workload": wl["desc"], "episodes_per_gpu": B, "peds_per_episode": N, "map": f"{wl['h']}x{wl['w']}",
-                       "step_cap": cap, "parallelism": f"episodes sharded over {world} GPU(s), no collective",
-                       "l2": "256 MiB L2 flush between timed iterations (untimed)",
-                       "kernel": {"name": "ffm_unified_rollout_kernel" if wl.get("model") == "unified" else "ffm_core_rollout_kernel", **info},
-                       "mean_evacuation_steps": float(steps_host.mean()), "ped_steps_per_pass_per_gpu": ped_per_pass},
-            "episodes_per_sec": B * world * args.steps / (total_ms * 1e-3),
-            "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(pos_np.nbytes + n_np.nbytes),
-                    "d2h_bytes_per_step": int(B * 4 + B * 8), "ms_per_step": e2e_ms / args.steps},
-            "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": prof.get("dram_bytes_per_launch") if B == prof.get("episodes") else None,
-                         "smem": {"wavefronts_pct_of_peak": prof.get("smem_wavefronts_pct_of_peak"),
-                                  "issue_active_pct": prof.get("issue_active_pct"), "source": prof.get("source")},
-                         "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6650 GB/s",
-                         "kernel_ms": kern_ms, "algorithmic_bytes_per_launch": alg_bytes,
-                         "note": "fields are shared-memory resident: the kernel moves its algorithmic bytes through SMEM, "
-                                 "not HBM; see DESIGN.md (roofline) for the SMEM-bandwidth and issue-slot views"},
-        }
-        if not args.no_cpu and world == 1:
+    line = run_workload(ctx, args.workload, wl)
+    secondary = {}
+    if args.workload == "c2" and not args.no_secondary and not args.episodes:
+        for name in SECONDARY:
+            try:
+                secondary[name] = run_workload(ctx, name, dict(WORKLOADS[name]))
+            except Exception as ex:      # a secondary workload never takes the headline down with it
+                secondary[name] = {"error": repr(ex)}
+    if ctx.rank == 0:
+        if secondary:
+            line["secondary"] = secondary
+        if not args.no_cpu and ctx.world == 1 and not wl.get("sff"):
             try:
                 if wl.get("model") == "unified":
                     line["cpu_baseline"] = cpu_numpy_port_unified(wl, budget_s=min(args.cpu_budget, 10.0))
@@ -473,8 +679,8 @@ def main():
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": f"failed: {ex!r}"}
         sys.stdout.flush()
         os.write(json_fd, (json.dumps(line) + "\n").encode())
-    if world > 1:
-        dist.destroy_process_group()
+    if ctx.world > 1:
+        ctx.dist.destroy_process_group()
 
 
 if __name__ == "__main__":

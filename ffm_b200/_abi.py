@@ -59,6 +59,7 @@ SIGNATURES = {
     "ffm_get_positions": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "ffm_set_dff": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "ffm_get_dff": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "ffm_update_dff": (C.c_int, [C.c_void_p, C.c_void_p]),
     "ffm_rollout": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(Draws), C.POINTER(RolloutOut), C.c_void_p]),
     "ffm_move_probs": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "ffm_get_counters": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),

@@ -289,6 +289,14 @@ __global__ void unpack_positions_kernel(const uint32_t* pos, const int32_t* n, i
     }
 }
 
+// stand-alone update_dff() (ffm_core.py:106-117 / ffm_unified.py:779-798 / ffm_trained_core.py:333-353) of every episode
+// of a handle: the same stencil the rollout kernels run per step, one CTA per episode, fields in global memory
+template <int NBR>
+__global__ void __launch_bounds__(256) dff_update_kernel(const float* in, float* out, int H, int W, float c0, float c1, float thr) {
+    const size_t off = (size_t)blockIdx.x * H * W;
+    dff_decay_diffuse<NBR>(in + off, out + off, H, W, c0, c1, thr, threadIdx.x, 256);
+}
+
 }  // namespace ffm
 
 namespace {
@@ -738,6 +746,26 @@ int ffm_get_dff(ffm_sim_t s, float* dff, int space, void* stream) {
     return copy_out(dff, s->d_dff, (size_t)s->cfg.n_episodes * s->HW * 4, space, (cudaStream_t)stream);
 }
 
+int ffm_update_dff(ffm_sim_t s, void* stream) {
+    if (!s) return fail(FFM_E_INVALID, "null argument");
+    if (!s->d_dff) return fail(FFM_E_STATE, "handle was created with track_dff = 0");
+    if (s->cfg.model == FFM_MODEL_MCQ) return fail(FFM_E_UNSUPPORTED, "the MC-Q model has no public update_dff()");
+    cudaStream_t st = (cudaStream_t)stream;
+    CU(cudaSetDevice(s->cfg.device));
+    const size_t bytes = (size_t)s->cfg.n_episodes * s->HW * 4;
+    float* tmp = s->d_dff_tmp;
+    if (!tmp) CU(cudaMallocAsync((void**)&tmp, bytes, st));
+    if (s->cfg.neighborhood == FFM_MOORE)
+        ffm::dff_update_kernel<8><<<s->cfg.n_episodes, 256, 0, st>>>(s->d_dff, tmp, s->cfg.height, s->cfg.width, s->cfg.dff_c0, s->cfg.dff_c1, s->cfg.dff_threshold);
+    else
+        ffm::dff_update_kernel<4><<<s->cfg.n_episodes, 256, 0, st>>>(s->d_dff, tmp, s->cfg.height, s->cfg.width, s->cfg.dff_c0, s->cfg.dff_c1, s->cfg.dff_threshold);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(s->d_dff, tmp, bytes, cudaMemcpyDeviceToDevice, st));
+    if (!s->d_dff_tmp) CU(cudaFreeAsync(tmp, st));
+    s->launches++;
+    return FFM_OK;
+}
+
 int ffm_rollout(ffm_sim_t s, int32_t max_steps, const ffm_draws_t* draws, const ffm_rollout_out_t* out, void* stream) {
     if (!s) return fail(FFM_E_INVALID, "null argument");
     if (!s->have_fields || !s->have_positions) return fail(FFM_E_STATE, "fields and positions must be set before ffm_rollout");
@@ -1134,6 +1162,7 @@ int ffm_sff_generate(const uint8_t* maps, int32_t n_maps, int32_t H, int32_t W, 
             int per_sm = 0, sms = 0;
             SFF_CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ffm::sff_relax_queue_kernel, 256, 0));
             SFF_CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+            if (const char* ev = getenv("FFM_SFF_CTAS_PER_SM")) { const int v = atoi(ev); if (v >= 1 && v < per_sm) per_sm = v; }   // tuning
             const size_t resident = (size_t)per_sm * sms;      // persistent CTAs: spinning consumers must all be resident
             const int grid = (int)(ntiles < resident ? ntiles : resident);
             ffm::sff_relax_queue_kernel<<<grid, 256, 0, st>>>(mp, d_dist, q, H, W, tiles_x, tiles_y, w_axis, w_diag);

@@ -228,6 +228,80 @@ static __device__ __noinline__ void refresh_alive_prefix(const uint32_t* alive, 
     }
 }
 
+
+// One step's row of the compact trajectory record (what run() collects per step, ffm_core.py:125): (row, col) int16 pairs
+// in alive-rank order, appended to the episode's stream at CSR offset ctr[14]; rows are padded with (-1, -1) to a multiple
+// of 4 entries.  single_cta: rank-order scatter into the (idle) work lists in shared memory, then 16-byte coalesced
+// streaming stores; a cluster's CTAs scatter their own cells straight to global memory.  Kept out of line so that the
+// recording code costs the hot loop no registers (the SFF-only variants run at a 40-register cap).
+struct RecArgs {             // what record_step_compact needs of CellParams, passed by value (taking the address of the
+    uint32_t* ctraj;         // kernel parameter block would copy all of it to the stack)
+    int32_t* ctraj_off;
+    int32_t* traj_n;
+    const uint32_t* wall_bits;
+    long long ctraj_cap;
+    uint32_t l_grid, l_blk, l_wall, l_alive, l_wpre, l_ctr, l_listA;
+    uint32_t magic_cpr;
+    int H, W, RW, RB, traj_steps, wall_in_smem, write_n;
+};
+
+static __device__ __noinline__ void record_step_compact(const RecArgs P, unsigned char* smem_raw, int e, int tl, int n, int band,
+                                                        bool single_cta) {
+    struct { uint32_t grid, blk, wall, alive, wpre, ctr, listA; } L = {P.l_grid, P.l_blk, P.l_wall, P.l_alive, P.l_wpre, P.l_ctr, P.l_listA};
+    const int tid = threadIdx.x, nthreads = blockDim.x;
+    const int W = P.W, RW = P.RW, G = W + 1;
+    const int r0 = band * P.RB, r1 = min(P.H, r0 + P.RB), RBl = max(0, r1 - r0), lo = r0 * W;
+    const uint16_t* grid_l = reinterpret_cast<const uint16_t*>(smem_raw + L.grid) + G;
+    const uint32_t* blk_l = reinterpret_cast<const uint32_t*>(smem_raw + L.blk);
+    const uint32_t* wall_l = reinterpret_cast<const uint32_t*>(smem_raw + L.wall);
+    const uint32_t* alive = reinterpret_cast<const uint32_t*>(smem_raw + L.alive);
+    const uint32_t* wpre = reinterpret_cast<const uint32_t*>(smem_raw + L.wpre);
+    uint32_t* ctr = reinterpret_cast<uint32_t*>(smem_raw + L.ctr);
+    const int cpr = RW - 2, nchunks = RBl * cpr;
+    const uint32_t npad = ((uint32_t)n + 3u) & ~3u;
+    int coff = (int)ctr[14];
+    const bool fits = coff >= 0 && (long long)coff + npad <= P.ctraj_cap;
+    if (fits) {
+        uint32_t* dst = P.ctraj + (size_t)e * P.ctraj_cap + coff;
+        uint32_t* stage = reinterpret_cast<uint32_t*>(smem_raw + L.listA);          // the work lists are idle until the next phase 1
+        const bool staged = single_cta && npad * 4u <= L.alive - L.listA;
+        uint32_t* out = staged ? stage : dst;
+#pragma unroll 1
+        for (int ch = tid; ch < nchunks; ch += nthreads) {
+            const int lr = cpr == 1 ? ch : (int)__umulhi((uint32_t)ch, P.magic_cpr), j = ch - lr * cpr;
+            const int idx = (lr + 1) * RW + 1 + j;
+            const uint32_t wv = P.wall_in_smem ? wall_l[idx] : __ldg(P.wall_bits + (size_t)r0 * RW + idx);
+            uint32_t occ = blk_l[idx] & ~wv;
+            const int cbase = (r0 + lr) * W + 32 * j;
+            while (occ) {
+                const int b = __ffs(occ) - 1;
+                occ &= occ - 1u;
+                const uint32_t id = (grid_l[cbase + b - lo] & OCC_MASK) - 1u;
+                const uint32_t rank = wpre[id >> 5] + (uint32_t)__popc(alive[id >> 5] & ((1u << (id & 31u)) - 1u));
+                out[rank] = (uint32_t)(r0 + lr) | ((uint32_t)(32 * j + b) << 16);
+            }
+        }
+        if ((staged || band == 0) && (uint32_t)tid < npad - (uint32_t)n) out[n + tid] = 0xFFFFFFFFu;
+        if (staged) {
+            __syncthreads();
+            uint4* d4 = reinterpret_cast<uint4*>(dst);
+            const uint4* s4 = reinterpret_cast<const uint4*>(stage);
+            for (uint32_t x = tid; x < npad / 4u; x += nthreads) __stcs(d4 + x, s4[x]);
+        }
+        coff += (int)npad;
+    } else {
+        coff = -1;
+    }
+    __syncthreads();                                      // the staging area and ctr[14] have been read by everybody
+    if (tid == 0) {
+        ctr[14] = (uint32_t)coff;
+        if (band == 0) {
+            P.ctraj_off[(size_t)e * (P.traj_steps + 1) + tl + 1] = coff;
+            if (P.write_n) P.traj_n[(size_t)e * P.traj_steps + tl] = n;
+        }
+    }
+}
+
 #ifndef FFM_CELL_MINB256
 #define FFM_CELL_MINB256 6      // resident CTAs per SM the 256-thread float32 variant is compiled for (register cap)
 #endif
@@ -431,7 +505,7 @@ ffm_cell_rollout_kernel(const CellParams P) {
         return ((fu >> 1) & 1u) | (((fd >> 1) & 1u) << 1) | ((fm & 1u) << 2) | ((fm & 4u) << 1);
     };
     // positions in alive-rank order -> dst[rank] (epilogue / dense trajectory rows)
-    auto emit_positions = [&](uint32_t* dst, bool as_row_col = false) {
+    auto emit_positions = [&](uint32_t* dst) {
 #pragma unroll 1
         for (int ch = tid; ch < nchunks; ch += THREADS) {
             const int lr = cpr == 1 ? ch : (int)__umulhi((uint32_t)ch, P.magic_cpr), j = ch - lr * cpr;
@@ -443,7 +517,7 @@ ffm_cell_rollout_kernel(const CellParams P) {
                 occ &= occ - 1u;
                 const int c = cbase + b;
                 const uint32_t id = (grid_l[c - lo] & OCC_MASK) - 1u;
-                dst[rank_of(id)] = as_row_col ? ((uint32_t)(r0 + lr) | ((uint32_t)(32 * j + b) << 16)) : (uint32_t)c;
+                dst[rank_of(id)] = (uint32_t)c;
             }
         }
     };
@@ -483,7 +557,8 @@ ffm_cell_rollout_kernel(const CellParams P) {
 #define FFM_TICK(i)
 #endif
     unsigned long long ped_steps = 0;
-    int coff = 0;                  // compact trajectory record: entries of this episode's stream written so far (-1: overflowed)
+    // compact trajectory record: entries of this episode's stream written so far (-1: overflowed) live in ctr[14], not in a
+    // register of the hot loop
     if (P.ctraj != nullptr && tid == 0 && band == 0) P.ctraj_off[(size_t)e * (P.traj_steps + 1)] = 0;
     bool need_prefix = false;      // somebody left since the prefix was last computed
     bool dff_pending = false;      // the DFF update of the previous step has not run yet
@@ -837,32 +912,12 @@ ffm_cell_rollout_kernel(const CellParams P) {
                 __syncthreads();
                 need_prefix = false;
             }
-            const uint32_t npad = ((uint32_t)n + 3u) & ~3u;
-            const bool fits = coff >= 0 && (long long)coff + npad <= P.ctraj_cap;
-            if (fits) {
-                uint32_t* dst = P.ctraj + (size_t)e * P.ctraj_cap + coff;
-                uint32_t* stage = reinterpret_cast<uint32_t*>(smem_raw + L.listA);   // the work lists are idle until the next phase 1
-                if (CL == 1 && npad * 4u <= L.alive - L.listA) {
-                    // rank-order scatter into shared memory, then 16-byte coalesced stores
-                    emit_positions(stage, true);
-                    if ((uint32_t)tid < npad - (uint32_t)n) stage[n + tid] = 0xFFFFFFFFu;
-                    __syncthreads();
-                    uint4* d4 = reinterpret_cast<uint4*>(dst);
-                    const uint4* s4 = reinterpret_cast<const uint4*>(stage);
-                    for (uint32_t x = tid; x < npad / 4u; x += THREADS) __stcs(d4 + x, s4[x]);
-                    __syncthreads();
-                } else {
-                    emit_positions(dst, true);
-                    if (band == 0 && (uint32_t)tid < npad - (uint32_t)n) dst[n + tid] = 0xFFFFFFFFu;
-                }
-                coff += (int)npad;
-            } else {
-                coff = -1;
-            }
-            if (tid == 0 && band == 0) {
-                P.ctraj_off[(size_t)e * (P.traj_steps + 1) + tl + 1] = coff;
-                if (P.traj == nullptr) P.traj_n[(size_t)e * P.traj_steps + tl] = n;
-            }
+            RecArgs R;
+            R.ctraj = P.ctraj; R.ctraj_off = P.ctraj_off; R.traj_n = P.traj_n; R.wall_bits = P.wall_bits; R.ctraj_cap = P.ctraj_cap;
+            R.l_grid = L.grid; R.l_blk = L.blk; R.l_wall = L.wall; R.l_alive = L.alive; R.l_wpre = L.wpre; R.l_ctr = L.ctr; R.l_listA = L.listA;
+            R.magic_cpr = P.magic_cpr; R.H = H; R.W = W; R.RW = RW; R.RB = RB; R.traj_steps = P.traj_steps;
+            R.wall_in_smem = P.wall_in_smem; R.write_n = P.traj == nullptr;
+            record_step_compact(R, smem_raw, e, tl, n, (int)band, CL == 1);
         }
     }
 

@@ -122,23 +122,24 @@ sff_relax_queue_kernel(const uint8_t* __restrict__ maps, float* dist, SffQueue q
     const int tiles_per_map = tiles_x * tiles_y;
     for (;;) {
         if (threadIdx.x == 0) {
+            // take the next ticket and wait for the push that fills it (idle CTAs wait on different ring slots: no contended
+            // word); nothing queued and nothing in flight means no push can follow -- done
             int tile = -1;
             volatile unsigned int* ctrl = q.ctrl;
+            const unsigned int h = atomicAdd(&q.ctrl[0], 1u);
+            volatile int* slot = q.ring + (h % q.cap);
             for (;;) {
-                const unsigned int h = ctrl[0], t = ctrl[1];
-                if ((int)(t - h) > 0) {
-                    if (atomicCAS(&q.ctrl[0], h, h + 1u) != h) continue;
-                    volatile int* slot = q.ring + (h % q.cap);
-                    while ((tile = *slot) == -1) __nanosleep(32);
-                    *slot = -1;
-                    __threadfence();
-                    atomicExch(&q.flag[tile], 0);                  // from here on an improved neighbour re-queues this tile
-                    __threadfence();
-                    atomicAdd(&q.ctrl[3], 1u);
-                    break;
-                }
-                if (ctrl[2] == 0u) break;                          // ring empty and nothing in flight: done
-                __nanosleep(200);
+                tile = *slot;
+                if (tile != -1) break;
+                if (ctrl[2] == 0u) break;
+                __nanosleep(64);
+            }
+            if (tile != -1) {
+                *slot = -1;
+                __threadfence();
+                atomicExch(&q.flag[tile], 0);                      // from here on an improved neighbour re-queues this tile
+                __threadfence();
+                atomicAdd(&q.ctrl[3], 1u);
             }
             s_tile = tile;
             rim_changed[0] = rim_changed[1] = rim_changed[2] = rim_changed[3] = 0;

@@ -92,16 +92,10 @@ class FloorFieldModel:
         self._host_dff = None
 
     def update_dff(self):
-        """ffm_core.py:106-117.  The reference calls it from step(); a stand-alone call is reproduced
-        on the host with the same float32 expression sequence (it is not on the hot path)."""
-        diffuse, decay = self.params["diffuse"], self.params["decay"]
-        new_dff = (1 - decay) * (1 - diffuse) * self.dff
-        padded = np.pad(new_dff, 1, mode="constant")
-        for dx, dy in self.neighbors:
-            new_dff += decay * (1 - diffuse) / len(self.neighbors) * padded[1 + dx:new_dff.shape[0] + 1 + dx,
-                                                                          1 + dy:new_dff.shape[1] + 1 + dy]
-        new_dff[new_dff < 1e-4] = 0
-        self.dff = new_dff
+        """ffm_core.py:106-117 as a stand-alone call: the kernels' stencil run once on the device (inside step() the step kernel
+        does it)."""
+        self._sim.update_dff()
+        self._host_dff = None
 
     def run(self, save_prefix=None, save_interval=100):
         """ffm_core.py:119-133: step until everybody has left; optional .npz dumps of the buffered

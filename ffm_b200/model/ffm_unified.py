@@ -160,15 +160,10 @@ class FloorFieldModelUnified:
         self._host_pos = self._host_dff = None
 
     def update_dff(self):
-        """ffm_unified.py:779-798 as a stand-alone call (host; inside step() the kernel does it)."""
-        diffuse, decay = self.params["diffuse"], self.params["decay"]
-        new_dff = (1 - decay) * (1 - diffuse) * self.dff
-        padded = np.pad(new_dff, 1, mode="constant")
-        for dx, dy in self.neighbors:
-            new_dff += decay * (1 - diffuse) / len(self.neighbors) * padded[1 + dx:new_dff.shape[0] + 1 + dx,
-                                                                          1 + dy:new_dff.shape[1] + 1 + dy]
-        new_dff[new_dff < 1e-4] = 0
-        self.dff = new_dff
+        """ffm_unified.py:779-798 as a stand-alone call: the kernels' stencil run once on the device (inside step() the step kernel
+        does it)."""
+        self._sim.update_dff()
+        self._host_dff = None
 
     def reset(self, exit_pos=None, radius=None):
         """ffm_unified.py:800-812: new placement, zero DFF, tables kept."""

@@ -157,6 +157,10 @@ class BatchSim:
         _abi.check(self._lib.ffm_set_dff(self._h, _ptr(dff), _abi.FFM_HOST, _stream()))
         torch.cuda.current_stream().synchronize()
 
+    def update_dff(self):
+        """One stand-alone decay + diffusion pass (update_dff(), ffm_core.py:106-117) over every episode's DFF, on the device."""
+        _abi.check(self._lib.ffm_update_dff(self._h, _stream()))
+
     def move_probs(self):
         """Probe: (probs float64 [B, n_max, neighbours+1] in slot order, kind int32 [B, n_max]) for the current state
         -- the distribution each pedestrian samples from in the next step (0 no request, 1 forced exit, 2 sampled)."""

@@ -175,6 +175,9 @@ int ffm_get_positions(ffm_sim_t sim, int32_t *pos_rc, int32_t *n, int space, voi
 /* `.dff` read / assignment (run_trained_ffm.py:236); float32 [B][H][W] */
 int ffm_set_dff(ffm_sim_t sim, const float *dff, int space, void *stream);
 int ffm_get_dff(ffm_sim_t sim, float *dff, int space, void *stream);
+/* update_dff() as a stand-alone call (ffm_core.py:106-117, ffm_unified.py:779-798, ffm_trained_core.py:333-353): one decay +
+ * diffusion pass over the DFF of every episode, on the device (inside ffm_rollout the step kernels do it themselves) */
+int ffm_update_dff(ffm_sim_t sim, void *stream);
 
 /* step() x max_steps, stopping each episode when nobody is left: the loop of run()
  * (ffm_core.py:119-126, main.py:44-46).  Continues from the current state and step counter. */

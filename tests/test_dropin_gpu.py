@@ -67,6 +67,28 @@ def test_run_and_attribute_assignment(cuda_device, tmp_path):
         FloorFieldModel(m, os.path.join(tmp_path, "missing.npy"), 3)
 
 
+@pytest.mark.parametrize("h,w,nbh", [(12, 12, "neumann"), (10, 14, "moore"), (16, 24, "moore")])
+def test_standalone_update_dff_runs_on_the_device_bit_exact(cuda_device, tmp_path, h, w, nbh):
+    """update_dff() outside step() (ffm_core.py:106-117): the library's stencil, not a host restatement; widths that
+    take the vectorised (w % 4 == 0) and the scalar walk."""
+    from ffm_b200.model.ffm_core import FloorFieldModel
+    from oracle import ffm_numpy
+
+    m = assets.room_map(h, w)
+    p = os.path.join(tmp_path, "sff.npy")
+    np.save(p, assets.sff_norm_min(m, "L1", np.float32))
+    model = FloorFieldModel(m, p, 5, {"seed": 1, "neighborhood": nbh, "diffuse": 0.3, "decay": 0.15})
+    rng = np.random.RandomState(3)
+    d = (rng.rand(h, w) * (rng.rand(h, w) < 0.4) * 3).astype(np.float32)
+    d[2, 3] = 1.2e-4                                         # decays below the 1e-4 cut
+    model.dff = d
+    want = d.copy()
+    for _ in range(3):
+        model.update_dff()
+        want = ffm_numpy.update_dff(want, model.params, model.neighbors)
+        assert np.array_equal(model.dff.view(np.uint32), want.view(np.uint32))
+
+
 def test_unified_dropin_like_training_driver(cuda_device, tmp_path):
     """run_unified_critic_training.py:164-225 / run_unified_actor_training.py:193-268 usage pattern: one
     model object, `.N = n`, reset(exit_pos, radius), run(max_steps), table accessors; compared with
