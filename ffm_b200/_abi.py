@@ -7,7 +7,7 @@ import os
 
 from . import build as _build
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 FFM_HOST, FFM_DEVICE = 0, 1
 FFM_NEUMANN, FFM_MOORE = 4, 8
 FFM_F32, FFM_F64 = 0, 1
@@ -31,7 +31,7 @@ class Config(C.Structure):
         ("k_A", C.c_double), ("gamma", C.c_double), ("alpha_v", C.c_double), ("alpha_h", C.c_double),
         ("exit_reward", C.c_double), ("step_penalty", C.c_double), ("collision_penalty", C.c_double),
         ("epsilon", C.c_double), ("sff_min", C.c_double), ("sff_max", C.c_double),
-        ("stop_penalty", C.c_double), ("timeout_penalty", C.c_double), ("step_cap", C.c_int32), ("reserved4", C.c_int32),
+        ("stop_penalty", C.c_double), ("timeout_penalty", C.c_double), ("step_cap", C.c_int32), ("q_log2_capacity", C.c_int32),
     ]
 
 
@@ -72,7 +72,13 @@ SIGNATURES = {
     "ffm_set_episode_base": (C.c_int, [C.c_void_p, C.c_uint32]),
     "ffm_q_shape": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
     "ffm_q_get": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
-    "ffm_q_set": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "ffm_q_set": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]),
+    "ffm_mcq_set_forced": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ffm_mcq_backup_ordered": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "ffm_mcq_accumulate": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "ffm_mcq_export_deltas": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    "ffm_mcq_import_deltas": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]),
+    "ffm_mcq_fold": (C.c_int, [C.c_void_p, C.c_void_p]),
     "ffm_set_beta": (C.c_int, [C.c_void_p, C.c_double]),
     "ffm_mcq_finalize_timeouts": (C.c_int, [C.c_void_p, C.c_void_p]),
     "ffm_sff_generate": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int,

@@ -81,10 +81,13 @@ struct ffm_sim_s {
     ffm::HStats* d_hstats;
     double* d_blk_lo; double* d_blk_hi; int* d_blk_any;
     double epsilon;
-    // MC-Q model
-    long long qS;
-    float* d_Q; uint8_t* d_qseen;
+    // MC-Q model: the Q dict as an open-addressing hash table
+    unsigned long long* d_qkeys; float* d_Q; unsigned int* d_qcount; uint32_t q_cap;
     uint32_t* d_path_state; uint8_t* d_path_code; int32_t* d_path_len; uint16_t* d_path_col;
+    int32_t* d_path_shift; uint16_t* d_fin_order; int32_t* d_fin_count;
+    int32_t* d_forced;        // [3][B]: target cell, from-direction, step cap of the teacher-forced mini-episodes
+    bool have_forced;
+    double* d_qG; double* d_qN;   // [q_cap][5] each: returns summed per (row, action) and their visit counts (batched learning)
     double beta;
 };
 
@@ -317,6 +320,7 @@ int check_device_flag(ffm_sim_t s, cudaStream_t st) {
     if (flag & 8) return fail(FFM_E_INVALID, "pedestrian position outside the map");
     if (flag & 16) return fail(FFM_E_INVALID, "pedestrian placed on a cell that is not free (map != 0)");
     if (flag & 32) return fail(FFM_E_UNSUPPORTED, "device placement: candidate buffer overflow");
+    if (flag & 64) return fail(FFM_E_UNSUPPORTED, "Q hash table more than half full: raise ffm_config_t.q_log2_capacity");
     return fail(FFM_E_INVALID, "device validation flag %d", flag);
 }
 
@@ -328,6 +332,29 @@ int copy_out(void* dst, const void* src, size_t bytes, int space, cudaStream_t s
     CU(cudaMemcpyAsync(dst, src, bytes, space == FFM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
     if (space == FFM_HOST) CU(cudaStreamSynchronize(st));
     return FFM_OK;
+}
+
+// everything of McqParams that does not depend on the launch
+void fill_mcq_params(ffm_sim_t s, ffm::McqParams& M, int max_steps) {
+    memset(&M, 0, sizeof(M));
+    M.H = s->cfg.height; M.W = s->cfg.width; M.HW = s->HW; M.n_max = s->cfg.n_max; M.B = s->cfg.n_episodes;
+    M.max_steps = max_steps < 0 ? 0 : max_steps; M.step_cap = s->cfg.step_cap; M.learn = s->cfg.learn; M.nby = s->nby;
+    M.force_finalize = max_steps < 0 ? 1 : 0;
+    M.type_grid = s->d_type_grid; M.sff = s->d_sff;
+    M.kS = s->cfg.k_S; M.kD = s->cfg.k_D; M.kQ = s->cfg.k_A; M.beta = s->beta; M.alpha = s->cfg.alpha_v; M.gamma = s->cfg.gamma;
+    M.rw[ffm::RW_STEP] = -s->cfg.step_penalty; M.rw[ffm::RW_STOP] = -s->cfg.stop_penalty; M.rw[ffm::RW_COLL] = -s->cfg.collision_penalty;
+    M.rw[ffm::RW_EXIT] = s->cfg.exit_reward; M.rw[ffm::RW_TIMEOUT] = -s->cfg.timeout_penalty;
+    M.c0 = s->cfg.dff_c0; M.c1 = s->cfg.dff_c1; M.thr = s->cfg.dff_threshold;
+    M.pos = s->d_pos; M.n_alive = s->d_n; M.t_done = s->d_t; M.ped_steps = s->d_ped_steps;
+    M.dff = s->d_dff; M.dff_tmp = s->d_dff_tmp;
+    M.qkeys = s->d_qkeys; M.Q = s->d_Q; M.qmask = s->q_cap - 1u; M.q_count = s->d_qcount; M.err = s->d_err;
+    M.path_state = s->d_path_state; M.path_code = s->d_path_code; M.path_len = s->d_path_len; M.path_col = s->d_path_col;
+    M.path_rows = s->cfg.step_cap + 2; M.path_shift = s->d_path_shift; M.fin_order = s->d_fin_order; M.fin_count = s->d_fin_count;
+    if (s->have_forced) {
+        const int B = s->cfg.n_episodes;
+        M.forced_target = s->d_forced; M.forced_dir = s->d_forced + B; M.ep_cap = s->d_forced + 2 * B;
+    }
+    M.seed = s->cfg.seed; M.episode_base = s->cfg.episode_base;
 }
 
 }  // namespace
@@ -353,7 +380,8 @@ int ffm_create(const ffm_config_t* cfg, ffm_sim_t* out) {
     const bool unified = cfg->model != FFM_MODEL_CORE && !mcq;
     if (mcq) {
         if (cfg->neighborhood != FFM_NEUMANN) return fail(FFM_E_INVALID, "the MC-Q model moves on the von Neumann neighbourhood (ffm_learning_core.py:73)");
-        if (cfg->learn != FFM_LEARN_NONE && cfg->learn != FFM_LEARN_EXACT) return fail(FFM_E_INVALID, "the MC-Q model supports FFM_LEARN_NONE and FFM_LEARN_EXACT");
+        if (cfg->learn < FFM_LEARN_NONE || cfg->learn > FFM_LEARN_BATCHED) return fail(FFM_E_INVALID, "unknown learn mode %d", cfg->learn);
+        if (cfg->q_log2_capacity != 0 && (cfg->q_log2_capacity < 10 || cfg->q_log2_capacity > 30)) return fail(FFM_E_INVALID, "q_log2_capacity must be 0 (default) or in [10, 30]");
         if (cfg->learn == FFM_LEARN_EXACT && cfg->n_episodes != 1) return fail(FFM_E_INVALID, "FFM_LEARN_EXACT needs n_episodes == 1");
         if (cfg->step_cap < 1) return fail(FFM_E_INVALID, "step_cap (params[\"max_steps\"]) must be >= 1");
         if (!cfg->track_dff) return fail(FFM_E_INVALID, "the MC-Q model always tracks the DFF");
@@ -566,19 +594,26 @@ int ffm_create(const ffm_config_t* cfg, ffm_sim_t* out) {
         if (two) s->d_dff_tmp = s->d_dff + (size_t)B * HW;
     }
     if (mcq) {
-        const int nby = (W + 2) / 3, nbx = (cfg->height + 2) / 3;
-        s->nby = nby;
-        s->qS = (long long)nbx * nby * (long long)ffm::MCQ_STATES_PER_BLOCK;
-        if (s->qS > 0xFFFFFFFFLL) { ffm_destroy(s); return fail(FFM_E_UNSUPPORTED, "Q table of %lld states exceeds 32-bit state ids", s->qS); }
-        ALLOC(s->d_Q, (size_t)s->qS * 5 * 4);
-        ALLOC(s->d_qseen, (size_t)s->qS);
-        ALLOC(s->d_path_state, (size_t)B * (cfg->step_cap + 1) * N * 4);
-        ALLOC(s->d_path_code, (size_t)B * (cfg->step_cap + 1) * N);
+        s->nby = (W + 2) / 3;
+        s->q_cap = 1u << (cfg->q_log2_capacity ? cfg->q_log2_capacity : 21);
+        const size_t rows = (size_t)cfg->step_cap + 2;
+        ALLOC(s->d_qkeys, (size_t)s->q_cap * 8);
+        ALLOC(s->d_Q, (size_t)s->q_cap * 5 * 4);
+        ALLOC(s->d_qcount, 4);
+        ALLOC(s->d_path_state, (size_t)B * rows * N * 4);
+        ALLOC(s->d_path_code, (size_t)B * rows * N);
         ALLOC(s->d_path_len, (size_t)B * N * 4);
         ALLOC(s->d_path_col, (size_t)B * N * 2);
-        cudaMemset(s->d_Q, 0, (size_t)s->qS * 5 * 4);
-        cudaMemset(s->d_qseen, 0, (size_t)s->qS);
+        ALLOC(s->d_path_shift, (size_t)B * 4);
+        ALLOC(s->d_fin_order, (size_t)B * N * 2);
+        ALLOC(s->d_fin_count, (size_t)B * 4);
+        ALLOC(s->d_forced, (size_t)B * 3 * 4);
+        cudaMemset(s->d_qkeys, 0xFF, (size_t)s->q_cap * 8);
+        cudaMemset(s->d_Q, 0, (size_t)s->q_cap * 5 * 4);
+        cudaMemset(s->d_qcount, 0, 4);
         cudaMemset(s->d_path_len, 0, (size_t)B * N * 4);
+        cudaMemset(s->d_path_shift, 0, (size_t)B * 4);
+        cudaMemset(s->d_fin_count, 0, (size_t)B * 4);
         s->beta = 1.0;
     }
     if (unified) {
@@ -614,7 +649,8 @@ int ffm_destroy(ffm_sim_t s) {
     cudaFree(s->d_free); cudaFree(s->d_free_count); cudaFree(s->d_n_req);
     cudaFree(s->d_V); cudaFree(s->d_vseen); cudaFree(s->d_H); cudaFree(s->d_hseen); cudaFree(s->d_hstats);
     cudaFree(s->d_blk_lo); cudaFree(s->d_blk_hi); cudaFree(s->d_blk_any);
-    cudaFree(s->d_Q); cudaFree(s->d_qseen); cudaFree(s->d_path_state); cudaFree(s->d_path_code); cudaFree(s->d_path_len); cudaFree(s->d_path_col);
+    cudaFree(s->d_Q); cudaFree(s->d_qkeys); cudaFree(s->d_qcount); cudaFree(s->d_path_shift); cudaFree(s->d_fin_order); cudaFree(s->d_fin_count);
+    cudaFree(s->d_forced); cudaFree(s->d_qG); cudaFree(s->d_qN); cudaFree(s->d_path_state); cudaFree(s->d_path_code); cudaFree(s->d_path_len); cudaFree(s->d_path_col);
     delete s;
     return FFM_OK;
 }
@@ -683,6 +719,7 @@ int ffm_place(ffm_sim_t s, const int32_t* n, int32_t exit_row, int32_t exit_col,
     int rcf = check_device_flag(s, st);  // synchronises (n[] is a host buffer of the caller) and surfaces a candidate-buffer overflow
     if (rcf) return rcf;
     s->have_positions = true;
+    s->have_forced = false;
     return FFM_OK;
 }
 
@@ -708,6 +745,7 @@ int ffm_set_positions(ffm_sim_t s, const int32_t* pos_rc, const int32_t* n, int 
     CU(cudaGetLastError());
     s->launches++;
     s->have_positions = true;
+    s->have_forced = false;
     return FFM_OK;
 }
 
@@ -779,20 +817,7 @@ int ffm_rollout(ffm_sim_t s, int32_t max_steps, const ffm_draws_t* draws, const 
     CU(cudaFuncSetAttribute(s->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, s->smem_bytes));
     if (s->cfg.model == FFM_MODEL_MCQ) {
         ffm::McqParams M;
-        memset(&M, 0, sizeof(M));
-        M.H = s->cfg.height; M.W = s->cfg.width; M.HW = s->HW; M.n_max = s->cfg.n_max; M.B = s->cfg.n_episodes;
-        M.max_steps = max_steps < 0 ? 0 : max_steps; M.step_cap = s->cfg.step_cap; M.learn = s->cfg.learn; M.nby = s->nby;
-        M.force_finalize = max_steps < 0 ? 1 : 0;
-        M.type_grid = s->d_type_grid; M.sff = s->d_sff;
-        M.kS = s->cfg.k_S; M.kD = s->cfg.k_D; M.kQ = s->cfg.k_A; M.beta = s->beta; M.alpha = s->cfg.alpha_v; M.gamma = s->cfg.gamma;
-        M.rw[ffm::RW_STEP] = -s->cfg.step_penalty; M.rw[ffm::RW_STOP] = -s->cfg.stop_penalty; M.rw[ffm::RW_COLL] = -s->cfg.collision_penalty;
-        M.rw[ffm::RW_EXIT] = s->cfg.exit_reward; M.rw[ffm::RW_TIMEOUT] = -s->cfg.timeout_penalty;
-        M.c0 = s->cfg.dff_c0; M.c1 = s->cfg.dff_c1; M.thr = s->cfg.dff_threshold;
-        M.pos = s->d_pos; M.n_alive = s->d_n; M.t_done = s->d_t; M.ped_steps = s->d_ped_steps;
-        M.dff = s->d_dff; M.dff_tmp = s->d_dff_tmp;
-        M.Q = s->d_Q; M.q_seen = s->d_qseen;
-        M.path_state = s->d_path_state; M.path_code = s->d_path_code; M.path_len = s->d_path_len; M.path_col = s->d_path_col;
-        M.seed = s->cfg.seed; M.episode_base = s->cfg.episode_base;
+        fill_mcq_params(s, M, max_steps);
         if (draws) { M.move_draws = draws->move; M.conflict_draws = draws->conflict; M.draw_steps = draws->steps; M.draw_first = draws->first_step; }
         if (out && out->traj_cells) {
             if (!out->traj_n) return fail(FFM_E_INVALID, "traj_cells without traj_n");
@@ -1040,31 +1065,147 @@ int ffm_set_epsilon(ffm_sim_t s, double epsilon) {
     return FFM_OK;
 }
 
-int ffm_q_shape(ffm_sim_t s, int64_t* n_states) {
-    if (!s || !n_states) return fail(FFM_E_INVALID, "null argument");
+int ffm_q_shape(ffm_sim_t s, int64_t* capacity) {
+    if (!s || !capacity) return fail(FFM_E_INVALID, "null argument");
     if (s->cfg.model != FFM_MODEL_MCQ) return fail(FFM_E_STATE, "only the MC-Q model has a Q table");
-    *n_states = s->qS;
+    *capacity = (int64_t)s->q_cap;
     return FFM_OK;
 }
 
-int ffm_q_get(ffm_sim_t s, float* Q, uint8_t* seen, int space, void* stream) {
+int ffm_q_get(ffm_sim_t s, uint64_t* keys, float* rows, int space, void* stream) {
     if (!s) return fail(FFM_E_INVALID, "null argument");
     if (s->cfg.model != FFM_MODEL_MCQ) return fail(FFM_E_STATE, "only the MC-Q model has a Q table");
     CU(cudaSetDevice(s->cfg.device));
     int rc;
-    if (Q && (rc = copy_out(Q, s->d_Q, (size_t)s->qS * 20, space, (cudaStream_t)stream))) return rc;
-    if (seen && (rc = copy_out(seen, s->d_qseen, (size_t)s->qS, space, (cudaStream_t)stream))) return rc;
+    if (space == FFM_HOST && (rc = check_device_flag(s, (cudaStream_t)stream))) return rc;
+    if (keys && (rc = copy_out(keys, s->d_qkeys, (size_t)s->q_cap * 8, space, (cudaStream_t)stream))) return rc;
+    if (rows && (rc = copy_out(rows, s->d_Q, (size_t)s->q_cap * 20, space, (cudaStream_t)stream))) return rc;
     return FFM_OK;
 }
 
-int ffm_q_set(ffm_sim_t s, const float* Q, const uint8_t* seen, int space, void* stream) {
-    if (!s) return fail(FFM_E_INVALID, "null argument");
+int ffm_q_set(ffm_sim_t s, const uint64_t* keys, const float* rows, int64_t n, int space, void* stream) {
+    if (!s || (n > 0 && (!keys || !rows))) return fail(FFM_E_INVALID, "null argument");
     if (s->cfg.model != FFM_MODEL_MCQ) return fail(FFM_E_STATE, "only the MC-Q model has a Q table");
+    if (n < 0 || n > (int64_t)(s->q_cap / 2)) return fail(FFM_E_UNSUPPORTED, "%lld rows do not fit a table of %u slots at load factor 1/2: raise q_log2_capacity", (long long)n, s->q_cap);
+    cudaStream_t st = (cudaStream_t)stream;
+    CU(cudaSetDevice(s->cfg.device));
+    CU(cudaMemsetAsync(s->d_qkeys, 0xFF, (size_t)s->q_cap * 8, st));
+    CU(cudaMemsetAsync(s->d_Q, 0, (size_t)s->q_cap * 20, st));
+    CU(cudaMemsetAsync(s->d_qcount, 0, 4, st));
+    if (n > 0) {
+        const unsigned long long* dk = reinterpret_cast<const unsigned long long*>(keys); const float* dr = rows;
+        unsigned long long* tk = nullptr; float* tr = nullptr;
+        if (space == FFM_HOST) {
+            CU(cudaMallocAsync((void**)&tk, (size_t)n * 8, st));
+            CU(cudaMallocAsync((void**)&tr, (size_t)n * 20, st));
+            CU(cudaMemcpyAsync(tk, keys, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+            CU(cudaMemcpyAsync(tr, rows, (size_t)n * 20, cudaMemcpyHostToDevice, st));
+            dk = tk; dr = tr;
+        }
+        ffm::McqParams M;
+        fill_mcq_params(s, M, 0);
+        ffm::mcq_insert_rows_kernel<<<(int)((n + 255) / 256 < 1184 ? (n + 255) / 256 : 1184), 256, 0, st>>>(M, dk, dr, (long long)n);
+        CU(cudaGetLastError());
+        s->launches++;
+        if (space == FFM_HOST) { CU(cudaFreeAsync(tk, st)); CU(cudaFreeAsync(tr, st)); CU(cudaStreamSynchronize(st)); }
+    }
+    return FFM_OK;
+}
+
+int ffm_mcq_set_forced(ffm_sim_t s, const int32_t* target_cell, const int32_t* from_dir, const int32_t* step_cap, void* stream) {
+    if (!s || !target_cell || !from_dir || !step_cap) return fail(FFM_E_INVALID, "null argument");
+    if (s->cfg.model != FFM_MODEL_MCQ) return fail(FFM_E_STATE, "only the MC-Q model takes teacher-forced first transitions");
+    if (!s->have_positions) return fail(FFM_E_STATE, "ffm_set_positions (the source cells) must precede ffm_mcq_set_forced");
+    const int B = s->cfg.n_episodes;
+    for (int e = 0; e < B; ++e) {
+        if (target_cell[e] >= s->HW) return fail(FFM_E_INVALID, "forced target outside the map");
+        if (target_cell[e] >= 0 && (from_dir[e] < 0 || from_dir[e] > 4)) return fail(FFM_E_INVALID, "from_dir must be one of FROM_UP..FROM_SELF (0..4)");
+        if (step_cap[e] < 0) return fail(FFM_E_INVALID, "negative step cap");
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    CU(cudaSetDevice(s->cfg.device));
+    CU(cudaMemcpyAsync(s->d_forced, target_cell, (size_t)B * 4, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(s->d_forced + B, from_dir, (size_t)B * 4, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(s->d_forced + 2 * B, step_cap, (size_t)B * 4, cudaMemcpyHostToDevice, st));
+    CU(cudaStreamSynchronize(st));
+    s->have_forced = true;
+    return FFM_OK;
+}
+
+int ffm_mcq_backup_ordered(ffm_sim_t s, void* stream) {
+    if (!s) return fail(FFM_E_INVALID, "null argument");
+    if (s->cfg.model != FFM_MODEL_MCQ || s->cfg.learn != FFM_LEARN_BATCHED) return fail(FFM_E_STATE, "needs an MC-Q handle created with FFM_LEARN_BATCHED");
+    CU(cudaSetDevice(s->cfg.device));
+    ffm::McqParams M;
+    fill_mcq_params(s, M, 0);
+    ffm::mcq_backup_ordered_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(M);
+    CU(cudaGetLastError());
+    s->launches++;
+    return FFM_OK;
+}
+
+static int mcq_ensure_deltas(ffm_sim_t s, cudaStream_t st) {
+    if (s->d_qG) return FFM_OK;
+    const size_t bytes = (size_t)s->q_cap * 5 * 8;
+    CU(cudaMalloc((void**)&s->d_qG, bytes));
+    CU(cudaMalloc((void**)&s->d_qN, bytes));
+    CU(cudaMemsetAsync(s->d_qG, 0, bytes, st));
+    CU(cudaMemsetAsync(s->d_qN, 0, bytes, st));
+    return FFM_OK;
+}
+
+int ffm_mcq_accumulate(ffm_sim_t s, void* stream) {
+    if (!s) return fail(FFM_E_INVALID, "null argument");
+    if (s->cfg.model != FFM_MODEL_MCQ || s->cfg.learn != FFM_LEARN_BATCHED) return fail(FFM_E_STATE, "needs an MC-Q handle created with FFM_LEARN_BATCHED");
+    cudaStream_t st = (cudaStream_t)stream;
     CU(cudaSetDevice(s->cfg.device));
     int rc;
-    if (Q && (rc = copy_in(s->d_Q, Q, (size_t)s->qS * 20, space, (cudaStream_t)stream))) return rc;
-    if (seen && (rc = copy_in(s->d_qseen, seen, (size_t)s->qS, space, (cudaStream_t)stream))) return rc;
-    CU(cudaStreamSynchronize((cudaStream_t)stream));
+    if ((rc = mcq_ensure_deltas(s, st))) return rc;
+    ffm::McqParams M;
+    fill_mcq_params(s, M, 0);
+    const long long total = (long long)s->cfg.n_episodes * s->cfg.n_max;
+    ffm::mcq_accumulate_kernel<<<(int)((total + 255) / 256 < 1184 ? (total + 255) / 256 : 1184), 256, 0, st>>>(M, s->d_qG, s->d_qN);
+    CU(cudaGetLastError());
+    s->launches++;
+    return FFM_OK;
+}
+
+int ffm_mcq_fold(ffm_sim_t s, void* stream) {
+    if (!s) return fail(FFM_E_INVALID, "null argument");
+    if (s->cfg.model != FFM_MODEL_MCQ || !s->d_qG) return fail(FFM_E_STATE, "no accumulated returns (ffm_mcq_accumulate / ffm_mcq_import_deltas first)");
+    CU(cudaSetDevice(s->cfg.device));
+    ffm::mcq_fold_kernel<<<1184, 256, 0, (cudaStream_t)stream>>>(s->d_Q, s->d_qG, s->d_qN, (size_t)s->q_cap * 5, s->cfg.alpha_v);
+    CU(cudaGetLastError());
+    s->launches++;
+    return FFM_OK;
+}
+
+int ffm_mcq_export_deltas(ffm_sim_t s, uint64_t* keys, double* rows, int64_t capacity, uint32_t* count, void* stream) {
+    if (!s || !keys || !rows || !count) return fail(FFM_E_INVALID, "null argument");
+    if (s->cfg.model != FFM_MODEL_MCQ || !s->d_qG) return fail(FFM_E_STATE, "no accumulated returns (ffm_mcq_accumulate first)");
+    if (capacity < 1 || capacity > 0x7fffffffLL) return fail(FFM_E_INVALID, "bad capacity");
+    cudaStream_t st = (cudaStream_t)stream;
+    CU(cudaSetDevice(s->cfg.device));
+    CU(cudaMemsetAsync(count, 0, 4, st));
+    ffm::mcq_export_deltas_kernel<<<1184, 256, 0, st>>>(s->d_qkeys, s->d_qG, s->d_qN, s->q_cap, reinterpret_cast<unsigned long long*>(keys), rows, count, (unsigned int)capacity);
+    CU(cudaGetLastError());
+    s->launches++;
+    return FFM_OK;
+}
+
+int ffm_mcq_import_deltas(ffm_sim_t s, const uint64_t* keys, const double* rows, uint32_t count, void* stream) {
+    if (!s || (count > 0 && (!keys || !rows))) return fail(FFM_E_INVALID, "null argument");
+    if (s->cfg.model != FFM_MODEL_MCQ) return fail(FFM_E_STATE, "only the MC-Q model exchanges return sums");
+    cudaStream_t st = (cudaStream_t)stream;
+    CU(cudaSetDevice(s->cfg.device));
+    int rc;
+    if ((rc = mcq_ensure_deltas(s, st))) return rc;
+    if (count == 0) return FFM_OK;
+    ffm::McqParams M;
+    fill_mcq_params(s, M, 0);
+    ffm::mcq_import_deltas_kernel<<<(int)((count + 255u) / 256u < 1184u ? (count + 255u) / 256u : 1184u), 256, 0, st>>>(M, reinterpret_cast<const unsigned long long*>(keys), rows, count, s->d_qG, s->d_qN);
+    CU(cudaGetLastError());
+    s->launches++;
     return FFM_OK;
 }
 

@@ -6,8 +6,10 @@
 // What differs from the other models and shapes the kernel:
 //   * von Neumann moves + STOP; every candidate's logit needs ITS OWN state: the 3x3 window around the TARGET
 //     (map codes, OOB = 2, +1 on free cells that are occupied -- the agent itself included, :132-135) and the
-//     coarse block (tx//3, ty//3).  Dense id: block * 4^9 + sum v_i * 4^i (row-major window), Q float32 [S][5]
-//     with a presence flag per row (rows are created by _ensure_qvec :289-291, never by the read path :190-191)
+//     coarse block (tx//3, ty//3).  64-bit key: block * 4^9 + sum v_i * 4^i (row-major window); the table is an
+//     open-addressing HASH TABLE in HBM (keys u64, rows float32 [5]; linear probing, insertion by atomicCAS) -- the
+//     reference's dict: rows are created by _ensure_qvec (:289-291, find-or-insert), never by the read path
+//     (:190-191, find only); only visited states take memory, any map size
 //   * logit = beta*(-k_S*sff) + k_D*dff + (1-beta)*k_Q*Q[s][from_dir] in Python floats (:193), also for STOP
 //   * contested cells always have one winner; losers overwrite their last reward with -collision_penalty
 //     (:253-257); only real moves leave a DFF footprint (:235,247)
@@ -21,7 +23,18 @@
 // Decisions of all agents are independent given the table at step start (rows created during the step are zero
 // rows and an absent row also reads as 0), so they run in parallel; the backups are the reference's sequential
 // loop, executed by one thread (learn = EXACT, one episode per handle).  With learn = NONE the table is frozen
-// and any number of episodes runs concurrently.
+// and any number of episodes runs concurrently.  learn = BATCHED also freezes the table during the rollout but
+// records, per episode, the order in which the agents' paths would have been backed up; afterwards either
+// mcq_backup_ordered_kernel applies the reference's backups in episode order (exact whenever the policy did not
+// depend on Q: beta = 1, i.e. the coverage pretrain and the warm-up episodes of
+// run_coverage_pretrain_and_training.py:173-216,313-333) or mcq_accumulate_kernel / mcq_fold_kernel reduce the
+// returns per (state, action) and fold them in with the visit count (the synchronous batched form whose deltas
+// all-reduce over GPUs).
+//
+// Coverage pretrain (run_coverage_pretrain_and_training.py:91-166, force_first_step_and_roll): an episode may start
+// with a teacher-forced first transition -- the single agent stands on src, the record (state of target T with src
+// occupied, from_dir, -step/-stop penalty) is appended, the agent is moved to T with a footprint on src, no DFF
+// update and no step counted -- and has its own step cap (SFF(src) + 10), after which finalize_timeouts runs.
 #pragma once
 #include "ffm_unified_kernel.cuh"
 
@@ -30,11 +43,14 @@ namespace ffm {
 constexpr uint32_t MCQ_STATES_PER_BLOCK = 262144u;   // 4^9
 enum { RW_STEP = 0, RW_STOP = 1, RW_COLL = 2, RW_EXIT = 3, RW_TIMEOUT = 4 };   // reward codes of a path record
 
+constexpr unsigned long long MCQ_EMPTY = ~0ULL;
+constexpr int MCQ_ERR_TABLE_FULL = 64;
+
 struct McqParams {
     int H, W, HW, n_max, B;
     int max_steps;           // steps to run in this launch
     int step_cap;            // params["max_steps"]: finalize_timeouts when the step counter reaches it
-    int learn;               // ULEARN_NONE | ULEARN_EXACT
+    int learn;               // ULEARN_NONE | ULEARN_EXACT | ULEARN_BATCHED (deferred: finish order recorded, table untouched)
     int force_finalize;      // finalize_timeouts() called by the driver before the cap (main_learning.py:96-97)
     int nby;
     const uint16_t* type_grid;
@@ -44,9 +60,18 @@ struct McqParams {
     float c0, c1, thr;
     uint32_t* pos; int32_t* n_alive; int32_t* t_done; unsigned long long* ped_steps;
     float* dff; float* dff_tmp;
-    float* Q; uint8_t* q_seen;                  // [S][5], [S]
-    uint32_t* path_state; uint8_t* path_code;   // [B][step_cap + 1][n_max]: state id; action | reward code << 4
+    unsigned long long* qkeys; float* Q;        // hash table: [cap] keys (MCQ_EMPTY = free slot), [cap][5] rows
+    uint32_t qmask;                             // cap - 1 (cap is a power of two)
+    unsigned int* q_count;                      // rows in the table
+    int32_t* err;                               // device error flag (MCQ_ERR_TABLE_FULL)
+    uint32_t* path_state; uint8_t* path_code;   // [B][path_rows][n_max]: table slot; action | reward code << 4
+    int path_rows;                              // step_cap + 2 (a forced first record and the timeout record)
     int32_t* path_len;                          // [B][n_max]
+    int32_t* path_shift;                        // [B] 1 when the episode began with a teacher-forced record (rows = step + shift)
+    uint16_t* fin_order; int32_t* fin_count;    // [B][n_max], [B]: columns in the order their paths are backed up
+    const int32_t* forced_target;               // [B] target cell T of the teacher-forced first transition, -1 = none; or null
+    const int32_t* forced_dir;                  // [B] its FROM_* action
+    const int32_t* ep_cap;                      // [B] per-episode cap on CA steps, then finalize_timeouts; or null
     uint16_t* path_col;                         // [B][n_max] column of the pedestrian at index i (survives launches)
     unsigned long long seed; uint32_t episode_base;
     const double* move_draws; const double* conflict_draws; int draw_steps, draw_first;
@@ -81,8 +106,8 @@ __device__ __forceinline__ uint32_t mcq_cell_code(uint32_t g) {
     return occ != 0u ? 1u : 0u;                                     // free cell: occupied or not
 }
 
-// dense state id of target (tr, tc) (:115-140 + _block_index :112-113)
-__device__ __forceinline__ uint32_t mcq_state(const uint16_t* grid, int tr, int tc, int H, int W, int nby) {
+// 64-bit key of target (tr, tc) (:115-140 + _block_index :112-113)
+__device__ __forceinline__ unsigned long long mcq_state(const uint16_t* grid, int tr, int tc, int H, int W, int nby) {
     uint32_t code = 0;
     const bool inner = tr >= 1 && tr < H - 1 && tc >= 1 && tc < W - 1;
     int k = 0;
@@ -96,20 +121,56 @@ __device__ __forceinline__ uint32_t mcq_state(const uint16_t* grid, int tr, int 
             code |= v << (2 * k);
             ++k;
         }
-    return (uint32_t)((tr / 3) * nby + tc / 3) * MCQ_STATES_PER_BLOCK + code;
+    return (unsigned long long)((tr / 3) * nby + tc / 3) * MCQ_STATES_PER_BLOCK + code;
+}
+
+// ---- the Q dict as an open-addressing hash table ------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t mcq_hash(unsigned long long k) {
+    k ^= k >> 33; k *= 0xff51afd7ed558ccdULL; k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ULL; k ^= k >> 33;
+    return (uint32_t)k;
+}
+// the read path (self.Q.get(state_key), :190): slot of the key or -1; never inserts.  A key being inserted concurrently
+// may be missed: its row is a zero row, and an absent row reads as 0 as well.
+__device__ __forceinline__ int mcq_find(const unsigned long long* keys, uint32_t mask, unsigned long long key) {
+    uint32_t s = mcq_hash(key) & mask;
+    for (uint32_t probe = 0; probe <= mask; ++probe) {
+        const unsigned long long cur = __ldcg(keys + s);
+        if (cur == key) return (int)s;
+        if (cur == MCQ_EMPTY) return -1;
+        s = (s + 1u) & mask;
+    }
+    return -1;
+}
+// _ensure_qvec (:289-291): slot of the key, inserted (zero row: the table is zero-filled and rows are never deleted) if absent
+__device__ __forceinline__ uint32_t mcq_find_or_insert(unsigned long long* keys, uint32_t mask, unsigned long long key,
+                                                      unsigned int* count, int32_t* err) {
+    uint32_t s = mcq_hash(key) & mask;
+    for (uint32_t probe = 0; probe <= mask; ++probe) {
+        unsigned long long cur = __ldcg(keys + s);
+        if (cur == MCQ_EMPTY) {
+            cur = atomicCAS(keys + s, MCQ_EMPTY, key);
+            if (cur == MCQ_EMPTY) {
+                if (atomicAdd(count, 1u) > (mask >> 1)) atomicOr(err, MCQ_ERR_TABLE_FULL);   // keep the load factor below 1/2
+                return s;
+            }
+        }
+        if (cur == key) return s;
+        s = (s + 1u) & mask;
+    }
+    atomicOr(err, MCQ_ERR_TABLE_FULL);
+    return 0u;
 }
 
 // reverse Monte-Carlo backup of one path (:262-267): Python-float returns, float32 table arithmetic
 __device__ __forceinline__ void mcq_backup(const McqParams& P, int e, int col, int len) {
     double G = 0.0;
     const float alpha32 = (float)P.alpha;
-    const size_t stride = (size_t)P.n_max, base = (size_t)e * (P.step_cap + 1) * stride + col;
+    const size_t stride = (size_t)P.n_max, base = (size_t)e * P.path_rows * stride + col;
     volatile float* Q = P.Q;
     for (int t = len - 1; t >= 0; --t) {
-        const uint32_t sid = P.path_state[base + (size_t)t * stride];
+        const uint32_t sid = P.path_state[base + (size_t)t * stride];              // table slot (the row exists: _ensure_qvec ran)
         const uint32_t pc = P.path_code[base + (size_t)t * stride];
         G = __dadd_rn(P.rw[pc >> 4], __dmul_rn(P.gamma, G));                       // G = r + gamma * G
-        P.q_seen[sid] = 1;                                                          // _ensure_qvec
         const size_t qi = (size_t)sid * 5 + (pc & 0xFu);
         const float q = Q[qi];
         Q[qi] = __fadd_rn(q, __fmul_rn(alpha32, __fsub_rn((float)G, q)));           // Q += alpha * (G - Q)   (float32)
@@ -148,19 +209,41 @@ ffm_mcq_rollout_kernel(const McqParams P) {
     int n = P.n_alive[e];
     const int t0 = P.t_done[e];
     uint32_t* gpos = P.pos + (size_t)e * P.n_max;
-    const size_t pstride = (size_t)P.n_max, pbase = (size_t)e * (P.step_cap + 1) * pstride;
+    const size_t pstride = (size_t)P.n_max, pbase = (size_t)e * P.path_rows * pstride;
     int32_t* plen = P.path_len + (size_t)e * P.n_max;
     uint16_t* gcol = P.path_col + (size_t)e * P.n_max;
     for (int i = tid; i < n; i += THREADS) { pos[i] = gpos[i]; orig[i] = (t0 == 0) ? (uint16_t)i : gcol[i]; }
     if (t0 == 0) for (int i = tid; i < P.n_max; i += THREADS) plen[i] = 0;
+    if (t0 == 0 && tid == 0) { P.path_shift[e] = 0; P.fin_count[e] = 0; }
     __syncthreads();
     for (int i = tid; i < n; i += THREADS) grid[pos[i]] |= (uint16_t)(i + 1);
     __syncthreads();
+    // teacher-forced first transition of a coverage-pretrain mini-episode (run_coverage_pretrain_and_training.py:116-147)
+    if (t0 == 0 && P.forced_target != nullptr && P.forced_target[e] >= 0 && n == 1 && tid == 0) {
+        const int c = (int)pos[0], T = P.forced_target[e], a = P.forced_dir[e];
+        const int tr = T / W, tcc = T - tr * W;
+        const uint32_t slot = mcq_find_or_insert(P.qkeys, P.qmask, mcq_state(grid, tr, tcc, H, W, P.nby), P.q_count, P.err);   // :128-130
+        P.path_state[pbase + orig[0]] = slot;
+        P.path_code[pbase + orig[0]] = (uint8_t)(a | ((a == 4 ? RW_STOP : RW_STEP) << 4));   // :135-147
+        plen[orig[0]] = 1;
+        P.path_shift[e] = 1;
+        if (a != 4) {                                     // footprint on src, agent now on T; no DFF update, no step counted
+            dffA[c] = __fadd_rn(dffA[c], 1.0f);
+            grid[c] &= (uint16_t)TYPE_BITS;
+            grid[T] |= (uint16_t)1;
+            pos[0] = (uint32_t)T;
+        }
+    }
+    __syncthreads();
+    const int shift = P.path_shift[e];
+    const int my_cap = P.ep_cap != nullptr ? P.ep_cap[e] : 0x7fffffff;
 
     const uint32_t episode = P.episode_base + (uint32_t)e;
     const double* mv_draws = P.move_draws ? P.move_draws + (size_t)e * P.draw_steps * P.n_max : nullptr;
     const double* cf_draws = P.conflict_draws ? P.conflict_draws + (size_t)e * P.draw_steps * HW * 2 : nullptr;
     const bool learn = P.learn == ULEARN_EXACT;
+    const bool deferred = P.learn == ULEARN_BATCHED;
+    uint16_t* fin_order = P.fin_order + (size_t)e * P.n_max;
     const double wq = __dmul_rn(1.0 - P.beta, P.kQ);       // (1 - beta) * k_Q
     const int doff[4] = {-W, W, -1, 1};                     // UP, DOWN, LEFT, RIGHT (:73)
     // finalize_timeouts() (:326-360): every remaining agent appends (state of its own cell, STOP, -timeout_penalty)
@@ -170,19 +253,25 @@ ffm_mcq_rollout_kernel(const McqParams P) {
             const int c = (int)pos[i];
             const int r = c / W, col = c - r * W;
             const size_t at = pbase + (size_t)row * pstride + orig[i];
-            P.path_state[at] = mcq_state(grid, r, col, H, W, P.nby);
+            P.path_state[at] = mcq_find_or_insert(P.qkeys, P.qmask, mcq_state(grid, r, col, H, W, P.nby), P.q_count, P.err);
             P.path_code[at] = (uint8_t)(4 | (RW_TIMEOUT << 4));
             plen[orig[i]] = row + 1;
         }
         __syncthreads();
         if (tid == 0 && learn)
             for (int i = 0; i < n; ++i) mcq_backup(P, e, orig[i], row + 1);
+        if (tid == 0 && deferred) {
+            int f = P.fin_count[e];
+            for (int i = 0; i < n; ++i) fin_order[f++] = orig[i];
+            P.fin_count[e] = f;
+        }
         __syncthreads();
     };
     unsigned long long ped_steps = 0;
     int tl = 0;
-    for (; tl < P.max_steps && n > 0; ++tl) {
+    for (; tl < P.max_steps && n > 0 && t0 + tl < my_cap; ++tl) {
         const int tstep = t0 + tl;
+        const int prow = tstep + shift;                     // row of this step's path record
         const uint32_t t = (uint32_t)tstep;
         ped_steps += (unsigned long long)n;
         const int di = tstep - P.draw_first;
@@ -194,7 +283,7 @@ ffm_mcq_rollout_kernel(const McqParams P) {
             const int c = (int)pos[i];
             const int r = c / W, col = c - r * W;
             int ccell[A], cact[A];
-            uint32_t csid[A];
+            unsigned long long csid[A];
             double e_[A];
             int nc = 0;
 #pragma unroll
@@ -213,9 +302,13 @@ ffm_mcq_rollout_kernel(const McqParams P) {
                 if (j < nc) {
                     const int tc_ = ccell[j];
                     const int tr = tc_ / W, tcc = tc_ - tr * W;
-                    const uint32_t sid = mcq_state(grid, tr, tcc, H, W, P.nby);
+                    const unsigned long long sid = mcq_state(grid, tr, tcc, H, W, P.nby);
                     csid[j] = sid;
-                    const double q_val = P.q_seen[sid] ? (double)P.Q[(size_t)sid * 5 + cact[j]] : 0.0;      // (:190-191)
+                    double q_val = 0.0;                                                                     // (:190-191)
+                    if (wq != 0.0) {                       // beta = 1: the Q term is 0 * q (tables hold finite values)
+                        const int slot = mcq_find(P.qkeys, P.qmask, sid);
+                        if (slot >= 0) q_val = (double)P.Q[(size_t)slot * 5 + cact[j]];
+                    }
                     const double a1 = __dmul_rn(P.beta, __dmul_rn(-P.kS, (double)sff[tc_]));
                     const double a2 = __dmul_rn(P.kD, (double)dffA[tc_]);
                     const double lg = __dadd_rn(__dadd_rn(a1, a2), __dmul_rn(wq, q_val));                   // (:193)
@@ -240,7 +333,8 @@ ffm_mcq_rollout_kernel(const McqParams P) {
                         if (run > thresh) { chosen = j; done = true; }
                     }
             }
-            uint32_t target = (uint32_t)c, sidc = csid[0];
+            uint32_t target = (uint32_t)c;
+            unsigned long long sidc = csid[0];
             int act = 4;
 #pragma unroll
             for (int j = 0; j < A; ++j)
@@ -249,10 +343,9 @@ ffm_mcq_rollout_kernel(const McqParams P) {
             info[i] = 0u;
             if (target != (uint32_t)c) atomicAdd(&claim32[target >> 2], 1u << (8 * (target & 3u)));
             // path record (:221-222); the loser / exit overwrites happen below
-            const size_t at = pbase + (size_t)tstep * pstride + orig[i];
-            P.path_state[at] = sidc;
+            const size_t at = pbase + (size_t)prow * pstride + orig[i];
+            P.path_state[at] = mcq_find_or_insert(P.qkeys, P.qmask, sidc, P.q_count, P.err);   // _ensure_qvec (:221)
             P.path_code[at] = (uint8_t)(act | ((act == 4 ? RW_STOP : RW_STEP) << 4));
-            if (learn) P.q_seen[sidc] = 1;                                       // _ensure_qvec (:221)
             (void)col;
         }
         __syncthreads();
@@ -284,7 +377,7 @@ ffm_mcq_rollout_kernel(const McqParams P) {
                     if (grid[T] == EXIT_EMPTY) w |= 2u;                          // arrival (:239,250)
                 } else {
                     w = 4u;                                                      // loser: last reward := -collision_penalty
-                    const size_t at = pbase + (size_t)tstep * pstride + orig[i];
+                    const size_t at = pbase + (size_t)prow * pstride + orig[i];
                     P.path_code[at] = (uint8_t)((P.path_code[at] & 0xFu) | (RW_COLL << 4));
                 }
             }
@@ -308,7 +401,7 @@ ffm_mcq_rollout_kernel(const McqParams P) {
                     nc_ = T;
                 }
                 posB[i] = nc_;
-                plen[orig[i]] = tstep + 1;
+                plen[orig[i]] = prow + 1;
                 arrived = (w & 2u) != 0u;
             }
             const uint32_t bal = __ballot_sync(0xffffffffu, arrived);
@@ -330,9 +423,10 @@ ffm_mcq_rollout_kernel(const McqParams P) {
                     if (arr[b] > arr[a]) { const uint16_t x = arr[a]; arr[a] = arr[b]; arr[b] = x; }
             for (int a = 0; a < n_arr; ++a) {
                 const int i = arr[a], colm = orig[i];
-                const size_t at = pbase + (size_t)tstep * pstride + colm;
+                const size_t at = pbase + (size_t)prow * pstride + colm;
                 P.path_code[at] = (uint8_t)((P.path_code[at] & 0xFu) | (RW_EXIT << 4));   // last reward := exit_reward
-                if (learn) mcq_backup(P, e, colm, tstep + 1);
+                if (learn) mcq_backup(P, e, colm, prow + 1);
+                if (deferred) fin_order[P.fin_count[e]++] = (uint16_t)colm;
             }
         }
         __syncthreads();
@@ -397,7 +491,7 @@ ffm_mcq_rollout_kernel(const McqParams P) {
 
         // ================= timeouts at the step cap (:284-285) ==================================
         if (tstep + 1 >= P.step_cap && n > 0) {
-            finalize(tstep + 1);
+            finalize(prow + 1);
             n = 0;                                                                      // everybody is cleared (:357-360)
         }
         if (P.traj != nullptr && tl < P.traj_steps) {
@@ -407,8 +501,10 @@ ffm_mcq_rollout_kernel(const McqParams P) {
         }
     }
 
-    if (P.force_finalize && n > 0 && t0 + tl <= P.step_cap) {
-        finalize(t0 + tl);
+    // finalize_timeouts() called by the driver: explicitly (main_learning.py:96-97) or at the mini-episode's own cap
+    // (run_coverage_pretrain_and_training.py:150-162)
+    if ((P.force_finalize || t0 + tl >= my_cap) && n > 0 && t0 + tl <= P.step_cap) {
+        finalize(t0 + tl + shift);
         n = 0;
     }
     for (int i = tid; i < n; i += THREADS) { gpos[i] = pos[i]; gcol[i] = orig[i]; }
@@ -418,6 +514,105 @@ ffm_mcq_rollout_kernel(const McqParams P) {
         P.n_alive[e] = n;
         P.t_done[e] = t0 + tl;
         P.ped_steps[e] += ped_steps;
+    }
+}
+
+// ---- after a BATCHED (deferred) rollout ----------------------------------------------------------------------------------
+// The reference's backups of a whole batch, in episode order and, within an episode, in the recorded finish order: exactly
+// what running the episodes one after the other on the shared dict does (:262-278, :350-355) whenever their policy did not
+// read Q.  Updates to different (row, action) entries commute, so thread k of the single CTA applies the entries whose
+// slot falls into its residue class, in sequence; every thread walks all records (broadcast loads) and recomputes G.
+static __global__ void __launch_bounds__(1024) mcq_backup_ordered_kernel(const McqParams P) {
+    const uint32_t tid = threadIdx.x;
+    const float alpha32 = (float)P.alpha;
+    const size_t stride = (size_t)P.n_max;
+    for (int e = 0; e < P.B; ++e) {
+        const int nf = P.fin_count[e];
+        for (int q = 0; q < nf; ++q) {
+            const int col = P.fin_order[(size_t)e * P.n_max + q];
+            const int len = P.path_len[(size_t)e * P.n_max + col];
+            const size_t base = (size_t)e * P.path_rows * stride + col;
+            double G = 0.0;
+            for (int t = len - 1; t >= 0; --t) {
+                const uint32_t sid = P.path_state[base + (size_t)t * stride];
+                const uint32_t pc = P.path_code[base + (size_t)t * stride];
+                G = __dadd_rn(P.rw[pc >> 4], __dmul_rn(P.gamma, G));
+                if ((sid & 1023u) == tid) {
+                    const size_t qi = (size_t)sid * 5 + (pc & 0xFu);
+                    const float qv = P.Q[qi];
+                    P.Q[qi] = __fadd_rn(qv, __fmul_rn(alpha32, __fsub_rn((float)G, qv)));
+                }
+            }
+        }
+    }
+}
+
+// Synchronous batched form: returns summed per (row, action) with their visit counts (one thread per finished path) ...
+static __global__ void mcq_accumulate_kernel(const McqParams P, double* dG, double* dN) {
+    const size_t stride = (size_t)P.n_max;
+    const long long total = (long long)P.B * P.n_max;
+    for (long long x = (long long)blockIdx.x * blockDim.x + threadIdx.x; x < total; x += (long long)gridDim.x * blockDim.x) {
+        const int e = (int)(x / P.n_max), q = (int)(x - (long long)e * P.n_max);
+        if (q >= P.fin_count[e]) continue;
+        const int col = P.fin_order[(size_t)e * P.n_max + q];
+        const int len = P.path_len[(size_t)e * P.n_max + col];
+        const size_t base = (size_t)e * P.path_rows * stride + col;
+        double G = 0.0;
+        for (int t = len - 1; t >= 0; --t) {
+            const uint32_t sid = P.path_state[base + (size_t)t * stride];
+            const uint32_t pc = P.path_code[base + (size_t)t * stride];
+            G = __dadd_rn(P.rw[pc >> 4], __dmul_rn(P.gamma, G));
+            atomicAdd(&dG[(size_t)sid * 5 + (pc & 0xFu)], G);
+            atomicAdd(&dN[(size_t)sid * 5 + (pc & 0xFu)], 1.0);
+        }
+    }
+}
+// ... and folded in: n sequential updates Q += alpha (G_i - Q) towards targets of mean m move Q by (1 - (1 - alpha)^n)(m - Q)
+// when the targets are equal, which is the commutative form used here (the deltas all-reduce over GPUs by key).
+static __global__ void mcq_fold_kernel(float* Q, double* dG, double* dN, size_t entries, double alpha) {
+    for (size_t x = (size_t)blockIdx.x * blockDim.x + threadIdx.x; x < entries; x += (size_t)gridDim.x * blockDim.x) {
+        const double n = dN[x];
+        if (n > 0.0) {
+            const double q = (double)Q[x];
+            Q[x] = (float)(q + (1.0 - pow(1.0 - alpha, n)) * (dG[x] / n - q));
+            dG[x] = 0.0; dN[x] = 0.0;
+        }
+    }
+}
+// exchange by key (the slot of a key differs between ranks): rows touched since the last fold -> (key, sum G[5], n[5])
+static __global__ void mcq_export_deltas_kernel(const unsigned long long* keys, double* dG, double* dN, uint32_t cap, unsigned long long* out_keys,
+                                         double* out_rows, unsigned int* out_count, unsigned int out_cap) {
+    for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < cap; s += gridDim.x * blockDim.x) {
+        double n[5]; bool any = false;
+#pragma unroll
+        for (int a = 0; a < 5; ++a) { n[a] = dN[(size_t)s * 5 + a]; any |= n[a] > 0.0; }
+        if (!any) continue;
+        const unsigned int k = atomicAdd(out_count, 1u);
+        if (k < out_cap) {
+            out_keys[k] = keys[s];
+#pragma unroll
+            for (int a = 0; a < 5; ++a) { out_rows[(size_t)k * 10 + a] = dG[(size_t)s * 5 + a]; out_rows[(size_t)k * 10 + 5 + a] = n[a]; }
+        }
+#pragma unroll
+        for (int a = 0; a < 5; ++a) { dG[(size_t)s * 5 + a] = 0.0; dN[(size_t)s * 5 + a] = 0.0; }
+    }
+}
+// one rank's exported list added into the local delta tables (keys are unique within a list: plain adds, so that importing the
+// lists in rank order gives every rank bit-identical sums)
+static __global__ void mcq_import_deltas_kernel(McqParams P, const unsigned long long* in_keys, const double* in_rows, unsigned int count,
+                                         double* dG, double* dN) {
+    for (unsigned int k = blockIdx.x * blockDim.x + threadIdx.x; k < count; k += gridDim.x * blockDim.x) {
+        const uint32_t s = mcq_find_or_insert(P.qkeys, P.qmask, in_keys[k], P.q_count, P.err);
+#pragma unroll
+        for (int a = 0; a < 5; ++a) { dG[(size_t)s * 5 + a] += in_rows[(size_t)k * 10 + a]; dN[(size_t)s * 5 + a] += in_rows[(size_t)k * 10 + 5 + a]; }
+    }
+}
+// `model.Q = shared_Q` (main_learning.py:81): insert n (key, row) pairs into a cleared table
+static __global__ void mcq_insert_rows_kernel(McqParams P, const unsigned long long* in_keys, const float* in_rows, long long n) {
+    for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (long long)gridDim.x * blockDim.x) {
+        const uint32_t s = mcq_find_or_insert(P.qkeys, P.qmask, in_keys[k], P.q_count, P.err);
+#pragma unroll
+        for (int a = 0; a < 5; ++a) P.Q[(size_t)s * 5 + a] = in_rows[(size_t)k * 5 + a];
     }
 }
 

@@ -427,23 +427,30 @@ MCQ_DEFAULTS = {"k_S": 3.0, "k_D": 1.0, "k_Q": 1.0, "diffuse": 0.2, "decay": 0.2
 class McqSim(BatchSim):
     """B episodes of the target-centric Monte-Carlo Q-learning model (model/ffm_learning_core.py).
 
-    learn  "exact"  the reference's reverse Monte-Carlo backups at arrivals / timeouts (n_episodes must be 1)
-           "none"   frozen Q table, any number of episodes
-    The Q table is dense: state id = ((tx//3)*nby + ty//3) * 4**9 + sum(v_i * 4**i) over the 3x3 window around the
-    target cell (``key_to_id``); rows float32 [5] in the reference's action order FROM_UP/DOWN/LEFT/RIGHT/SELF.
+    learn  "exact"    the reference's reverse Monte-Carlo backups at arrivals / timeouts (n_episodes must be 1)
+           "none"     frozen Q table, any number of episodes
+           "batched"  frozen table during the rollout, every path's finish order recorded; afterwards either
+                      ``backup_ordered()`` (the reference's backups in episode order: exact when the policy did not read
+                      Q, i.e. beta = 1 -- coverage pretrain, warm-up episodes) or ``accumulate()`` + ``fold()`` (returns
+                      reduced per (state, action) and folded in with the visit count; ``McqBatchedLearner`` adds the
+                      multi-GPU exchange)
+    The Q dict is a hash table on the device: 64-bit key = ((tx//3)*nby + ty//3) * 4**9 + sum(v_i * 4**i) over the 3x3
+    window around the target cell (``key_to_id``); rows float32 [5] in the reference's action order
+    FROM_UP/DOWN/LEFT/RIGHT/SELF.  ``q_log2_capacity``: log2 of its slots (default 21; rows may fill half of them).
     """
 
     DEFAULTS = MCQ_DEFAULTS
 
     def __init__(self, map_array, sff, n_episodes, n_max, learn="exact", params=None, seed=0, episode_base=0,
-                 alpha=0.1, gamma=0.99, device=None):
+                 alpha=0.1, gamma=0.99, device=None, q_log2_capacity=0):
         self.learn, self.alpha, self.gamma = learn, float(alpha), float(gamma)
+        self._q_log2 = int(q_log2_capacity)
         if params is not None and params.get("neighborhood", "neumann") != "neumann":
             params = {**params, "neighborhood": "neumann"}          # the model forces von Neumann (ffm_learning_core.py:72-73)
         super().__init__(map_array, sff, n_episodes, n_max, params, seed, episode_base, True, device)
-        S = C.c_int64()
-        _abi.check(self._lib.ffm_q_shape(self._h, C.byref(S)))
-        self.S = S.value
+        cap = C.c_int64()
+        _abi.check(self._lib.ffm_q_shape(self._h, C.byref(cap)))
+        self.q_capacity = cap.value
         self.nby = -(-self.W // 3)
 
     def _configure(self, cfg):
@@ -455,6 +462,7 @@ class McqSim(BatchSim):
         cfg.step_penalty, cfg.stop_penalty = float(p["step_penalty"]), float(p["stop_penalty"])
         cfg.collision_penalty, cfg.exit_reward = float(p["collision_penalty"]), float(p["exit_reward"])
         cfg.timeout_penalty, cfg.step_cap = float(p["timeout_penalty"]), int(p["max_steps"])
+        cfg.q_log2_capacity = self._q_log2
         # _update_dff (ffm_learning_core.py:307-321) is always Moore: the neighbour weight divides by 8
         decay, diffuse = float(p["decay"]), float(p["diffuse"])
         cfg.dff_c0 = float(np.float32((1.0 - decay) * (1.0 - diffuse)))
@@ -476,13 +484,13 @@ class McqSim(BatchSim):
         return (bytes((code >> (2 * k)) & 3 for k in range(9)), (blk // self.nby, blk % self.nby))
 
     def get_q(self):
-        """-> (ids int64 [K], rows float32 [K, 5]) of the rows that exist."""
-        seen = np.empty(self.S, np.uint8)
-        _abi.check(self._lib.ffm_q_get(self._h, None, _ptr(seen), _abi.FFM_HOST, _stream()))
-        ids = np.flatnonzero(seen)
-        Q = np.empty((self.S, 5), np.float32)
-        _abi.check(self._lib.ffm_q_get(self._h, _ptr(Q), None, _abi.FFM_HOST, _stream()))
-        return ids, Q[ids].copy()
+        """-> (ids int64 [K] ascending, rows float32 [K, 5]) of the rows that exist."""
+        keys = np.empty(self.q_capacity, np.uint64)
+        rows = np.empty((self.q_capacity, 5), np.float32)
+        _abi.check(self._lib.ffm_q_get(self._h, _ptr(keys), _ptr(rows), _abi.FFM_HOST, _stream()))
+        used = np.flatnonzero(keys != np.uint64(0xFFFFFFFFFFFFFFFF))
+        order = used[np.argsort(keys[used], kind="stable")]
+        return keys[order].astype(np.int64), rows[order].copy()
 
     def q_dict(self):
         """The reference's ``self.Q``: {(combined3x3 bytes, (bx, by)): float32[5]}."""
@@ -490,9 +498,41 @@ class McqSim(BatchSim):
         return {self.id_to_key(i): rows[k] for k, i in enumerate(ids)}
 
     def load_q_dict(self, d):
-        Q = np.zeros((self.S, 5), np.float32)
-        seen = np.zeros(self.S, np.uint8)
-        for k, v in d.items():
-            Q[self.key_to_id(k)] = v
-            seen[self.key_to_id(k)] = 1
-        _abi.check(self._lib.ffm_q_set(self._h, _ptr(Q), _ptr(seen), _abi.FFM_HOST, _stream()))
+        keys = np.fromiter((self.key_to_id(k) for k in d), dtype=np.uint64, count=len(d))
+        rows = np.ascontiguousarray(np.stack([np.asarray(v, np.float32) for v in d.values()]) if len(d) else np.zeros((0, 5), np.float32))
+        _abi.check(self._lib.ffm_q_set(self._h, _ptr(keys), _ptr(rows), len(d), _abi.FFM_HOST, _stream()))
+
+    # -- coverage pretrain / batched learning ------------------------------------------------------------------------
+    def set_forced(self, target_rc, from_dir, step_cap):
+        """Teacher-forced first transition of every episode (force_first_step_and_roll,
+        run_coverage_pretrain_and_training.py:91-166); call after set_positions placed one agent per episode on its
+        source cell.  target_rc int [B, 2] (row < 0: none), from_dir int [B] (FROM_* 0..4), step_cap int [B]."""
+        t = np.asarray(target_rc, np.int64).reshape(self.B, 2)
+        cell = np.where(t[:, 0] < 0, -1, t[:, 0] * self.W + t[:, 1]).astype(np.int32)
+        fd = np.ascontiguousarray(np.asarray(from_dir, np.int32).reshape(self.B))
+        cap = np.ascontiguousarray(np.asarray(step_cap, np.int32).reshape(self.B))
+        _abi.check(self._lib.ffm_mcq_set_forced(self._h, _ptr(cell), _ptr(fd), _ptr(cap), _stream()))
+
+    def backup_ordered(self):
+        _abi.check(self._lib.ffm_mcq_backup_ordered(self._h, _stream()))
+
+    def accumulate(self):
+        _abi.check(self._lib.ffm_mcq_accumulate(self._h, _stream()))
+
+    def fold(self):
+        _abi.check(self._lib.ffm_mcq_fold(self._h, _stream()))
+
+    def export_deltas(self, capacity):
+        """-> (keys int64 [capacity], rows float64 [capacity, 10], count uint32 [1]) CUDA tensors: the rows touched since the
+        last fold, by key; the local delta tables are cleared."""
+        dev = f"cuda:{self.device}"
+        keys = torch.zeros(capacity, dtype=torch.int64, device=dev)
+        rows = torch.zeros((capacity, 10), dtype=torch.float64, device=dev)
+        count = torch.zeros(1, dtype=torch.int32, device=dev)
+        _abi.check(self._lib.ffm_mcq_export_deltas(self._h, _ptr(keys), _ptr(rows), int(capacity), _ptr(count), _stream()))
+        return keys, rows, count
+
+    def import_deltas(self, keys, rows, count):
+        assert keys.is_cuda and rows.is_cuda and keys.is_contiguous() and rows.is_contiguous()
+        self._keep = [keys, rows]
+        _abi.check(self._lib.ffm_mcq_import_deltas(self._h, _ptr(keys), _ptr(rows), int(count), _stream()))

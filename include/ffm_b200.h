@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define FFM_ABI_VERSION 5
+#define FFM_ABI_VERSION 6
 
 enum {
     FFM_OK = 0,
@@ -96,7 +96,7 @@ typedef struct ffm_config {
      *      step_penalty / collision_penalty / exit_reward are the (positive) costs / reward of the params dict ---- */
     double stop_penalty, timeout_penalty;
     int32_t step_cap;      /* params["max_steps"]: finalize_timeouts() when the step counter reaches it */
-    int32_t reserved4;
+    int32_t q_log2_capacity; /* log2 of the slots of the Q hash table, 10..30; 0 = default (21: 2 M slots, 59 MB) */
 } ffm_config_t;
 
 /* Optional recorded uniforms that override the keyed Philox streams (parity tests: "both sides
@@ -222,12 +222,34 @@ int ffm_set_epsilon(ffm_sim_t sim, double epsilon);   /* set_epsilon() :859-867 
 int ffm_set_episode_base(ffm_sim_t sim, uint32_t episode_base);
 
 /* ---- Q table of FFM_MODEL_MCQ -----------------------------------------------------------------------
- * Dense image of self.Q (ffm_learning_core.py:75): state id = ((tx/3)*nby + ty/3) * 4^9 + sum_i v_i * 4^i over the
- * row-major 3x3 window around the TARGET cell (v = map code with OOB = 2, +1 on occupied free cells,
- * _combined3x3_at_target :115-140), nby = ceil(width/3);  Q float32 [S][5], seen uint8 [S] (row exists). */
-int ffm_q_shape(ffm_sim_t sim, int64_t *n_states);
-int ffm_q_get(ffm_sim_t sim, float *Q, uint8_t *seen, int space, void *stream);
-int ffm_q_set(ffm_sim_t sim, const float *Q, const uint8_t *seen, int space, void *stream);   /* model.Q = shared_Q, main_learning.py:81 */
+ * self.Q (ffm_learning_core.py:75) is an open-addressing hash table in device memory: 64-bit key = ((tx/3)*nby + ty/3) * 4^9 +
+ * sum_i v_i * 4^i over the row-major 3x3 window around the TARGET cell (v = map code with OOB = 2, +1 on occupied free
+ * cells, _combined3x3_at_target :115-140), nby = ceil(width/3); rows float32 [5].  Only rows that exist in the dict take a
+ * slot (rows are created by _ensure_qvec :289-291, never by the read path :190-191), so the table's size follows the
+ * visited states, not the map.  ffm_q_get copies the whole table out: keys uint64 [capacity] (all ones = free slot), rows
+ * float32 [capacity][5]; ffm_q_set clears it and inserts n (key, row) pairs (`model.Q = shared_Q`, main_learning.py:81). */
+int ffm_q_shape(ffm_sim_t sim, int64_t *capacity);
+int ffm_q_get(ffm_sim_t sim, uint64_t *keys, float *rows, int space, void *stream);
+int ffm_q_set(ffm_sim_t sim, const uint64_t *keys, const float *rows, int64_t n, int space, void *stream);
+/* Coverage pretrain (run_coverage_pretrain_and_training.py:91-166, force_first_step_and_roll): after ffm_set_positions placed
+ * ONE agent per episode on its source cell, give every episode its teacher-forced first transition -- target cell T (linear
+ * index, -1 = none), the FROM_* action (0..4) and the cap on CA steps after which finalize_timeouts() runs
+ * (min(200, max(1, SFF(src) + 10)), :150-162).  Host arrays int32 [B].  Cleared by the next ffm_set_positions. */
+int ffm_mcq_set_forced(ffm_sim_t sim, const int32_t *target_cell, const int32_t *from_dir, const int32_t *step_cap, void *stream);
+/* After a rollout with FFM_LEARN_BATCHED (table frozen, finish order of every path recorded):
+ *   ffm_mcq_backup_ordered   the reference's reverse Monte-Carlo backups (:262-278, :350-355) of the whole batch in episode
+ *                            order -- bit-identical to running the episodes one after the other on the shared dict whenever
+ *                            the policy did not read Q (beta = 1: coverage pretrain, warm-up episodes)
+ *   ffm_mcq_accumulate       returns summed per (row, action) with visit counts into the handle's delta tables
+ *   ffm_mcq_export_deltas    multi-GPU exchange by KEY: touched rows -> keys uint64 [capacity], rows float64 [capacity][10]
+ *                            (sum G[5], n[5]), *count = rows written (device pointers); clears the local delta tables
+ *   ffm_mcq_import_deltas    one rank's exported list added into the local delta tables (import the lists in rank order)
+ *   ffm_mcq_fold             Q += (1 - (1 - alpha)^n) (sum G / n - Q) per touched entry, delta tables zeroed */
+int ffm_mcq_backup_ordered(ffm_sim_t sim, void *stream);
+int ffm_mcq_accumulate(ffm_sim_t sim, void *stream);
+int ffm_mcq_export_deltas(ffm_sim_t sim, uint64_t *keys, double *rows, int64_t capacity, uint32_t *count, void *stream);
+int ffm_mcq_import_deltas(ffm_sim_t sim, const uint64_t *keys, const double *rows, uint32_t count, void *stream);
+int ffm_mcq_fold(ffm_sim_t sim, void *stream);
 int ffm_set_beta(ffm_sim_t sim, double beta);   /* the beta argument of step(beta), ffm_learning_core.py:145 */
 int ffm_mcq_finalize_timeouts(ffm_sim_t sim, void *stream);   /* finalize_timeouts(), ffm_learning_core.py:326-360 */
 

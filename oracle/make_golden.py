@@ -14,6 +14,7 @@ import hashlib
 import json
 import os
 import random
+import sys
 import tempfile
 
 import numpy as np
@@ -222,7 +223,59 @@ def mcq_case(name, h, w, N, seed, params, betas, sff_dtype=np.float64):
     print(name, "steps", steps, "min_margin %.1e" % min(margins), "|Q|", len(ids))
 
 
+def pretrain_case(name, h, w, seed, params, shuffle_seed=5):
+    """coverage_pretrain_empty of the UNMODIFIED run_coverage_pretrain_and_training.py (:173-216) on a small room: the
+    module's own loop, shuffles and force_first_step_and_roll; only the draw call sites are keyed (mini-episode k =
+    Philox episode k, CA step = the model's own _step_count) and the order of the patterns is logged."""
+    import importlib
+    import random as pyrandom
+    from . import mcq_numpy
+    if inject.REFERENCE_ROOT not in sys.path:
+        sys.path.insert(0, inject.REFERENCE_ROOT)
+    drv = importlib.import_module("run_coverage_pretrain_and_training")
+    cls = drv.FloorFieldModel
+    m = assets.room_map(h, w)
+    sff = assets.sff_norm_min(m, "L1", np.float64)
+    order, steps = [], []
+    with tempfile.TemporaryDirectory() as tmp:
+        p = os.path.join(tmp, "sff.npy")
+        np.save(p, sff)
+        with inject.injected(inject.PhiloxSource(seed, 0), w) as st:
+            o_step, o_force = cls.step, drv.force_first_step_and_roll
+
+            def step(self, beta):
+                st.step = self._step_count              # the CA step about to run (incremented inside, :158)
+                steps[-1] += 1
+                return o_step(self, beta)
+
+            def force(map_array, sff_path, params, shared_Q, T, from_dir, step_buffer=10, save_episode_path=None):
+                st.source = inject.PhiloxSource(seed, len(order))
+                order.append((int(T[0]), int(T[1]), int(from_dir)))
+                steps.append(0)
+                return o_force(map_array=map_array, sff_path=sff_path, params=params, shared_Q=shared_Q, T=T, from_dir=from_dir,
+                               step_buffer=step_buffer, save_episode_path=save_episode_path)
+
+            cls.step, drv.force_first_step_and_roll = step, force
+            try:
+                np.random.seed(seed)
+                pyrandom.seed(shuffle_seed)
+                Q = {}
+                drv.coverage_pretrain_empty(map_array=m, sff_path=p, params=dict(params), shared_Q=Q, shuffle=True, save_dir=None)
+            finally:
+                cls.step, drv.force_first_step_and_roll = o_step, o_force
+    helper = mcq_numpy.McqOracle(m, sff, np.zeros((0, 2)), params)
+    ids = np.array(sorted(helper.id_of(k) for k in Q), np.int64)
+    rows = np.stack([Q[helper.key_of(i)] for i in ids]).astype(np.float32)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), map=m, sff=sff, params=json.dumps(params), seed=np.uint64(seed),
+                        order=np.array(order, np.int32), steps=np.array(steps, np.int32), q_ids=ids, q_rows=rows,
+                        alpha=np.float64(params.get("alpha", 0.1)), gamma=np.float64(params.get("gamma", 0.99)),
+                        min_margin=np.float64(st.min_margin))
+    print(name, "patterns", len(order), "CA steps", int(np.sum(steps)), "|Q|", len(ids), "min_margin %.1e" % st.min_margin)
+
+
 def mcq_all():
+    pretrain_case("mcq_pretrain_12x12", 12, 12, 41, {"max_steps": 500, "alpha": 0.1, "gamma": 0.99, "step_penalty": 0.01, "stop_penalty": 0.3})
+    pretrain_case("mcq_pretrain_9x14", 9, 14, 42, {"max_steps": 500, "alpha": 0.2, "gamma": 0.9, "timeout_penalty": 20.0})
     mcq_case("mcq_12x12_penalties", 12, 12, 20, 31, {"max_steps": 60, "step_penalty": 0.01, "stop_penalty": 0.3, "collision_penalty": 0.7},
              [1.0, 0.6, 0.2, 0.0], np.float32)
     mcq_case("mcq_12x12_default", 12, 12, 40, 32, {"max_steps": 500}, [1.0, 0.5, 0.1])

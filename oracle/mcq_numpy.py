@@ -187,3 +187,75 @@ class McqOracle:
             self.step(beta)
             traj.append(self.positions.copy())
         return dict(steps=self.t, traj=traj, min_margin=self.min_margin)
+
+
+# ---- coverage pretrain (run_coverage_pretrain_and_training.py:60-216) --------------------------------------------------
+DIR_TO_DXY = {FROM_UP: (-1, 0), FROM_DOWN: (1, 0), FROM_LEFT: (0, -1), FROM_RIGHT: (0, 1), FROM_SELF: (0, 0)}   # :61-67, src = T + delta
+
+
+def valid_from_dirs_for_target(map_array, tx, ty):
+    """run_coverage_pretrain_and_training.py:78-88: the FROM_* whose source cell is free, STOP always."""
+    H, W = map_array.shape
+    out = []
+    for a, (dx, dy) in DIR_TO_DXY.items():
+        sx, sy = tx + dx, ty + dy
+        if a == FROM_SELF or (0 <= sx < H and 0 <= sy < W and map_array[sx, sy] == 0):
+            out.append(a)
+    return out
+
+
+def coverage_order(map_array):
+    """Every (tx, ty, from_dir) pattern of coverage_pretrain_empty (:173-216) in its UNSHUFFLED order: free targets in
+    np.where order, directions in dict order."""
+    xs, ys = np.where(np.asarray(map_array) == 0)
+    return [(int(x), int(y), a) for x, y in zip(xs, ys) for a in valid_from_dirs_for_target(map_array, int(x), int(y))]
+
+
+def forced_step_cap(sff, sx, sy, step_buffer=10):
+    return int(min(200, max(1, float(sff[sx, sy]) + step_buffer)))       # :150-151
+
+
+def force_first_step_and_roll(o, T, from_dir, step_buffer=10):
+    """force_first_step_and_roll (:91-166) on a McqOracle whose table is the shared Q: one agent, teacher-forced first
+    record, then step(beta=1.0) until exit or the SFF-derived cap, then finalize_timeouts.  Returns the CA steps run."""
+    tx, ty = T
+    dx, dy = DIR_TO_DXY[from_dir]
+    sx, sy = tx + dx, ty + dy
+    m = o.map_array
+    if m[tx, ty] != 0:
+        return 0
+    if from_dir != FROM_SELF and not (0 <= sx < o.H and 0 <= sy < o.W and m[sx, sy] == 0):
+        return 0
+    o.reset(np.array([[sx, sy]]))
+    occ = np.zeros((o.H, o.W), bool)
+    occ[sx, sy] = True
+    sid = o.state_id(tx, ty, occ)
+    o.q_seen[sid] = True
+    p = o.params
+    if from_dir == FROM_SELF:
+        reward = -float(p["stop_penalty"])
+    else:
+        reward = -float(p["step_penalty"])
+        o.dff[sx, sy] += 1.0
+        o.positions[0] = (tx, ty)
+    o.paths[0].append((sid, from_dir, reward))
+    cap = forced_step_cap(o.sff, sx, sy, step_buffer)
+    steps = 0
+    while len(o.positions) > 0 and steps < cap:
+        o.step(1.0)
+        steps += 1
+    if len(o.positions) > 0:
+        o.finalize_timeouts()
+    return steps
+
+
+def coverage_pretrain(map_array, sff, params, order, seed, alpha=0.1, gamma=0.99):
+    """coverage_pretrain_empty (:173-216) over the given (tx, ty, from_dir) order; mini-episode k draws from the keyed
+    streams of episode k.  Returns (oracle holding the shared Q, steps per mini-episode)."""
+    from .inject import PhiloxSource
+    o = McqOracle(map_array, sff, np.zeros((0, 2)), params, None, alpha, gamma)
+    steps = []
+    for k, (tx, ty, a) in enumerate(order):
+        o.source = PhiloxSource(seed, k)
+        steps.append(force_first_step_and_roll(o, (tx, ty), a))
+    return o, steps

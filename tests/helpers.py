@@ -90,3 +90,13 @@ def load_mcq(name):
         g["ep"].append(dict(pos0=g[f"pos0_{ep}"].astype(np.int64),
                             traj=[g[f"traj_{ep}"][offs[t]:offs[t + 1]].astype(np.int64) for t in range(len(counts))]))
     return g
+
+
+PRETRAIN_FIXTURES = ["mcq_pretrain_12x12", "mcq_pretrain_9x14"]
+
+
+def load_pretrain(name):
+    z = np.load(os.path.join(GOLDEN, name + ".npz"))
+    g = {k: z[k] for k in z.files}
+    g["params"] = json.loads(str(g["params"]))
+    return g

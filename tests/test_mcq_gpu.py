@@ -71,3 +71,82 @@ def test_mcq_frozen_table_batch(cuda_device):
         assert steps[e] == r["steps"] == 40                    # nobody is left after the timeout
         for t, want in enumerate(r["traj"]):
             assert np.array_equal(cells[e, t, :cnt[e, t]], want[:, 0] * 15 + want[:, 1]), (e, t)
+
+
+from helpers import PRETRAIN_FIXTURES, load_pretrain
+
+
+@pytest.mark.parametrize("name", PRETRAIN_FIXTURES)
+def test_coverage_pretrain_matches_the_reference_driver(cuda_device, name):
+    """All patterns of coverage_pretrain_empty (run_coverage_pretrain_and_training.py:173-216) as ONE launch + the ordered
+    backup pass: the shared Q of the unmodified driver, keys and float32 bits, and every mini-episode's step count."""
+    from ffm_b200.mcq_training import coverage_pretrain
+    g = load_pretrain(name)
+    assert float(g["min_margin"]) >= MARGIN_GUARD
+    Q, steps = coverage_pretrain(g["map"], g["sff"], g["params"], {}, order=g["order"], seed=int(g["seed"]), return_steps=True)
+    assert np.array_equal(steps, g["steps"])
+    from oracle import mcq_numpy
+    helper = mcq_numpy.McqOracle(g["map"], g["sff"], np.zeros((0, 2)), g["params"])
+    ids = np.array(sorted(helper.id_of(k) for k in Q), np.int64)
+    assert np.array_equal(ids, g["q_ids"])
+    rows = np.stack([Q[helper.key_of(i)] for i in ids])
+    assert np.array_equal(rows.view(np.uint32), g["q_rows"].view(np.uint32)), "Q rows (float32 bits)"
+    # a second pretrain pass continues from the shared dict (Q is loaded, updated, returned)
+    Q2 = coverage_pretrain(g["map"], g["sff"], g["params"], dict(Q), order=g["order"][:50], seed=int(g["seed"]))
+    o, _ = mcq_numpy.coverage_pretrain(g["map"], g["sff"], g["params"], g["order"], int(g["seed"]), float(g["alpha"]), float(g["gamma"]))
+    from oracle.inject import PhiloxSource
+    for k, (tx, ty, a) in enumerate(g["order"][:50]):
+        o.source = PhiloxSource(int(g["seed"]), k)
+        mcq_numpy.force_first_step_and_roll(o, (int(tx), int(ty)), int(a))
+    want = o.q_dict()
+    assert set(Q2) == set(want) and all(np.array_equal(Q2[k].view(np.uint32), want[k].view(np.uint32)) for k in want)
+
+
+def test_batched_mc_learning_fold(cuda_device):
+    """learn="batched" + accumulate + fold: per (state, action) the table moves by (1 - (1 - alpha)^n)(mean G - Q); checked
+    against returns collected from the oracle on the same keyed episodes (beta = 1: the policy does not read Q)."""
+    from ffm_b200 import McqSim
+    from ffm_b200.mcq_training import McqBatchedLearner
+    from helpers import random_positions
+    from oracle import assets, mcq_numpy
+    from oracle.inject import PhiloxSource
+    m = assets.room_map(12, 12)
+    sff = assets.sff_norm_min(m, "L1", np.float64)
+    params = {"max_steps": 60, "step_penalty": 0.02, "stop_penalty": 0.1, "collision_penalty": 0.5}
+    alpha, gamma, B, N = 0.25, 0.97, 24, 12
+    rng = np.random.RandomState(1)
+    pos0 = [random_positions(m, N, rng) for _ in range(B)]
+    sim = McqSim(m, sff, B, N, learn="batched", params=params, seed=99, alpha=alpha, gamma=gamma, q_log2_capacity=14)
+    sim.set_beta(1.0)
+    sim.set_positions(*pack_positions(pos0, N))
+    sim.rollout(61)
+    McqBatchedLearner(sim, distributed=False).sync()
+    got = sim.q_dict()
+
+    class Collect(mcq_numpy.McqOracle):
+        def _backup(self, path):
+            G = 0.0
+            for sid, ac, r in reversed(path):
+                G = r + self.gamma * G
+                self.q_seen[sid] = True
+                self.sums.setdefault((sid, ac), []).append(G)
+
+    sums, knife = {}, False
+    for e in range(B):
+        o = Collect(m, sff, pos0[e], params, PhiloxSource(99, e), alpha, gamma)
+        o.sums = sums
+        knife |= o.run(1.0)["min_margin"] < MARGIN_GUARD
+    assert not knife
+    helper = mcq_numpy.McqOracle(m, sff, np.zeros((0, 2)), params)
+    want = {}
+    for (sid, ac), gs in sums.items():
+        row = want.setdefault(helper.key_of(sid), np.zeros(5))
+        row[ac] = (1.0 - (1.0 - alpha) ** len(gs)) * np.mean(gs)
+    assert set(want) <= set(got)                                  # rows ensured at decision time may stay zero rows
+    for k, row in want.items():
+        assert np.allclose(got[k], row, rtol=2e-6, atol=1e-6), k
+    assert all(not got[k].any() for k in set(got) - set(want))
+    # a second sync without new episodes changes nothing (the deltas were cleared)
+    sim.fold()
+    again = sim.q_dict()
+    assert all(np.array_equal(again[k], got[k]) for k in got)
