@@ -72,6 +72,57 @@ def main():
         assert np.array_equal(vs, vs1) and np.array_equal(hs, hs1)
         assert np.allclose(V, V1, rtol=1e-9, atol=1e-12) and np.allclose(H, H1, rtol=1e-9, atol=1e-12)   # atomics reorder sums
         print("batched learner over", ws, "ranks == single rank: OK")
+    # (2b) the same with the exchange overlapped with the next rollout (staleness 1): ranks still agree bit for bit
+    sim2 = UnifiedSim(m, sff, count, Np, mode="both", learn="batched", params=P, seed=7, episode_base=first, device=local)
+    l2 = BatchedLearner(sim2, overlap=True)
+    for r in range(3):
+        sim2.set_episode_base(first + r * E)
+        l2.round(*pack_positions(pos[first:first + count], Np), 100, sync_every=25)
+    tv = torch.from_numpy(sim2.get_tables()[0]).cuda()
+    lo, hi = tv.clone(), tv.clone()
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    assert torch.equal(lo, hi), "overlapped exchange: ranks hold different V tables"
+    if rank == 0:
+        print("overlapped exchange: identical tables on", ws, "ranks: OK")
+
+    # (3) Monte-Carlo Q-learning: returns exchanged BY KEY (hash-table slots are a local matter) -> identical dicts on all
+    #     ranks == one rank running all episodes
+    from ffm_b200 import McqSim
+    from ffm_b200.mcq_training import McqBatchedLearner
+    sffd = assets.sff_norm_min(m, "L1", np.float64)
+    QP = {"max_steps": 60, "step_penalty": 0.02, "stop_penalty": 0.1, "collision_penalty": 0.5}
+    msim = McqSim(m, sffd, count, Np, learn="batched", params=QP, seed=21, episode_base=first, alpha=0.2, gamma=0.97, device=local,
+                  q_log2_capacity=15)
+    ml = McqBatchedLearner(msim)
+    for r, beta in enumerate((1.0, 0.5, 0.0)):
+        msim.set_episode_base(first + r * E)
+        msim.set_beta(beta)
+        msim.set_positions(*pack_positions(pos[first:first + count], Np))
+        msim.rollout(61)
+        ml.sync()
+    ids, rows = msim.get_q()
+    n_ids = torch.tensor([len(ids)], device="cuda")
+    all_n = [torch.zeros_like(n_ids) for _ in range(ws)]
+    dist.all_gather(all_n, n_ids)
+    assert len({int(x.item()) for x in all_n}) == 1, "ranks hold Q dicts of different size"
+    ti, tr = torch.from_numpy(ids).cuda(), torch.from_numpy(rows).cuda()
+    for t in (ti, tr):
+        lo, hi = t.clone(), t.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        assert torch.equal(lo, hi), "ranks hold different Q dicts"
+    if rank == 0:
+        one = McqSim(m, sffd, E, Np, learn="batched", params=QP, seed=21, episode_base=0, alpha=0.2, gamma=0.97, device=local,
+                     q_log2_capacity=15)
+        l1 = McqBatchedLearner(one, distributed=False)
+        for r, beta in enumerate((1.0, 0.5, 0.0)):
+            one.set_episode_base(r * E)
+            one.set_beta(beta)
+            one.set_positions(*pack_positions(pos, Np))
+            one.rollout(61)
+            l1.sync()
+        ids1, rows1 = one.get_q()
+        assert np.array_equal(ids, ids1) and np.allclose(rows, rows1, rtol=1e-5, atol=1e-5)
+        print("MC-Q batched learner (by-key exchange) over", ws, "ranks == single rank: OK,", len(ids), "rows")
     dist.barrier()
     dist.destroy_process_group()
 
