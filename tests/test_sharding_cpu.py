@@ -60,3 +60,65 @@ def test_delta_allreduce_gloo_world2():
     assert np.array_equal(res[0][4], res[1][4])
     want_seen = np.zeros(64, np.uint8); want_seen[0::3] = 1; want_seen[1::3] = 1
     assert np.array_equal(res[0][5], want_seen) and np.array_equal(res[1][5], want_seen)
+
+
+class _FakeMcqSim:
+    """Stand-in for McqSim on CPU tensors: the by-key exchange logic of McqBatchedLearner.sync without a GPU."""
+    learn = "batched"
+
+    def __init__(self, rank):
+        self.rank, self.table, self.folded = rank, {}, 0
+        # rank r touched keys {r, r + 1, ..., r + 3 + r}: ragged lists, one key shared between the ranks
+        self.local = {100 + k: np.full(10, float(10 * rank + k)) for k in range(rank, rank + 4 + rank)}
+
+    def accumulate(self):
+        pass
+
+    def export_deltas(self, capacity):
+        keys = torch.zeros(capacity, dtype=torch.int64)
+        rows = torch.zeros((capacity, 10), dtype=torch.float64)
+        for i, (k, v) in enumerate(sorted(self.local.items())):
+            keys[i] = k
+            rows[i] = torch.from_numpy(v)
+        return keys, rows, torch.tensor([len(self.local)], dtype=torch.int32)
+
+    def import_deltas(self, keys, rows, count):
+        for i in range(int(count)):
+            k = int(keys[i])
+            self.table[k] = self.table.get(k, np.zeros(10)) + rows[i].numpy()
+
+    def fold(self):
+        self.folded += 1
+
+
+def _mcq_worker(rank, ws, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(ws))
+    dist.init_process_group("gloo", rank=rank, world_size=ws)
+    try:
+        from ffm_b200.mcq_training import McqBatchedLearner
+        sim = _FakeMcqSim(rank)
+        McqBatchedLearner(sim, export_capacity=16).sync()
+        out.put((rank, sorted((k, v.tolist()) for k, v in sim.table.items()), sim.folded))
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_mcq_by_key_exchange_gloo_world2():
+    """Ragged per-rank lists of touched (key, sums) rows: all-gathered padded, imported in rank order on every rank."""
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_mcq_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in procs], key=lambda x: x[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res[0][1] == res[1][1] and res[0][2] == res[1][2] == 1
+    table = dict(res[0][1])
+    assert sorted(table) == [100, 101, 102, 103, 104, 105]
+    assert table[100] == [0.0] * 10 and table[101] == [1.0 + 11.0] * 10 and table[105] == [15.0] * 10
