@@ -320,6 +320,7 @@ int check_device_flag(ffm_sim_t s, cudaStream_t st) {
     if (flag & 8) return fail(FFM_E_INVALID, "pedestrian position outside the map");
     if (flag & 16) return fail(FFM_E_INVALID, "pedestrian placed on a cell that is not free (map != 0)");
     if (flag & 32) return fail(FFM_E_UNSUPPORTED, "device placement: candidate buffer overflow");
+    if (flag & 128) return fail(FFM_E_INVALID, "two pedestrians were placed on the same cell");
     if (flag & 64) return fail(FFM_E_UNSUPPORTED, "Q hash table more than half full: raise ffm_config_t.q_log2_capacity");
     return fail(FFM_E_INVALID, "device validation flag %d", flag);
 }
@@ -526,6 +527,10 @@ int ffm_create(const ffm_config_t* cfg, ffm_sim_t* out) {
             if (v == 128 || v == 256 || v == 1024) s->threads = v;
         }
         if (unified || mcq) s->threads = N <= 128 ? 128 : 256;
+        // small crowds on small maps (the 12x12 training configurations): two warps per episode -- more episodes (barrier
+        // domains) per SM and fewer idle lanes
+        if (unified && N <= 64 && HW <= 1024) s->threads = 64;
+        if (unified) if (const char* ev = getenv("FFM_THREADS")) { const int v = atoi(ev); if (v == 64 || v == 128 || v == 256) s->threads = v; }
         // Fields (score, DFF) in shared memory or left in global memory (L1/L2)?  Shared memory is faster per access
         // but costs residency.  Rule: shared unless the global variant keeps at least 1.5x as many CTAs resident.
         auto kernel_for = [&](bool fs) {
@@ -851,7 +856,7 @@ int ffm_rollout(ffm_sim_t s, int32_t max_steps, const ffm_draws_t* draws, const 
         }
         s->hstats_stale = false;
         U.hstats = s->d_hstats;
-        U.seed = s->cfg.seed; U.episode_base = s->cfg.episode_base;
+        U.seed = s->cfg.seed; U.episode_base = s->cfg.episode_base; U.err = s->d_err;
         if (draws) { U.move_draws = draws->move; U.conflict_draws = draws->conflict; U.draw_steps = draws->steps; U.draw_first = draws->first_step; }
         if (out && out->traj_cells) {
             if (!out->traj_n) return fail(FFM_E_INVALID, "traj_cells without traj_n");
@@ -881,7 +886,7 @@ int ffm_rollout(ffm_sim_t s, int32_t max_steps, const ffm_draws_t* draws, const 
         C.kd = (float)s->cfg.k_D; C.c0 = s->cfg.dff_c0; C.c1 = s->cfg.dff_c1; C.thr = s->cfg.dff_threshold;
         C.pos = s->d_pos; C.n_alive = s->d_n; C.t_done = s->d_t; C.ped_steps = s->d_ped_steps;
         C.dff = s->d_dff; C.dff_tmp = s->d_dff_tmp;
-        C.seed = s->cfg.seed; C.episode_base = s->cfg.episode_base;
+        C.seed = s->cfg.seed; C.episode_base = s->cfg.episode_base; C.err = s->d_err;
         if (draws) { C.move_draws = draws->move; C.conflict_draws = draws->conflict; C.draw_steps = draws->steps; C.draw_first = draws->first_step; }
         if (out && out->traj_cells) {
             if (!out->traj_n) return fail(FFM_E_INVALID, "traj_cells without traj_n");
@@ -940,7 +945,7 @@ int ffm_rollout(ffm_sim_t s, int32_t max_steps, const ffm_draws_t* draws, const 
     P.c0 = s->cfg.dff_c0; P.c1 = s->cfg.dff_c1; P.thr = s->cfg.dff_threshold;
     P.pos = s->d_pos; P.n_alive = s->d_n; P.t_done = s->d_t; P.ped_steps = s->d_ped_steps;
     P.dff = s->d_dff; P.dff_tmp = s->d_dff_tmp;
-    P.seed = s->cfg.seed; P.episode_base = s->cfg.episode_base;
+    P.seed = s->cfg.seed; P.episode_base = s->cfg.episode_base; P.err = s->d_err;
     if (draws) {
         P.move_draws = draws->move; P.conflict_draws = draws->conflict;
         P.draw_steps = draws->steps; P.draw_first = draws->first_step;

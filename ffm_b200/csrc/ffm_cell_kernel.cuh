@@ -86,6 +86,7 @@ struct CellParams {
     int traj_steps;
     // compact trajectory record (what run() collects, ffm_core.py:125 / main.py:44-52): per episode a stream of
     // (row, col) int16 pairs, the rows of consecutive steps back to back, each padded to a multiple of 4 entries
+    int32_t* err;                // device validation flag (128: two pedestrians on one cell)
     unsigned long long* dbg;     // FFM_PHASE_TIMING builds: [8] accumulated cycles (work / wait per phase), else unused
     uint32_t* ctraj;             // [B][ctraj_cap]  low half = row, high half = col (an int16 pair in memory)
     int32_t* ctraj_off;          // [B][traj_steps + 1]: entry offset of each step's row (CSR); [steps] = end
@@ -464,7 +465,8 @@ ffm_cell_rollout_kernel(const CellParams P) {
         if (c >= lo && c < hi) {
             grid_l[c - lo] |= (uint16_t)(i + 1);
             const int r = (int)__umulhi((uint32_t)c, P.magic_w), col = c - r * W;
-            atomicOr(&blk_l[(r - r0 + 1) * RW + 1 + (col >> 5)], 1u << (col & 31));
+            const uint32_t prev = atomicOr(&blk_l[(r - r0 + 1) * RW + 1 + (col >> 5)], 1u << (col & 31));
+            if ((prev >> (col & 31)) & 1u) atomicOr(P.err, 128);       // the cell already holds a pedestrian (or is a wall)
         }
     }
     sync_all();

@@ -78,6 +78,7 @@ struct RolloutParams {
     uint32_t* traj;              // [B][traj_steps][n_max] or null
     int32_t* traj_n;             // [B][traj_steps]
     int traj_steps;
+    int32_t* err;                // device validation flag (128: two pedestrians on one cell)
 };
 
 struct SmemLayout {
@@ -323,6 +324,9 @@ ffm_core_rollout_kernel(const RolloutParams P) {
     __syncthreads();
     for (int i = tid; i < n; i += THREADS) grid[pos[i]] |= (uint16_t)(i + 1);
     __syncthreads();
+    // two pedestrians on one cell would OR their ids together: at least one of them then reads back a foreign id
+    for (int i = tid; i < n; i += THREADS)
+        if ((grid[pos[i]] & OCC_MASK) != (uint32_t)(i + 1) && P.err != nullptr) atomicOr(P.err, 128);
 
     const uint32_t episode = P.episode_base + (uint32_t)e;
     const double* mv_draws = P.move_draws ? P.move_draws + (size_t)e * P.draw_steps * P.n_max : nullptr;

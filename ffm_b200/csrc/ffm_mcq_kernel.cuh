@@ -218,6 +218,8 @@ ffm_mcq_rollout_kernel(const McqParams P) {
     __syncthreads();
     for (int i = tid; i < n; i += THREADS) grid[pos[i]] |= (uint16_t)(i + 1);
     __syncthreads();
+    for (int i = tid; i < n; i += THREADS)      // duplicates OR their ids together: somebody reads back a foreign id
+        if ((grid[pos[i]] & OCC_MASK) != (uint32_t)(i + 1)) atomicOr(P.err, 128);
     // teacher-forced first transition of a coverage-pretrain mini-episode (run_coverage_pretrain_and_training.py:116-147)
     if (t0 == 0 && P.forced_target != nullptr && P.forced_target[e] >= 0 && n == 1 && tid == 0) {
         const int c = (int)pos[0], T = P.forced_target[e], a = P.forced_dir[e];

@@ -7,6 +7,7 @@ namespace {
 template <typename S, int NBR, bool FS>
 const void* upick_threads(int threads) {
     if (threads >= 256) return (const void*)ffm_unified_rollout_kernel<S, NBR, FS, 256>;
+    if (threads <= 64) return (const void*)ffm_unified_rollout_kernel<S, NBR, FS, 64>;
     return (const void*)ffm_unified_rollout_kernel<S, NBR, FS, 128>;
 }
 template <typename S, int NBR>

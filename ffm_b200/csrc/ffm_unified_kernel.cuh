@@ -69,6 +69,7 @@ struct UnifiedParams {
     const double* move_draws; const double* conflict_draws; int draw_steps, draw_first;
     uint32_t* traj; int32_t* traj_n; int traj_steps;
     uint32_t* rec_state; uint8_t* rec_action; float* rec_reward; int32_t* rec_len;   // rollout buffer [B][traj_steps][n_max]
+    int32_t* err;                // device validation flag (128: two pedestrians on one cell)
 };
 
 struct USmemLayout {
@@ -211,6 +212,8 @@ ffm_unified_rollout_kernel(const UnifiedParams P) {
     __syncthreads();
     for (int i = tid; i < n; i += THREADS) grid[pos[i]] |= (uint16_t)(i + 1);
     __syncthreads();
+    for (int i = tid; i < n; i += THREADS)      // duplicates OR their ids together: somebody reads back a foreign id
+        if ((grid[pos[i]] & OCC_MASK) != (uint32_t)(i + 1) && P.err != nullptr) atomicOr(P.err, 128);
 
     const uint32_t episode = P.episode_base + (uint32_t)e;
     const double* mv_draws = P.move_draws ? P.move_draws + (size_t)e * P.draw_steps * P.n_max : nullptr;

@@ -225,3 +225,33 @@ def test_handles_of_one_kernel_variant_with_different_shared_memory(cuda_device)
         sim.set_positions(*pack_positions([random_positions(m, N, rng) for _ in range(2)], N))
         sim.rollout(3000)
         assert (sim.get_positions()[1] == 0).all()
+
+
+def test_two_pedestrians_on_one_cell_are_rejected(cuda_device, core_kernel):
+    """ffm_set_positions validates map codes and bounds per pedestrian; a DUPLICATE cell is caught by the rollout kernel's
+    placement (the second arrival finds the cell taken) and surfaces as ValueError at the next host read."""
+    from ffm_b200 import BatchSim
+    m = assets.room_map(16, 20)
+    sff = assets.sff_norm_min_fast(m, "L2", np.float32)
+    pos = np.full((2, 8, 2), -1, np.int32)
+    pos[0, :3] = [(3, 3), (4, 4), (5, 5)]
+    pos[1, :3] = [(3, 3), (7, 7), (3, 3)]                   # episode 1 holds a duplicate
+    sim = BatchSim(m, sff, 2, 8, {"neighborhood": "moore"}, seed=1)
+    sim.set_positions(pos, np.array([3, 3], np.int32))
+    sim.rollout(1)
+    with pytest.raises(ValueError, match="same cell"):
+        sim.counters()
+
+
+def test_duplicates_rejected_in_the_table_models(cuda_device):
+    from ffm_b200 import McqSim, UnifiedSim
+    m = assets.room_map(12, 12)
+    sff = assets.sff_norm_min(m, "L1", np.float32)
+    pos = np.full((1, 4, 2), -1, np.int32)
+    pos[0, :3] = [(3, 3), (5, 5), (3, 3)]
+    for sim in (UnifiedSim(m, sff, 1, 4, mode="critic_only", learn="none", params={"block_size": 1}, seed=1),
+                McqSim(m, sff, 1, 4, learn="none", params={"max_steps": 10}, seed=1)):
+        sim.set_positions(pos, np.array([3], np.int32))
+        sim.rollout(1)
+        with pytest.raises(ValueError, match="same cell"):
+            sim.counters()
