@@ -150,3 +150,20 @@ def test_batched_mc_learning_fold(cuda_device):
     sim.fold()
     again = sim.q_dict()
     assert all(np.array_equal(again[k], got[k]) for k in got)
+
+
+def test_mcq_training_schedule_runs_batched(cuda_device):
+    """run_training: the N ramp / beta schedule of run_coverage_pretrain_and_training.py:313-333 with a batch of episodes per
+    entry, starting from a coverage-pretrained table: the table stays finite, grows, and exit-adjacent rows carry the exit
+    reward's scale."""
+    from ffm_b200.mcq_training import coverage_pretrain, run_training
+    from oracle import assets
+    m = assets.room_map(12, 12)
+    sff = assets.sff_norm_min(m, "L1", np.float64)
+    params = {"max_steps": 120, "alpha": 0.1, "gamma": 0.99, "step_penalty": 0.01}
+    Q0 = coverage_pretrain(m, sff, params, {}, shuffle=False, seed=3)
+    Q, mean_steps = run_training(m, sff, params, full_N=40, shared_Q=Q0, num_episodes=12, batch=32, seed=4)
+    assert len(mean_steps) == 12 and all(0 < s <= 120 for s in mean_steps)
+    assert set(Q0) <= set(Q) and len(Q) > len(Q0)
+    rows = np.stack(list(Q.values()))
+    assert np.isfinite(rows).all() and rows.max() > 50.0 and rows.max() <= 100.0 + 1e-3
