@@ -69,7 +69,7 @@ class FloorFieldModelUnified:
             print(f"✓ 事前学習済みCriticを読み込みました: {self.initial_v_size}状態")
         elif learning_mode == "actor_only":
             print("⚠ 警告: actor_onlyモードですが事前学習済みCriticが指定されていません")
-        self._host_pos = self._host_dff = None
+        self._host_pos = self._host_dff = self._v_cache = self._h_cache = None
         self._upload(self.initialize_agents(), keep_dff=False)                                       # :80
 
     # -- reference helpers ----------------------------------------------------------------------
@@ -146,18 +146,24 @@ class FloorFieldModelUnified:
 
     @property
     def V(self):
-        return defaultdict(lambda: 0.0, self._sim.v_dict())
+        """The reference's ``self.V`` materialised from the device table; cached until the tables can have changed (a step,
+        a run, a table upload), so that drivers reading ``len(model.V)`` every episode do not rebuild it per access."""
+        if self._v_cache is None:
+            self._v_cache = defaultdict(lambda: 0.0, self._sim.v_dict())
+        return self._v_cache
 
     @property
     def H(self):
         if self.learning_mode not in ["actor_only", "both"]:
             return None
-        return defaultdict(lambda: [], self._sim.h_dict())
+        if self._h_cache is None:
+            self._h_cache = defaultdict(lambda: [], self._sim.h_dict())
+        return self._h_cache
 
     # -- stepping -------------------------------------------------------------------------------
     def step(self):
         self._sim.rollout(1)
-        self._host_pos = self._host_dff = None
+        self._host_pos = self._host_dff = self._v_cache = self._h_cache = None
 
     def update_dff(self):
         """ffm_unified.py:779-798 as a stand-alone call: the kernels' stencil run once on the device (inside step() the step kernel
@@ -181,7 +187,7 @@ class FloorFieldModelUnified:
                 chunk = min(chunk, max_steps - step)
             out = self._sim.rollout(chunk, record=chunk if record else 0)
             done = int(self._sim.counters()[0][0]) - step
-            self._host_pos = self._host_dff = None
+            self._host_pos = self._host_dff = self._v_cache = self._h_cache = None
             if record and done > 0:
                 torch.cuda.synchronize()
                 cells, cnt = out[0].cpu().numpy()[0], out[1].cpu().numpy()[0]
@@ -207,6 +213,7 @@ class FloorFieldModelUnified:
 
     def set_v_table(self, v_table):
         self._sim.load_v_dict(dict(v_table))                        # :823-830
+        self._v_cache = None
 
     def get_v_table_size(self):
         size = int(self._sim.get_tables()[1].sum())
