@@ -121,17 +121,25 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append(line.strip())
 
-    def stop(self):
+    def mark(self):
+        """Row index now: the samples of a workload are rows[mark_before : mark_after] of the one long-running sampler
+        (nvidia-smi needs ~0.5 s to start, longer than the short workloads' timed regions)."""
+        return len(self.rows)
+
+    def close(self):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+
+    def window(self, first, last=None):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except subprocess.TimeoutExpired:
-            self.proc.kill()
         sm, mx, reasons, power = [], [], set(), []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for r in self.rows[first:last]:
             f = [x.strip() for x in r.split(",")]
             if len(f) < 7:
                 continue
@@ -324,6 +332,8 @@ class Ctx:
         self.hbm_peak = float(self.peaks.get("hbm_gbs", 6650.0))
         self.hbm_peak_source = "measured (MEASURED_PEAKS.json hbm_gbs)" if self.peaks else "fallback 6650 GB/s"
         self._smem = None
+        self.sampler = ClockSampler(self.local)     # one sampler for the whole run, 25 ms period; workloads take windows of it
+        self.sampler.start()
         try:
             self.profile = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))
         except OSError:
@@ -440,8 +450,8 @@ def run_rollout_workload(ctx, name, wl):
     ped_per_pass = ped_per_round * rounds
     steps_host = steps_dev.cpu().numpy()
 
-    sampler = ClockSampler(local)
-    sampler.start()
+    sampler = ctx.sampler
+    mark0 = sampler.mark()
     evs = event_pairs(torch, args.steps, 4)
     l0 = sim.launch_count
     ctx.barrier()
@@ -478,7 +488,7 @@ def run_rollout_workload(ctx, name, wl):
         e2e_ped += one_pass_e2e()
         e2e_evs[k][1].record()
     ctx.barrier()
-    clocks = sampler.stop()
+    clocks = sampler.window(mark0)
     e2e_ms = sum(e[0].elapsed_time(e[1]) for e in e2e_evs)
 
     (total_ms, e2e_ms, kern_ms), (ped_all, e2e_ped_all) = ctx.reduce([total_ms, e2e_ms, kern_ms], [float(ped_per_pass), float(e2e_ped)])
@@ -569,8 +579,8 @@ def run_sff_workload(ctx, name, wl):
     for _ in range(args.warmup):
         sweep()
     ctx.barrier()
-    sampler = ClockSampler(ctx.local)
-    sampler.start()
+    sampler = ctx.sampler
+    mark0 = sampler.mark()
     evs = event_pairs(torch, args.steps, len(modes) + 1)
     ctx.barrier()
     for k in range(args.steps):
@@ -590,7 +600,7 @@ def run_sff_workload(ctx, name, wl):
         torch.cuda.synchronize()
         e2[k][1].record()
     ctx.barrier()
-    clocks = sampler.stop()
+    clocks = sampler.window(mark0)
     e2e_ms = sum(e[0].elapsed_time(e[1]) for e in e2)
     cells = float(M * H * W * len(modes))
     (total_ms, e2e_ms, *mode_ms), (cells_all,) = ctx.reduce([total_ms, e2e_ms] + mode_ms, [cells])
@@ -679,6 +689,7 @@ def main():
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": f"failed: {ex!r}"}
         sys.stdout.flush()
         os.write(json_fd, (json.dumps(line) + "\n").encode())
+    ctx.sampler.close()
     if ctx.world > 1:
         ctx.dist.destroy_process_group()
 

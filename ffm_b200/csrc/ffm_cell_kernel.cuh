@@ -533,7 +533,7 @@ ffm_cell_rollout_kernel(const CellParams P) {
             const float* in_up = (CL > 1 && !top) ? cg::this_cluster().map_shared_rank(const_cast<float*>(inb), band - 1) + (RB - 1) * W : nullptr;
             const float* in_dn = (CL > 1 && !bottom) ? cg::this_cluster().map_shared_rank(const_cast<float*>(inb), band + 1) : nullptr;
             auto edge = [&](int r) -> const float* { return r < r0 ? in_up : in_dn; };   // nullptr outside the map
-            if ((W & 3) == 0)
+            if ((W & 3) == 0 && W >= 32)
                 dff_stencil_v4<NBR>([&](int r) -> const float* { return inb + (r - r0) * W; }, edge,
                                     [&](int r) -> float* { return outb + (r - r0) * W; }, r0, r1, W, P.c0, P.c1, P.thr, tid, THREADS);
             else
@@ -543,7 +543,7 @@ ffm_cell_rollout_kernel(const CellParams P) {
             const float* inb = dpar ? dffB_g : dffA_g;
             float* outb = dpar ? dffA_g : dffB_g;
             auto edge = [&](int r) -> const float* { return (r < 0 || r >= H) ? nullptr : inb + (size_t)r * W; };
-            if ((W & 3) == 0)
+            if ((W & 3) == 0 && W >= 32)
                 dff_stencil_v4<NBR>([&](int r) -> const float* { return inb + (size_t)r * W; }, edge,
                                     [&](int r) -> float* { return outb + (size_t)r * W; }, r0, r1, W, P.c0, P.c1, P.thr, tid, THREADS);
             else

@@ -192,7 +192,7 @@ __device__ __forceinline__ double move_weights(uint32_t mm, int ncand, int c, in
 template <int NBR>
 __device__ __forceinline__ void dff_decay_diffuse(const float* __restrict__ in, float* __restrict__ out, int H, int W,
                                                   float c0, float c1, float thr, int tid, int nthreads) {
-    if ((W & 3) == 0) {   // rows are 16-byte aligned: the vectorised walk (ffm_dff_stencil.cuh), same arithmetic
+    if ((W & 3) == 0 && W >= 32) {   // rows are 16-byte aligned and long enough to fill lanes: the vectorised walk (ffm_dff_stencil.cuh), same arithmetic; tiny maps (12x12: 3 column groups) keep the scalar walk, measured faster there
         dff_stencil_v4<NBR>([&](int r) -> const float* { return in + (size_t)r * W; }, [](int) -> const float* { return nullptr; },
                             [&](int r) -> float* { return out + (size_t)r * W; }, 0, H, W, c0, c1, thr, tid, nthreads);
         return;

@@ -67,10 +67,10 @@ def test_run_and_attribute_assignment(cuda_device, tmp_path):
         FloorFieldModel(m, os.path.join(tmp_path, "missing.npy"), 3)
 
 
-@pytest.mark.parametrize("h,w,nbh", [(12, 12, "neumann"), (10, 14, "moore"), (16, 24, "moore")])
+@pytest.mark.parametrize("h,w,nbh", [(12, 12, "neumann"), (10, 14, "moore"), (16, 36, "moore"), (9, 64, "neumann")])
 def test_standalone_update_dff_runs_on_the_device_bit_exact(cuda_device, tmp_path, h, w, nbh):
     """update_dff() outside step() (ffm_core.py:106-117): the library's stencil, not a host restatement; widths that
-    take the vectorised (w % 4 == 0) and the scalar walk."""
+    take the vectorised (w % 4 == 0, w >= 32) and the scalar walk."""
     from ffm_b200.model.ffm_core import FloorFieldModel
     from oracle import ffm_numpy
 
