@@ -297,7 +297,7 @@ __global__ void unpack_positions_kernel(const uint32_t* pos, const int32_t* n, i
 template <int NBR>
 __global__ void __launch_bounds__(256) dff_update_kernel(const float* in, float* out, int H, int W, float c0, float c1, float thr) {
     const size_t off = (size_t)blockIdx.x * H * W;
-    dff_decay_diffuse<NBR>(in + off, out + off, H, W, c0, c1, thr, threadIdx.x, 256);
+    dff_decay_diffuse<NBR>(in + off, out + off, H, W, c0, c1, thr, threadIdx.x, make_stencil_geom(H, W, threadIdx.x, 256));
 }
 
 }  // namespace ffm
@@ -841,6 +841,8 @@ int ffm_rollout(ffm_sim_t s, int32_t max_steps, const ffm_draws_t* draws, const 
         U.max_steps = max_steps;
         U.mode = s->cfg.model - 1; U.learn = s->cfg.learn;
         U.block_size = s->cfg.block_size; U.nby = s->nby; U.S = s->S;
+        U.magic_w = (uint32_t)(((1ULL << 32) + (uint64_t)U.W - 1) / (uint64_t)U.W);
+        U.magic_bs = s->cfg.block_size > 1 ? (uint32_t)(((1ULL << 32) + (uint64_t)s->cfg.block_size - 1) / (uint64_t)s->cfg.block_size) : 0u;
         U.type_grid = s->d_type_grid; U.score = s->d_score;
         U.kd = (float)s->cfg.k_D; U.c0 = s->cfg.dff_c0; U.c1 = s->cfg.dff_c1; U.thr = s->cfg.dff_threshold;
         U.kA = s->cfg.k_A; U.gamma = s->cfg.gamma; U.alpha_v = s->cfg.alpha_v; U.alpha_h = s->cfg.alpha_h;

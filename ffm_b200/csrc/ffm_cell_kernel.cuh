@@ -154,12 +154,9 @@ __device__ __forceinline__ void sort_keys(uint32_t (&v)[NBR]) {
 // (nullptr outside the map: np.pad of the scaled field, :111) -- same arithmetic as dff_decay_diffuse.
 template <int NBR, typename RowIn, typename RowOut>
 __device__ __forceinline__ void dff_stencil_rows(RowIn in_row, RowOut out_row, int r0, int r1, int W, float c0, float c1, float thr,
-                                                 int tid, int nthreads) {
-    const int Hb = r1 - r0;
-    const int cw = W < nthreads ? W : nthreads;
-    const int bands = W < nthreads ? nthreads / W : 1;
-    const int rpb = (Hb + bands - 1) / bands;
-    const int band = tid / cw, colb = tid - band * cw;
+                                                 int tid, const StencilGeom& geom) {
+    const int cw = geom.cw, bands = geom.bands, rpb = geom.srpb;
+    const int band = geom.band, colb = geom.colb;
     if (band >= bands) return;
     const int a0 = r0 + band * rpb, a1 = min(r1, a0 + rpb);
     if (a0 >= a1) return;
@@ -524,6 +521,7 @@ ffm_cell_rollout_kernel(const CellParams P) {
         }
     };
 
+    const StencilGeom sgeom = make_stencil_geom(RBl, W, tid, THREADS);   // DFF stencil geometry of this band, once (not per step)
     // update_dff (:106-117) of this CTA's rows: current buffer -> the other one.  Width a multiple of 4: the vectorised
     // stencil; rows of a neighbouring band (cluster) come through distributed shared memory.
     auto dff_update = [&]() {
@@ -535,19 +533,19 @@ ffm_cell_rollout_kernel(const CellParams P) {
             auto edge = [&](int r) -> const float* { return r < r0 ? in_up : in_dn; };   // nullptr outside the map
             if ((W & 3) == 0 && W >= 32)
                 dff_stencil_v4<NBR>([&](int r) -> const float* { return inb + (r - r0) * W; }, edge,
-                                    [&](int r) -> float* { return outb + (r - r0) * W; }, r0, r1, W, P.c0, P.c1, P.thr, tid, THREADS);
+                                    [&](int r) -> float* { return outb + (r - r0) * W; }, r0, r1, W, P.c0, P.c1, P.thr, tid, sgeom);
             else
                 dff_stencil_rows<NBR>([&](int r) -> const float* { return (r >= r0 && r < r1) ? inb + (r - r0) * W : edge(r); },
-                                      [&](int r) -> float* { return outb + (r - r0) * W; }, r0, r1, W, P.c0, P.c1, P.thr, tid, THREADS);
+                                      [&](int r) -> float* { return outb + (r - r0) * W; }, r0, r1, W, P.c0, P.c1, P.thr, tid, sgeom);
         } else {
             const float* inb = dpar ? dffB_g : dffA_g;
             float* outb = dpar ? dffA_g : dffB_g;
             auto edge = [&](int r) -> const float* { return (r < 0 || r >= H) ? nullptr : inb + (size_t)r * W; };
             if ((W & 3) == 0 && W >= 32)
                 dff_stencil_v4<NBR>([&](int r) -> const float* { return inb + (size_t)r * W; }, edge,
-                                    [&](int r) -> float* { return outb + (size_t)r * W; }, r0, r1, W, P.c0, P.c1, P.thr, tid, THREADS);
+                                    [&](int r) -> float* { return outb + (size_t)r * W; }, r0, r1, W, P.c0, P.c1, P.thr, tid, sgeom);
             else
-                dff_stencil_rows<NBR>(edge, [&](int r) -> float* { return outb + (size_t)r * W; }, r0, r1, W, P.c0, P.c1, P.thr, tid, THREADS);
+                dff_stencil_rows<NBR>(edge, [&](int r) -> float* { return outb + (size_t)r * W; }, r0, r1, W, P.c0, P.c1, P.thr, tid, sgeom);
         }
     };
 

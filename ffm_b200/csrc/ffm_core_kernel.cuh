@@ -191,16 +191,16 @@ __device__ __forceinline__ double move_weights(uint32_t mm, int ncand, int c, in
 // c1 * s is formed once; out-of-map neighbours contribute exactly 0 (np.pad of the scaled field, :111).
 template <int NBR>
 __device__ __forceinline__ void dff_decay_diffuse(const float* __restrict__ in, float* __restrict__ out, int H, int W,
-                                                  float c0, float c1, float thr, int tid, int nthreads) {
+                                                  float c0, float c1, float thr, int tid, const StencilGeom& geom) {
     if ((W & 3) == 0 && W >= 32) {   // rows are 16-byte aligned and long enough to fill lanes: the vectorised walk (ffm_dff_stencil.cuh), same arithmetic; tiny maps (12x12: 3 column groups) keep the scalar walk, measured faster there
         dff_stencil_v4<NBR>([&](int r) -> const float* { return in + (size_t)r * W; }, [](int) -> const float* { return nullptr; },
-                            [&](int r) -> float* { return out + (size_t)r * W; }, 0, H, W, c0, c1, thr, tid, nthreads);
+                            [&](int r) -> float* { return out + (size_t)r * W; }, 0, H, W, c0, c1, thr, tid, geom);
         return;
     }
-    const int cw = W < nthreads ? W : nthreads;          // columns handled per sweep
-    const int bands = W < nthreads ? nthreads / W : 1;   // row bands working in parallel on one column sweep
-    const int rpb = (H + bands - 1) / bands;
-    const int band = tid / cw, colb = tid - band * cw;
+    const int cw = geom.cw;                              // columns handled per sweep
+    const int bands = geom.bands;                        // row bands working in parallel on one column sweep
+    const int rpb = geom.srpb;
+    const int band = geom.band, colb = geom.colb;
     if (band >= bands) return;
     const int r0 = band * rpb, r1 = min(H, r0 + rpb);
     for (int col = colb; col < W; col += cw) {
@@ -332,6 +332,7 @@ ffm_core_rollout_kernel(const RolloutParams P) {
     const double* mv_draws = P.move_draws ? P.move_draws + (size_t)e * P.draw_steps * P.n_max : nullptr;
     const double* cf_draws = P.conflict_draws ? P.conflict_draws + (size_t)e * P.draw_steps * HW * 2 : nullptr;
 
+    const StencilGeom sgeom = make_stencil_geom(H, W, tid, THREADS);   // DFF stencil geometry, once (not per step)
     unsigned long long ped_steps = 0;
     int tl = 0;
     for (; tl < P.max_steps && n > 0; ++tl) {
@@ -490,7 +491,7 @@ ffm_core_rollout_kernel(const RolloutParams P) {
         }
         for (int c = tid; c < claim_words; c += THREADS) claim32[c] = 0u;    // claim counters clean for the next step
         // DFF decay + diffusion reads the bumped field (phase B wrote it before the last barrier) -> other buffer
-        if (DFF) dff_decay_diffuse<NBR>(dffA, dffB, H, W, P.c0, P.c1, P.thr, tid, THREADS);
+        if (DFF) dff_decay_diffuse<NBR>(dffA, dffB, H, W, P.c0, P.c1, P.thr, tid, sgeom);
         __syncthreads();
 
         const int n_exit = (int)cnt[2];

@@ -15,25 +15,48 @@
 
 namespace ffm {
 
+// Per-thread geometry of the walk: depends on the band height, the width and the CTA size only, so a persistent kernel computes it
+// ONCE before its step loop (the integer divisions below were 6 % of the unified kernel's instructions when redone every step).
+struct StencilGeom {
+    int G4, rpb, strip, gfirst, gstep;   // vectorised walk (dff_stencil_v4)
+    bool strip_in_range;
+    int cw, bands, srpb, band, colb;     // scalar walk (dff_stencil_rows / dff_decay_diffuse)
+};
+__device__ __forceinline__ StencilGeom make_stencil_geom(int Hb, int W, int tid, int nthreads) {
+    StencilGeom g;
+    g.G4 = W >> 2;
+    const int G4 = g.G4 > 0 ? g.G4 : 1;
+    const int strips = G4 < nthreads ? nthreads / G4 : 1;
+    g.rpb = (max(Hb, 1) + strips - 1) / strips;
+    g.strip = G4 < nthreads ? tid / G4 : 0;
+    g.gfirst = G4 < nthreads ? tid - g.strip * G4 : tid;
+    g.gstep = G4 < nthreads ? G4 : nthreads;
+    g.strip_in_range = g.strip < strips;
+    g.cw = W < nthreads ? W : nthreads;
+    g.bands = W < nthreads ? nthreads / W : 1;
+    g.srpb = (max(Hb, 1) + g.bands - 1) / g.bands;
+    g.band = tid / g.cw;
+    g.colb = tid - g.band * g.cw;
+    return g;
+}
+
 // in_band(r)  -> row r of the input for r0 <= r < r1 (the caller's own rows: plain shared / global pointer)
 // in_edge(r)  -> row r outside [r0, r1): the neighbouring band's row (distributed shared memory) or nullptr outside the map
 // out_band(r) -> row r of the output, r0 <= r < r1
 // All rows are 16-byte aligned, W % 4 == 0.  Every thread of the CTA must call (warp shuffles inside).
 template <int NBR, typename InBand, typename InEdge, typename OutBand>
 __device__ __forceinline__ void dff_stencil_v4(InBand in_band, InEdge in_edge, OutBand out_band, int r0, int r1, int W, float c0,
-                                               float c1, float thr, int tid, int nthreads) {
-    const int G4 = W >> 2;                                    // column groups per row
+                                               float c1, float thr, int tid, const StencilGeom& geom) {
+    const int G4 = geom.G4;                                   // column groups per row
     const int Hb = r1 - r0;
     if (Hb <= 0) return;
     const int lane = tid & 31;
-    const int strips = G4 < nthreads ? nthreads / G4 : 1;     // row strips worked on at once
-    const int rpb = (Hb + strips - 1) / strips;               // rows per strip (uniform trip count: shuffles stay converged)
-    const int strip = G4 < nthreads ? tid / G4 : 0;
-    const int gfirst = G4 < nthreads ? tid - strip * G4 : tid;
-    const int gstep = G4 < nthreads ? G4 : nthreads;          // column passes when a row has more groups than the CTA threads
+    const int rpb = geom.rpb;                                 // rows per strip (uniform trip count: shuffles stay converged)
+    const int strip = geom.strip, gfirst = geom.gfirst;
+    const int gstep = geom.gstep;                             // column passes when a row has more groups than the CTA threads
     const int a0 = r0 + strip * rpb;
     const int a1 = min(r1, a0 + rpb);
-    const bool strip_ok = strip < strips && a0 < r1;
+    const bool strip_ok = geom.strip_in_range && a0 < r1;
     for (int gb = 0; gb < G4; gb += gstep) {
         const int g = gb + gfirst;
         const bool act = strip_ok && g < G4;

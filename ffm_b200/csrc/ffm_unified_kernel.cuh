@@ -70,6 +70,7 @@ struct UnifiedParams {
     uint32_t* traj; int32_t* traj_n; int traj_steps;
     uint32_t* rec_state; uint8_t* rec_action; float* rec_reward; int32_t* rec_len;   // rollout buffer [B][traj_steps][n_max]
     int32_t* err;                // device validation flag (128: two pedestrians on one cell)
+    uint32_t magic_w, magic_bs;  // ceil(2^32 / W), ceil(2^32 / block_size): x / d = umulhi(x, magic) for x * d < 2^32
 };
 
 struct USmemLayout {
@@ -111,7 +112,7 @@ __device__ __forceinline__ bool cell_blocked(uint32_t g) { return (g & OCC_MASK)
 __device__ __forceinline__ bool cell_is_ped(uint32_t g) { const uint32_t o = g & OCC_MASK; return o != 0u && o != OCC_MASK; }
 
 // _encode_state (ffm_unified.py:188-269) on the owner grid; (r, col) = coordinates of linear cell c
-__device__ __forceinline__ uint32_t encode_state(const uint16_t* grid, int c, int r, int col, int H, int W, int bs, int nby) {
+__device__ __forceinline__ uint32_t encode_state(const uint16_t* grid, int c, int r, int col, int H, int W, uint32_t magic_bs, int nby) {
     uint32_t code = 0;
 #pragma unroll
     for (int d = 0; d < 4; ++d) {                     // up, down, left, right (:209)
@@ -142,7 +143,10 @@ __device__ __forceinline__ uint32_t encode_state(const uint16_t* grid, int c, in
         }
         code = code * 4u + rank;
     }
-    return (uint32_t)((r / bs) * nby + (col / bs)) * 256u + code;
+    // block index (x // bs, y // bs) without integer divisions (coordinates are < 4096, bs >= 1)
+    const uint32_t bx = magic_bs ? __umulhi((uint32_t)r, magic_bs) : (uint32_t)r;      // magic_bs == 0: block_size 1
+    const uint32_t by = magic_bs ? __umulhi((uint32_t)col, magic_bs) : (uint32_t)col;
+    return (bx * (uint32_t)nby + by) * 256u + code;
 }
 
 // reward of one agent-step (:636-648): Python float arithmetic in the reference's order
@@ -231,6 +235,7 @@ ffm_unified_rollout_kernel(const UnifiedParams P) {
 
     unsigned long long ped_steps = 0;
     int tl = 0;
+    const StencilGeom sgeom = make_stencil_geom(H, W, tid, THREADS);   // DFF stencil geometry, once (not per step)
     for (; tl < P.max_steps && n > 0; ++tl) {
         const uint32_t t = (uint32_t)(t0 + tl);
         ped_steps += (unsigned long long)n;
@@ -277,8 +282,8 @@ ffm_unified_rollout_kernel(const UnifiedParams P) {
         // ================= U1: state, validity, forced exit =====================================
         for (int i = tid; i < n; i += THREADS) {
             const int c = (int)pos[i];
-            const int r = c / W, col = c - r * W;
-            const uint32_t sid = encode_state(grid, c, r, col, H, W, P.block_size, P.nby);     // :293
+            const int r = (int)__umulhi((uint32_t)c, P.magic_w), col = c - r * W;
+            const uint32_t sid = encode_state(grid, c, r, col, H, W, P.magic_bs, P.nby);     // :293
             st[i] = sid;
             uint32_t valid = 1u << NBR, ex = 0;                       // "stay" is always valid (:318-319)
 #pragma unroll
@@ -484,8 +489,8 @@ ffm_unified_rollout_kernel(const UnifiedParams P) {
                 uint32_t ns = NO_STATE;
                 if (!(info[i] & INFO_EXIT)) {                            // :651-658
                     const int c = (int)posB[i];
-                    const int r = c / W, col = c - r * W;
-                    ns = encode_state(grid, c, r, col, H, W, P.block_size, P.nby);
+                    const int r = (int)__umulhi((uint32_t)c, P.magic_w), col = c - r * W;
+                    ns = encode_state(grid, c, r, col, H, W, P.magic_bs, P.nby);
                     if (exact) P.v_seen[ns] = 1; else if (P.dF) P.dF[ns] = 1.0;
                 }
                 nst[i] = ns;
@@ -596,7 +601,7 @@ ffm_unified_rollout_kernel(const UnifiedParams P) {
         }
         { uint16_t* tmpo = orig; orig = origB; origB = tmpo; }
         // ================= D: DFF decay + diffusion (:779-798) ==================================
-        dff_decay_diffuse<NBR>(dffA, dffB, H, W, P.c0, P.c1, P.thr, tid, THREADS);
+        dff_decay_diffuse<NBR>(dffA, dffB, H, W, P.c0, P.c1, P.thr, tid, sgeom);
         { float* tmp = dffA; dffA = dffB; dffB = tmp; }
         __syncthreads();
         n = n_new;
