@@ -394,6 +394,8 @@ int ffm_create(const ffm_config_t* cfg, ffm_sim_t* out) {
             return fail(FFM_E_INVALID, "FFM_LEARN_EXACT reproduces the reference's sequential table updates and needs n_episodes == 1");
         if (cfg->model == FFM_MODEL_TRAINED && cfg->learn != FFM_LEARN_NONE) return fail(FFM_E_INVALID, "the trained-actor model does not learn");
         if (!cfg->track_dff) return fail(FFM_E_INVALID, "the unified models always track the DFF");
+        if (cfg->model != FFM_MODEL_UNIFIED_CRITIC && cfg->sff_dtype != FFM_F32)
+            return fail(FFM_E_INVALID, "the actor / trained modes score with the float32 SFF (inf -> 0 and astype(float32), ffm_unified.py:72-76)");
     }
     int ndev = 0;
     CU(cudaGetDeviceCount(&ndev));
@@ -535,7 +537,7 @@ int ffm_create(const ffm_config_t* cfg, ffm_sim_t* out) {
         // but costs residency.  Rule: shared unless the global variant keeps at least 1.5x as many CTAs resident.
         auto kernel_for = [&](bool fs) {
             if (mcq) return ffm::pick_mcq_kernel(f64, s->threads);
-            if (unified) return ffm::pick_unified_kernel(f64, cfg->neighborhood, fs, s->threads);
+            if (unified) return ffm::pick_unified_kernel(f64, cfg->neighborhood, fs, s->threads, cfg->model != FFM_MODEL_UNIFIED_CRITIC);
             return pick_kernel(f64, HW <= 65536, cfg->neighborhood, dff, fs, s->threads);
         };
         const int occ_out = occupancy(kernel_for(false), s->threads, (int)tot_out);

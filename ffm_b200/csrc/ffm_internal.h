@@ -18,7 +18,7 @@ const void* pick_core_kernel_f32(bool small, int nbr, bool dff, bool fields_in_s
 const void* pick_core_kernel_f64(bool small, int nbr, bool dff, bool fields_in_smem, int threads);
 
 // ---- unified / trained models (ffm_unified_kernel.cuh) --------------------------------------------
-const void* pick_unified_kernel(bool f64, int nbr, bool fields_in_smem, int threads);
+const void* pick_unified_kernel(bool f64, int nbr, bool fields_in_smem, int threads, bool actor);
 // dF (may be null): per-state "key touched in this sync" marks (0 / >0), folded into v_seen; a state with dN > 0 also
 // gets its H row marked present when the actor learns (Hm != null)
 cudaError_t launch_apply_deltas(double* V, double* dV, double* dN, double* dF, double alpha_v, double* Hm, double* dH,

@@ -4,20 +4,22 @@
 
 namespace ffm {
 namespace {
-template <typename S, int NBR, bool FS>
+template <typename S, int NBR, bool FS, bool ACTOR>
 const void* upick_threads(int threads) {
-    if (threads >= 256) return (const void*)ffm_unified_rollout_kernel<S, NBR, FS, 256>;
-    if (threads <= 64) return (const void*)ffm_unified_rollout_kernel<S, NBR, FS, 64>;
-    return (const void*)ffm_unified_rollout_kernel<S, NBR, FS, 128>;
+    if (threads >= 256) return (const void*)ffm_unified_rollout_kernel<S, NBR, FS, 256, ACTOR>;
+    if (threads <= 64) return (const void*)ffm_unified_rollout_kernel<S, NBR, FS, 64, ACTOR>;
+    return (const void*)ffm_unified_rollout_kernel<S, NBR, FS, 128, ACTOR>;
 }
-template <typename S, int NBR>
-const void* upick_fs(bool fs, int threads) { return fs ? upick_threads<S, NBR, true>(threads) : upick_threads<S, NBR, false>(threads); }
-template <typename S>
-const void* upick_nbr(int nbr, bool fs, int threads) { return nbr == 4 ? upick_fs<S, 4>(fs, threads) : upick_fs<S, 8>(fs, threads); }
+template <typename S, int NBR, bool ACTOR>
+const void* upick_fs(bool fs, int threads) { return fs ? upick_threads<S, NBR, true, ACTOR>(threads) : upick_threads<S, NBR, false, ACTOR>(threads); }
+template <typename S, bool ACTOR>
+const void* upick_nbr(int nbr, bool fs, int threads) { return nbr == 4 ? upick_fs<S, 4, ACTOR>(fs, threads) : upick_fs<S, 8, ACTOR>(fs, threads); }
 }  // namespace
 
-const void* pick_unified_kernel(bool f64, int nbr, bool fs, int threads) {
-    return f64 ? upick_nbr<double>(nbr, fs, threads) : upick_nbr<float>(nbr, fs, threads);
+const void* pick_unified_kernel(bool f64, int nbr, bool fs, int threads, bool actor) {
+    // the actor / trained modes always score in float32 (the SFF is cast, ffm_unified.py:72-76): no float64 actor variants
+    if (actor) return upick_nbr<float, true>(nbr, fs, threads);
+    return f64 ? upick_nbr<double, false>(nbr, fs, threads) : upick_nbr<float, false>(nbr, fs, threads);
 }
 
 cudaError_t launch_apply_deltas(double* V, double* dV, double* dN, double* dF, double alpha_v, double* Hm, double* dH,

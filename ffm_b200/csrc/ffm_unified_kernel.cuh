@@ -156,7 +156,10 @@ __device__ __forceinline__ double agent_reward(const UnifiedParams& P, uint32_t 
     return __dadd_rn(rew, __dmul_rn((double)((w >> INFO_COLL_SHIFT) & 0xFu), P.collision_penalty));
 }
 
-template <typename S, int NBR, bool FIELDS_IN_SMEM, int THREADS>
+// ACTOR = false: critic_only (scores from the SFF in its own dtype, no H table): the actor paths (float64 scoring, H rows,
+// extremes) compile out, which is worth ~30 registers per thread (c4: 10 instead of 8 CTAs per SM, +10 %; capping the registers further to reach 12
+// CTAs measured slower: 4.09e9 vs 4.31e9)
+template <typename S, int NBR, bool FIELDS_IN_SMEM, int THREADS, bool ACTOR>
 __global__ void __launch_bounds__(THREADS)
 ffm_unified_rollout_kernel(const UnifiedParams P) {
     constexpr int A = NBR + 1;
@@ -222,13 +225,13 @@ ffm_unified_rollout_kernel(const UnifiedParams P) {
     const uint32_t episode = P.episode_base + (uint32_t)e;
     const double* mv_draws = P.move_draws ? P.move_draws + (size_t)e * P.draw_steps * P.n_max : nullptr;
     const double* cf_draws = P.conflict_draws ? P.conflict_draws + (size_t)e * P.draw_steps * HW * 2 : nullptr;
-    const bool actor = P.mode != UMODE_CRITIC;
+    const bool actor = ACTOR;                                                    // == (P.mode != UMODE_CRITIC), checked by the host
     // The tables are written in place only by FFM_LEARN_EXACT (one episode = one CTA per handle).  With frozen tables
     // (NONE) or batched learning many CTAs share them: rows are never inserted by lookups, the extremes of H are the
     // ones found at launch (ffm_rollout refreshes them beforehand when they are stale) and every table write goes
     // through the delta tables.
     const bool exact = P.learn == ULEARN_EXACT;
-    const bool trains_h = (P.mode == UMODE_ACTOR || P.mode == UMODE_BOTH);
+    const bool trains_h = ACTOR && (P.mode == UMODE_ACTOR || P.mode == UMODE_BOTH);
     const bool inserts_rows = trains_h && exact;                                 // H lookups insert zero rows (:405-410)
     const bool learn_actor = trains_h && P.learn != ULEARN_NONE;
     const bool track_stats = actor && exact;
