@@ -442,23 +442,23 @@ int ffm_create(const ffm_config_t* cfg, ffm_sim_t* out) {
     if (const char* ev = getenv("FFM_CLUSTER")) force_cluster = atoi(ev);
     if (s->cell_kernel && (force_cluster > 1 ||
                            ffm::make_cell_layout(s->RB, W, s->RW, N, ssz, esz, dff, false, false).total > (unsigned)MAX_SMEM_OPTIN)) {
-        // Measured on BASELINE C3 (256x256, 10 000 pedestrians, DFF on; profiles/r2j_*): the pedestrian-centric kernel with
-        // one CTA of 1024 threads per SM and the fields in L2 does 1.83e10 ped-steps/s, the 4-CTA cluster with everything
-        // on chip 1.31e10 (33 clusters resident, three cluster barriers per step, 16 warps per SM to hide the latency of
-        // the decide chains).  So a map that still fits the pedestrian-centric layout runs there unless a cluster is asked for.
-        const bool ped_fits = ffm::make_layout(HW, W, N, ssz, dff, false).total <= (unsigned)MAX_SMEM_OPTIN;
-        if (force_cluster <= 1 && ped_fits && !getenv("FFM_KERNEL")) s->cell_kernel = false;
-    }
-    if (s->cell_kernel && (force_cluster > 1 ||
-                           ffm::make_cell_layout(s->RB, W, s->RW, N, ssz, esz, dff, false, false).total > (unsigned)MAX_SMEM_OPTIN)) {
+        // Measured on BASELINE C3 (256x256, 10 000 pedestrians, DFF on; profiles/r2_c3_kernel_variants.jsonl), ped-steps/s:
+        //   2-CTA cluster, 1024 threads, score + DFF in L2 (74 clusters resident, ping-pong working set 38 MB = L2-resident)  2.05e10
+        //   2-CTA cluster, 512 threads, the same                                                                              1.98e10
+        //   pedestrian-centric kernel, one CTA of 1024 threads per SM, fields in L2 (76 MB working set, 71 GB written back)   1.84e10
+        //   4-CTA cluster, everything on chip (33 resident, three cluster barriers per step, 16 warps per SM)                 1.31e10
+        //   4- / 8-CTA clusters with the fields in L2, two CTAs per SM                                                        1.27e10 / 1.02e10
+        // So: the SMALLEST cluster whose owner grid + claim masks fit, with the fields left in L2; on-chip fields only on
+        // request (FFM_FIELDS_SMEM=1).  FFM_KERNEL=ped keeps the pedestrian-centric kernel.
         const int cls[3] = {2, 4, 8};
+        const bool want_smem = getenv("FFM_FIELDS_SMEM") != nullptr;
         bool found = false;
-        for (int fsi = 1; fsi >= 0 && !found; --fsi)           // fields on chip first; else DFF + score stay in L2 (any map size)
-            for (int ci = 0; ci < 3 && !found; ++ci) {
-                const int cl = cls[ci];
-                if (force_cluster > 1 && cl != force_cluster) continue;
+        for (int ci = 0; ci < 3 && !found; ++ci) {
+            const int cl = cls[ci];
+            if (force_cluster > 1 && cl != force_cluster) continue;
+            const int rb = (cfg->height + cl - 1) / cl;
+            for (int fsi = want_smem ? 1 : 0; fsi >= 0 && !found; --fsi) {
                 if (fsi == 1 && getenv("FFM_FIELDS_GLOBAL")) continue;
-                const int rb = (cfg->height + cl - 1) / cl;
                 for (int si = fsi; si >= 0 && !found; --si) {
                     if (si == 1 && getenv("FFM_SCORE_GLOBAL")) continue;
                     for (int wi = 1; wi >= 0 && !found; --wi) {
@@ -469,6 +469,7 @@ int ffm_create(const ffm_config_t* cfg, ffm_sim_t* out) {
                     }
                 }
             }
+        }
         if (!found) s->cell_kernel = false;
     }
     auto occupancy = [&](const void* k, int threads, int smem) {
@@ -480,8 +481,9 @@ int ffm_create(const ffm_config_t* cfg, ffm_sim_t* out) {
     };
     const bool f64 = cfg->sff_dtype == FFM_F64;
     if (s->cell_kernel && s->cluster > 1) {
-        // one cluster per episode, one CTA of 512 threads per SM (1024 threads measured slower on C3: 64 registers, spills)
-        s->threads = 512;
+        // one cluster per episode
+        s->threads = (s->cluster == 2 && !s->fields_in_smem) ? 1024 : 512;    // measured (C3): 2.05e10 vs 1.98e10; larger clusters / on-chip fields: 512
+        if (const char* ev = getenv("FFM_THREADS")) { const int v = atoi(ev); if (v == 512 || v == 1024) s->threads = v; }   // tuning
         s->smem_bytes = (int)ffm::make_cell_layout(s->RB, W, s->RW, N, ssz, esz, dff, s->fields_in_smem, s->wall_in_smem, s->score_in_smem).total;
         s->kernel = ffm::pick_cell_kernel(f64, HW <= 65536, cfg->neighborhood, dff, s->fields_in_smem, s->threads, s->cluster);
         if (!s->kernel) { delete s; return fail(FFM_E_UNSUPPORTED, "no cluster variant of the rollout kernel for this configuration"); }

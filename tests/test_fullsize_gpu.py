@@ -117,20 +117,26 @@ def test_properties_at_full_size(cuda_device):
     assert np.array_equal(b.get_dff().view(np.uint32), a.get_dff()[B // 2:].view(np.uint32))
 
 
-@pytest.mark.parametrize("variant,B,T", [("cl4", 2, 200), ("ped", 2, 200), ("cl8", 2, 200), ("cl4", 8, 1000), ("ped", 8, 1000)])
+@pytest.mark.parametrize("variant,B,T", [("auto", 2, 200), ("ped", 2, 200), ("cl4smem", 2, 200), ("cl8", 2, 200), ("auto", 8, 1000),
+                                         ("cl4smem", 8, 1000), ("ped", 8, 1000)])
 def test_c3_floor_plan_matches_c_oracle(cuda_device, monkeypatch, variant, B, T):
     """BASELINE configs[2] geometry: 256x256 rooms-and-doors plan, geodesic SFF (generated on the GPU), DFF on,
-    10 000 pedestrians.  "cl4" / "cl8" = the cell-centric kernel as a cluster of 4 / 8 CTAs per episode, DFF + owner
-    grid in distributed shared memory; "ped" = the pedestrian-centric kernel (one CTA, fields in L2), which is what
-    ffm_create picks at this size because it measures faster.  Recorded-draw protocol; the long cases
-    cover 8 episodes x 1000 steps."""
+    10 000 pedestrians.  "auto" = what ffm_create picks by measurement: the cell-centric kernel as a 2-CTA cluster (row
+    bands of the owner grid / claim masks in distributed shared memory, score + DFF in L2); "cl4smem" = 4 CTAs with the
+    DFF ping-pong on chip as well; "cl8" = 8 CTAs; "ped" = the pedestrian-centric kernel (one CTA, fields in L2).
+    Recorded-draw protocol; the long cases cover 8 episodes x 1000 steps."""
     import torch
     from ffm_b200 import BatchSim
     from ffm_b200.sff import generate_sff
     from ffm_b200.workloads import place, rooms_map_c3
     from oracle import c_oracle
 
-    if variant.startswith("cl"):
+    if variant == "ped":
+        monkeypatch.setenv("FFM_KERNEL", "ped")
+    elif variant == "cl4smem":
+        monkeypatch.setenv("FFM_CLUSTER", "4")
+        monkeypatch.setenv("FFM_FIELDS_SMEM", "1")
+    elif variant.startswith("cl"):
         monkeypatch.setenv("FFM_CLUSTER", variant[2:])
     m = rooms_map_c3()
     sff = generate_sff(m, "bfs8", np.float32)
@@ -146,8 +152,9 @@ def test_c3_floor_plan_matches_c_oracle(cuda_device, monkeypatch, variant, B, T)
     if variant == "ped":
         assert info["name"] == "ffm_core_rollout_kernel" and not info["fields_in_smem"]
     else:
-        assert info["name"] == "ffm_cell_rollout_kernel" and info["fields_in_smem"]
-        assert info["cluster"] == int(variant[2:]), info
+        assert info["name"] == "ffm_cell_rollout_kernel"
+        assert info["cluster"] == {"auto": 2, "cl4smem": 4, "cl8": 8}[variant], info
+        assert info["fields_in_smem"] == (variant == "cl4smem"), info
     sim.set_positions(pos, n)
     cells, cnt = sim.rollout(T, draws=dict(move=torch.from_numpy(ref["move_draws"]).cuda()), record=T)
     torch.cuda.synchronize()
