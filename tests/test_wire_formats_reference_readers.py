@@ -1,0 +1,65 @@
+"""The reference's OWN inspection scripts read files written by the CUDA path.
+
+tests/golden/gpu_wire_* were produced on a B200 by tests/make_gpu_wire_fixtures.py (drop-in classes driven like main.py /
+the training drivers).  Here -- in the container that holds /root/reference -- the unmodified inspect_trajectory.py and
+q_inspect.py consume them; where the reference is absent (the GPU box) the format checks still run."""
+import importlib
+import io
+import os
+import pickle
+import sys
+from contextlib import redirect_stdout
+
+import numpy as np
+import pytest
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+REF = "/root/reference"
+needs_reference = pytest.mark.skipif(not os.path.isdir(REF), reason="the reference tree is only present in the build container")
+
+
+def _ref_module(name):
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    return importlib.import_module(name)
+
+
+def test_positions_npy_has_the_main_py_shape():
+    log = np.load(os.path.join(GOLDEN, "gpu_wire_positions.npy"), allow_pickle=True)     # main.py:52
+    assert log.dtype == object and len(log) > 20
+    n = [len(p) for p in log]
+    assert n[0] <= 25 and n[-1] == 0 and all(a >= b for a, b in zip(n, n[1:]))           # people only ever leave
+    assert all(p.dtype == np.int64 and p.ndim == 2 and p.shape[1] == 2 for p in log if len(p))
+
+
+@needs_reference
+def test_reference_inspect_trajectory_reads_the_gpu_npz():
+    mod = _ref_module("inspect_trajectory")
+    mod.TRAJECTORY_PATH = os.path.join(GOLDEN, "gpu_wire_trajectory_N12_ep00001_total00001.npz")
+    out = io.StringIO()
+    with redirect_stdout(out):
+        mod.main()                                                                       # inspect_trajectory.py:12-76, unmodified
+    text = out.getvalue()
+    assert "positions" in text and "12" in text and "(12, 2)" in text                    # first step: 12 agents x (row, col)
+    z = np.load(mod.TRAJECTORY_PATH, allow_pickle=True)
+    assert f"{len(z['positions'])}" in text and int(z["steps"]) == len(z["positions"])
+
+
+@needs_reference
+def test_reference_q_inspect_reads_the_gpu_q_pickle():
+    mod = _ref_module("q_inspect")
+    summary, per_block, crowd = mod.analyze_q(os.path.join(GOLDEN, "gpu_wire_Q.pkl"))    # q_inspect.py:52-139, unmodified
+    with open(os.path.join(GOLDEN, "gpu_wire_Q.pkl"), "rb") as f:
+        Q = pickle.load(f)
+    assert int(summary["n_states_total"][0]) == len(Q) > 100 and int(summary["action_size"][0]) == 5
+    assert mod._schema(next(iter(Q))) == "tuple_block2"                                   # (bytes, (bx, by)) keys
+    assert set(zip(per_block["block_x"], per_block["block_y"])) <= {(a, b) for a in range(4) for b in range(4)}
+    assert int(per_block["n_states"].sum()) == len(Q)
+
+
+def test_v_pickle_is_the_driver_format():
+    with open(os.path.join(GOLDEN, "gpu_wire_V.pkl"), "rb") as f:                         # run_unified_critic_training.py:290-299
+        V = pickle.load(f)
+    assert isinstance(V, dict) and len(V) > 20
+    for (ranks, blk), v in V.items():
+        assert len(ranks) == 4 and all(0 <= r <= 3 for r in ranks) and len(blk) == 2 and isinstance(v, float)
