@@ -59,7 +59,13 @@ def stale_objects():
 
 
 def is_stale():
-    if not os.path.exists(LIB) or stale_objects():
+    if not os.path.exists(LIB):
+        return True
+    if not glob.glob(os.path.join(OBJDIR, "*.o")):
+        # a prebuilt library shipped without its objects (a gpurun snapshot carries the .so, not the build directory):
+        # stale only if a source or header is newer than the library
+        return os.path.getmtime(LIB) < max(_newest(headers()), _newest(sources()))
+    if stale_objects():
         return True
     objs = [_obj(s) for s in sources()]
     stray = set(glob.glob(os.path.join(OBJDIR, "*.o"))) - set(objs)     # a deleted source leaves its object behind
@@ -70,7 +76,7 @@ def build(force=False, verbose=False, jobs=None):
     if not force and not is_stale():
         return LIB
     os.makedirs(OBJDIR, exist_ok=True)
-    todo = sources() if force else stale_objects()
+    todo = sources() if force or not glob.glob(os.path.join(OBJDIR, "*.o")) else stale_objects()
     nvcc = _nvcc()
 
     def compile_one(src):
