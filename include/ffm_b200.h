@@ -262,7 +262,8 @@ int ffm_mcq_finalize_timeouts(ffm_sim_t sim, void *stream);   /* finalize_timeou
  *   FFM_SFF_DIJKSTRA8        geodesic distance with step costs (1, float32(sqrt 2)), float32 sums
  * `rounds` (may be NULL; non-NULL costs one 4-byte read-back + synchronisation) receives the number of tile visits of the
  * geodesic modes' work queue.
- * Synchronous with respect to the host on return. */
+ * Host-space calls return with `out` filled; device-space calls are stream-ordered (the geodesic modes never synchronise the
+ * host: one launch of persistent CTAs driven by a device-side tile queue). */
 enum { FFM_SFF_L1 = 0, FFM_SFF_L2 = 1, FFM_SFF_LINF = 2, FFM_SFF_BFS4 = 3, FFM_SFF_BFS8 = 4, FFM_SFF_DIJKSTRA8 = 5 };
 int ffm_sff_generate(const uint8_t *maps, int32_t n_maps, int32_t height, int32_t width, int32_t mode, int32_t out_dtype,
                      void *out, int space, int32_t device, void *stream, int32_t *rounds);

@@ -167,3 +167,24 @@ def test_mcq_training_schedule_runs_batched(cuda_device):
     assert set(Q0) <= set(Q) and len(Q) > len(Q0)
     rows = np.stack(list(Q.values()))
     assert np.isfinite(rows).all() and rows.max() > 50.0 and rows.max() <= 100.0 + 1e-3
+
+
+def test_q_table_overflow_is_reported(cuda_device):
+    """A hash table too small for the visited states reports it (load factor above 1/2) instead of corrupting rows."""
+    from ffm_b200 import McqSim
+    from ffm_b200._abi import FfmError
+    from helpers import random_positions
+    from oracle import assets
+    m = assets.room_map(20, 20)
+    sff = assets.sff_norm_min(m, "L1", np.float64)
+    rng = np.random.RandomState(0)
+    B, N = 16, 60
+    sim = McqSim(m, sff, B, N, learn="batched", params={"max_steps": 100}, seed=5, q_log2_capacity=10)
+    assert sim.q_capacity == 1024
+    sim.set_beta(1.0)
+    sim.set_positions(*pack_positions([random_positions(m, N, rng) for _ in range(B)], N))
+    sim.rollout(100)
+    with pytest.raises(FfmError, match="half full"):
+        sim.get_q()
+    with pytest.raises(Exception):
+        McqSim(m, sff, 1, 4, learn="none", seed=1, q_log2_capacity=40)
