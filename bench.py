@@ -68,11 +68,15 @@ WORKLOADS = {
     "c2traj": dict(h=64, w=64, n=1024, episodes=256, cap=4096, nbh="moore", k_S=3, k_D=0, track_dff=False, record=True,
                    desc="C2 geometry, 256 episodes/GPU, with the compact trajectory record (int16 row/col pairs, 4 B per "
                         "pedestrian-step; what run() collects, ffm_core.py:125 / main.py:44-52)"),
+    "c4train": dict(h=12, w=12, train=True, batch=256, rounds=2,
+                    desc="C4 pipeline: the unified model's curricula (run_unified_critic_training.py / run_unified_actor_training.py: radius "
+                         "3..15 step 2 x N in {1, 10..90}, epsilon 0.2 -> 0.01 per configuration) as batched GPU runs -- critic, then actor on "
+                         "the critic's V -- 256 episodes/GPU per round, 2 rounds per configuration, table deltas all-reduced every 8 CA steps"),
     "sff": dict(h=1024, w=1024, maps=64, sff=True,
                 desc="C5: static-floor-field sweep, 64 maps/GPU of 1024x1024 with 20 % random rectangular obstacles and 8 exits: "
                      "geodesic BFS-4, BFS-8, (1, sqrt2)-Dijkstra fields + the obstacle-blind L1 field of Create_SFF.py"),
 }
-SECONDARY = ("c3", "c4", "c2traj", "sff")
+SECONDARY = ("c3", "c4", "c4train", "c2traj", "sff")
 C4_ROUNDS = 16          # rollout + exchange rounds per timed step of the c4 workload (>= 50 syncs over the default 5 steps)
 
 
@@ -629,8 +633,68 @@ def run_sff_workload(ctx, name, wl):
     }
 
 
+def run_training_workload(ctx, name, wl):
+    """C4 as a pipeline: critic curriculum, then actor curriculum, then the frozen-H evaluation the reference accepts a training
+    by.  A step = both curricula from scratch; value = training episodes per second (all ranks)."""
+    torch, args = ctx.torch, ctx.args
+    from ffm_b200 import unified_training as ut
+    m = room_map(wl["h"], wl["w"])
+    sff = sff_room(m, "neumann")
+    exit_pos = tuple(int(v) for v in np.argwhere(m == 3)[0])
+    configs = ut.curriculum(m, exit_pos)
+    batch, rounds = wl["batch"], wl["rounds"]
+    episodes = 2 * len(configs) * rounds * batch                     # critic + actor, per rank
+    out = {}
+
+    def one(seed):
+        V, _ = ut.train_critic(m, sff, exit_pos, configs=configs, batch=batch, rounds=rounds, seed=seed, device=ctx.local)
+        H, _, _ = ut.train_actor(m, sff, exit_pos, V, configs=configs, batch=batch, rounds=rounds, seed=seed + 1, device=ctx.local)
+        out["H"], out["V"] = H, V
+
+    for k in range(min(args.warmup, 2)):
+        one(10 + k)
+    ctx.barrier()
+    mark0 = ctx.sampler.mark()
+    evs = event_pairs(torch, args.steps, 2)
+    for k in range(args.steps):
+        evs[k][0].record()
+        one(100 + 2 * k)
+        evs[k][1].record()
+    ctx.barrier()
+    clocks = ctx.sampler.window(mark0)
+    total_ms = sum(e[0].elapsed_time(e[1]) for e in evs)
+    (total_ms,), (eps_all,) = ctx.reduce([total_ms], [float(episodes)])
+    band = {}
+    for N in (10, 50, 90):
+        steps, frac = ut.evaluate_trained(m, sff, exit_pos, out["H"], N, episodes=256, device=ctx.local)
+        band[str(N)] = {"mean_steps": float(steps.mean()), "in_band_2N-1..2N+14": frac}
+    if ctx.rank != 0:
+        return None
+    value = eps_all * args.steps / (total_ms * 1e-3)
+    return {
+        "metric": "training_episodes_per_sec", "value": value, "unit": "episodes/s", "n_gpus": ctx.world, "steps": args.steps,
+        "warmup": min(args.warmup, 2), "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": wl["desc"], "configurations": len(configs), "episodes_per_step_per_gpu": episodes,
+                   "parallelism": f"episodes sharded over {ctx.world} GPU(s); one NCCL all-reduce of the flat table-delta buffer per sync",
+                   "reference": "run_20260115_234109/summary.txt: 45 000 actor episodes in 17:18:51 = 0.72 episodes/s (hardware unknown)"},
+        "acceptance": band, "tables": {"V_states": len(out["V"]), "H_rows": len(out["H"])},
+        "clocks": clocks,
+        "e2e": {"value": value, "unit": "episodes/s", "h2d_bytes_per_step": int(m.nbytes + sff.nbytes) * 2,
+                "d2h_bytes_per_step": int((len(out["V"]) + 5 * len(out["H"])) * 8), "ms_per_step": total_ms / args.steps,
+                "note": "the pipeline is driven from the host API as is: maps / fields in, V and H dicts out, inside the timed region"},
+        "gpu_launches": int(args.steps * 2 * len(configs) * rounds * (2 + (-(-ut.MAX_STEPS // 8)) * 2)),   # place + (rollout, apply) per sync
+        "roofline": {"bound": "hbm", "achieved": None, "peak": ctx.hbm_peak, "unit": "GB/s", "frac": None, "traffic": None,
+                     "note": "latency-bound pipeline of short launches (ffm_unified_rollout_kernel + apply_deltas + NCCL); see c4 for the kernel"},
+    }
+
+
 def run_workload(ctx, name, wl):
-    return run_sff_workload(ctx, name, wl) if wl.get("sff") else run_rollout_workload(ctx, name, wl)
+    if wl.get("sff"):
+        return run_sff_workload(ctx, name, wl)
+    if wl.get("train"):
+        return run_training_workload(ctx, name, wl)
+    return run_rollout_workload(ctx, name, wl)
 
 
 def main():
@@ -651,7 +715,7 @@ def main():
     if args.episodes:
         wl["episodes"] = args.episodes
     if args.impl == "reference":
-        if wl.get("sff") or wl.get("record"):
+        if wl.get("sff") or wl.get("record") or wl.get("train"):
             raise SystemExit("the reference arm covers the rollout workloads")
         run_reference_arm(args, wl)
         return
@@ -676,7 +740,7 @@ def main():
     if ctx.rank == 0:
         if secondary:
             line["secondary"] = secondary
-        if not args.no_cpu and ctx.world == 1 and not wl.get("sff"):
+        if not args.no_cpu and ctx.world == 1 and not wl.get("sff") and not wl.get("train"):
             try:
                 if wl.get("model") == "unified":
                     line["cpu_baseline"] = cpu_numpy_port_unified(wl, budget_s=min(args.cpu_budget, 10.0))
