@@ -114,7 +114,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "25"],
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thr = threading.Thread(target=self._read, daemon=True)
             self.thr.start()
@@ -336,7 +336,7 @@ class Ctx:
         self.hbm_peak = float(self.peaks.get("hbm_gbs", 6650.0))
         self.hbm_peak_source = "measured (MEASURED_PEAKS.json hbm_gbs)" if self.peaks else "fallback 6650 GB/s"
         self._smem = None
-        self.sampler = ClockSampler(self.local)     # one sampler for the whole run, 25 ms period; workloads take windows of it
+        self.sampler = ClockSampler(self.local)     # one sampler for the whole run, 50 ms period; workloads take windows of it
         self.sampler.start()
         try:
             self.profile = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))
