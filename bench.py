@@ -72,11 +72,16 @@ WORKLOADS = {
                     desc="C4 pipeline: the unified model's curricula (run_unified_critic_training.py / run_unified_actor_training.py: radius "
                          "3..15 step 2 x N in {1, 10..90}, epsilon 0.2 -> 0.01 per configuration) as batched GPU runs -- critic, then actor on "
                          "the critic's V -- 256 episodes/GPU per round, 2 rounds per configuration, table deltas all-reduced every 8 CA steps"),
+    "c5train": dict(h=50, w=50, train="mcq", batch=64, stride=10,
+                    desc="C5 pipeline (run_coverage_pretrain_and_training.py on its default configuration: 50x50 room, L1 SFF float64, N = 100, "
+                         "max_steps 500): coverage pretrain -- all 11 328 (target, from-direction) mini-episodes as ONE launch + the ordered backup "
+                         "pass -- then the N ramp / beta schedule, every 10th of its 1200 entries, 64 episodes/GPU per entry, returns exchanged "
+                         "by key between GPUs"),
     "sff": dict(h=1024, w=1024, maps=64, sff=True,
                 desc="C5: static-floor-field sweep, 64 maps/GPU of 1024x1024 with 20 % random rectangular obstacles and 8 exits: "
                      "geodesic BFS-4, BFS-8, (1, sqrt2)-Dijkstra fields + the obstacle-blind L1 field of Create_SFF.py"),
 }
-SECONDARY = ("c3", "c4", "c4train", "c2traj", "sff")
+SECONDARY = ("c3", "c4", "c4train", "c5train", "c2traj", "sff")
 C4_ROUNDS = 16          # rollout + exchange rounds per timed step of the c4 workload (>= 50 syncs over the default 5 steps)
 
 
@@ -689,7 +694,64 @@ def run_training_workload(ctx, name, wl):
     }
 
 
+def run_mcq_training_workload(ctx, name, wl):
+    """C5 as a pipeline: coverage pretrain (replicated on every rank: its result is the shared starting table) + the training
+    schedule (episodes sharded over ranks, by-key exchange of the returns).  value = training episodes per second."""
+    torch, args = ctx.torch, ctx.args
+    from ffm_b200.mcq_training import coverage_patterns, coverage_pretrain, run_training
+    m = room_map(wl["h"], wl["w"])
+    sff = sff_room(m, "neumann").astype(np.float64)
+    params = {"k_S": 3, "k_D": 1, "diffuse": 0.2, "decay": 0.2, "max_steps": 500, "alpha": 0.1, "gamma": 0.99}    # config/default_config.yaml
+    order = coverage_patterns(m, shuffle=False)
+    entries = list(range(0, 1200, wl["stride"]))
+    batch = wl["batch"]
+    out = {}
+
+    def one(seed):
+        Q, steps = coverage_pretrain(m, sff, params, {}, order=order, seed=seed, device=ctx.local, return_steps=True)
+        out["pre"], out["pre_steps"] = len(Q), int(steps.sum())
+        Q, mean_steps = run_training(m, sff, params, full_N=100, shared_Q=Q, batch=batch, seed=seed + 1, device=ctx.local, entries=entries)
+        out["Q"], out["mean_steps"] = len(Q), mean_steps
+
+    for k in range(min(args.warmup, 2)):
+        one(10 + k)
+    ctx.barrier()
+    mark0 = ctx.sampler.mark()
+    evs = event_pairs(torch, args.steps, 2)
+    for k in range(args.steps):
+        evs[k][0].record()
+        one(100 + 2 * k)
+        evs[k][1].record()
+    ctx.barrier()
+    clocks = ctx.sampler.window(mark0)
+    total_ms = sum(e[0].elapsed_time(e[1]) for e in evs)
+    (total_ms,), (sched_all,) = ctx.reduce([total_ms], [float(len(entries) * batch)])
+    if ctx.rank != 0:
+        return None
+    episodes = len(order) + sched_all                      # the pretrain is replicated: counted once
+    value = episodes * args.steps / (total_ms * 1e-3)
+    return {
+        "metric": "training_episodes_per_sec", "value": value, "unit": "episodes/s", "n_gpus": ctx.world, "steps": args.steps,
+        "warmup": min(args.warmup, 2), "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": wl["desc"], "pretrain_patterns": len(order), "pretrain_ca_steps": out["pre_steps"],
+                   "schedule_entries": len(entries), "episodes_per_entry_per_gpu": batch,
+                   "parallelism": f"pretrain replicated; schedule episodes sharded over {ctx.world} GPU(s), one all-gather of the touched (key, return sums) rows per entry"},
+        "tables": {"Q_rows_after_pretrain": out["pre"], "Q_rows_after_training": out["Q"]},
+        "mean_steps_first_last_entry": [out["mean_steps"][0], out["mean_steps"][-1]],
+        "clocks": clocks,
+        "e2e": {"value": value, "unit": "episodes/s", "h2d_bytes_per_step": int(m.nbytes + sff.nbytes) * 2, "d2h_bytes_per_step": int(out["Q"] * 28),
+                "ms_per_step": total_ms / args.steps,
+                "note": "the pipeline is driven from the host API as is: map / field in, Q dict out, inside the timed region"},
+        "gpu_launches": int(args.steps * (3 + len(entries) * 5)),     # pretrain: place-free rollout + ordered backup (+ table load); per entry: place, rollout, accumulate, fold (+ exchange)
+        "roofline": {"bound": "hbm", "achieved": None, "peak": ctx.hbm_peak, "unit": "GB/s", "frac": None, "traffic": None,
+                     "note": "latency-bound pipeline (ffm_mcq_rollout_kernel: hash-table lookups in L2, paths in HBM)"},
+    }
+
+
 def run_workload(ctx, name, wl):
+    if wl.get("train") == "mcq":
+        return run_mcq_training_workload(ctx, name, wl)
     if wl.get("sff"):
         return run_sff_workload(ctx, name, wl)
     if wl.get("train"):

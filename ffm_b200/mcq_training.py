@@ -132,10 +132,11 @@ class McqBatchedLearner:
         sim.fold()
 
 
-def run_training(map_array, sff, params, full_N, shared_Q=None, num_episodes=1200, batch=64, seed=0, device=None, log=None):
+def run_training(map_array, sff, params, full_N, shared_Q=None, num_episodes=1200, batch=64, seed=0, device=None, log=None,
+                 entries=None):
     """The schedule of main() (:313-333) with ``batch`` episodes per entry: entry k uses N = compute_agent_count(k) agents and
     beta = 1.0 for k < 500, compute_beta(k - 500) afterwards; the table is folded after every entry (McqBatchedLearner).
-    Returns (Q dict, mean steps per entry)."""
+    ``entries``: the schedule entries to run (default: all of range(num_episodes)).  Returns (Q dict, mean steps per entry)."""
     m = np.ascontiguousarray(np.asarray(map_array).astype(np.uint8))
     p = {**MCQ_DEFAULTS, **(params or {})}
     rank, world = (dist.get_rank(), dist.get_world_size()) if dist.is_available() and dist.is_initialized() else (0, 1)
@@ -145,7 +146,7 @@ def run_training(map_array, sff, params, full_N, shared_Q=None, num_episodes=120
         sim.load_q_dict(shared_Q)
     learner = McqBatchedLearner(sim)
     mean_steps = []
-    for k in range(int(num_episodes)):
+    for k in (range(int(num_episodes)) if entries is None else entries):
         N = compute_agent_count(k, int(full_N))
         beta = 1.0 if k < 500 else compute_beta(k - 500)
         sim.set_episode_base((k * world + rank) * batch)
