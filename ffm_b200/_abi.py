@@ -7,7 +7,7 @@ import os
 
 from . import build as _build
 
-ABI_VERSION = 6
+ABI_VERSION = 7
 FFM_HOST, FFM_DEVICE = 0, 1
 FFM_NEUMANN, FFM_MOORE = 4, 8
 FFM_F32, FFM_F64 = 0, 1
@@ -77,7 +77,7 @@ SIGNATURES = {
     "ffm_mcq_backup_ordered": (C.c_int, [C.c_void_p, C.c_void_p]),
     "ffm_mcq_accumulate": (C.c_int, [C.c_void_p, C.c_void_p]),
     "ffm_mcq_export_deltas": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
-    "ffm_mcq_import_deltas": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]),
+    "ffm_mcq_import_deltas": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]),
     "ffm_mcq_fold": (C.c_int, [C.c_void_p, C.c_void_p]),
     "ffm_set_beta": (C.c_int, [C.c_void_p, C.c_double]),
     "ffm_mcq_finalize_timeouts": (C.c_int, [C.c_void_p, C.c_void_p]),

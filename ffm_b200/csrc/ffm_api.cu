@@ -320,6 +320,7 @@ int check_device_flag(ffm_sim_t s, cudaStream_t st) {
     if (flag & 8) return fail(FFM_E_INVALID, "pedestrian position outside the map");
     if (flag & 16) return fail(FFM_E_INVALID, "pedestrian placed on a cell that is not free (map != 0)");
     if (flag & 32) return fail(FFM_E_UNSUPPORTED, "device placement: candidate buffer overflow");
+    if (flag & 256) return fail(FFM_E_UNSUPPORTED, "MC-Q exchange: more touched rows than the export list holds (raise export_capacity)");
     if (flag & 128) return fail(FFM_E_INVALID, "two pedestrians were placed on the same cell");
     if (flag & 64) return fail(FFM_E_UNSUPPORTED, "Q hash table more than half full: raise ffm_config_t.q_log2_capacity");
     return fail(FFM_E_INVALID, "device validation flag %d", flag);
@@ -1198,13 +1199,13 @@ int ffm_mcq_export_deltas(ffm_sim_t s, uint64_t* keys, double* rows, int64_t cap
     cudaStream_t st = (cudaStream_t)stream;
     CU(cudaSetDevice(s->cfg.device));
     CU(cudaMemsetAsync(count, 0, 4, st));
-    ffm::mcq_export_deltas_kernel<<<1184, 256, 0, st>>>(s->d_qkeys, s->d_qG, s->d_qN, s->q_cap, reinterpret_cast<unsigned long long*>(keys), rows, count, (unsigned int)capacity);
+    ffm::mcq_export_deltas_kernel<<<1184, 256, 0, st>>>(s->d_qkeys, s->d_qG, s->d_qN, s->q_cap, reinterpret_cast<unsigned long long*>(keys), rows, count, (unsigned int)capacity, s->d_err);
     CU(cudaGetLastError());
     s->launches++;
     return FFM_OK;
 }
 
-int ffm_mcq_import_deltas(ffm_sim_t s, const uint64_t* keys, const double* rows, uint32_t count, void* stream) {
+int ffm_mcq_import_deltas(ffm_sim_t s, const uint64_t* keys, const double* rows, uint32_t count, const uint32_t* count_dev, void* stream) {
     if (!s || (count > 0 && (!keys || !rows))) return fail(FFM_E_INVALID, "null argument");
     if (s->cfg.model != FFM_MODEL_MCQ) return fail(FFM_E_STATE, "only the MC-Q model exchanges return sums");
     cudaStream_t st = (cudaStream_t)stream;
@@ -1214,7 +1215,7 @@ int ffm_mcq_import_deltas(ffm_sim_t s, const uint64_t* keys, const double* rows,
     if (count == 0) return FFM_OK;
     ffm::McqParams M;
     fill_mcq_params(s, M, 0);
-    ffm::mcq_import_deltas_kernel<<<(int)((count + 255u) / 256u < 1184u ? (count + 255u) / 256u : 1184u), 256, 0, st>>>(M, reinterpret_cast<const unsigned long long*>(keys), rows, count, s->d_qG, s->d_qN);
+    ffm::mcq_import_deltas_kernel<<<(int)((count + 255u) / 256u < 1184u ? (count + 255u) / 256u : 1184u), 256, 0, st>>>(M, reinterpret_cast<const unsigned long long*>(keys), rows, count, count_dev, s->d_qG, s->d_qN);
     CU(cudaGetLastError());
     s->launches++;
     return FFM_OK;

@@ -583,13 +583,14 @@ static __global__ void mcq_fold_kernel(float* Q, double* dG, double* dN, size_t 
 }
 // exchange by key (the slot of a key differs between ranks): rows touched since the last fold -> (key, sum G[5], n[5])
 static __global__ void mcq_export_deltas_kernel(const unsigned long long* keys, double* dG, double* dN, uint32_t cap, unsigned long long* out_keys,
-                                         double* out_rows, unsigned int* out_count, unsigned int out_cap) {
+                                         double* out_rows, unsigned int* out_count, unsigned int out_cap, int32_t* err) {
     for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < cap; s += gridDim.x * blockDim.x) {
         double n[5]; bool any = false;
 #pragma unroll
         for (int a = 0; a < 5; ++a) { n[a] = dN[(size_t)s * 5 + a]; any |= n[a] > 0.0; }
         if (!any) continue;
         const unsigned int k = atomicAdd(out_count, 1u);
+        if (k >= out_cap) atomicOr(err, 256);                  // the caller's list is too short: reported at the next host read
         if (k < out_cap) {
             out_keys[k] = keys[s];
 #pragma unroll
@@ -602,7 +603,8 @@ static __global__ void mcq_export_deltas_kernel(const unsigned long long* keys, 
 // one rank's exported list added into the local delta tables (keys are unique within a list: plain adds, so that importing the
 // lists in rank order gives every rank bit-identical sums)
 static __global__ void mcq_import_deltas_kernel(McqParams P, const unsigned long long* in_keys, const double* in_rows, unsigned int count,
-                                         double* dG, double* dN) {
+                                         const unsigned int* count_dev, double* dG, double* dN) {
+    if (count_dev != nullptr) count = min(*count_dev, count);          // the exporting rank's count travels with its list
     for (unsigned int k = blockIdx.x * blockDim.x + threadIdx.x; k < count; k += gridDim.x * blockDim.x) {
         const uint32_t s = mcq_find_or_insert(P.qkeys, P.qmask, in_keys[k], P.q_count, P.err);
 #pragma unroll

@@ -107,28 +107,29 @@ class McqBatchedLearner:
     lists: the path's only collective), imports every rank's list in rank order -- so all ranks hold bit-identical sums and
     therefore bit-identical tables -- and folds them in."""
 
-    def __init__(self, sim, distributed=True, export_capacity=1 << 18):
+    def __init__(self, sim, distributed=True, export_capacity=1 << 15):
         assert sim.learn == "batched"
         self.sim, self.distributed, self.capacity = sim, distributed, int(export_capacity)
+        self._send = self._recv = None
 
     def sync(self):
+        """No host synchronisation: export kernel -> ONE all-gather of the fixed-size [count | keys | rows] messages -> one
+        import kernel per rank (each reads its list's count on the device) -> fold.  A list longer than ``export_capacity``
+        raises at the next host read of the handle."""
         sim = self.sim
         sim.accumulate()
         world = dist.get_world_size() if self.distributed and dist.is_available() and dist.is_initialized() else 1
         if world > 1:
-            keys, rows, count = sim.export_deltas(self.capacity)
-            counts = [torch.zeros_like(count) for _ in range(world)]
-            dist.all_gather(counts, count)
-            n = [int(c.item()) for c in counts]
-            if max(n) > self.capacity:
-                raise RuntimeError(f"{max(n)} touched rows exceed the export capacity {self.capacity}")
-            k = max(max(n), 1)
-            gk = [torch.empty(k, dtype=keys.dtype, device=keys.device) for _ in range(world)]
-            gr = [torch.empty((k, 10), dtype=rows.dtype, device=rows.device) for _ in range(world)]
-            dist.all_gather(gk, keys[:k].contiguous())
-            dist.all_gather(gr, rows[:k].contiguous())
+            cap = self.capacity
+            size = 1 + 11 * cap
+            if self._send is None:
+                self._send = torch.zeros(size, dtype=torch.float64, device=sim.delta_device())
+                self._recv = torch.zeros(world * size, dtype=torch.float64, device=sim.delta_device())
+            sim.export_deltas(cap, out=self._send)
+            dist.all_gather_into_tensor(self._recv, self._send)
             for r in range(world):
-                sim.import_deltas(gk[r], gr[r], n[r])
+                msg = self._recv[r * size:(r + 1) * size]
+                sim.import_deltas(msg[1:1 + cap].view(torch.int64), msg[1 + cap:].view(cap, 10), cap, count_dev=msg[:1].view(torch.int32)[:1])
         sim.fold()
 
 

@@ -522,17 +522,26 @@ class McqSim(BatchSim):
     def fold(self):
         _abi.check(self._lib.ffm_mcq_fold(self._h, _stream()))
 
-    def export_deltas(self, capacity):
-        """-> (keys int64 [capacity], rows float64 [capacity, 10], count uint32 [1]) CUDA tensors: the rows touched since the
-        last fold, by key; the local delta tables are cleared."""
+    def delta_device(self):
+        return f"cuda:{self.device}"
+
+    def export_deltas(self, capacity, out=None):
+        """-> (keys int64 [capacity], rows float64 [capacity, 10], count int32 [1]) CUDA tensors: the rows touched since the
+        last fold, by key; the local delta tables are cleared.  ``out``: a flat float64 CUDA tensor of 1 + 11 * capacity
+        elements to write into ([count | keys | rows], the views are returned) so that the whole list travels as one message."""
         dev = f"cuda:{self.device}"
-        keys = torch.zeros(capacity, dtype=torch.int64, device=dev)
-        rows = torch.zeros((capacity, 10), dtype=torch.float64, device=dev)
-        count = torch.zeros(1, dtype=torch.int32, device=dev)
+        if out is None:
+            out = torch.zeros(1 + 11 * capacity, dtype=torch.float64, device=dev)
+        assert out.is_cuda and out.dtype == torch.float64 and out.is_contiguous() and out.numel() == 1 + 11 * capacity
+        count = out[:1].view(torch.int32)[:1]
+        keys = out[1:1 + capacity].view(torch.int64)
+        rows = out[1 + capacity:].view(capacity, 10)
         _abi.check(self._lib.ffm_mcq_export_deltas(self._h, _ptr(keys), _ptr(rows), int(capacity), _ptr(count), _stream()))
         return keys, rows, count
 
-    def import_deltas(self, keys, rows, count):
+    def import_deltas(self, keys, rows, count, count_dev=None):
+        """Add one rank's exported list into the local delta tables: ``count`` rows, or min(count, *count_dev) when the
+        exporter's count arrives on the device with its list."""
         assert keys.is_cuda and rows.is_cuda and keys.is_contiguous() and rows.is_contiguous()
-        self._keep = [keys, rows]
-        _abi.check(self._lib.ffm_mcq_import_deltas(self._h, _ptr(keys), _ptr(rows), int(count), _stream()))
+        self._keep = [keys, rows, count_dev]
+        _abi.check(self._lib.ffm_mcq_import_deltas(self._h, _ptr(keys), _ptr(rows), int(count), _ptr(count_dev), _stream()))

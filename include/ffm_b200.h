@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define FFM_ABI_VERSION 6
+#define FFM_ABI_VERSION 7
 
 enum {
     FFM_OK = 0,
@@ -243,12 +243,14 @@ int ffm_mcq_set_forced(ffm_sim_t sim, const int32_t *target_cell, const int32_t 
  *   ffm_mcq_accumulate       returns summed per (row, action) with visit counts into the handle's delta tables
  *   ffm_mcq_export_deltas    multi-GPU exchange by KEY: touched rows -> keys uint64 [capacity], rows float64 [capacity][10]
  *                            (sum G[5], n[5]), *count = rows written (device pointers); clears the local delta tables
- *   ffm_mcq_import_deltas    one rank's exported list added into the local delta tables (import the lists in rank order)
+ *   ffm_mcq_import_deltas    one rank's exported list added into the local delta tables (import the lists in rank order);
+ *                            count = rows to import, or, with count_dev != NULL (a device pointer: the exporter's count that
+ *                            travelled with its list), min(*count_dev, count) -- no host synchronisation anywhere in the exchange
  *   ffm_mcq_fold             Q += (1 - (1 - alpha)^n) (sum G / n - Q) per touched entry, delta tables zeroed */
 int ffm_mcq_backup_ordered(ffm_sim_t sim, void *stream);
 int ffm_mcq_accumulate(ffm_sim_t sim, void *stream);
 int ffm_mcq_export_deltas(ffm_sim_t sim, uint64_t *keys, double *rows, int64_t capacity, uint32_t *count, void *stream);
-int ffm_mcq_import_deltas(ffm_sim_t sim, const uint64_t *keys, const double *rows, uint32_t count, void *stream);
+int ffm_mcq_import_deltas(ffm_sim_t sim, const uint64_t *keys, const double *rows, uint32_t count, const uint32_t *count_dev, void *stream);
 int ffm_mcq_fold(ffm_sim_t sim, void *stream);
 int ffm_set_beta(ffm_sim_t sim, double beta);   /* the beta argument of step(beta), ffm_learning_core.py:145 */
 int ffm_mcq_finalize_timeouts(ffm_sim_t sim, void *stream);   /* finalize_timeouts(), ffm_learning_core.py:326-360 */

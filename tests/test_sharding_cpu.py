@@ -71,19 +71,26 @@ class _FakeMcqSim:
         # rank r touched keys {r, r + 1, ..., r + 3 + r}: ragged lists, one key shared between the ranks
         self.local = {100 + k: np.full(10, float(10 * rank + k)) for k in range(rank, rank + 4 + rank)}
 
+    def delta_device(self):
+        return "cpu"
+
     def accumulate(self):
         pass
 
-    def export_deltas(self, capacity):
-        keys = torch.zeros(capacity, dtype=torch.int64)
-        rows = torch.zeros((capacity, 10), dtype=torch.float64)
+    def export_deltas(self, capacity, out=None):
+        out.zero_()
+        count = out[:1].view(torch.int32)[:1]
+        keys = out[1:1 + capacity].view(torch.int64)
+        rows = out[1 + capacity:].view(capacity, 10)
         for i, (k, v) in enumerate(sorted(self.local.items())):
             keys[i] = k
             rows[i] = torch.from_numpy(v)
-        return keys, rows, torch.tensor([len(self.local)], dtype=torch.int32)
+        count[0] = len(self.local)
+        return keys, rows, count
 
-    def import_deltas(self, keys, rows, count):
-        for i in range(int(count)):
+    def import_deltas(self, keys, rows, count, count_dev=None):
+        n = min(int(count), int(count_dev[0])) if count_dev is not None else int(count)
+        for i in range(n):
             k = int(keys[i])
             self.table[k] = self.table.get(k, np.zeros(10)) + rows[i].numpy()
 
