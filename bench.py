@@ -65,8 +65,8 @@ WORKLOADS = {
                     "4096 episodes/GPU per sync, all-reduce of the table deltas, cap 300"),
     "c1": dict(h=12, w=12, n=100, episodes=4096, cap=4096, nbh="neumann", k_S=3, k_D=1, track_dff=True,
                desc="C1 geometry batched: 12x12 room, neumann, N=100, DFF on"),
-    "c2traj": dict(h=64, w=64, n=1024, episodes=256, cap=4096, nbh="moore", k_S=3, k_D=0, track_dff=False, record=True,
-                   desc="C2 geometry, 256 episodes/GPU, with the compact trajectory record (int16 row/col pairs, 4 B per "
+    "c2traj": dict(h=64, w=64, n=1024, episodes=1024, cap=4096, nbh="moore", k_S=3, k_D=0, track_dff=False, record=True,
+                   desc="C2 geometry, 1024 episodes/GPU, with the compact trajectory record (int16 row/col pairs, 4 B per "
                         "pedestrian-step; what run() collects, ffm_core.py:125 / main.py:44-52)"),
     "c4train": dict(h=12, w=12, train=True, batch=256, rounds=2,
                     desc="C4 pipeline: the unified model's curricula (run_unified_critic_training.py / run_unified_actor_training.py: radius "
