@@ -7,7 +7,7 @@ import os
 
 from . import build as _build
 
-ABI_VERSION = 7
+ABI_VERSION = 8
 FFM_HOST, FFM_DEVICE = 0, 1
 FFM_NEUMANN, FFM_MOORE = 4, 8
 FFM_F32, FFM_F64 = 0, 1
@@ -69,6 +69,7 @@ SIGNATURES = {
     "ffm_tables_bind_deltas": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ffm_tables_apply_deltas": (C.c_int, [C.c_void_p, C.c_void_p]),
     "ffm_set_epsilon": (C.c_int, [C.c_void_p, C.c_double]),
+    "ffm_bind_dynamic": (C.c_int, [C.c_void_p, C.c_void_p]),
     "ffm_set_episode_base": (C.c_int, [C.c_void_p, C.c_uint32]),
     "ffm_q_shape": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
     "ffm_q_get": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),

@@ -81,6 +81,7 @@ struct ffm_sim_s {
     ffm::HStats* d_hstats;
     double* d_blk_lo; double* d_blk_hi; int* d_blk_any;
     double epsilon;
+    const void* d_dyn;   // caller-owned device struct {double epsilon; uint32 episode_base; uint32 pad} overriding both (CUDA-graph replays)
     // MC-Q model: the Q dict as an open-addressing hash table
     unsigned long long* d_qkeys; float* d_Q; unsigned int* d_qcount; uint32_t q_cap;
     uint32_t* d_path_state; uint8_t* d_path_code; int32_t* d_path_len; uint16_t* d_path_col;
@@ -864,6 +865,7 @@ int ffm_rollout(ffm_sim_t s, int32_t max_steps, const ffm_draws_t* draws, const 
         s->hstats_stale = false;
         U.hstats = s->d_hstats;
         U.seed = s->cfg.seed; U.episode_base = s->cfg.episode_base; U.err = s->d_err;
+        U.dyn = reinterpret_cast<const ffm::UnifiedDyn*>(s->d_dyn);
         if (draws) { U.move_draws = draws->move; U.conflict_draws = draws->conflict; U.draw_steps = draws->steps; U.draw_first = draws->first_step; }
         if (out && out->traj_cells) {
             if (!out->traj_n) return fail(FFM_E_INVALID, "traj_cells without traj_n");
@@ -1068,6 +1070,13 @@ int ffm_tables_apply_deltas(ffm_sim_t s, void* stream) {
                                 s->S, s->A, s->d_hstats, s->d_blk_lo, s->d_blk_hi, s->d_blk_any, 148, st));
     s->launches += has_h ? 2 : 1;
     if (has_h) s->hstats_stale = false;
+    return FFM_OK;
+}
+
+int ffm_bind_dynamic(ffm_sim_t s, const void* dyn) {
+    if (!s) return fail(FFM_E_INVALID, "null argument");
+    if (s->cfg.model == FFM_MODEL_CORE || s->cfg.model == FFM_MODEL_MCQ) return fail(FFM_E_STATE, "only the unified models take device-resident round parameters");
+    s->d_dyn = dyn;
     return FFM_OK;
 }
 

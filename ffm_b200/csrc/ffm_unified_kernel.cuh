@@ -47,6 +47,8 @@ struct HStats {           // running min / max over every value of the touched r
     int any;              // at least one row exists
 };
 
+struct UnifiedDyn { double epsilon; uint32_t episode_base; uint32_t pad; };
+
 struct UnifiedParams {
     int H, W, HW, n_max, B;
     int max_steps;
@@ -70,6 +72,8 @@ struct UnifiedParams {
     uint32_t* traj; int32_t* traj_n; int traj_steps;
     uint32_t* rec_state; uint8_t* rec_action; float* rec_reward; int32_t* rec_len;   // rollout buffer [B][traj_steps][n_max]
     int32_t* err;                // device validation flag (128: two pedestrians on one cell)
+    const struct UnifiedDyn* dyn; // optional device-resident overrides of episode_base / epsilon (CUDA-graph replays: a captured
+                                 // launch freezes its by-value parameters, these two change every round)
     uint32_t magic_w, magic_bs;  // ceil(2^32 / W), ceil(2^32 / block_size): x / d = umulhi(x, magic) for x * d < 2^32
 };
 
@@ -222,7 +226,8 @@ ffm_unified_rollout_kernel(const UnifiedParams P) {
     for (int i = tid; i < n; i += THREADS)      // duplicates OR their ids together: somebody reads back a foreign id
         if ((grid[pos[i]] & OCC_MASK) != (uint32_t)(i + 1) && P.err != nullptr) atomicOr(P.err, 128);
 
-    const uint32_t episode = P.episode_base + (uint32_t)e;
+    const uint32_t episode = (P.dyn != nullptr ? P.dyn->episode_base : P.episode_base) + (uint32_t)e;
+    const double epsilon = P.dyn != nullptr ? P.dyn->epsilon : P.epsilon;
     const double* mv_draws = P.move_draws ? P.move_draws + (size_t)e * P.draw_steps * P.n_max : nullptr;
     const double* cf_draws = P.conflict_draws ? P.conflict_draws + (size_t)e * P.draw_steps * HW * 2 : nullptr;
     const bool actor = ACTOR;                                                    // == (P.mode != UMODE_CRITIC), checked by the host
@@ -398,9 +403,9 @@ ffm_unified_rollout_kernel(const UnifiedParams P) {
                 for (int k = 0; k < A; ++k) { e_[k] = ((valid >> k) & 1u) ? 1.0 : 0.0; tot += e_[k]; }
             }
             int slot = -1;
-            if (learn_actor && P.epsilon > 0.0) {                       // epsilon-greedy (:478-495)
+            if (learn_actor && epsilon > 0.0) {                       // epsilon-greedy (:478-495)
                 const Draw2 d = draw2(P.seed, episode, t, STREAM_EPS, (uint32_t)i);
-                if (d.u0 < P.epsilon) {
+                if (d.u0 < epsilon) {
                     const int nv = __popc(valid);
                     slot = (int)__fns(valid, 0, (int)(d.u1 * (double)nv) + 1);
                 }

@@ -388,6 +388,11 @@ class UnifiedSim(BatchSim):
     def set_epsilon(self, epsilon):
         _abi.check(self._lib.ffm_set_epsilon(self._h, float(epsilon)))
 
+    def bind_dynamic(self, dyn):
+        """Read epsilon / episode_base from a device buffer from now on (CUDA-graph replays; see RoundParams); None unbinds."""
+        self._dyn = dyn
+        _abi.check(self._lib.ffm_bind_dynamic(self._h, None if dyn is None else _ptr(dyn)))
+
     # -- batched learning: ONE flat float64 buffer [dV | dN | dF | dH] per sync, so that the cross-GPU exchange is a
     #    single all-reduce(sum) -----------------------------------------------------------------------
     def new_delta_buffer(self):
@@ -405,6 +410,21 @@ class UnifiedSim(BatchSim):
         """Fold the bound delta buffer in (call after all-reducing it): V += (1-(1-alpha_v)^n) * mean TD error,
         H += dH, touched keys marked present, deltas zeroed, H extremes refreshed.  Stream-ordered."""
         _abi.check(self._lib.ffm_tables_apply_deltas(self._h, _stream()))
+
+
+class RoundParams:
+    """The two per-round parameters of a unified-model rollout as a device-resident struct {double epsilon; uint32
+    episode_base; uint32 pad}, so that a CUDA graph holding the round's launches can be replayed with new values:
+    ``set()`` copies them stream-ordered."""
+
+    def __init__(self, device):
+        self.dev = torch.zeros(16, dtype=torch.uint8, device=device)
+
+    def set(self, epsilon, episode_base):
+        h = np.zeros(16, np.uint8)
+        h[:8] = np.frombuffer(np.float64(epsilon).tobytes(), np.uint8)
+        h[8:12] = np.frombuffer(np.uint32(int(episode_base) & 0xFFFFFFFF).tobytes(), np.uint8)
+        self.dev.copy_(torch.from_numpy(h))          # pageable source: staged before the call returns, stream-ordered on the device
 
 
 def rollout_returns(reward, length, gamma):

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define FFM_ABI_VERSION 7
+#define FFM_ABI_VERSION 8
 
 enum {
     FFM_OK = 0,
@@ -218,6 +218,10 @@ int ffm_tables_get(ffm_sim_t sim, double *V, uint8_t *v_seen, double *H, uint8_t
 int ffm_tables_bind_deltas(ffm_sim_t sim, double *dV, double *dN, double *dF, double *dH);
 int ffm_tables_apply_deltas(ffm_sim_t sim, void *stream);
 int ffm_set_epsilon(ffm_sim_t sim, double epsilon);   /* set_epsilon() :859-867 */
+/* CUDA-graph replays: a captured ffm_rollout freezes its by-value parameters, but epsilon (set_epsilon) and the episode key
+ * (reset()) change every round.  Bind a caller-owned DEVICE struct {double epsilon; uint32_t episode_base; uint32_t pad}: the
+ * following rollouts read both from it (update it with a stream-ordered copy before each replay); NULL unbinds. */
+int ffm_bind_dynamic(ffm_sim_t sim, const void *dyn);
 /* global id of episode 0 for the following rollouts (a drop-in object advances it on every reset()) */
 int ffm_set_episode_base(ffm_sim_t sim, uint32_t episode_base);
 

@@ -28,3 +28,22 @@ def test_actor_training_reaches_the_reference_band(cuda_device):
     # control: the same evaluation with an untrained (empty) H table does not evacuate on that schedule
     steps0, frac0 = ut.evaluate_trained(m, sff, exit_pos, {}, 50, episodes=64, seed=12)
     assert frac0 < 0.5, frac0
+
+
+def test_graph_replayed_rounds_equal_eager_rounds(cuda_device):
+    """The round's launch chain captured in a CUDA graph (epsilon and the episode key read from a device struct,
+    ffm_bind_dynamic) trains the same tables as eager launches: same keyed draws, same trajectories; the sums differ only by
+    the order of the float64 atomics."""
+    from ffm_b200 import unified_training as ut
+    m = assets.room_map(12, 12)
+    sff = assets.sff_norm_min(m, "L1", np.float32)
+    cfgs = [(5, 10), (9, 30), (15, 50)]
+    out = []
+    for use_graph in (False, True):
+        V, _ = ut.train_critic(m, sff, (0, 6), configs=cfgs, batch=64, rounds=3, sync_every=8, seed=21, use_graph=use_graph)
+        H, V2, _ = ut.train_actor(m, sff, (0, 6), V, configs=cfgs, batch=64, rounds=3, sync_every=8, seed=22, use_graph=use_graph)
+        out.append((V, H))
+    (Ve, He), (Vg, Hg) = out
+    assert set(Ve) == set(Vg) and set(He) == set(Hg) and len(Ve) > 500
+    assert np.allclose([Ve[k] for k in Ve], [Vg[k] for k in Ve], rtol=1e-9, atol=1e-9)
+    assert np.allclose([He[k] for k in He], [Hg[k] for k in He], rtol=1e-7, atol=1e-7)
