@@ -166,7 +166,7 @@ __device__ __forceinline__ void mcq_backup(const McqParams& P, int e, int col, i
     double G = 0.0;
     const float alpha32 = (float)P.alpha;
     const size_t stride = (size_t)P.n_max, base = (size_t)e * P.path_rows * stride + col;
-    volatile float* Q = P.Q;
+    float* Q = P.Q;      // one CTA owns the table in the EXACT mode: plain (L1-cached) accesses, program order per thread
     for (int t = len - 1; t >= 0; --t) {
         const uint32_t sid = P.path_state[base + (size_t)t * stride];              // table slot (the row exists: _ensure_qvec ran)
         const uint32_t pc = P.path_code[base + (size_t)t * stride];

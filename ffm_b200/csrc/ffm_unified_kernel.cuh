@@ -508,7 +508,7 @@ ffm_unified_rollout_kernel(const UnifiedParams P) {
             if (P.learn == ULEARN_EXACT) {
                 // T2: the reference's sequential loop over agents on the shared table (:633-665)
                 if (tid == 0) {
-                    volatile double* V = P.V;
+                    double* V = P.V;              // one CTA owns the tables in this mode: plain (L1-cached) accesses, program order per thread
                     for (int i = 0; i < n; ++i) {
                         const uint32_t w = info[i];
                         const double rew = agent_reward(P, w);
@@ -534,7 +534,7 @@ ffm_unified_rollout_kernel(const UnifiedParams P) {
                     HStats* hs = P.hstats;
                     double hmin = hs->hmin, hmax = hs->hmax;
                     int any = hs->any, dirty = hs->dirty;
-                    volatile double* Hm = P.Hm;
+                    double* Hm = P.Hm;
                     for (int i = 0; i < n; ++i) {
                         const uint32_t w = info[i], sid = st[i];
                         if (!P.h_seen[sid]) {                            // row inserted as zeros (:769-773)
