@@ -525,6 +525,10 @@ def run_rollout_workload(ctx, name, wl):
             roof = {"bound": "hbm", **hbm,
                     "note": ("record stores stream to HBM; " if record else "") +
                             ("score/DFF fields live in L2/HBM at this map size" if not info["fields_in_smem"] else "")}
+        if prof.get("issue_active_pct") is not None:
+            # what actually bounds the on-chip rollouts: instruction issue (from the committed ncu capture of this command)
+            roof["issue"] = {"achieved": prof.get("ipc"), "peak": 4.0, "unit": "warp instructions / clk / SM",
+                             "frac": prof["issue_active_pct"] / 100.0, "source": prof.get("source")}
         roof.update({"traffic": prof.get("dram_bytes_per_launch") if B == prof.get("episodes") else None,
                      "kernel_ms": kern_ms, "algorithmic_bytes_per_launch": alg_bytes,
                      "ncu": {k: prof.get(k) for k in ("smem_wavefronts_pct_of_peak", "smem_bank_conflict_share", "issue_active_pct",
