@@ -485,7 +485,7 @@ int ffm_create(const ffm_config_t* cfg, ffm_sim_t* out) {
     if (s->cell_kernel && s->cluster > 1) {
         // one cluster per episode
         s->threads = (s->cluster == 2 && !s->fields_in_smem) ? 1024 : 512;    // measured (C3): 2.05e10 vs 1.98e10; larger clusters / on-chip fields: 512
-        if (const char* ev = getenv("FFM_THREADS")) { const int v = atoi(ev); if (v == 512 || v == 1024) s->threads = v; }   // tuning
+        if (const char* ev = getenv("FFM_THREADS")) { const int v = atoi(ev); if (v == 512 || (v == 1024 && s->cluster == 2)) s->threads = v; }   // tuning
         s->smem_bytes = (int)ffm::make_cell_layout(s->RB, W, s->RW, N, ssz, esz, dff, s->fields_in_smem, s->wall_in_smem, s->score_in_smem).total;
         s->kernel = ffm::pick_cell_kernel(f64, HW <= 65536, cfg->neighborhood, dff, s->fields_in_smem, s->threads, s->cluster);
         if (!s->kernel) { delete s; return fail(FFM_E_UNSUPPORTED, "no cluster variant of the rollout kernel for this configuration"); }

@@ -4,7 +4,9 @@ namespace ffm { namespace {
 template <typename S, typename EntT, int NBR, bool DFF, bool FS, int CL>
 const void* cpick_threads(int threads) {
     if constexpr (CL > 1) {   // cluster variants: 512 threads per CTA (1024 measured slower: 64 registers, spills)
-        if (threads == 1024) return (const void*)ffm_cell_rollout_kernel<S, EntT, NBR, DFF, FS, 1024, CL>;
+        if constexpr (CL == 2) {   // 1024 threads only pay in the 2-CTA form (measured on C3); larger clusters: 512
+            if (threads == 1024) return (const void*)ffm_cell_rollout_kernel<S, EntT, NBR, DFF, FS, 1024, CL>;
+        }
         return (const void*)ffm_cell_rollout_kernel<S, EntT, NBR, DFF, FS, 512, CL>;
     } else {
         if (threads == 1024) return (const void*)ffm_cell_rollout_kernel<S, EntT, NBR, DFF, FS, 1024, 1>;
