@@ -13,7 +13,7 @@ pytestmark = pytest.mark.gpu
 
 def _case(seed):
     rng = np.random.RandomState(1000 + seed)
-    H, W = int(rng.randint(9, 72)), int(rng.randint(9, 90))
+    H, W = int(rng.randint(12, 72)), int(rng.randint(12, 90))
     if seed % 3 == 0:
         W = 4 * (W // 4)                                  # widths that take the vectorised DFF stencil
     m = assets.obstacle_map_c5(H, W, index=seed, fill=float(rng.uniform(0.0, 0.25)), n_exits=int(rng.choice([4, 8])))
