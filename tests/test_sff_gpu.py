@@ -68,3 +68,17 @@ def test_geodesic_c3_and_c5_maps(cuda_device):
     for mode in ("bfs4", "dijkstra8"):
         got = generate_sff(torch.from_numpy(m5).cuda(), mode, np.float32).cpu().numpy()
         assert np.array_equal(got.view(np.uint32), c_oracle.geodesic(m5, mode).view(np.uint32)), mode
+
+
+@pytest.mark.parametrize("mode", ["bfs8", "dijkstra8"])
+def test_geodesic_work_queue_is_order_independent(cuda_device, mode):
+    """The tile work queue relaxes in whatever order the persistent CTAs happen to pop; the fixpoint must not depend on it:
+    the same batch, many times over, always equals the heap-Dijkstra oracle bit for bit (odd sizes: ragged edge tiles)."""
+    import torch
+    from ffm_b200.sff import generate_sff
+    maps = np.stack([assets.obstacle_map_c5(257, 301, index=40 + i, fill=0.3, n_exits=8) for i in range(12)])
+    want = np.stack([c_oracle.geodesic(mm, mode) for mm in maps])
+    dm = torch.from_numpy(maps).cuda()
+    for rep in range(12):
+        got = generate_sff(dm, mode, np.float32).cpu().numpy()
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), rep
