@@ -172,3 +172,38 @@ def test_c3_floor_plan_matches_c_oracle(cuda_device, monkeypatch, variant, B, T)
     for e in range(B):
         assert np.array_equal(p_gpu[e, :n_gpu[e], 0] * W + p_gpu[e, :n_gpu[e], 1], ref["final_pos"][e, :n_gpu[e]])
     assert np.array_equal(sim.get_dff().view(np.uint32), ref["final_dff"].view(np.uint32))
+
+
+def test_c3_all_kernel_variants_agree_under_keyed_draws(cuda_device, monkeypatch):
+    """C3 geometry, pure Philox mode (no recorded draws), 8 episodes x 400 steps: the pedestrian-centric kernel, the 2-CTA cluster
+    with the fields in L2 (twice: run-to-run determinism), the 4-CTA cluster with the fields in distributed shared memory and the
+    8-CTA cluster compute the same function -- positions, counts, pedestrian-steps and DFF bits are identical.  (Races in the
+    cross-CTA paths would show up here as run-to-run or variant-to-variant differences.)"""
+    from ffm_b200 import BatchSim
+    from ffm_b200.sff import generate_sff
+    from ffm_b200.workloads import place, rooms_map_c3
+    m = rooms_map_c3()
+    sff = generate_sff(m, "bfs8", np.float32)
+    B, N, seed, T = 8, 10000, 0xC0FFEE, 400
+    params = {"k_S": 3, "k_D": 1, "neighborhood": "moore"}
+    pos = place(m, N, B, 0, seed)
+    n = np.full((B,), N, np.int32)
+    results = {}
+    for tag, env in (("ped", {"FFM_KERNEL": "ped"}), ("cl2", {}), ("cl2_again", {}), ("cl4smem", {"FFM_CLUSTER": "4", "FFM_FIELDS_SMEM": "1"}),
+                     ("cl8", {"FFM_CLUSTER": "8"})):
+        for k in ("FFM_KERNEL", "FFM_CLUSTER", "FFM_FIELDS_SMEM"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        sim = BatchSim(m, sff, B, N, params, seed=seed)
+        sim.set_positions(pos, n)
+        sim.rollout(T // 2)
+        sim.rollout(T - T // 2)
+        p, k = sim.get_positions()
+        results[tag] = (sim.kernel_info()["cluster"], p, k, sim.counters()[1].copy(), sim.get_dff().view(np.uint32).copy())
+        sim.close()
+    assert [results[t][0] for t in ("ped", "cl2", "cl4smem", "cl8")] == [1, 2, 4, 8]
+    ref = results["ped"]
+    for tag, got in results.items():
+        assert np.array_equal(got[2], ref[2]) and np.array_equal(got[1], ref[1]), tag
+        assert np.array_equal(got[3], ref[3]) and np.array_equal(got[4], ref[4]), tag
