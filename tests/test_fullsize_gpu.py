@@ -207,3 +207,35 @@ def test_c3_all_kernel_variants_agree_under_keyed_draws(cuda_device, monkeypatch
     for tag, got in results.items():
         assert np.array_equal(got[2], ref[2]) and np.array_equal(got[1], ref[1]), tag
         assert np.array_equal(got[3], ref[3]) and np.array_equal(got[4], ref[4]), tag
+
+
+@pytest.mark.parametrize("k_D,track", [(0, False), (1, True)])
+def test_c2_kernel_variants_agree_to_evacuation(cuda_device, monkeypatch, k_D, track):
+    """C2 geometry to full evacuation (~1700 steps, ~4.5e5 draws per episode), 96 episodes, pure Philox mode: the cell-centric
+    kernel (one CTA), the same as 2- and 4-CTA clusters, and the pedestrian-centric kernel give identical evacuation times,
+    pedestrian-step counts and final DFF bits."""
+    import bench
+    from ffm_b200 import BatchSim
+    m, sff = _c2()
+    B, N, seed = 96, 1024, 0xD1CE
+    params = {"k_S": 3, "k_D": k_D, "neighborhood": "moore"}
+    pos = bench.place(m, N, B, 500, seed)
+    n = np.full((B,), N, np.int32)
+    out = {}
+    for tag, env in (("cell", {"FFM_KERNEL": "cell"}), ("ped", {"FFM_KERNEL": "ped"}), ("cl2", {"FFM_KERNEL": "cell", "FFM_CLUSTER": "2", "FFM_FIELDS_SMEM": "1"}),
+                     ("cl4g", {"FFM_KERNEL": "cell", "FFM_CLUSTER": "4"})):
+        for k in ("FFM_KERNEL", "FFM_CLUSTER", "FFM_FIELDS_SMEM"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        sim = BatchSim(m, sff, B, N, params, seed=seed, episode_base=500, track_dff=track)
+        sim.set_positions(pos, n)
+        sim.rollout(4096)
+        steps, ped = sim.counters()
+        assert (sim.get_positions()[1] == 0).all()
+        out[tag] = (steps.copy(), ped.copy(), sim.get_dff().view(np.uint32).copy() if track else None)
+        sim.close()
+    for tag in ("ped", "cl2", "cl4g"):
+        assert np.array_equal(out[tag][0], out["cell"][0]) and np.array_equal(out[tag][1], out["cell"][1]), tag
+        if track:
+            assert np.array_equal(out[tag][2], out["cell"][2]), tag
