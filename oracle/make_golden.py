@@ -282,6 +282,52 @@ def mcq_all():
     mcq_case("mcq_20x20_kq", 20, 20, 30, 33, {"max_steps": 80, "k_Q": 2.0, "step_penalty": 0.05}, [0.8, 0.3])
 
 
+def legacy_ac_case(name, h, w, N, episodes, seed, params, sff_dtype=np.float32, metric="L1", max_steps=400, set_v_after=None):
+    """Multi-episode run of the legacy TD critic model/ffm_ac_core.py under keyed draws: V carries over the episodes like
+    run_critic_training.py does (reset() between episodes).  `set_v_after` = episode index after which the table is passed
+    through get_v_table() / set_v_table(), which switches the default of unseen states to -1.0 (ffm_ac_core.py:340)."""
+    import pickle
+    from . import legacy_numpy
+    ref = inject.import_reference("ffm_ac_core")
+    m = assets.room_map(h, w)
+    sff = assets.sff_norm_min(m, metric, sff_dtype)
+    with tempfile.TemporaryDirectory() as tmp:
+        p = os.path.join(tmp, "sff.npy")
+        np.save(p, sff)
+        np.random.seed(seed)
+        model = ref.FloorFieldModel(m, p, N, params)
+        pos0s, trajs, counts, steps, margins = [], [], [], [], []
+        for ep in range(episodes):
+            if ep > 0:
+                model.reset()
+            pos0s.append(np.array(model.positions, dtype=np.int16).reshape(-1, 2))
+            r = inject.run_reference(model, inject.PhiloxSource(seed, ep), max_steps=max_steps, keep_dff=False)
+            flat, cnt = _flatten(r["traj"])
+            trajs.append(flat); counts.append(cnt); steps.append(r["steps"]); margins.append(r["min_margin"])
+            if set_v_after is not None and ep == set_v_after:
+                model.set_v_table(model.get_v_table())
+    bs = model.block_size
+    nby = (w + bs - 1) // bs
+    tab = {legacy_numpy.state_to_key(pickle.loads(k), nby): float(v) for k, v in model.V.items()}
+    keys = np.array(sorted(tab), np.uint64)
+    vals = np.array([tab[int(k)] for k in keys], np.float64)
+    save = dict(map=m, sff=sff, params=json.dumps(params), seed=np.uint64(seed), max_steps=np.int32(max_steps),
+                episodes=np.int32(episodes), steps=np.array(steps, np.int32), min_margin=np.array(margins), v_keys=keys, v_vals=vals,
+                final_dff=np.array(model.dff, np.float32), set_v_after=np.int32(-1 if set_v_after is None else set_v_after))
+    for ep in range(episodes):
+        save[f"pos0_{ep}"] = pos0s[ep]; save[f"traj_{ep}"] = trajs[ep]; save[f"counts_{ep}"] = counts[ep]
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **save)
+    print(name, "steps", steps, "min_margin %.1e" % min(margins), "|V|", len(keys))
+
+
+def legacy_all():
+    legacy_ac_case("legacy_ac_12x12", 12, 12, 30, 4, 51, {"neighborhood": "neumann"})
+    legacy_ac_case("legacy_ac_moore_f64", 16, 20, 60, 3, 52, {"neighborhood": "moore", "block_size": 5, "k_S": 3, "k_D": 0.5, "gamma": 0.9,
+                                                             "alpha_v": 0.2, "step_penalty": -1.0, "collision_penalty": -2.5},
+                   sff_dtype=np.float64, metric="L2", set_v_after=0)
+    legacy_ac_case("legacy_ac_12x12_full", 12, 12, 100, 2, 53, {"neighborhood": "neumann", "block_size": 1}, max_steps=120)
+
+
 def shipped():
     out = {}
     for rel in ("data/maps/simple_room.npy", "data/sff/distance_L1.npy", "data/sff/distance_L2.npy", "data/sff/distance_Linf.npy"):
@@ -299,7 +345,9 @@ def main():
     only = [a for a in sys.argv[1:] if not a.startswith("-")]
     if only:                      # python -m oracle.make_golden core_50x50_moore_f64 ...: regenerate the named core fixtures
         for name in only:
-            if name == "core_50x50_moore_f64":
+            if name == "legacy":
+                legacy_all()
+            elif name == "core_50x50_moore_f64":
                 core_case(name, 50, 50, 100, "moore", "L2", np.float64, 13, 5, dff_every=20)
             else:
                 raise SystemExit(f"no single-fixture recipe for {name}; run without arguments")
@@ -315,6 +363,7 @@ def main():
     shipped()
     unified_all()
     mcq_all()
+    legacy_all()
 
 
 if __name__ == "__main__":

@@ -100,3 +100,19 @@ def load_pretrain(name):
     g = {k: z[k] for k in z.files}
     g["params"] = json.loads(str(g["params"]))
     return g
+
+
+LEGACY_AC_FIXTURES = ["legacy_ac_12x12", "legacy_ac_moore_f64", "legacy_ac_12x12_full"]
+
+
+def load_legacy(name):
+    z = np.load(os.path.join(GOLDEN, name + ".npz"))
+    g = {k: z[k] for k in z.files}
+    g["params"] = json.loads(str(g["params"]))
+    g["ep"] = []
+    for ep in range(int(g["episodes"])):
+        counts = g[f"counts_{ep}"]
+        offs = np.concatenate([[0], np.cumsum(counts)])
+        g["ep"].append(dict(pos0=g[f"pos0_{ep}"].astype(np.int64),
+                            traj=[g[f"traj_{ep}"][offs[t]:offs[t + 1]].astype(np.int64) for t in range(len(counts))]))
+    return g

@@ -1,0 +1,32 @@
+"""The NumPy restatement of the legacy 13-cell models (oracle/legacy_numpy.py) against fixtures written by the UNMODIFIED
+reference classes under keyed draws (oracle/make_golden.py::legacy_all)."""
+import numpy as np
+import pytest
+
+from helpers import LEGACY_AC_FIXTURES, load_legacy
+from oracle import legacy_numpy
+from oracle.inject import PhiloxSource
+
+
+@pytest.mark.parametrize("name", LEGACY_AC_FIXTURES)
+def test_ac_oracle_reproduces_reference(name):
+    g = load_legacy(name)
+    V, default = {}, 0.0
+    for ep, e in enumerate(g["ep"]):
+        o = legacy_numpy.AcOracle(g["map"], g["sff"], e["pos0"], g["params"], PhiloxSource(int(g["seed"]), ep), v_table=V, v_default=default)
+        traj = o.run(max_steps=int(g["max_steps"]))
+        assert len(traj) == len(e["traj"])
+        for a, b in zip(traj, e["traj"]):
+            assert np.array_equal(a, b)
+        V = o.V
+        if ep == int(g["set_v_after"]):
+            default = -1.0
+    keys = np.array(sorted(V), np.uint64)
+    assert np.array_equal(keys, g["v_keys"])
+    assert np.array_equal(np.array([V[int(k)] for k in keys]), g["v_vals"])       # bit for bit
+    assert np.array_equal(o.dff, g["final_dff"])
+
+
+def test_key_roundtrip():
+    st = ((0, 1, 2, 3, 0, 1, 2, 3, 0, 1, 2, 3, 1), (3, 2))
+    assert legacy_numpy.key_to_state(legacy_numpy.state_to_key(st, 7), 7) == st
