@@ -14,6 +14,8 @@ FFM_F32, FFM_F64 = 0, 1
 E_INVALID, E_CUDA, E_UNSUPPORTED, E_STATE = -1, -2, -3, -4
 MODEL_CORE, MODEL_UNIFIED_CRITIC, MODEL_UNIFIED_ACTOR, MODEL_UNIFIED_BOTH, MODEL_TRAINED, MODEL_MCQ = range(6)
 LEARN_NONE, LEARN_EXACT, LEARN_BATCHED = range(3)
+LEGACY_AC, LEGACY_ACTOR_ONLY = 0, 1
+LEGACY_TABLE_V, LEGACY_TABLE_H = 0, 1
 SFF_L1, SFF_L2, SFF_LINF, SFF_BFS4, SFF_BFS8, SFF_DIJKSTRA8 = range(6)
 
 
@@ -32,6 +34,23 @@ class Config(C.Structure):
         ("exit_reward", C.c_double), ("step_penalty", C.c_double), ("collision_penalty", C.c_double),
         ("epsilon", C.c_double), ("sff_min", C.c_double), ("sff_max", C.c_double),
         ("stop_penalty", C.c_double), ("timeout_penalty", C.c_double), ("step_cap", C.c_int32), ("q_log2_capacity", C.c_int32),
+    ]
+
+
+class LegacyConfig(C.Structure):
+    _fields_ = [
+        ("abi_version", C.c_int32), ("device", C.c_int32),
+        ("height", C.c_int32), ("width", C.c_int32),
+        ("neighborhood", C.c_int32), ("sff_dtype", C.c_int32),
+        ("n_episodes", C.c_int32), ("n_max", C.c_int32),
+        ("model", C.c_int32), ("learn", C.c_int32),
+        ("block_size", C.c_int32), ("table_log2_capacity", C.c_int32),
+        ("k_S", C.c_double), ("k_D", C.c_double), ("k_A", C.c_double),
+        ("dff_c0", C.c_float), ("dff_c1", C.c_float), ("dff_threshold", C.c_float), ("reserved0", C.c_float),
+        ("gamma", C.c_double), ("alpha_v", C.c_double), ("alpha_h", C.c_double), ("exit_reward", C.c_double),
+        ("step_penalty", C.c_double), ("collision_penalty", C.c_double), ("epsilon", C.c_double),
+        ("sff_min", C.c_double), ("sff_max", C.c_double),
+        ("seed", C.c_uint64), ("episode_base", C.c_uint32), ("reserved1", C.c_uint32),
     ]
 
 
@@ -92,6 +111,22 @@ SIGNATURES = {
                                   C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "ffm_cluster_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32),
                                    C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "ffm_legacy_create": (C.c_int, [C.POINTER(LegacyConfig), C.POINTER(C.c_void_p)]),
+    "ffm_legacy_destroy": (C.c_int, [C.c_void_p]),
+    "ffm_legacy_set_fields": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ffm_legacy_set_positions": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ffm_legacy_get_positions": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ffm_legacy_set_dff": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "ffm_legacy_get_dff": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "ffm_legacy_update_dff": (C.c_int, [C.c_void_p]),
+    "ffm_legacy_rollout": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32]),
+    "ffm_legacy_get_counters": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ffm_legacy_table_size": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_int64)]),
+    "ffm_legacy_table_get": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]),
+    "ffm_legacy_table_set": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, C.c_double]),
+    "ffm_legacy_set_epsilon": (C.c_int, [C.c_void_p, C.c_double]),
+    "ffm_legacy_set_episode_base": (C.c_int, [C.c_void_p, C.c_uint32]),
+    "ffm_legacy_launch_count": (C.c_int64, [C.c_void_p]),
 }
 
 _lib = None

@@ -41,6 +41,12 @@ constexpr int MAX_SMEM_OPTIN = 232448;  // 227 KB per CTA on sm_100
 
 }  // namespace
 
+// error text of the calling thread, for the other translation units (ffm_legacy.cu)
+int ffm::set_error(int code, const char* fmt, va_list ap) {
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    return code;
+}
+
 struct ffm_sim_s {
     ffm_config_t cfg;
     int HW;

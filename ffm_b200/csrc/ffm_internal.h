@@ -3,9 +3,13 @@
 // the handles and the extern "C" surface of include/ffm_b200.h.
 #pragma once
 #include <cuda_runtime.h>
+#include <stdarg.h>
 #include <stdint.h>
 
 namespace ffm {
+
+// stores the message ffm_last_error() returns for the calling thread; returns `code`
+int set_error(int code, const char* fmt, va_list ap);
 
 struct HStats;
 

@@ -297,6 +297,59 @@ int ffm_kernel_info(ffm_sim_t sim, int32_t *smem_bytes, int32_t *threads, int32_
  * field is staged on chip, and which kernel runs (0 = pedestrian-centric, 1 = cell-centric; -1 for the other models) */
 int ffm_cluster_info(ffm_sim_t sim, int32_t *cluster, int32_t *max_clusters, int32_t *score_in_smem, int32_t *cell_kernel);
 
+/* ---- Legacy 13-cell models ----------------------------------------------------------------------
+ * model/ffm_ac_core.py FloorFieldModel (TD(0) critic over the FFM policy: `step` :111-244, `_encode_state` :62-109,
+ * `_update_critic` :246-296) and model/ffm_actor_only.py FloorFieldModelActorOnly (`step` :150-413 -- including the
+ * per-neighbour repetition of its decision block, :214-355 --, `_update_critic` :415-474, `_update_actor` :476-540).
+ * The state of a pedestrian is the 13 cell values around it plus a coarse block index; the reference keys its dict tables
+ * with pickle.dumps((tuple(state_13), (bx, by))).  Here the tables are open-addressing hash tables in HBM keyed by
+ *     key = ((bx * nby + by) << 26) | sum_j cell_j << (2 j),   j = 0..12 in state_13 order, nby = ceil(width / block_size)
+ * (3x3 block row-major, then the cells two steps up, down, left, right).  A handle of its own: the legacy models share
+ * nothing with ffm_sim_t but the draw streams.  All buffers of these calls are HOST buffers; the calls return when done. */
+enum {
+    FFM_LEGACY_AC = 0,         /* model/ffm_ac_core.py */
+    FFM_LEGACY_ACTOR_ONLY = 1  /* model/ffm_actor_only.py */
+};
+enum { FFM_LEGACY_TABLE_V = 0, FFM_LEGACY_TABLE_H = 1 };
+typedef struct ffm_legacy_config {
+    int32_t abi_version, device;
+    int32_t height, width;
+    int32_t neighborhood, sff_dtype;        /* AC: dtype of the SFF file (ffm_ac_core.py:28); actor-only: FFM_F32 (:45-48) */
+    int32_t n_episodes, n_max;
+    int32_t model, learn;                   /* FFM_LEGACY_*; FFM_LEARN_NONE (frozen tables, any n_episodes) | FFM_LEARN_EXACT (n_episodes == 1) */
+    int32_t block_size, table_log2_capacity;/* params["block_size"] (actor-only: 5, ffm_actor_only.py:144); slots per table = 2^k, 0 = 2^20 */
+    double k_S, k_D, k_A;
+    float dff_c0, dff_c1, dff_threshold, reserved0;
+    double gamma, alpha_v, alpha_h, exit_reward, step_penalty, collision_penalty, epsilon;
+    double sff_min, sff_max;                /* actor-only: extremes of the inf->0 float32 SFF (:277-278) */
+    uint64_t seed;
+    uint32_t episode_base, reserved1;
+} ffm_legacy_config_t;
+typedef struct ffm_legacy_s *ffm_legacy_t;
+
+int ffm_legacy_create(const ffm_legacy_config_t *cfg, ffm_legacy_t *out);         /* __init__: ffm_ac_core.py:9-38, ffm_actor_only.py:21-80 */
+int ffm_legacy_destroy(ffm_legacy_t h);
+/* map uint8 [H][W] (codes 0..3, no free cell on the border), sff [H][W] of cfg.sff_dtype */
+int ffm_legacy_set_fields(ffm_legacy_t h, const uint8_t *map, const void *sff);
+/* positions int32 [n_episodes][n_max][2] (row, col), counts int32 [n_episodes]; step counters restart at 0 (reset()) */
+int ffm_legacy_set_positions(ffm_legacy_t h, const int32_t *pos_rc, const int32_t *n);
+int ffm_legacy_get_positions(ffm_legacy_t h, int32_t *pos_rc, int32_t *n);
+int ffm_legacy_set_dff(ffm_legacy_t h, const float *dff);                         /* float32 [n_episodes][H][W] */
+int ffm_legacy_get_dff(ffm_legacy_t h, float *dff);
+int ffm_legacy_update_dff(ffm_legacy_t h);                                        /* update_dff(): ffm_ac_core.py:298-318 */
+/* up to max_steps calls of step() per episode (run(): ffm_ac_core.py:362-390), stopping at evacuation.  traj (may be NULL):
+ * uint32 [n_episodes][traj_steps][n_max] linear cells after each step, traj_n int32 [n_episodes][traj_steps] their counts. */
+int ffm_legacy_rollout(ffm_legacy_t h, int32_t max_steps, uint32_t *traj, int32_t *traj_n, int32_t traj_steps);
+int ffm_legacy_get_counters(ffm_legacy_t h, int32_t *steps_done, uint64_t *ped_steps);   /* [n_episodes] each */
+/* the dict tables: number of keys; all (key, row) pairs (row width: 1 for V, neighborhood + 1 for H); replace the table
+ * (set_v_table(): ffm_ac_core.py:333-340 -- `default_value` is what an unseen key reads as afterwards, -1.0 there) */
+int ffm_legacy_table_size(ffm_legacy_t h, int32_t which, int64_t *n);
+int ffm_legacy_table_get(ffm_legacy_t h, int32_t which, uint64_t *keys, double *rows, int64_t capacity, int64_t *n);
+int ffm_legacy_table_set(ffm_legacy_t h, int32_t which, const uint64_t *keys, const double *rows, int64_t n, double default_value);
+int ffm_legacy_set_epsilon(ffm_legacy_t h, double epsilon);                      /* set_epsilon(): ffm_actor_only.py:578-585 */
+int ffm_legacy_set_episode_base(ffm_legacy_t h, uint32_t episode_base);
+int64_t ffm_legacy_launch_count(ffm_legacy_t h);
+
 #ifdef __cplusplus
 }
 #endif
