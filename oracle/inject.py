@@ -10,6 +10,7 @@ The reference draws from process-global generators, in agent order:
   * ``random.choice(agents)``              model/ffm_core.py:96, model/ffm_unified.py:530
   * ``random.random() < epsilon``          model/ffm_unified.py:481
   * ``np.random.randint(len(valid))``      model/ffm_unified.py:487
+(the legacy models draw at the same kinds of call sites: model/ffm_ac_core.py:194,215; model/ffm_actor_only.py:329,333,343,370)
 Those five call sites are monkey-patched for the duration of a ``with injected(...)`` block.
 Each patched function reads the caller's frame to learn WHICH agent / target cell the draw
 is for and asks a *draw source* for the uniform, which it maps to a result exactly the way
@@ -160,13 +161,19 @@ class _State:
         self.min_margin = np.inf
         self.n_move = self.n_coin = self.n_winner = self.n_eps = 0
         self.probs_log = None
+        self.sub_key = False      # model/ffm_actor_only.py draws up to `neighbours` times per agent and step: entity = idx * 8 + i
 
 
 @contextlib.contextmanager
-def injected(source, width, log_probs=False):
+def injected(source, width, log_probs=False, sub_key=False):
     """Patch the five draw call sites; yields a state object whose ``.step`` the caller sets to
     the CA step number before each ``model.step()``."""
     st = _State(source, width)
+    st.sub_key = sub_key
+
+    def _agent(frame):
+        loc = frame.f_locals
+        return int(loc["idx"]) * 8 + int(loc["i"]) if st.sub_key else int(loc["idx"])
     if log_probs:
         st.probs_log = []
     o_choice, o_rand, o_randint = np.random.choice, np.random.rand, np.random.randint
@@ -180,7 +187,7 @@ def injected(source, width, log_probs=False):
     def choice(a, size=None, replace=True, p=None):
         if p is None:                      # placement draw in the constructor (ffm_core.py:25)
             return o_choice(a, size=size, replace=replace, p=p)
-        idx = int(sys._getframe(1).f_locals["idx"])
+        idx = _agent(sys._getframe(1))
         cdf = choice_cdf(p)
         u = st.source.move(st.step, idx, cdf)
         st.min_margin = min(st.min_margin, float(np.min(np.abs(cdf - u))))
@@ -202,12 +209,12 @@ def injected(source, width, log_probs=False):
 
     def py_random():
         st.n_eps += 1
-        return st.source.eps_coin(st.step, int(sys._getframe(1).f_locals["idx"]))
+        return st.source.eps_coin(st.step, _agent(sys._getframe(1)))
 
     def randint(low, high=None, size=None, dtype=int):
         if high is not None or size is not None:
             return o_randint(low, high, size, dtype)
-        return int(st.source.eps_pick(st.step, int(sys._getframe(1).f_locals["idx"]), low) * low)
+        return int(st.source.eps_pick(st.step, _agent(sys._getframe(1)), low) * low)
 
     np.random.choice, np.random.rand, np.random.randint = choice, rand, randint
     _pyrandom.choice, _pyrandom.random = py_choice, py_random
@@ -218,7 +225,7 @@ def injected(source, width, log_probs=False):
         _pyrandom.choice, _pyrandom.random = o_pychoice, o_pyrandom
 
 
-def run_reference(model, source, max_steps=None, log_probs=False, keep_dff=True):
+def run_reference(model, source, max_steps=None, log_probs=False, keep_dff=True, sub_key=False):
     """Drive a reference model object (any ``model/ffm_*.py`` class) step by step under injected
     draws until evacuation / ``max_steps``.
 
@@ -226,7 +233,7 @@ def run_reference(model, source, max_steps=None, log_probs=False, keep_dff=True)
     min_margin, n_move, n_coin, n_winner, n_eps, probs_log)."""
     width = model.map_array.shape[1]
     traj, dffs = [], []
-    with injected(source, width, log_probs=log_probs) as st:
+    with injected(source, width, log_probs=log_probs, sub_key=sub_key) as st:
         t = 0
         while model.positions.shape[0] > 0 and (max_steps is None or t < max_steps):
             st.step = t

@@ -164,3 +164,162 @@ class AcOracle:
             self.step()
             traj.append(self.positions.copy())
         return traj
+
+
+class ActorOnlyOracle:
+    """Legacy actor (ffm_actor_only.py).  The decision block of ``step`` is nested inside the loop that collects
+    the exit flags (:214-355), so an agent decides once per neighbour slot i -- with the exit flags of slots
+    <= i only -- and files one request per slot; the last decision is the recorded action (:350-355).  Draw
+    entities are ``idx * 8 + i``.  ``V`` lookups use the pickled state as key, so a pretrained table loaded
+    under tuple keys (:61-66) is never read: ``v_inert`` only counts towards the table size."""
+
+    BLOCK = 5                                     # :144
+
+    def __init__(self, map_array, sff, positions, params=None, source=None, v_table=None, h_table=None, epsilon=None):
+        self.params = dict(ACTOR_ONLY_DEFAULTS) if params is None else {**ACTOR_ONLY_DEFAULTS, **params}
+        self.map_array = np.asarray(map_array).astype(np.uint8)
+        sff = np.asarray(sff)
+        self.sff = np.where(np.isinf(sff), 0.0, sff).astype(np.float32)          # :45-48
+        self.dff = np.zeros_like(self.map_array, dtype=np.float32)
+        self.positions = np.array(positions, dtype=np.int64).reshape(-1, 2)
+        self.neighbors = list(NEUMANN) if self.params["neighborhood"] == "neumann" else list(MOORE)
+        self.A = len(self.neighbors) + 1
+        self.nby = (self.map_array.shape[1] + self.BLOCK - 1) // self.BLOCK
+        self.V = dict(v_table) if v_table else {}
+        self.H = {k: list(v) for k, v in h_table.items()} if h_table else {}
+        self.epsilon = self.params.get("epsilon", 0.0) if epsilon is None else epsilon
+        self.source = source
+        self.t = 0
+        self.min_margin = np.inf
+
+    def key(self, x, y, occ):
+        return (((x // self.BLOCK) * self.nby + (y // self.BLOCK)) << 26) | code13(x, y, occ, 0)
+
+    def _v(self, k):
+        if k not in self.V:
+            self.V[k] = 0.0                       # :70
+        return self.V[k]
+
+    def step(self):
+        P, m = self.params, self.map_array
+        h, w = m.shape
+        pos = self.positions
+        n = pos.shape[0]
+        nb = len(self.neighbors)
+        occ = m.copy()                                                          # :163-165
+        for x, y in pos:
+            occ[x, y] = 1
+        occupied = {(int(x), int(y)) for x, y in pos}
+        states, will_exit, actions, valid_of = {}, {}, {}, {}
+        requests = {}
+        sff_min, sff_max = float(np.min(self.sff)), float(np.max(self.sff))
+        for idx in range(n):
+            x, y = int(pos[idx, 0]), int(pos[idx, 1])
+            state = self.key(x, y, occ)                                         # :174-175
+            states[idx] = state
+            coords = [(x + dx, y + dy) for dx, dy in self.neighbors]
+            inb = [0 <= a < h and 0 <= b < w for a, b in coords]
+            valid = [inb[k] and m[coords[k]] in (0, 3) and coords[k] not in occupied for k in range(nb)] + [True]   # :180-206
+            valid = np.array(valid, dtype=bool)
+            allc = coords + [(x, y)]                                            # :210
+            exit_mask = np.zeros(self.A, dtype=bool)
+            for i in range(nb):                                                 # :216
+                if inb[i] and m[coords[i]] == 3:
+                    exit_mask[i] = True
+                if np.any(exit_mask):                                           # :223-241 (nested in the loop)
+                    e = int(np.where(exit_mask)[0][0])
+                    will_exit[idx] = True
+                    requests.setdefault(allc[e], []).append(idx)
+                    actions[idx] = allc[e]
+                    valid_of[idx] = valid
+                    continue
+                dff_vals = np.array([self.dff[c] for c in allc])                # :244-246 (float32)
+                if state not in self.H or len(self.H[state]) != self.A:         # :252-257
+                    self.H[state] = [0.0] * self.A
+                h_vals = np.array(self.H[state])
+                allh = [v for row in self.H.values() for v in row]              # :263-269
+                hmin, hmax = float(np.min(allh)), float(np.max(allh))
+                if not (np.isnan(hmin) or np.isnan(hmax) or np.isinf(hmin) or np.isinf(hmax)):
+                    if hmax - hmin > 1e-6:                                      # :288-293
+                        h_vals = ((hmax - h_vals) / (hmax - hmin)) * (sff_max - sff_min) + sff_min
+                score = -P["k_A"] * h_vals + P["k_D"] * dff_vals                # :295-298
+                score[~valid] = -np.inf
+                if np.any(np.isnan(score)) or np.any(np.isinf(score)):          # :304-312: any invalid slot -> flat scores
+                    score = np.zeros_like(score)
+                    score[valid] = 1.0
+                score_max = np.max(score[valid])                                # :315-319
+                probs = np.exp(score - score_max)
+                probs[~valid] = 0.0
+                s = probs.sum()
+                if np.isfinite(s) and s > 0:                                    # :324-333
+                    probs /= s
+                else:
+                    vi = np.where(valid)[0]
+                    probs = np.zeros_like(score)
+                    probs[vi] = 1.0 / len(vi)
+                ent = idx * 8 + i
+                if self.epsilon > 0 and self.source.eps_coin(self.t, ent) < self.epsilon:   # :329-341
+                    vi = np.where(valid)[0]
+                    chosen = int(vi[int(self.source.eps_pick(self.t, ent, len(vi)) * len(vi))])
+                else:
+                    cdf = choice_cdf(probs)
+                    u = self.source.move(self.t, ent, cdf)
+                    self.min_margin = min(self.min_margin, float(np.min(np.abs(cdf - u))))
+                    chosen = int(cdf.searchsorted(u, side="right"))             # :343
+                requests.setdefault(allc[chosen], []).append(idx)               # :346-349
+                actions[idx] = allc[chosen]
+                valid_of[idx] = valid
+        nxt = pos.copy()
+        coll = {}
+        for target, agents in requests.items():                                 # :360-384 (duplicates stay in the lists)
+            if len(agents) == 1:
+                a = agents[0]
+                nxt[a] = target
+                self.dff[pos[a, 0], pos[a, 1]] += 1
+                coll[a] = 0
+            else:
+                k = len(agents)
+                wn = agents[int(self.source.winner(self.t, target[0] * w + target[1], k) * k)]
+                nxt[wn] = target
+                self.dff[pos[wn, 0], pos[wn, 1]] += 1
+                coll[wn] = k - 1
+                for a in agents:
+                    if a != wn:
+                        coll[a] = k - 1
+        occ_next = m.copy()                                                     # :388-391
+        for x, y in nxt:
+            if m[x, y] != 3:
+                occ_next[x, y] = 1
+        td = {}
+        for idx in range(n):                                                    # :434-472
+            reward = P["step_penalty"]
+            if will_exit.get(idx):
+                reward += P["exit_reward"]
+            if idx in coll:
+                reward += coll[idx] * P["collision_penalty"]
+            if will_exit.get(idx):
+                v_next = 0.0
+            else:
+                v_next = self._v(self.key(int(nxt[idx, 0]), int(nxt[idx, 1]), occ_next))
+            v_cur = self._v(states[idx])
+            td[idx] = reward + P["gamma"] * v_next - v_cur
+            self.V[states[idx]] = v_cur + P["alpha_v"] * td[idx]
+        for idx in range(n):                                                    # :495-536
+            x, y = int(pos[idx, 0]), int(pos[idx, 1])
+            allc = [(x + dx, y + dy) for dx, dy in self.neighbors] + [(x, y)]
+            ci = allc.index(actions[idx])
+            st = states[idx]
+            if st not in self.H or len(self.H[st]) != self.A:
+                self.H[st] = [0.0] * self.A
+            if valid_of[idx][ci]:
+                self.H[st][ci] += P["alpha_h"] * td[idx]                        # :534
+        self.positions = nxt[m[nxt[:, 0], nxt[:, 1]] != 3]                      # :408-411
+        self.dff = update_dff(self.dff, P, self.neighbors)
+        self.t += 1
+
+    def run(self, max_steps=None):
+        traj = []
+        while self.positions.shape[0] > 0 and (max_steps is None or len(traj) < max_steps):
+            self.step()
+            traj.append(self.positions.copy())
+        return traj

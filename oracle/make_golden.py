@@ -320,12 +320,58 @@ def legacy_ac_case(name, h, w, N, episodes, seed, params, sff_dtype=np.float32, 
     print(name, "steps", steps, "min_margin %.1e" % min(margins), "|V|", len(keys))
 
 
+def legacy_actor_case(name, h, w, N, episodes, seed, params, eps=0.0, max_steps=60, obstacles=()):
+    """Multi-episode run of the legacy actor model/ffm_actor_only.py under keyed draws (entity = idx * 8 + i: the class decides
+    once per neighbour slot, ffm_actor_only.py:214-355); V and H carry over the episodes like run_actor_only_training.py."""
+    import contextlib, io, pickle
+    from . import legacy_numpy
+    ref = inject.import_reference("ffm_actor_only")
+    m = assets.room_map(h, w)
+    for r, c in obstacles:
+        m[r, c] = 2
+    sff = assets.sff_norm_min(m, "L1", np.float32)
+    with tempfile.TemporaryDirectory() as tmp:
+        p = os.path.join(tmp, "sff.npy")
+        np.save(p, sff)
+        np.random.seed(seed)
+        with contextlib.redirect_stdout(io.StringIO()):
+            model = ref.FloorFieldModelActorOnly(m, p, N, params=params)
+        model.set_epsilon(eps)
+        pos0s, trajs, counts, steps, margins = [], [], [], [], []
+        for ep in range(episodes):
+            if ep > 0:
+                model.reset()
+            pos0s.append(np.array(model.positions, dtype=np.int16).reshape(-1, 2))
+            r = inject.run_reference(model, inject.PhiloxSource(seed, ep), max_steps=max_steps, keep_dff=False, sub_key=True)
+            flat, cnt = _flatten(r["traj"])
+            trajs.append(flat); counts.append(cnt); steps.append(r["steps"]); margins.append(r["min_margin"])
+    nby = (w + 4) // 5
+    vt = {legacy_numpy.state_to_key(pickle.loads(k), nby): float(v) for k, v in model.V.items()}
+    ht = {legacy_numpy.state_to_key(pickle.loads(k), nby): [float(x) for x in v] for k, v in model.H.items()}
+    vk = np.array(sorted(vt), np.uint64)
+    hk = np.array(sorted(ht), np.uint64)
+    save = dict(map=m, sff=sff, params=json.dumps(params), seed=np.uint64(seed), eps=np.float64(eps), max_steps=np.int32(max_steps),
+                episodes=np.int32(episodes), steps=np.array(steps, np.int32), min_margin=np.array(margins),
+                v_keys=vk, v_vals=np.array([vt[int(k)] for k in vk], np.float64),
+                h_keys=hk, h_vals=np.array([ht[int(k)] for k in hk], np.float64).reshape(len(hk), -1),
+                final_dff=np.array(model.dff, np.float32), set_v_after=np.int32(-1))
+    for ep in range(episodes):
+        save[f"pos0_{ep}"] = pos0s[ep]; save[f"traj_{ep}"] = trajs[ep]; save[f"counts_{ep}"] = counts[ep]
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **save)
+    print(name, "steps", steps, "min_margin %.1e" % min(margins), "|V|", len(vk), "|H|", len(hk), "draws", r["n_move"], r["n_eps"], r["n_winner"])
+
+
 def legacy_all():
     legacy_ac_case("legacy_ac_12x12", 12, 12, 30, 4, 51, {"neighborhood": "neumann"})
     legacy_ac_case("legacy_ac_moore_f64", 16, 20, 60, 3, 52, {"neighborhood": "moore", "block_size": 5, "k_S": 3, "k_D": 0.5, "gamma": 0.9,
                                                              "alpha_v": 0.2, "step_penalty": -1.0, "collision_penalty": -2.5},
                    sff_dtype=np.float64, metric="L2", set_v_after=0)
     legacy_ac_case("legacy_ac_12x12_full", 12, 12, 100, 2, 53, {"neighborhood": "neumann", "block_size": 1}, max_steps=120)
+    legacy_actor_case("legacy_actor_12x12", 12, 12, 12, 4, 66, {"neighborhood": "neumann"}, eps=0.0, max_steps=50)
+    legacy_actor_case("legacy_actor_eps_moore", 14, 16, 24, 3, 62, {"neighborhood": "moore", "k_A": 4, "k_D": 0.5, "alpha_h": 0.3, "alpha_v": 0.2,
+                                                                   "gamma": 0.9, "step_penalty": -1.0, "collision_penalty": -0.5},
+                      eps=0.15, max_steps=40, obstacles=((5, 5), (5, 6), (8, 10)))
+    legacy_actor_case("legacy_actor_crowded", 10, 10, 40, 2, 63, {"neighborhood": "neumann", "step_penalty": -1.0}, eps=0.05, max_steps=40)
 
 
 def shipped():

@@ -116,3 +116,4 @@ def load_legacy(name):
         g["ep"].append(dict(pos0=g[f"pos0_{ep}"].astype(np.int64),
                             traj=[g[f"traj_{ep}"][offs[t]:offs[t + 1]].astype(np.int64) for t in range(len(counts))]))
     return g
+LEGACY_ACTOR_FIXTURES = ["legacy_actor_12x12", "legacy_actor_eps_moore", "legacy_actor_crowded"]

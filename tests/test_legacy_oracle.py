@@ -3,7 +3,7 @@ reference classes under keyed draws (oracle/make_golden.py::legacy_all)."""
 import numpy as np
 import pytest
 
-from helpers import LEGACY_AC_FIXTURES, load_legacy
+from helpers import LEGACY_AC_FIXTURES, LEGACY_ACTOR_FIXTURES, load_legacy
 from oracle import legacy_numpy
 from oracle.inject import PhiloxSource
 
@@ -30,3 +30,23 @@ def test_ac_oracle_reproduces_reference(name):
 def test_key_roundtrip():
     st = ((0, 1, 2, 3, 0, 1, 2, 3, 0, 1, 2, 3, 1), (3, 2))
     assert legacy_numpy.key_to_state(legacy_numpy.state_to_key(st, 7), 7) == st
+
+
+@pytest.mark.parametrize("name", LEGACY_ACTOR_FIXTURES)
+def test_actor_only_oracle_reproduces_reference(name):
+    g = load_legacy(name)
+    V, Ht = {}, {}
+    for ep, e in enumerate(g["ep"]):
+        o = legacy_numpy.ActorOnlyOracle(g["map"], g["sff"], e["pos0"], g["params"], PhiloxSource(int(g["seed"]), ep),
+                                         v_table=V, h_table=Ht, epsilon=float(g["eps"]))
+        traj = o.run(max_steps=int(g["max_steps"]))
+        assert len(traj) == len(e["traj"])
+        for t, (a, b) in enumerate(zip(traj, e["traj"])):
+            assert np.array_equal(a, b), (ep, t)
+        V, Ht = o.V, o.H
+    vk = np.array(sorted(V), np.uint64)
+    hk = np.array(sorted(Ht), np.uint64)
+    assert np.array_equal(vk, g["v_keys"]) and np.array_equal(hk, g["h_keys"])
+    assert np.array_equal(np.array([V[int(k)] for k in vk]), g["v_vals"])
+    assert np.array_equal(np.array([Ht[int(k)] for k in hk]).reshape(len(hk), -1), g["h_vals"])
+    assert np.array_equal(o.dff, g["final_dff"])
