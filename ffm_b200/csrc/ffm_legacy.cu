@@ -396,6 +396,361 @@ ffm_legacy_ac_kernel(const LegacyParams P) {
     }
 }
 
+// ---- model/ffm_actor_only.py ---------------------------------------------------------------------------------------------
+// The reference's decision block is nested inside the loop that collects the exit flags (:214-355): an agent decides once
+// per neighbour slot i, seeing only the exit flags of slots <= i, and files one request per slot.  Requests to one cell form
+// a list WITH duplicates, ordered by (agent, slot); cells are resolved in the order of their first request (dict order,
+// :360); a later grant overwrites an earlier one of the same agent (:362, :372), every grant leaves a DFF footprint
+// (:363-365, :373-375), and the collision count of an agent is the one of the last resolved cell it asked for (:366, :376-380).
+// Phases per step:
+//   A0 state key -> V slot; validity of the slots; does the H row exist?  (the first agent whose lookup inserts a row decides
+//      from where on the table extremes include the zeros of a fresh row, :252-269)
+//   A1 H row (inserted as zeros if absent), scores -- flat over the valid slots as soon as ONE slot is invalid (the -inf of
+//      :300 trips the isinf test of :304) --, one epsilon-greedy / keyed draw per slot i < first exit slot, one forced exit
+//      request per slot i >= first exit slot; claim counters and first-request order per cell
+//   B  per agent and distinct requested cell: position of its requests in the cell's list, winner = floor(u*k)-th entry
+//      (:370); final cell = granted cell with the latest first request; footprints
+//   C  apply the moves (owner grid becomes occupancy_next, :388-391), clear the per-cell scratch
+//   T  next-state V slots and H slots of all agents (parallel), then ONE thread: TD(0) in agent order (:434-472), then
+//      H[s][a] += alpha_h * delta for the LAST decision of each agent (:495-536), keeping the table extremes current
+//   K  exit removal;  D  DFF
+constexpr uint32_t AI_ACT_MASK = 0xFu;
+constexpr uint32_t AI_VALID_SHIFT = 4;          // 9 bits
+constexpr uint32_t AI_EXIT = 1u << 13;
+constexpr uint32_t AI_HASCOLL = 1u << 14;       // always set: every agent files requests
+constexpr uint32_t AI_COLL_SHIFT = 16;          // 8 bits
+
+template <int NBR, int THREADS>
+__global__ void __launch_bounds__(THREADS)
+ffm_legacy_actor_kernel(const LegacyParams P) {
+    constexpr int A = NBR + 1;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int e = blockIdx.x;
+    const int W = P.W, HW = P.HW, H = P.H;
+    const int G = W + 1;
+    const LSmemLayout L = make_llayout(HW, W, P.n_max, true);
+    constexpr uint32_t EXIT_EMPTY = TYPE_EXIT << TYPE_SHIFT;
+    const double DINF = __longlong_as_double(0x7ff0000000000000LL);
+
+    uint16_t* grid = reinterpret_cast<uint16_t*>(smem_raw + L.grid) + G;
+    uint8_t* claim = smem_raw + L.claim;
+    uint32_t* claim32 = reinterpret_cast<uint32_t*>(smem_raw + L.claim);
+    uint32_t* first = reinterpret_cast<uint32_t*>(smem_raw + L.first);
+    uint32_t* pos = reinterpret_cast<uint32_t*>(smem_raw + L.pos);
+    uint32_t* posB = reinterpret_cast<uint32_t*>(smem_raw + L.posB);
+    uint32_t* hs = reinterpret_cast<uint32_t*>(smem_raw + L.tgt);        // H slot of the agent's state (LEG_NONE: no row)
+    uint32_t* info = reinterpret_cast<uint32_t*>(smem_raw + L.info);
+    uint32_t* st = reinterpret_cast<uint32_t*>(smem_raw + L.st);
+    uint32_t* nst = reinterpret_cast<uint32_t*>(smem_raw + L.nst);
+    double* tdv = reinterpret_cast<double*>(smem_raw + L.td);
+    uint32_t* req = reinterpret_cast<uint32_t*>(smem_raw + L.req);       // [n][8]
+    uint32_t* wcnt = reinterpret_cast<uint32_t*>(smem_raw + L.wcnt);
+    int* misc = reinterpret_cast<int*>(smem_raw + L.misc);               // [0] first agent inserting an H row, [1] dirty, [2] rows inserted
+    double* dmisc = reinterpret_cast<double*>(smem_raw + L.misc + 16);   // [0] hmin, [1] hmax at step start
+    __shared__ double red_lo[32], red_hi[32];
+
+    float* dff_home = P.dff + (size_t)e * HW;
+    float* dffA = dff_home;
+    float* dffB = P.dff_tmp + (size_t)e * HW;
+    for (int c = tid; c < HW + 2 * G; c += THREADS) grid[c - G] = P.type_grid[c];
+    for (int c = tid; c < HW / 4 + 1; c += THREADS) claim32[c] = 0u;
+    for (int c = tid; c < HW; c += THREADS) first[c] = 0xFFFFFFFFu;
+    int n = P.n_alive[e];
+    const int t0 = P.t_done[e];
+    uint32_t* gpos = P.pos + (size_t)e * P.n_max;
+    for (int i = tid; i < n; i += THREADS) pos[i] = gpos[i];
+    __syncthreads();
+    for (int i = tid; i < n; i += THREADS) grid[pos[i]] |= (uint16_t)(i + 1);
+    __syncthreads();
+    for (int i = tid; i < n; i += THREADS)
+        if ((grid[pos[i]] & OCC_MASK) != (uint32_t)(i + 1)) atomicOr(P.err, LEG_ERR_DUP);
+
+    const uint32_t episode = P.episode_base + (uint32_t)e;
+    const bool learn = P.learn != 0;
+    unsigned long long ped_steps = 0;
+    int tl = 0;
+    const StencilGeom sgeom = make_stencil_geom(H, W, tid, THREADS);
+    for (; tl < P.max_steps && n > 0; ++tl) {
+        const uint32_t t = (uint32_t)(t0 + tl);
+        ped_steps += (unsigned long long)n;
+
+        // ---- extremes of the H table at step start (rescan when an extreme value moved inwards) --
+        if (tid == 0) { misc[1] = learn ? P.hstats->dirty : 0; misc[0] = 0x7fffffff; misc[2] = 0; }
+        __syncthreads();
+        if (misc[1]) {
+            double lo = DINF, hi = -DINF;
+            const unsigned int cnt = *P.Ht.count;
+            for (unsigned int x = tid; x < cnt; x += THREADS) {
+                const double* row = P.Ht.rows + (size_t)P.Ht.order[x] * A;
+#pragma unroll
+                for (int a = 0; a < A; ++a) { lo = fmin(lo, row[a]); hi = fmax(hi, row[a]); }
+            }
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) {
+                lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, d));
+                hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, d));
+            }
+            if (lane == 0) { red_lo[warp] = lo; red_hi[warp] = hi; }
+            __syncthreads();
+            if (tid == 0) {
+                for (int w = 1; w < THREADS / 32; ++w) { lo = fmin(lo, red_lo[w]); hi = fmax(hi, red_hi[w]); }
+                P.hstats->hmin = lo; P.hstats->hmax = hi; P.hstats->any = cnt > 0; P.hstats->dirty = 0;
+            }
+            __syncthreads();
+        }
+        if (tid == 0) {
+            dmisc[0] = P.hstats->any ? P.hstats->hmin : DINF;
+            dmisc[1] = P.hstats->any ? P.hstats->hmax : -DINF;
+        }
+
+        // ================= A0 ===================================================================
+        for (int i = tid; i < n; i += THREADS) {
+            const int c = (int)pos[i];
+            const int r = c / W, col = c - r * W;
+            const unsigned long long key = leg_key13<0u>(grid, r, col, H, W, P.block_size, P.nby);      // :174-175
+            if (learn) st[i] = leg_find_or_insert(P.V, key, P.err);
+            uint32_t valid = 1u << NBR, ex = 0;                       // "stay" is always valid (:212)
+#pragma unroll
+            for (int k = 0; k < NBR; ++k) {
+                const uint32_t g = grid[c + nbr_off<NBR>(k, W)];
+                if ((g & OCC_MASK) == 0u) valid |= 1u << k;           // in bounds, map 0 / 3, nobody else there (:180-206)
+                if ((g >> TYPE_SHIFT) == TYPE_EXIT) ex |= 1u << k;    // :217-221
+            }
+            const int first_exit = ex ? __ffs(ex) - 1 : NBR;
+            const int slot = leg_find(P.Ht, key);
+            if (slot < 0 && first_exit != 0 && learn) atomicMin(&misc[0], i);   // this agent's first lookup inserts the row
+            hs[i] = slot < 0 ? LEG_NONE : (uint32_t)slot;
+            info[i] = (valid << AI_VALID_SHIFT) | (ex ? AI_EXIT : 0u) | (uint32_t)first_exit;           // act field: first exit slot for now
+            nst[i] = (uint32_t)(key & 0xFFFFFFFFu);                  // the key travels to A1 in two halves
+            posB[i] = (uint32_t)(key >> 32);
+        }
+        __syncthreads();
+
+        // ================= A1 ===================================================================
+        const int first_new = misc[0];
+        for (int i = tid; i < n; i += THREADS) {
+            const int c = (int)pos[i];
+            uint32_t w = info[i];
+            const uint32_t valid = (w >> AI_VALID_SHIFT) & ((1u << A) - 1u);
+            const int first_exit = (int)(w & AI_ACT_MASK);
+            int act = first_exit;
+            if (first_exit > 0) {
+                // H row: inserted as zeros by the first lookup (:252-257)
+                uint32_t slot = hs[i];
+                const bool have = slot != LEG_NONE;
+                if (!have && learn) {
+                    bool ins = false;
+                    slot = leg_find_or_insert(P.Ht, ((unsigned long long)posB[i] << 32) | nst[i], P.err, &ins);
+                    hs[i] = slot;
+                    if (ins) misc[2] = 1;
+                }
+                double h[A];
+#pragma unroll
+                for (int k = 0; k < A; ++k) h[k] = have ? P.Ht.rows[(size_t)slot * A + k] : 0.0;
+                double hmin = dmisc[0], hmax = dmisc[1];
+                if (first_new <= i || (!learn && !have)) { hmin = fmin(hmin, 0.0); hmax = fmax(hmax, 0.0); }
+                if (hmax - hmin > 1e-6) {                               // :288-293
+                    const double den = hmax - hmin, rng = P.sff_max - P.sff_min;
+#pragma unroll
+                    for (int k = 0; k < A; ++k)
+                        h[k] = __dadd_rn(__dmul_rn(__ddiv_rn(__dadd_rn(hmax, -h[k]), den), rng), P.sff_min);
+                }
+                double e_[A], mx = -DINF;
+                bool flat = valid != ((1u << A) - 1u);                  // an invalid slot scores -inf (:300) -> isinf (:304) -> flat
+#pragma unroll
+                for (int k = 0; k < A; ++k) {
+                    const int cc = (k == NBR) ? c : c + nbr_off<NBR>(k, W);
+                    e_[k] = __dadd_rn(__dmul_rn(-P.kA, h[k]), (double)__fmul_rn(P.kd, dffA[cc]));        // :295-298
+                    if (!isfinite(e_[k])) flat = true;
+                    mx = fmax(mx, e_[k]);
+                }
+                double tot = 0.0;
+                if (!flat) {
+#pragma unroll
+                    for (int k = 0; k < A; ++k) { e_[k] = exp(__dadd_rn(e_[k], -mx)); tot += e_[k]; }   // :321
+                }
+                if (flat || !(isfinite(tot) && tot > 0.0)) {            // flat scores: exp(1 - 1) = 1 per valid slot (:306-312, :321-333)
+                    tot = 0.0;
+#pragma unroll
+                    for (int k = 0; k < A; ++k) { e_[k] = ((valid >> k) & 1u) ? 1.0 : 0.0; tot += e_[k]; }
+                }
+                const int nv = __popc(valid);
+                for (int s = 0; s < NBR && s < first_exit; ++s) {       // one decision per slot before the first exit slot
+                    const uint32_t ent = (uint32_t)i * 8u + (uint32_t)s;
+                    int slot_c = -1;
+                    if (P.epsilon > 0.0) {                              // :329-341
+                        const Draw2 d = draw2(P.seed, episode, t, STREAM_EPS, ent);
+                        if (d.u0 < P.epsilon) slot_c = (int)__fns(valid, 0, (int)(d.u1 * (double)nv) + 1);
+                    }
+                    if (slot_c < 0) {
+                        const double thresh = draw_u0(P.seed, episode, t, STREAM_MOVE, ent) * tot;      // :343
+                        double run = 0.0;
+                        slot_c = NBR;
+                        bool done = false;
+#pragma unroll
+                        for (int k = 0; k < NBR; ++k)
+                            if (!done) {
+                                run += e_[k];
+                                if (run > thresh) { slot_c = k; done = true; }
+                            }
+                    }
+                    const uint32_t target = (slot_c == NBR) ? (uint32_t)c : (uint32_t)(c + nbr_off_rt<NBR>(slot_c, W));
+                    req[i * 8 + s] = target;
+                    atomicAdd(&claim32[target >> 2], 1u << (8 * (target & 3u)));
+                    atomicMin(&first[target], ent);
+                    act = slot_c;
+                }
+            }
+            if (first_exit < NBR) {                                     // forced exit request for every slot from the first exit on (:223-241)
+                const uint32_t target = (uint32_t)(c + nbr_off_rt<NBR>(first_exit, W));
+                for (int s = first_exit; s < NBR; ++s) {
+                    req[i * 8 + s] = target;
+                    atomicAdd(&claim32[target >> 2], 1u << (8 * (target & 3u)));
+                    atomicMin(&first[target], (uint32_t)i * 8u + (uint32_t)s);
+                }
+                act = first_exit;
+            }
+            info[i] = (w & ~AI_ACT_MASK) | (uint32_t)act;
+        }
+        __syncthreads();
+
+        // ================= B ====================================================================
+        for (int i = tid; i < n; i += THREADS) {
+            const int c = (int)pos[i];
+            uint32_t best_ord = 0, last_ord = 0, nxt = (uint32_t)c, coll = 0;
+            bool any_won = false, any_req = false;
+            int wins = 0;
+            for (int s = 0; s < NBR; ++s) {
+                const uint32_t T = req[i * 8 + s];
+                bool dup = false;
+                int m = 0;
+                for (int j = 0; j < NBR; ++j) {
+                    if (req[i * 8 + j] == T) { if (j < s) dup = true; ++m; }
+                }
+                if (dup) continue;                                     // each distinct cell once
+                const int k = (int)claim[T];
+                bool won = true;
+                uint32_t cc = 0;
+                if (k > 1) {
+                    int r0 = 0;                                        // entries of the cell's list filed by agents before this one
+                    if (T != (uint32_t)c) {
+#pragma unroll
+                        for (int q = 0; q < NBR; ++q) {
+                            const uint32_t o = (grid[(int)T + nbr_off<NBR>(q, W)] & OCC_MASK) - 1u;
+                            if (o < (uint32_t)i)
+                                for (int j = 0; j < NBR; ++j) r0 += (req[o * 8 + j] == T) ? 1 : 0;
+                        }
+                    }
+                    const int p = (int)(draw2(P.seed, episode, t, STREAM_CONFLICT, T).u1 * (double)k);   // random.choice(agents) (:370)
+                    won = p >= r0 && p < r0 + m;
+                    cc = (uint32_t)(k - 1);
+                }
+                const uint32_t ord = first[T];
+                if (!any_req || ord > last_ord) { last_ord = ord; coll = cc; any_req = true; }
+                if (won) {
+                    ++wins;
+                    if (!any_won || ord > best_ord) { best_ord = ord; nxt = T; any_won = true; }
+                }
+            }
+            float d = dffA[c];
+            for (int q = 0; q < wins; ++q) d = __fadd_rn(d, 1.0f);     // one footprint per grant (:363-365, :373-375)
+            dffA[c] = d;
+            posB[i] = nxt;
+            info[i] = (info[i] & 0xFFFFu) | AI_HASCOLL | (coll << AI_COLL_SHIFT);
+        }
+        __syncthreads();
+
+        // ================= C ====================================================================
+        for (int i = tid; i < n; i += THREADS) {
+            const int c = (int)pos[i];
+            for (int s = 0; s < NBR; ++s) { const uint32_t T = req[i * 8 + s]; claim[T] = 0; first[T] = 0xFFFFFFFFu; }
+            const uint32_t T = posB[i];
+            if (T != (uint32_t)c) {
+                grid[c] &= (uint16_t)TYPE_BITS;
+                if (grid[T] != EXIT_EMPTY) grid[T] |= (uint16_t)(i + 1);
+            }
+        }
+        __syncthreads();
+
+        // ================= T ====================================================================
+        if (learn) {
+            for (int i = tid; i < n; i += THREADS) {
+                uint32_t ns = LEG_NONE;
+                const int c0 = (int)pos[i];
+                if (!(info[i] & AI_EXIT)) {                            // :452-458
+                    const int c = (int)posB[i];
+                    const int r = c / W, col = c - r * W;
+                    ns = leg_find_or_insert(P.V, leg_key13<0u>(grid, r, col, H, W, P.block_size, P.nby), P.err);
+                }
+                nst[i] = ns;
+                if (hs[i] == LEG_NONE) {                               // agents that never looked their row up get it in _update_actor (:520-525)
+                    // the state key of time t cannot be rebuilt from the moved grid: it was parked in st's table slot -> V keys
+                    bool ins = false;
+                    hs[i] = leg_find_or_insert(P.Ht, P.V.keys[st[i]], P.err, &ins);
+                    if (ins) misc[2] = 1;
+                }
+                (void)c0;
+            }
+            __syncthreads();
+            if (tid == 0) {
+                double* V = P.V.rows;
+                for (int i = 0; i < n; ++i) {                          // :434-472
+                    const uint32_t w = info[i];
+                    const double rew = leg_reward(P, (w & AI_EXIT) != 0u, true, (int)((w >> AI_COLL_SHIFT) & 0xFFu));
+                    const double v_next = (w & AI_EXIT) ? 0.0 : V[nst[i]];
+                    const double v_cur = V[st[i]];
+                    const double td = __dadd_rn(__dadd_rn(rew, __dmul_rn(P.gamma, v_next)), -v_cur);
+                    V[st[i]] = __dadd_rn(v_cur, __dmul_rn(P.alpha_v, td));
+                    tdv[i] = td;
+                }
+                LegStats* hsx = P.hstats;
+                double hmin = hsx->hmin, hmax = hsx->hmax;
+                int any = hsx->any, dirty = hsx->dirty;
+                if (misc[2]) {                                         // zero rows joined the table in this step
+                    if (!any) { any = 1; hmin = 0.0; hmax = 0.0; } else { hmin = fmin(hmin, 0.0); hmax = fmax(hmax, 0.0); }
+                }
+                double* Hm = P.Ht.rows;
+                for (int i = 0; i < n; ++i) {                          // :495-536
+                    const uint32_t w = info[i];
+                    const uint32_t a = w & AI_ACT_MASK;
+                    if ((w >> (AI_VALID_SHIFT + a)) & 1u) {
+                        double* cell = Hm + (size_t)hs[i] * A + a;
+                        const double old = *cell;
+                        const double nw = __dadd_rn(old, __dmul_rn(P.alpha_h, tdv[i]));                 // :534
+                        *cell = nw;
+                        if (nw < hmin) hmin = nw; else if (old == hmin && nw > old) dirty = 1;
+                        if (nw > hmax) hmax = nw; else if (old == hmax && nw < old) dirty = 1;
+                    }
+                }
+                hsx->hmin = hmin; hsx->hmax = hmax; hsx->any = any; hsx->dirty = dirty;
+            }
+            __syncthreads();
+        }
+
+        // ================= K, D =================================================================
+        const int n_new = leg_compact<THREADS>(grid, posB, pos, wcnt, n, tid);
+        dff_decay_diffuse<NBR>(dffA, dffB, H, W, P.c0, P.c1, P.thr, tid, sgeom);
+        { float* tmp = dffA; dffA = dffB; dffB = tmp; }
+        __syncthreads();
+        n = n_new;
+        if (P.traj != nullptr && tl < P.traj_steps) {
+            uint32_t* row = P.traj + ((size_t)e * P.traj_steps + tl) * P.n_max;
+            for (int i = tid; i < n; i += THREADS) row[i] = pos[i];
+            if (tid == 0) P.traj_n[(size_t)e * P.traj_steps + tl] = n;
+        }
+    }
+
+    for (int i = tid; i < n; i += THREADS) gpos[i] = pos[i];
+    if (dffA != dff_home)
+        for (int c = tid; c < HW; c += THREADS) dff_home[c] = dffA[c];
+    if (tid == 0) {
+        P.n_alive[e] = n;
+        P.t_done[e] = t0 + tl;
+        P.ped_steps[e] += ped_steps;
+    }
+}
+
 template <int NBR>
 __global__ void __launch_bounds__(256) leg_dff_update_kernel(const float* in, float* out, int H, int W, float c0, float c1, float thr) {
     const size_t off = (size_t)blockIdx.x * H * W;
@@ -465,6 +820,11 @@ const void* pick_ac(int nbr, int threads) {
     return threads == 128 ? (const void*)ffm::ffm_legacy_ac_kernel<S, 8, 128> : (const void*)ffm::ffm_legacy_ac_kernel<S, 8, 256>;
 }
 
+const void* pick_actor(int nbr, int threads) {
+    if (nbr == 4) return threads == 128 ? (const void*)ffm::ffm_legacy_actor_kernel<4, 128> : (const void*)ffm::ffm_legacy_actor_kernel<4, 256>;
+    return threads == 128 ? (const void*)ffm::ffm_legacy_actor_kernel<8, 128> : (const void*)ffm::ffm_legacy_actor_kernel<8, 256>;
+}
+
 int table_alloc(HostTable& T, uint32_t cap, int width) {
     T.cap = cap; T.width = width; T.default_value = 0.0;
     T.d.mask = cap - 1u;
@@ -511,7 +871,8 @@ int ffm_legacy_create(const ffm_legacy_config_t* cfg, ffm_legacy_t* out) {
     if (cfg->neighborhood != FFM_NEUMANN && cfg->neighborhood != FFM_MOORE) return fail(FFM_E_INVALID, "neighborhood must be 4 or 8");
     if (cfg->sff_dtype != FFM_F32 && cfg->sff_dtype != FFM_F64) return fail(FFM_E_INVALID, "sff_dtype must be FFM_F32 or FFM_F64");
     if (cfg->model != FFM_LEGACY_AC && cfg->model != FFM_LEGACY_ACTOR_ONLY) return fail(FFM_E_INVALID, "unknown legacy model %d", cfg->model);
-    if (cfg->model == FFM_LEGACY_ACTOR_ONLY) return fail(FFM_E_UNSUPPORTED, "the actor-only legacy model is not built");
+    if (cfg->model == FFM_LEGACY_ACTOR_ONLY && cfg->sff_dtype != FFM_F32)
+        return fail(FFM_E_INVALID, "the actor-only model keeps the SFF as float32 (inf -> 0 and astype(float32), ffm_actor_only.py:45-48)");
     if (cfg->learn != FFM_LEARN_NONE && cfg->learn != FFM_LEARN_EXACT) return fail(FFM_E_INVALID, "the legacy models learn sequentially (FFM_LEARN_EXACT) or not at all");
     if (cfg->n_episodes < 1) return fail(FFM_E_INVALID, "n_episodes must be >= 1");
     if (cfg->learn == FFM_LEARN_EXACT && cfg->n_episodes != 1) return fail(FFM_E_INVALID, "FFM_LEARN_EXACT reproduces the reference's sequential table updates and needs n_episodes == 1");
@@ -538,7 +899,8 @@ int ffm_legacy_create(const ffm_legacy_config_t* cfg, ffm_legacy_t* out) {
     h->threads = N <= 128 ? 128 : 256;
     h->smem_bytes = (int)ffm::make_llayout(HW, W, N, cfg->model == FFM_LEGACY_ACTOR_ONLY).total;
     if (h->smem_bytes > MAX_SMEM_OPTIN) { delete h; return fail(FFM_E_UNSUPPORTED, "episode state (%d B) does not fit the shared memory of one SM", h->smem_bytes); }
-    h->kernel = cfg->sff_dtype == FFM_F64 ? pick_ac<double>(cfg->neighborhood, h->threads) : pick_ac<float>(cfg->neighborhood, h->threads);
+    if (cfg->model == FFM_LEGACY_ACTOR_ONLY) h->kernel = pick_actor(cfg->neighborhood, h->threads);
+    else h->kernel = cfg->sff_dtype == FFM_F64 ? pick_ac<double>(cfg->neighborhood, h->threads) : pick_ac<float>(cfg->neighborhood, h->threads);
     cudaError_t ce = cudaFuncSetAttribute(h->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_bytes);
     if (ce != cudaSuccess) { delete h; return fail(FFM_E_CUDA, "cudaFuncSetAttribute(smem=%d): %s", h->smem_bytes, cudaGetErrorString(ce)); }
 #define LALLOC(ptr, bytes)                                                                    \
@@ -799,6 +1161,12 @@ int ffm_legacy_table_set(ffm_legacy_t h, int32_t which, const uint64_t* keys, co
     CU(cudaMemcpy(T->d.order, order.data(), (size_t)n * 4, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(T->d.count, &c, 4, cudaMemcpyHostToDevice));
     T->default_value = default_value;
+    if (which == FFM_LEGACY_TABLE_H) {     // extremes over every value of the table (ffm_actor_only.py:263-276)
+        ffm::LegStats stt;
+        stt.hmin = INFINITY; stt.hmax = -INFINITY; stt.any = n > 0; stt.dirty = 0;
+        for (int64_t i = 0; i < n * T->width; ++i) { stt.hmin = fmin(stt.hmin, rows[i]); stt.hmax = fmax(stt.hmax, rows[i]); }
+        CU(cudaMemcpy(h->d_hstats, &stt, sizeof(stt), cudaMemcpyHostToDevice));
+    }
     return FFM_OK;
 }
 

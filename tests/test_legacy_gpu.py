@@ -191,3 +191,169 @@ def test_ac_errors():
     bad = m.copy(); bad[0, 1] = 0
     with pytest.raises(ValueError):
         LegacySim(bad, sff, 1, 4, model="ac")
+
+
+# ---- model/ffm_actor_only.py -------------------------------------------------------------------------------------------------
+from helpers import LEGACY_ACTOR_FIXTURES  # noqa: E402
+
+
+def _sorted_table(sim, which):
+    keys, rows = sim.get_table(which)
+    order = np.argsort(keys)
+    return keys[order], rows[order]
+
+
+@pytest.mark.parametrize("name", LEGACY_ACTOR_FIXTURES)
+def test_actor_only_fixture_bit_exact(name):
+    from ffm_b200.legacy import LegacySim
+    g = load_legacy(name)
+    assert float(np.min(g["min_margin"])) > MARGIN_GUARD
+    H, W = g["map"].shape
+    cap = max(len(e["pos0"]) for e in g["ep"])
+    sim = LegacySim(g["map"], g["sff"], 1, cap, model="actor_only", learn="exact", params=g["params"], seed=int(g["seed"]))
+    sim.set_epsilon(float(g["eps"]))
+    T = int(g["max_steps"])
+    for ep, e in enumerate(g["ep"]):
+        sim.set_episode_base(ep)
+        sim.set_positions(*_pack(e["pos0"], cap))
+        sim.set_dff(np.zeros((1, H, W), np.float32))
+        cells, cnt = sim.rollout(T, record=T)
+        steps = int(sim.counters()[0][0])
+        assert steps == len(e["traj"])
+        for t in range(steps):
+            ref = e["traj"][t][:, 0] * W + e["traj"][t][:, 1]
+            assert cnt[0, t] == len(ref), (ep, t)
+            assert np.array_equal(cells[0, t, :cnt[0, t]].astype(np.int64), ref), (ep, t)
+    vk, vr = _sorted_table(sim, "V")
+    hk, hr = _sorted_table(sim, "H")
+    assert np.array_equal(vk, g["v_keys"]) and np.array_equal(vr[:, 0], g["v_vals"])
+    assert np.array_equal(hk, g["h_keys"]) and np.array_equal(hr, g["h_vals"])
+    assert np.array_equal(sim.get_dff()[0], g["final_dff"])
+
+
+def test_actor_only_random_configurations_vs_oracle():
+    """Random rooms, both neighbourhoods, random parameters and exploration rates, tables carried over episodes and passed
+    through table_get / table_set in between: trajectories, V, H and DFF bit for bit."""
+    from ffm_b200.legacy import LegacySim
+    rng = np.random.RandomState(99)
+    checked = 0
+    for case in range(8):
+        h, w = int(rng.randint(8, 18)), int(rng.randint(8, 18))
+        m = assets.room_map(h, w)
+        m[rng.randint(2, h - 2, 4), rng.randint(1, w - 1, 4)] = 2
+        if case % 3 == 1:
+            m[h - 1, w // 3] = 3
+        sff = assets.sff_norm_min(m, "L1", np.float32)
+        params = {"neighborhood": "moore" if case % 2 else "neumann", "k_A": float(rng.uniform(1, 10)), "k_D": float(rng.uniform(0, 2)),
+                  "alpha_v": float(rng.uniform(0.05, 0.5)), "alpha_h": float(rng.uniform(0.05, 0.5)), "gamma": float(rng.uniform(0.8, 1.0)),
+                  "step_penalty": float(-rng.uniform(0, 1)), "collision_penalty": float(-rng.uniform(0, 3))}
+        eps = [0.0, 0.1, 0.3][case % 3]
+        n = int(rng.randint(1, max(2, int((m == 0).sum() * 0.5))))
+        seed = 2000 + case
+        sim = LegacySim(m, sff, 1, n, model="actor_only", learn="exact", params=params, seed=seed)
+        sim.set_epsilon(eps)
+        V, Ht, bad = {}, {}, False
+        for ep in range(3):
+            pos0 = random_positions(m, n, rng)
+            o = legacy_numpy.ActorOnlyOracle(m, sff, pos0, params, PhiloxSource(seed, ep), v_table=V, h_table=Ht, epsilon=eps)
+            traj = o.run(max_steps=30)
+            V, Ht = o.V, o.H
+            sim.set_episode_base(ep)
+            sim.set_positions(*_pack(pos0, n))
+            sim.set_dff(np.zeros((1, h, w), np.float32))
+            cells, cnt = sim.rollout(30, record=30)
+            if o.min_margin < MARGIN_GUARD:
+                bad = True
+                break
+            assert int(sim.counters()[0][0]) == len(traj)
+            for t, p in enumerate(traj):
+                assert np.array_equal(cells[0, t, :cnt[0, t]].astype(np.int64), p[:, 0] * w + p[:, 1]), (case, ep, t)
+            assert np.array_equal(sim.get_dff()[0], o.dff), (case, ep)
+            if ep == 0:                                          # round trip of both tables through the host
+                for which in ("V", "H"):
+                    k, r = sim.get_table(which)
+                    sim.set_table(k, r, which)
+        if bad:
+            continue
+        vk, vr = _sorted_table(sim, "V")
+        hk, hr = _sorted_table(sim, "H")
+        ok = np.array(sorted(V), np.uint64)
+        assert np.array_equal(vk, ok) and np.array_equal(vr[:, 0], np.array([V[int(k)] for k in ok])), case
+        ok = np.array(sorted(Ht), np.uint64)
+        assert np.array_equal(hk, ok) and np.array_equal(hr, np.array([Ht[int(k)] for k in ok]).reshape(len(ok), -1)), case
+        checked += 1
+    assert checked >= 6
+
+
+def test_actor_only_dropin_interface(tmp_path):
+    from ffm_b200.model.ffm_actor_only import FloorFieldModelActorOnly
+    m = assets.room_map(12, 12)
+    sff = assets.sff_norm_min(m, "L1", np.float32)
+    p = os.path.join(tmp_path, "sff.npy")
+    np.save(p, sff)
+    # a pretrained critic table in the format run_critic_training.py pickles (bytes keys): loaded, counted, never read
+    vp = os.path.join(tmp_path, "v.pkl")
+    with open(vp, "wb") as f:
+        pickle.dump({pickle.dumps(((0,) * 13, (1, 1))): 3.5, pickle.dumps(((2,) * 13, (0, 0))): -1.0}, f)
+    params = {"neighborhood": "neumann", "seed": 777}
+    np.random.seed(3)
+    model = FloorFieldModelActorOnly(m, p, 10, pretrained_v_path=vp, params=params)
+    model.set_epsilon(0.1)
+    assert model.initial_v_size == 2 and model.get_v_table_size() == (2, 2, 0) and model.get_h_table_size() == (0, 0)
+    pos0 = np.array(model.positions)
+    o = legacy_numpy.ActorOnlyOracle(m, sff, pos0, params, PhiloxSource(777, 0), epsilon=0.1)
+    for t in range(4):
+        model.step()
+        o.step()
+        assert np.array_equal(model.positions, o.positions)
+        assert np.array_equal(model.dff, o.dff)
+    steps, traj = model.run(max_steps=20, return_trajectory=True)
+    ot = [o.step() or o.positions.copy() for _ in range(steps)]
+    assert steps == 20 and len(traj) == 20
+    for a, b in zip(traj, ot):
+        assert np.array_equal(np.asarray(a, dtype=np.int64).reshape(-1, 2), b)
+    nby = (12 + 4) // 5
+    ht = model.get_h_table()
+    assert {legacy_numpy.state_to_key(pickle.loads(k), nby): v for k, v in ht.items()} == o.H
+    vt = model.get_v_table()
+    dev = {legacy_numpy.state_to_key(pickle.loads(k), nby): v for k, v in vt.items() if isinstance(k, bytes)}
+    assert dev == o.V and len(vt) == len(o.V) + 2
+    assert model.get_v_table_size() == (2, len(o.V) + 2, len(o.V))
+    assert model.get_h_table_size() == (len(o.H), len(o.H) * 5)
+    assert model.H[b"unseen"] == [] and model.V[b"unseen"] == 0.0
+    np.random.seed(4)
+    model.reset()
+    assert not model.dff.any() and model.get_h_table_size()[0] == len(o.H)
+
+
+def test_actor_only_frozen_batch():
+    """learn="none": a batch of episodes with frozen tables; rows that do not exist read as zeros and are not inserted."""
+    from ffm_b200.legacy import LegacySim
+    m = assets.room_map(12, 12)
+    sff = assets.sff_norm_min(m, "L1", np.float32)
+    rng = np.random.RandomState(6)
+    # train one episode, then evaluate a batch with the learned tables
+    tr = LegacySim(m, sff, 1, 20, model="actor_only", learn="exact", seed=3)
+    tr.set_epsilon(0.2)
+    tr.set_positions(*_pack(random_positions(m, 20, rng), 20))
+    tr.rollout(60)
+    B, n = 16, 20
+    buf = np.stack([np.concatenate([random_positions(m, n, rng)]) for _ in range(B)]).astype(np.int32)
+    ev = LegacySim(m, sff, B, n, model="actor_only", learn="none", seed=11)
+    for which in ("V", "H"):
+        k, r = tr.get_table(which)
+        ev.set_table(k, r, which)
+    sizes = (ev.table_size("V"), ev.table_size("H"))
+    ev.set_positions(buf, np.full((B,), n, np.int32))
+    ev.rollout(400)
+    steps, ped_steps = ev.counters()
+    pos, left = ev.get_positions()
+    assert (ev.table_size("V"), ev.table_size("H")) == sizes
+    assert (left >= 0).all() and (steps > 0).all() and (ped_steps >= n).all()
+    ev2 = LegacySim(m, sff, B, n, model="actor_only", learn="none", seed=11)          # run to run identical
+    for which in ("V", "H"):
+        k, r = tr.get_table(which)
+        ev2.set_table(k, r, which)
+    ev2.set_positions(buf, np.full((B,), n, np.int32))
+    ev2.rollout(400)
+    assert np.array_equal(ev2.counters()[0], steps) and np.array_equal(ev2.get_positions()[0], pos)
