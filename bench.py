@@ -81,7 +81,11 @@ WORKLOADS = {
                 desc="C5: static-floor-field sweep, 64 maps/GPU of 1024x1024 with 20 % random rectangular obstacles and 8 exits: "
                      "geodesic BFS-4, BFS-8, (1, sqrt2)-Dijkstra fields + the obstacle-blind L1 field of Create_SFF.py"),
 }
-SECONDARY = ("c3", "c4", "c4train", "c5train", "c2traj", "sff")
+WORKLOADS["legacy"] = dict(h=50, w=50, n=100, episodes=8, cap=500, legacy=True, batch=2048,
+                           desc="legacy 13-cell models (SURVEY 8 f4) on run_critic_training.py's configuration: 50x50 room, float64 L1 SFF, "
+                                "MODEL_PARAMS, N = 100, MAX_STEPS 500 -- sequential-exact TD(0) learning episodes (ffm_ac_core), the same for the "
+                                "legacy actor (ffm_actor_only, N = 10, epsilon 0.1), and a frozen-table batch of 2048 episodes")
+SECONDARY = ("c3", "c4", "c4train", "c5train", "c2traj", "sff", "legacy")
 C4_ROUNDS = 16          # rollout + exchange rounds per timed step of the c4 workload (>= 50 syncs over the default 5 steps)
 
 
@@ -753,7 +757,94 @@ def run_mcq_training_workload(ctx, name, wl):
     }
 
 
+LEGACY_PARAMS = {"k_S": 10, "k_D": 1, "alpha_v": 0.01, "gamma": 0.99, "exit_reward": 100.0, "step_penalty": -1.0,
+                 "collision_penalty": -1.0, "neighborhood": "neumann", "block_size": 5}     # run_critic_training.py:34-44
+
+
+def run_legacy_workload(ctx, name, wl):
+    """Legacy 13-cell models.  A step = `episodes` sequential-exact learning episodes of the TD critic on one handle per GPU
+    (the reference's own semantics: one episode after the other on a shared V dict -- "replicas only" across GPUs).
+    The ffm_legacy_* calls take HOST buffers and return when done, so value and e2e are the same measurement."""
+    torch, args = ctx.torch, ctx.args
+    from ffm_b200.legacy import LegacySim
+    m = room_map(wl["h"], wl["w"])
+    sff64 = sff_room(m, "neumann").astype(np.float64)
+    E, N, cap, HW = wl["episodes"], wl["n"], wl["cap"], wl["h"] * wl["w"]
+    pos = place(m, N, E, ctx.rank * E, args.seed)
+    zero = np.zeros((1, wl["h"], wl["w"]), np.float32)
+    ac = LegacySim(m, sff64, 1, N, model="ac", learn="exact", params=LEGACY_PARAMS, seed=args.seed, device=ctx.local)
+    Na = 10
+    actor = LegacySim(m, sff64, 1, Na, model="actor_only", learn="exact", params={**LEGACY_PARAMS, "k_A": 10, "alpha_h": 0.1},
+                      seed=args.seed, device=ctx.local)
+    actor.set_epsilon(0.1)
+    B = wl["batch"]
+    frozen = LegacySim(m, sff64, B, N, model="ac", learn="none", params=LEGACY_PARAMS, seed=args.seed, episode_base=ctx.rank * B,
+                       device=ctx.local)
+    bpos = place(m, N, B, ctx.rank * B, args.seed + 1)
+    counts = {}
+
+    def episodes(sim, n, tag):
+        ps = 0
+        for e in range(E):
+            sim.set_episode_base(ctx.rank * E + e)
+            sim.set_positions(np.ascontiguousarray(pos[e:e + 1, :n]), np.array([n], np.int32))
+            sim.set_dff(zero)
+            sim.rollout(cap)
+            ps += int(sim.counters()[1][0])
+        counts[tag] = ps
+
+    def batch():
+        frozen.set_positions(bpos, np.full((B,), N, np.int32))
+        frozen.set_dff(np.zeros((B, wl["h"], wl["w"]), np.float32))
+        frozen.rollout(cap)
+        counts["frozen"] = int(frozen.counters()[1].sum())
+
+    for _ in range(min(args.warmup, 2)):
+        episodes(ac, N, "ac"); episodes(actor, Na, "actor"); batch()
+    ctx.barrier()
+    mark0 = ctx.sampler.mark()
+    evs = event_pairs(torch, args.steps, 4)
+    tot = {"ac": 0, "actor": 0, "frozen": 0}
+    for k in range(args.steps):
+        evs[k][0].record()
+        episodes(ac, N, "ac")
+        evs[k][1].record()
+        episodes(actor, Na, "actor")
+        evs[k][2].record()
+        batch()
+        evs[k][3].record()
+        for t in tot:
+            tot[t] += counts[t]
+    ctx.barrier()
+    clocks = ctx.sampler.window(mark0)
+    ms = [sum(e[i].elapsed_time(e[i + 1]) for e in evs) for i in range(3)]
+    ms, sums = ctx.reduce(ms, [float(tot["ac"]), float(tot["actor"]), float(tot["frozen"])])
+    if ctx.rank != 0:
+        return None
+    value = sums[0] / (ms[0] * 1e-3)
+    return {
+        "metric": "ped_steps_per_sec", "value": value, "unit": UNIT, "n_gpus": ctx.world, "steps": args.steps, "warmup": min(args.warmup, 2),
+        "ms_per_step": ms[0] / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": wl["desc"], "episodes_per_step_per_gpu": E, "parallelism": f"replicas only: {ctx.world} independent learner(s), no collective",
+                   "reference": "critic_training/run_20251206_153157/summary.txt: 11 000 episodes in 03:25:36 = 0.89 episodes/s (hardware unknown)"},
+        "episodes_per_sec": ctx.world * E * args.steps / (ms[0] * 1e-3),
+        "actor_only": {"value": sums[1] / (ms[1] * 1e-3), "unit": UNIT, "episodes_per_sec": ctx.world * E * args.steps / (ms[1] * 1e-3), "N": Na,
+                       "epsilon": 0.1, "ms_per_step": ms[1] / args.steps},
+        "frozen_batch": {"value": sums[2] / (ms[2] * 1e-3), "unit": UNIT, "episodes_per_gpu": B, "ms_per_step": ms[2] / args.steps},
+        "tables": {"V_states": ac.table_size("V"), "actor_V_states": actor.table_size("V"), "actor_H_rows": actor.table_size("H")},
+        "clocks": clocks,
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": int(E * (N * 8 + 4 + HW * 4)), "d2h_bytes_per_step": int(E * 8),
+                "ms_per_step": ms[0] / args.steps, "note": "the legacy entry points take host buffers: positions and a zero DFF in, counters out, every episode"},
+        "gpu_launches": int(args.steps * (2 * E + 1)),
+        "roofline": {"bound": "hbm", "achieved": None, "peak": ctx.hbm_peak, "unit": "GB/s", "frac": None, "traffic": None,
+                     "note": "sequential-exact learning: one CTA, the TD / actor updates of a step applied by ONE thread in agent order (the reference's "
+                             "semantics) -- latency-bound by construction; the frozen batch shows the kernel's parallel rate"},
+    }
+
+
 def run_workload(ctx, name, wl):
+    if wl.get("legacy"):
+        return run_legacy_workload(ctx, name, wl)
     if wl.get("train") == "mcq":
         return run_mcq_training_workload(ctx, name, wl)
     if wl.get("sff"):
@@ -781,7 +872,7 @@ def main():
     if args.episodes:
         wl["episodes"] = args.episodes
     if args.impl == "reference":
-        if wl.get("sff") or wl.get("record") or wl.get("train"):
+        if wl.get("sff") or wl.get("record") or wl.get("train") or wl.get("legacy"):
             raise SystemExit("the reference arm covers the rollout workloads")
         run_reference_arm(args, wl)
         return
@@ -806,7 +897,7 @@ def main():
     if ctx.rank == 0:
         if secondary:
             line["secondary"] = secondary
-        if not args.no_cpu and ctx.world == 1 and not wl.get("sff") and not wl.get("train"):
+        if not args.no_cpu and ctx.world == 1 and not wl.get("sff") and not wl.get("train") and not wl.get("legacy"):
             try:
                 if wl.get("model") == "unified":
                     line["cpu_baseline"] = cpu_numpy_port_unified(wl, budget_s=min(args.cpu_budget, 10.0))
