@@ -12,7 +12,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
-def main(out):
+def main(out, only_legacy=False):
     from ffm_b200 import workloads
     from ffm_b200.model.ffm_core import FloorFieldModel as Core
     from ffm_b200.model.ffm_learning_core import FloorFieldModel as Mcq
@@ -49,6 +49,29 @@ def main(out):
             while mcq.positions.shape[0] > 0:
                 mcq.step(beta=beta)
         mcq.save_Q(os.path.join(out, "gpu_wire_Q.pkl"))
+    with tempfile.TemporaryDirectory() as tmp:
+        # legacy drivers: run_critic_training.py:219-226 -> V_integrated_total*.pkl, run_actor_only_training.py:293-299 -> H_actor_N*.pkl
+        from ffm_b200.model.ffm_ac_core import FloorFieldModel as LegacyCritic
+        from ffm_b200.model.ffm_actor_only import FloorFieldModelActorOnly
+        p32 = os.path.join(tmp, "sff32.npy")
+        np.save(p32, workloads.sff_room(m, "neumann"))
+        np.random.seed(2)
+        critic = LegacyCritic(m, p32, 20, {"seed": 404, "neighborhood": "neumann", "block_size": 5, "step_penalty": -1.0})
+        for ep in range(3):
+            if ep:
+                critic.reset()
+            critic.run(max_steps=100)
+        vp = os.path.join(out, "gpu_wire_legacy_V.pkl")
+        with open(vp, "wb") as f:
+            pickle.dump(critic.get_v_table(), f)
+        actor = FloorFieldModelActorOnly(m, p32, 1, pretrained_v_path=vp, params={"seed": 505, "neighborhood": "neumann", "step_penalty": -1.0})
+        actor.set_epsilon(0.2)
+        for ep in range(40):
+            if ep:
+                actor.reset()
+            actor.run(max_steps=100)
+        with open(os.path.join(out, "gpu_wire_legacy_H_actor.pkl"), "wb") as f:
+            pickle.dump(actor.get_h_table(), f)
     print("written:", sorted(os.listdir(out)))
 
 

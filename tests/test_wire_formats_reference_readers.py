@@ -63,3 +63,56 @@ def test_v_pickle_is_the_driver_format():
     assert isinstance(V, dict) and len(V) > 20
     for (ranks, blk), v in V.items():
         assert len(ranks) == 4 and all(0 <= r <= 3 for r in ranks) and len(blk) == 2 and isinstance(v, float)
+
+
+def test_legacy_table_pickles_are_the_driver_format():
+    """run_critic_training.py:219-226 / run_actor_only_training.py:293-299: dicts keyed by pickle.dumps((state_13, (bx, by)))."""
+    with open(os.path.join(GOLDEN, "gpu_wire_legacy_V.pkl"), "rb") as f:
+        V = pickle.load(f)
+    with open(os.path.join(GOLDEN, "gpu_wire_legacy_H_actor.pkl"), "rb") as f:
+        Ht = pickle.load(f)
+    assert len(V) > 100 and len(Ht) > 10
+    for k, v in V.items():
+        cells, blk = pickle.loads(k)
+        assert len(cells) == 13 and all(0 <= c <= 3 for c in cells) and cells[4] == 1 and len(blk) == 2 and isinstance(v, float)
+    for k, row in Ht.items():
+        cells, blk = pickle.loads(k)
+        assert len(cells) == 13 and cells[4] == 1 and isinstance(row, list) and len(row) == 5
+
+
+@needs_reference
+def test_reference_inspect_h_actor_reads_the_gpu_h_pickle(tmp_path):
+    """inspect_h_actor_formatted.py (a script with a hard-wired relative path) run unmodified, from a directory that holds the
+    GPU-written H table under that path; its report must list every state without a decode error."""
+    import runpy
+    import shutil
+    src = open(os.path.join(REF, "inspect_h_actor_formatted.py")).read()
+    date = src.split('date = "')[1].split('"')[0]
+    name = src.split('file_name = "')[1].split('"')[0]
+    d = os.path.join(tmp_path, "output", "logs", "actor_only_training", f"run_{date}")
+    os.makedirs(d)
+    shutil.copy(os.path.join(GOLDEN, "gpu_wire_legacy_H_actor.pkl"), os.path.join(d, name))
+    cwd = os.getcwd()
+    os.chdir(tmp_path)
+    try:
+        with redirect_stdout(io.StringIO()):
+            runpy.run_path(os.path.join(REF, "inspect_h_actor_formatted.py"), run_name="__main__")
+    finally:
+        os.chdir(cwd)
+    report = open(os.path.join(tmp_path, "H_actor_analysis.txt"), encoding="utf-8").read()
+    with open(os.path.join(GOLDEN, "gpu_wire_legacy_H_actor.pkl"), "rb") as f:
+        n = len(pickle.load(f))
+    assert f"総状態数: {n}" in report and f"ソート済み状態数: {n}" in report and "デコードエラー" not in report
+
+
+@needs_reference
+def test_reference_actor_class_loads_the_gpu_legacy_v_pickle(tmp_path):
+    """The UNMODIFIED legacy actor class reads the GPU-written critic table as its pretrained_v_path (ffm_actor_only.py:56-69)."""
+    mod = _ref_module("model.ffm_actor_only")
+    m = np.zeros((12, 12), np.uint8); m[0, :] = 2; m[-1, :] = 2; m[:, 0] = 2; m[:, -1] = 2; m[0, 6] = 3
+    p = os.path.join(tmp_path, "sff.npy")
+    np.save(p, np.zeros((12, 12), np.float32))
+    with redirect_stdout(io.StringIO()):
+        model = mod.FloorFieldModelActorOnly(m, p, 1, pretrained_v_path=os.path.join(GOLDEN, "gpu_wire_legacy_V.pkl"))
+    with open(os.path.join(GOLDEN, "gpu_wire_legacy_V.pkl"), "rb") as f:
+        assert model.initial_v_size == len(pickle.load(f))
