@@ -771,7 +771,6 @@ def run_legacy_workload(ctx, name, wl):
     sff64 = sff_room(m, "neumann").astype(np.float64)
     E, N, cap, HW = wl["episodes"], wl["n"], wl["cap"], wl["h"] * wl["w"]
     pos = place(m, N, E, ctx.rank * E, args.seed)
-    zero = np.zeros((1, wl["h"], wl["w"]), np.float32)
     ac = LegacySim(m, sff64, 1, N, model="ac", learn="exact", params=LEGACY_PARAMS, seed=args.seed, device=ctx.local)
     Na = 10
     actor = LegacySim(m, sff64, 1, Na, model="actor_only", learn="exact", params={**LEGACY_PARAMS, "k_A": 10, "alpha_h": 0.1},
@@ -788,14 +787,14 @@ def run_legacy_workload(ctx, name, wl):
         for e in range(E):
             sim.set_episode_base(ctx.rank * E + e)
             sim.set_positions(np.ascontiguousarray(pos[e:e + 1, :n]), np.array([n], np.int32))
-            sim.set_dff(zero)
+            sim.zero_dff()
             sim.rollout(cap)
             ps += int(sim.counters()[1][0])
         counts[tag] = ps
 
     def batch():
         frozen.set_positions(bpos, np.full((B,), N, np.int32))
-        frozen.set_dff(np.zeros((B, wl["h"], wl["w"]), np.float32))
+        frozen.zero_dff()
         frozen.rollout(cap)
         counts["frozen"] = int(frozen.counters()[1].sum())
 
@@ -833,8 +832,8 @@ def run_legacy_workload(ctx, name, wl):
         "frozen_batch": {"value": sums[2] / (ms[2] * 1e-3), "unit": UNIT, "episodes_per_gpu": B, "ms_per_step": ms[2] / args.steps},
         "tables": {"V_states": ac.table_size("V"), "actor_V_states": actor.table_size("V"), "actor_H_rows": actor.table_size("H")},
         "clocks": clocks,
-        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": int(E * (N * 8 + 4 + HW * 4)), "d2h_bytes_per_step": int(E * 8),
-                "ms_per_step": ms[0] / args.steps, "note": "the legacy entry points take host buffers: positions and a zero DFF in, counters out, every episode"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": int(E * (N * 8 + 4)), "d2h_bytes_per_step": int(E * 12),
+                "ms_per_step": ms[0] / args.steps, "note": "the legacy entry points take host buffers: positions in, counters out, every episode"},
         "gpu_launches": int(args.steps * (2 * E + 1)),
         "roofline": {"bound": "hbm", "achieved": None, "peak": ctx.hbm_peak, "unit": "GB/s", "frac": None, "traffic": None,
                      "note": "sequential-exact learning: one CTA, the TD / actor updates of a step applied by ONE thread in agent order (the reference's "

@@ -118,6 +118,7 @@ SIGNATURES = {
     "ffm_legacy_get_positions": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "ffm_legacy_set_dff": (C.c_int, [C.c_void_p, C.c_void_p]),
     "ffm_legacy_get_dff": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "ffm_legacy_zero_dff": (C.c_int, [C.c_void_p]),
     "ffm_legacy_update_dff": (C.c_int, [C.c_void_p]),
     "ffm_legacy_rollout": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32]),
     "ffm_legacy_get_counters": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -1034,6 +1034,13 @@ int ffm_legacy_get_dff(ffm_legacy_t h, float* dff) {
     return FFM_OK;
 }
 
+int ffm_legacy_zero_dff(ffm_legacy_t h) {
+    if (!h) return fail(FFM_E_INVALID, "null argument");
+    CU(cudaSetDevice(h->cfg.device));
+    CU(cudaMemsetAsync(h->d_dff, 0, (size_t)h->cfg.n_episodes * h->HW * 4, nullptr));
+    return FFM_OK;
+}
+
 int ffm_legacy_update_dff(ffm_legacy_t h) {
     if (!h) return fail(FFM_E_INVALID, "null argument");
     CU(cudaSetDevice(h->cfg.device));

@@ -123,6 +123,9 @@ class LegacySim:
         _abi.check(self._lib.ffm_legacy_get_dff(self._h, dff.ctypes.data))
         return dff
 
+    def zero_dff(self):
+        _abi.check(self._lib.ffm_legacy_zero_dff(self._h))
+
     def update_dff(self):
         _abi.check(self._lib.ffm_legacy_update_dff(self._h))
 

@@ -70,7 +70,7 @@ class FloorFieldModel:
         self._sim.set_episode_base(self._episode)
         self._sim.set_positions(buf, np.array([len(positions)], dtype=np.int32))
         if not keep_dff:
-            self._sim.set_dff(np.zeros((1,) + self.map_array.shape, np.float32))
+            self._sim.zero_dff()
         self._episode += 1
         self._host_pos = positions.astype(np.int64) if len(positions) else positions
         self._host_dff = None

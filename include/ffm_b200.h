@@ -336,6 +336,7 @@ int ffm_legacy_set_positions(ffm_legacy_t h, const int32_t *pos_rc, const int32_
 int ffm_legacy_get_positions(ffm_legacy_t h, int32_t *pos_rc, int32_t *n);
 int ffm_legacy_set_dff(ffm_legacy_t h, const float *dff);                         /* float32 [n_episodes][H][W] */
 int ffm_legacy_get_dff(ffm_legacy_t h, float *dff);
+int ffm_legacy_zero_dff(ffm_legacy_t h);                                          /* reset(): self.dff = np.zeros_like(...), ffm_ac_core.py:326 (device-side memset) */
 int ffm_legacy_update_dff(ffm_legacy_t h);                                        /* update_dff(): ffm_ac_core.py:298-318 */
 /* up to max_steps calls of step() per episode (run(): ffm_ac_core.py:362-390), stopping at evacuation.  traj (may be NULL):
  * uint32 [n_episodes][traj_steps][n_max] linear cells after each step, traj_n int32 [n_episodes][traj_steps] their counts. */
