@@ -677,7 +677,6 @@ ffm_legacy_actor_kernel(const LegacyParams P) {
         if (learn) {
             for (int i = tid; i < n; i += THREADS) {
                 uint32_t ns = LEG_NONE;
-                const int c0 = (int)pos[i];
                 if (!(info[i] & AI_EXIT)) {                            // :452-458
                     const int c = (int)posB[i];
                     const int r = c / W, col = c - r * W;
@@ -690,7 +689,6 @@ ffm_legacy_actor_kernel(const LegacyParams P) {
                     hs[i] = leg_find_or_insert(P.Ht, P.V.keys[st[i]], P.err, &ins);
                     if (ins) misc[2] = 1;
                 }
-                (void)c0;
             }
             __syncthreads();
             if (tid == 0) {
