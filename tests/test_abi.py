@@ -30,6 +30,7 @@ def test_abi_version_and_struct_sizes(ffm_lib):
     assert ffm_lib.ffm_abi_version() == _abi.ABI_VERSION
     assert ctypes.sizeof(_abi.Config) == 88 + 16 + 10 * 8 + 24   # core block + 4 x int32 + 10 x double + MCQ block
     assert ctypes.sizeof(_abi.Draws) == 32 and ctypes.sizeof(_abi.RolloutOut) == 80
+    assert ctypes.sizeof(_abi.LegacyConfig) == 12 * 4 + 3 * 8 + 4 * 4 + 9 * 8 + 8 + 8      # ffm_legacy_config_t
 
 
 def test_no_cpu_fallback_without_gpu():
@@ -43,6 +44,9 @@ def test_no_cpu_fallback_without_gpu():
     m = np.zeros((5, 5), np.uint8)
     with pytest.raises(RuntimeError):
         BatchSim(m, np.zeros((5, 5), np.float32), 1, 1)
+    from ffm_b200.legacy import LegacySim
+    with pytest.raises(RuntimeError):
+        LegacySim(m, np.zeros((5, 5), np.float32), 1, 1)
 
 
 def test_product_does_not_import_oracle():
