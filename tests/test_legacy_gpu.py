@@ -357,3 +357,61 @@ def test_actor_only_frozen_batch():
     ev2.set_positions(buf, np.full((B,), n, np.int32))
     ev2.rollout(400)
     assert np.array_equal(ev2.counters()[0], steps) and np.array_equal(ev2.get_positions()[0], pos)
+
+
+def test_legacy_dropins_driven_like_the_training_scripts(tmp_path):
+    """The loops of run_critic_training.py:125-226 (N patterns x episodes on ONE model, V pickled at the end) and of
+    run_actor_only_training.py:151-299 (pretrained V, epsilon ramp, `model.N = N`, a trajectory .npz every few episodes,
+    H pickled per N), written out here with the drop-in classes in place of the reference's."""
+    from ffm_b200.model.ffm_ac_core import FloorFieldModel
+    from ffm_b200.model.ffm_actor_only import FloorFieldModelActorOnly
+    m = assets.room_map(12, 12)
+    p = os.path.join(tmp_path, "sff.npy")
+    np.save(p, assets.sff_norm_min(m, "L1", np.float64))
+    params = {"k_S": 10, "k_D": 1, "alpha_v": 0.01, "gamma": 0.99, "exit_reward": 100.0, "step_penalty": -1.0,
+              "collision_penalty": -1.0, "neighborhood": "neumann", "block_size": 5}          # run_critic_training.py:34-44
+    np.random.seed(0)
+    model = FloorFieldModel(map_array=m, sff_path=p, N=1, params=params)
+    sizes = []
+    for N in (1, 10, 30):
+        for episode in range(3):
+            model.N = N
+            model.reset()
+            steps = model.run(max_steps=500)
+            assert 0 < steps <= 500 and model.positions.shape[0] == 0                         # everybody out well before the cap
+            sizes.append(model.get_v_table_size())
+    assert sizes == sorted(sizes) and sizes[-1] > 100                                         # the shared table only grows
+    v_table = model.get_v_table()
+    vp = os.path.join(tmp_path, "V_integrated_total9ep.pkl")
+    with open(vp, "wb") as f:
+        pickle.dump(v_table, f)
+    vals = np.array(list(v_table.values()))
+    assert np.isfinite(vals).all() and vals.max() <= 100.0 + 1e-9 and vals.max() > 1.0        # bounded by the exit reward
+
+    actor = FloorFieldModelActorOnly(map_array=m, sff_path=p, N=1, pretrained_v_path=vp,
+                                     params={**params, "k_A": 10, "alpha_h": 0.1})
+    assert actor.initial_v_size == len(v_table)
+    n_list, per_n = (1, 5), 6
+    total, cur = len(n_list) * per_n, 0
+    for N in n_list:
+        actor.N = N
+        for episode in range(1, per_n + 1):
+            cur += 1
+            actor.set_epsilon(float(np.clip(0.5 + (0.01 - 0.5) * (cur - 1) / (total - 1), 0.0, 1.0)))
+            actor.reset()
+            if episode % 3 == 0:
+                steps, trajectory = actor.run(max_steps=200, return_trajectory=True)
+                fn = os.path.join(tmp_path, f"trajectory_N{N}_ep{episode:05d}_total{cur:05d}.npz")
+                np.savez_compressed(fn, positions=trajectory, episode=episode, N=N, total_episode=cur, steps=steps)
+                z = np.load(fn, allow_pickle=True)
+                assert len(z["positions"]) == steps and z["positions"][0].shape[1] == 2
+            else:
+                steps = actor.run(max_steps=200, return_trajectory=False)
+            assert 0 < steps <= 200
+            v0, v1, vnew = actor.get_v_table_size()
+            assert v0 == len(v_table) and v1 == v0 + vnew
+            h_states, h_actions = actor.get_h_table_size()
+            assert h_actions == 5 * h_states
+        with open(os.path.join(tmp_path, f"H_actor_N{N}_total{per_n}ep.pkl"), "wb") as f:
+            pickle.dump(actor.get_h_table(), f)
+    assert actor.get_h_table_size()[0] > 10 and abs(actor.epsilon - 0.01) < 1e-12
