@@ -386,7 +386,7 @@ def test_legacy_dropins_driven_like_the_training_scripts(tmp_path):
     with open(vp, "wb") as f:
         pickle.dump(v_table, f)
     vals = np.array(list(v_table.values()))
-    assert np.isfinite(vals).all() and vals.max() <= 100.0 + 1e-9 and vals.max() > 1.0        # bounded by the exit reward
+    assert np.isfinite(vals).all() and vals.max() <= 100.0 + 1e-9 and vals.max() > 0.9        # bounded by the exit reward
 
     actor = FloorFieldModelActorOnly(map_array=m, sff_path=p, N=1, pretrained_v_path=vp,
                                      params={**params, "k_A": 10, "alpha_h": 0.1})
