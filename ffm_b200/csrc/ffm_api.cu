@@ -1327,13 +1327,21 @@ int ffm_sff_generate(const uint8_t* maps, int32_t n_maps, int32_t H, int32_t W, 
             const float INF = __builtin_huge_valf();
             const float w_axis = 1.0f;
             const float w_diag = mode == FFM_SFF_BFS4 ? INF : (mode == FFM_SFF_BFS8 ? 1.0f : (float)1.4142135623730951);
+            // unit-cost modes: one warp per tile visit (sff_bfs_warp_kernel); Dijkstra-8 (float costs): one CTA per visit.
+            // FFM_SFF_KERNEL=tile forces the CTA-per-tile kernel for the unit-cost modes too (A/B measurements).
+            const bool warp_kernel = mode != FFM_SFF_DIJKSTRA8 && !(getenv("FFM_SFF_KERNEL") && strcmp(getenv("FFM_SFF_KERNEL"), "tile") == 0);
+            const void* kq = warp_kernel ? (mode == FFM_SFF_BFS8 ? (const void*)ffm::sff_bfs_warp_kernel<true> : (const void*)ffm::sff_bfs_warp_kernel<false>)
+                                         : (const void*)ffm::sff_relax_queue_kernel;
             int per_sm = 0, sms = 0;
-            SFF_CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ffm::sff_relax_queue_kernel, 256, 0));
+            SFF_CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kq, 256, 0));
             SFF_CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
             if (const char* ev = getenv("FFM_SFF_CTAS_PER_SM")) { const int v = atoi(ev); if (v >= 1 && v < per_sm) per_sm = v; }   // tuning
             const size_t resident = (size_t)per_sm * sms;      // persistent CTAs: spinning consumers must all be resident
-            const int grid = (int)(ntiles < resident ? ntiles : resident);
-            ffm::sff_relax_queue_kernel<<<grid, 256, 0, st>>>(mp, d_dist, q, H, W, tiles_x, tiles_y, w_axis, w_diag);
+            const size_t want = warp_kernel ? (ntiles + 7) / 8 : ntiles;
+            const int grid = (int)(want < resident ? want : resident);
+            if (!warp_kernel) ffm::sff_relax_queue_kernel<<<grid, 256, 0, st>>>(mp, d_dist, q, H, W, tiles_x, tiles_y, w_axis, w_diag);
+            else if (mode == FFM_SFF_BFS8) ffm::sff_bfs_warp_kernel<true><<<grid, 256, 0, st>>>(mp, d_dist, q, H, W, tiles_x, tiles_y);
+            else ffm::sff_bfs_warp_kernel<false><<<grid, 256, 0, st>>>(mp, d_dist, q, H, W, tiles_x, tiles_y);
             SFF_CU(cudaGetLastError());
             if (rounds_out) {                                  // tile visits, for the caller that asks (one 4-byte read-back)
                 unsigned int visits = 0;

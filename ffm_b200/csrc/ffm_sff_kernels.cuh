@@ -226,6 +226,192 @@ sff_relax_queue_kernel(const uint8_t* __restrict__ maps, float* dist, SffQueue q
     }
 }
 
+// Unit-cost geodesic modes (BFS-4 / BFS-8): one WARP per tile, no shared-memory sweeps and no block barriers.
+// Lane r owns row r of the 32x32 tile: its 32 distances live in registers, sets of cells are 32-bit words (bit j = column
+// j), and "the neighbours of the cells at distance L" is two shifts and two shuffles.  After one relaxation of the rim from
+// the halo (every path into the tile enters through a rim cell at halo + 1), the tile is solved by levels: for L ascending,
+// frontier = {d == L}; its passable neighbours not yet settled take min(d, L + 1).  Levels with an empty frontier are jumped
+// over.  That is Dijkstra with unit weights from many sources at different offsets -- the fixpoint the sweeps of
+// sff_relax_queue_kernel converge to, reached with ~10x fewer instructions per tile visit.  Queue protocol, fold with
+// atomicMin and neighbour wake-up are the same as there; eight warps of a CTA are eight independent consumers.
+template <bool DIAG>
+__global__ void __launch_bounds__(256)
+sff_bfs_warp_kernel(const uint8_t* __restrict__ maps, float* dist, SffQueue q, int H, int W, int tiles_x, int tiles_y) {
+    constexpr int T = SFF_TILE, P = SFF_TILE + 2;
+    constexpr int BIG = 0x3fffffff;
+    constexpr uint32_t FULL = 0xffffffffu;
+    static_assert(T == 32, "one lane per tile row");
+    __shared__ int sm[8][P][P + 1];
+    const int lane = threadIdx.x & 31;
+    int (*s)[P + 1] = sm[threadIdx.x >> 5];
+    const size_t HW = (size_t)H * W;
+    const int tiles_per_map = tiles_x * tiles_y;
+    for (;;) {
+        int tile = -1;
+        if (lane == 0) {
+            volatile unsigned int* ctrl = q.ctrl;
+            const unsigned int h = atomicAdd(&q.ctrl[0], 1u);
+            volatile int* slot = q.ring + (h % q.cap);
+            for (;;) {
+                tile = *slot;
+                if (tile != -1) break;
+                if (ctrl[2] == 0u) break;
+                __nanosleep(64);
+            }
+            if (tile != -1) {
+                *slot = -1;
+                __threadfence();
+                atomicExch(&q.flag[tile], 0);                      // from here on an improved neighbour re-queues this tile
+                __threadfence();
+                atomicAdd(&q.ctrl[3], 1u);
+            }
+        }
+        tile = __shfl_sync(FULL, tile, 0);
+        if (tile < 0) return;
+        const int mapi = tile / tiles_per_map, trem = tile - mapi * tiles_per_map;
+        const int ty = trem / tiles_x, tx = trem - ty * tiles_x;
+        const uint8_t* map = maps + mapi * HW;
+        float* g = dist + mapi * HW;
+        const int r0 = ty * T, c0 = tx * T;
+        // tile + halo as integers (the field holds whole numbers in these modes), coalesced; passable cells as one word per
+        // row.  A tile visit is on the critical path of the wavefront, so its latency counts: the loads are issued in
+        // batches of independent requests (one L2 round trip per batch, not per row).
+        {
+            constexpr int PER = (P * P + 31) / 32;         // 37 cells per lane
+#pragma unroll
+            for (int b0 = 0; b0 < PER; b0 += 13) {
+                float f[13];
+#pragma unroll
+                for (int u = 0; u < 13; ++u) {
+                    const int x = (b0 + u) * 32 + lane;
+                    const int rr = x / P, cc = x - rr * P;
+                    const int r = r0 + rr - 1, c = c0 + cc - 1;
+                    f[u] = 2.0e9f;
+                    if (b0 + u < PER && x < P * P && r >= 0 && r < H && c >= 0 && c < W) f[u] = __ldcg(g + (size_t)r * W + c);
+                }
+#pragma unroll
+                for (int u = 0; u < 13; ++u) {
+                    const int x = (b0 + u) * 32 + lane;
+                    const int rr = x / P, cc = x - rr * P;
+                    if (b0 + u < PER && x < P * P) s[rr][cc] = f[u] < 1.0e9f ? (int)f[u] : BIG;
+                }
+            }
+        }
+        uint32_t pass = 0;
+        {
+            uint8_t mv[T];
+            const int c = c0 + lane;
+#pragma unroll
+            for (int rr = 0; rr < T; ++rr) {
+                const int r = r0 + rr;
+                mv[rr] = (r < H && c < W) ? map[(size_t)r * W + c] : (uint8_t)2;
+            }
+#pragma unroll
+            for (int rr = 0; rr < T; ++rr) {
+                const uint32_t wv = __ballot_sync(FULL, mv[rr] == 0 || mv[rr] == 3);
+                if (lane == rr) pass = wv;
+            }
+        }
+        __syncwarp();
+        int d[T];
+#pragma unroll
+        for (int j = 0; j < T; ++j) d[j] = s[lane + 1][j + 1];
+        // rim <- halo + 1
+        {
+            int hl = s[lane + 1][0], hr = s[lane + 1][P - 1];
+            if (DIAG) {
+                hl = min(hl, min(s[lane][0], s[lane + 2][0]));
+                hr = min(hr, min(s[lane][P - 1], s[lane + 2][P - 1]));
+            }
+            if ((pass & 1u) && hl + 1 < d[0]) d[0] = hl + 1;
+            if ((pass >> 31) && hr + 1 < d[T - 1]) d[T - 1] = hr + 1;
+            if (lane == 0 || lane == T - 1) {
+                const int hrow = lane == 0 ? 0 : P - 1;
+#pragma unroll
+                for (int j = 0; j < T; ++j) {
+                    int hv = s[hrow][j + 1];
+                    if (DIAG) hv = min(hv, min(s[hrow][j], s[hrow][j + 2]));
+                    if (((pass >> j) & 1u) && hv + 1 < d[j]) d[j] = hv + 1;
+                }
+            }
+        }
+        int lo = BIG, hi = -1;
+#pragma unroll
+        for (int j = 0; j < T; ++j)
+            if (d[j] < BIG) { lo = min(lo, d[j]); hi = max(hi, d[j]); }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lo = min(lo, __shfl_xor_sync(FULL, lo, o));
+            hi = max(hi, __shfl_xor_sync(FULL, hi, o));
+        }
+        uint32_t le = 0;                                   // cells with d <= L
+        int L = lo;
+        while (L <= hi) {                                  // warp-uniform
+            uint32_t eq = 0;
+#pragma unroll
+            for (int j = 0; j < T; ++j) eq |= (d[j] == L ? 1u : 0u) << j;
+            le |= eq;
+            if (!__any_sync(FULL, eq != 0u)) {             // nobody at this distance: jump to the next one present
+                int nx = BIG;
+#pragma unroll
+                for (int j = 0; j < T; ++j)
+                    if (d[j] > L) nx = min(nx, d[j]);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) nx = min(nx, __shfl_xor_sync(FULL, nx, o));
+                L = nx;
+                continue;
+            }
+            const uint32_t wide = DIAG ? (eq | (eq << 1) | (eq >> 1)) : eq;
+            uint32_t up = __shfl_up_sync(FULL, wide, 1), dn = __shfl_down_sync(FULL, wide, 1);
+            if (lane == 0) up = 0u;
+            if (lane == T - 1) dn = 0u;
+            const uint32_t cand = ((eq << 1) | (eq >> 1) | up | dn) & pass & ~le;
+            if (cand != 0u) {
+#pragma unroll
+                for (int j = 0; j < T; ++j)
+                    if ((cand >> j) & 1u) d[j] = min(d[j], L + 1);
+            }
+            if (__any_sync(FULL, cand != 0u)) hi = max(hi, L + 1);
+            ++L;
+        }
+        // improved cells go back through shared memory so that the fold is coalesced
+#pragma unroll
+        for (int j = 0; j < T; ++j) {
+            const int o = s[lane + 1][j + 1];
+            s[lane + 1][j + 1] = d[j] < o ? d[j] : -1;
+        }
+        __syncwarp();
+        // fire-and-forget minima (no round trip per row); a rim cell improved against what this visit loaded wakes the
+        // neighbour even if somebody else got there first (a superset of the necessary wake-ups)
+        bool ct = false, cb = false, cl = false, cr = false;
+#pragma unroll 8
+        for (int rr = 0; rr < T; ++rr) {
+            const int v = s[rr + 1][lane + 1];
+            if (v >= 0) {
+                atomicMin(reinterpret_cast<int*>(g + (size_t)(r0 + rr) * W + c0 + lane), __float_as_int((float)v));
+                if (rr == 0) ct = true;
+                if (rr == T - 1) cb = true;
+                if (lane == 0) cl = true;
+                if (lane == T - 1) cr = true;
+            }
+        }
+        const uint32_t rim = (__any_sync(FULL, ct) ? 1u : 0u) | (__any_sync(FULL, cb) ? 2u : 0u) | (__any_sync(FULL, cl) ? 4u : 0u) |
+                             (__any_sync(FULL, cr) ? 8u : 0u);
+        __threadfence();
+        __syncwarp();
+        if (lane < 12) {
+            const int side = lane / 3, k = lane - side * 3 - 1;
+            if ((rim >> side) & 1u) {
+                const int ny = side == 0 ? ty - 1 : (side == 1 ? ty + 1 : ty + k);
+                const int nx = side == 2 ? tx - 1 : (side == 3 ? tx + 1 : tx + k);
+                if (ny >= 0 && ny < tiles_y && nx >= 0 && nx < tiles_x) sff_push(q, (mapi * tiles_y + ny) * tiles_x + nx);
+            }
+        }
+        __syncwarp();
+        if (lane == 0) { __threadfence(); atomicSub(&q.ctrl[2], 1u); }
+    }
+}
+
 template <typename OutT>
 __global__ void sff_convert_kernel(const float* __restrict__ dist, OutT* __restrict__ out, size_t n) {
     for (size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x; c < n; c += (size_t)gridDim.x * blockDim.x)
