@@ -167,6 +167,9 @@ sff_relax_queue_kernel(const uint8_t* __restrict__ maps, float* dist, SffQueue q
         __syncthreads();
         // 256 threads x 4 cells; in-place (Gauss-Seidel style) min-relaxation: a concurrently updated
         // neighbour is read as either its old or its new value, both valid upper bounds of the fixpoint
+        float orig4[4];
+#pragma unroll
+        for (int qd = 0; qd < 4; ++qd) { const int x = threadIdx.x + qd * 256; orig4[qd] = d[x / T + 1][x % T + 1]; }
         volatile float (*vd)[P + 1] = d;
         for (int it = 0; it < 4 * T * T; ++it) {
             bool ch = false;
@@ -192,22 +195,19 @@ sff_relax_queue_kernel(const uint8_t* __restrict__ maps, float* dist, SffQueue q
             }
             if (!__syncthreads_or(ch ? 1 : 0)) break;
         }
-        // fold into the global field; detect rim changes to wake the neighbours
-        for (int x = threadIdx.x; x < T * T; x += blockDim.x) {
+        // fold into the global field with fire-and-forget minima (a visit is on the wavefront's critical path: no round trip per
+        // cell); a rim cell improved against what this visit loaded wakes the neighbour (a superset of the necessary wake-ups)
+#pragma unroll
+        for (int qd = 0; qd < 4; ++qd) {
+            const int x = threadIdx.x + qd * 256;
             const int lr = x / T, lc = x - lr * T;
-            const int r = r0 + lr, c = c0 + lc;
-            if (r < H && c < W && pass[lr][lc]) {
-                const float v = d[lr + 1][lc + 1];
-                if (v < INF) {
-                    const int vi = __float_as_int(v);
-                    const int oldi = atomicMin(reinterpret_cast<int*>(g + (size_t)r * W + c), vi);
-                    if (vi < oldi) {
-                        if (lr == 0) rim_changed[0] = 1;
-                        if (lr == T - 1) rim_changed[1] = 1;
-                        if (lc == 0) rim_changed[2] = 1;
-                        if (lc == T - 1) rim_changed[3] = 1;
-                    }
-                }
+            const float v = d[lr + 1][lc + 1];
+            if (v < orig4[qd]) {                                   // only passable in-map cells are ever lowered
+                atomicMin(reinterpret_cast<int*>(g + (size_t)(r0 + lr) * W + c0 + lc), __float_as_int(v));
+                if (lr == 0) rim_changed[0] = 1;
+                if (lr == T - 1) rim_changed[1] = 1;
+                if (lc == 0) rim_changed[2] = 1;
+                if (lc == T - 1) rim_changed[3] = 1;
             }
         }
         __threadfence();
