@@ -297,7 +297,7 @@ sff_bfs_warp_kernel(const uint8_t* __restrict__ maps, float* dist, SffQueue q, i
                 }
             }
         }
-        uint32_t pass = 0;
+        uint32_t pass = 0, exw = 0;                        // passable cells / exit cells of this lane's row
         {
             uint8_t mv[T];
             const int c = c0 + lane;
@@ -309,71 +309,108 @@ sff_bfs_warp_kernel(const uint8_t* __restrict__ maps, float* dist, SffQueue q, i
 #pragma unroll
             for (int rr = 0; rr < T; ++rr) {
                 const uint32_t wv = __ballot_sync(FULL, mv[rr] == 0 || mv[rr] == 3);
-                if (lane == rr) pass = wv;
+                const uint32_t we = __ballot_sync(FULL, mv[rr] == 3);
+                if (lane == rr) { pass = wv; exw = we; }
             }
         }
         __syncwarp();
-        int d[T];
+        // The interior is a function of the halo and of the exits inside the tile (every path into it enters through the halo),
+        // so the tile is solved from those sources alone, by levels: F_L = (neighbours of F_{L-1} | cells next to a halo cell of
+        // value L-1 | exits if L == 0) & passable & ~visited.  The level of a cell is recorded in bit planes (plane b collects the
+        // frontiers of the levels whose bit b is set): ~50 instructions per level instead of a compare and a select per cell.
+        const int top = s[0][lane + 1], bot = s[P - 1][lane + 1];      // lane j: halo cells above / below column j
+        const int lft = s[lane + 1][0], rgt = s[lane + 1][P - 1];      // lane r: halo cells left / right of row r
+        const int c00 = s[0][0], c01 = s[0][P - 1], c10 = s[P - 1][0], c11 = s[P - 1][P - 1];
+        const bool has_exit = __any_sync(FULL, exw != 0u);
+        int base = min(min(top, bot), min(lft, rgt));
+        if (DIAG) base = min(base, min(min(c00, c01), min(c10, c11)));
 #pragma unroll
-        for (int j = 0; j < T; ++j) d[j] = s[lane + 1][j + 1];
-        // rim <- halo + 1
-        {
-            int hl = s[lane + 1][0], hr = s[lane + 1][P - 1];
-            if (DIAG) {
-                hl = min(hl, min(s[lane][0], s[lane + 2][0]));
-                hr = min(hr, min(s[lane][P - 1], s[lane + 2][P - 1]));
-            }
-            if ((pass & 1u) && hl + 1 < d[0]) d[0] = hl + 1;
-            if ((pass >> 31) && hr + 1 < d[T - 1]) d[T - 1] = hr + 1;
-            if (lane == 0 || lane == T - 1) {
-                const int hrow = lane == 0 ? 0 : P - 1;
-#pragma unroll
-                for (int j = 0; j < T; ++j) {
-                    int hv = s[hrow][j + 1];
-                    if (DIAG) hv = min(hv, min(s[hrow][j], s[hrow][j + 2]));
-                    if (((pass >> j) & 1u) && hv + 1 < d[j]) d[j] = hv + 1;
+        for (int o = 16; o > 0; o >>= 1) base = min(base, __shfl_xor_sync(FULL, base, o));
+        base = has_exit ? 0 : (base < BIG ? base + 1 : BIG);            // first level at which anything appears
+        uint32_t V = 0, F = 0;
+        uint32_t pl[8] = {0, 0, 0, 0, 0, 0, 0, 0}, ph[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+        int relmax = 0;
+        int L = base;
+        while (L < BIG) {                                  // warp-uniform
+            const int hv = L - 1;                          // halo value that injects at this level
+            uint32_t inj = 0;
+            {
+                uint32_t tb = __ballot_sync(FULL, top == hv), bb = __ballot_sync(FULL, bot == hv);
+                if (DIAG) {
+                    tb |= (tb << 1) | (tb >> 1); bb |= (bb << 1) | (bb >> 1);
+                    if (c00 == hv) tb |= 1u;
+                    if (c01 == hv) tb |= 0x80000000u;
+                    if (c10 == hv) bb |= 1u;
+                    if (c11 == hv) bb |= 0x80000000u;
+                    uint32_t lw = __ballot_sync(FULL, lft == hv), rw = __ballot_sync(FULL, rgt == hv);
+                    lw |= (lw << 1) | (lw >> 1); rw |= (rw << 1) | (rw >> 1);
+                    if ((lw >> lane) & 1u) inj |= 1u;
+                    if ((rw >> lane) & 1u) inj |= 0x80000000u;
+                } else {
+                    if (lft == hv) inj |= 1u;
+                    if (rgt == hv) inj |= 0x80000000u;
                 }
+                if (lane == 0) inj |= tb;
+                if (lane == T - 1) inj |= bb;
+                if (L == 0) inj |= exw;
             }
-        }
-        int lo = BIG, hi = -1;
-#pragma unroll
-        for (int j = 0; j < T; ++j)
-            if (d[j] < BIG) { lo = min(lo, d[j]); hi = max(hi, d[j]); }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            lo = min(lo, __shfl_xor_sync(FULL, lo, o));
-            hi = max(hi, __shfl_xor_sync(FULL, hi, o));
-        }
-        uint32_t le = 0;                                   // cells with d <= L
-        int L = lo;
-        while (L <= hi) {                                  // warp-uniform
-            uint32_t eq = 0;
-#pragma unroll
-            for (int j = 0; j < T; ++j) eq |= (d[j] == L ? 1u : 0u) << j;
-            le |= eq;
-            if (!__any_sync(FULL, eq != 0u)) {             // nobody at this distance: jump to the next one present
-                int nx = BIG;
-#pragma unroll
-                for (int j = 0; j < T; ++j)
-                    if (d[j] > L) nx = min(nx, d[j]);
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) nx = min(nx, __shfl_xor_sync(FULL, nx, o));
-                L = nx;
-                continue;
-            }
-            const uint32_t wide = DIAG ? (eq | (eq << 1) | (eq >> 1)) : eq;
+            const uint32_t wide = DIAG ? (F | (F << 1) | (F >> 1)) : F;
             uint32_t up = __shfl_up_sync(FULL, wide, 1), dn = __shfl_down_sync(FULL, wide, 1);
             if (lane == 0) up = 0u;
             if (lane == T - 1) dn = 0u;
-            const uint32_t cand = ((eq << 1) | (eq >> 1) | up | dn) & pass & ~le;
-            if (cand != 0u) {
+            const uint32_t nf = ((F << 1) | (F >> 1) | up | dn | inj) & pass & ~V;
+            if (!__any_sync(FULL, nf != 0u)) {             // the front died out: jump to the next level a halo cell injects at
+                int nx = BIG;
+                if (top < BIG && top + 1 > L) nx = min(nx, top + 1);
+                if (bot < BIG && bot + 1 > L) nx = min(nx, bot + 1);
+                if (lft < BIG && lft + 1 > L) nx = min(nx, lft + 1);
+                if (rgt < BIG && rgt + 1 > L) nx = min(nx, rgt + 1);
+                if (DIAG) {
+                    if (c00 < BIG && c00 + 1 > L) nx = min(nx, c00 + 1);
+                    if (c01 < BIG && c01 + 1 > L) nx = min(nx, c01 + 1);
+                    if (c10 < BIG && c10 + 1 > L) nx = min(nx, c10 + 1);
+                    if (c11 < BIG && c11 + 1 > L) nx = min(nx, c11 + 1);
+                }
 #pragma unroll
-                for (int j = 0; j < T; ++j)
-                    if ((cand >> j) & 1u) d[j] = min(d[j], L + 1);
+                for (int o = 16; o > 0; o >>= 1) nx = min(nx, __shfl_xor_sync(FULL, nx, o));
+                L = nx;
+                F = 0u;
+                continue;
             }
-            if (__any_sync(FULL, cand != 0u)) hi = max(hi, L + 1);
+            V |= nf;
+            const int rel = L - base;
+            relmax = rel;
+#pragma unroll
+            for (int b2 = 0; b2 < 8; ++b2)
+                if ((rel >> b2) & 1) pl[b2] |= nf;
+            if (rel >> 8) {
+#pragma unroll
+                for (int b2 = 0; b2 < 16; ++b2)
+                    if ((rel >> (8 + b2)) & 1) ph[b2] |= nf;
+            }
+            F = nf;
             ++L;
         }
+        // levels of this lane's row from the bit planes
+        int d[T];
+#pragma unroll
+        for (int j = 0; j < T; ++j) {
+            uint32_t v = 0;
+#pragma unroll
+            for (int b2 = 0; b2 < 8; ++b2) v |= ((pl[b2] >> j) & 1u) << b2;
+            d[j] = (int)v;
+        }
+        if (relmax >> 8) {
+#pragma unroll
+            for (int j = 0; j < T; ++j) {
+                uint32_t v = 0;
+#pragma unroll
+                for (int b2 = 0; b2 < 16; ++b2) v |= ((ph[b2] >> j) & 1u) << (8 + b2);
+                d[j] |= (int)v;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < T; ++j) d[j] = ((V >> j) & 1u) ? base + d[j] : BIG;
         // improved cells go back through shared memory so that the fold is coalesced
 #pragma unroll
         for (int j = 0; j < T; ++j) {
