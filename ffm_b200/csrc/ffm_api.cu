@@ -1316,13 +1316,13 @@ int ffm_sff_generate(const uint8_t* maps, int32_t n_maps, int32_t H, int32_t W, 
             if (ntiles > 0x3FFFFFFFULL) { rc = fail(FFM_E_UNSUPPORTED, "too many tiles for one call"); goto done; }
             SFF_CU(cudaMallocAsync((void**)&d_dist, total * sizeof(float), st));
             // queue scratch in ONE allocation: ring [2 * tiles] | flags [tiles] | 4 counters
-            const size_t qwords = 3 * ntiles + 4;
+            const size_t qwords = 3 * ntiles + 32 + ffm::SFF_Q_WORDS;   // ring [2 * tiles] | flags [tiles] | pad to a 128-byte line | counters
             SFF_CU(cudaMallocAsync((void**)&d_queue, qwords * sizeof(int), st));
             ffm::SffQueue q;
-            q.ring = d_queue; q.flag = d_queue + 2 * ntiles; q.ctrl = reinterpret_cast<unsigned int*>(d_queue + 3 * ntiles);
+            q.ring = d_queue; q.flag = d_queue + 2 * ntiles; q.ctrl = reinterpret_cast<unsigned int*>(d_queue + ((3 * ntiles + 31) & ~(size_t)31));
             q.cap = (unsigned int)(2 * ntiles);
             SFF_CU(cudaMemsetAsync(q.ring, 0xFF, 2 * ntiles * sizeof(int), st));        // -1 = empty slot
-            SFF_CU(cudaMemsetAsync(q.flag, 0, (ntiles + 4) * sizeof(int), st));
+            SFF_CU(cudaMemsetAsync(q.flag, 0, (qwords - 2 * ntiles) * sizeof(int), st));
             ffm::sff_relax_init_kernel<<<dim3(bx, n_maps), 256, 0, st>>>(mp, d_dist, q, H, W, tiles_x, tiles_y);
             const float INF = __builtin_huge_valf();
             const float w_axis = 1.0f;
@@ -1345,7 +1345,7 @@ int ffm_sff_generate(const uint8_t* maps, int32_t n_maps, int32_t H, int32_t W, 
             SFF_CU(cudaGetLastError());
             if (rounds_out) {                                  // tile visits, for the caller that asks (one 4-byte read-back)
                 unsigned int visits = 0;
-                SFF_CU(cudaMemcpyAsync(&visits, q.ctrl + 3, sizeof(visits), cudaMemcpyDeviceToHost, st));
+                SFF_CU(cudaMemcpyAsync(&visits, q.ctrl + ffm::SFF_Q_VISITS, sizeof(visits), cudaMemcpyDeviceToHost, st));
                 SFF_CU(cudaStreamSynchronize(st));
                 rounds = (int)visits;
             }

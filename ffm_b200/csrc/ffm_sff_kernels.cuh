@@ -73,17 +73,19 @@ __global__ void sff_norm_min_kernel(const uint8_t* __restrict__ maps, const int3
 // Scratch of one ffm_sff_generate call: a ring of tile ids (capacity 2 x tiles), a "queued" flag per tile (so a tile is
 // in the ring at most once) and three counters.  No host round trip: the persistent CTAs of sff_relax_queue_kernel pop
 // tiles until the ring is empty and nothing is in flight.
+constexpr int SFF_Q_HEAD = 0, SFF_Q_TAIL = 32, SFF_Q_PENDING = 64, SFF_Q_VISITS = 96, SFF_Q_WORDS = 128;
 struct SffQueue {
     int* ring;                 // [cap] tile id or -1 (empty slot)
     int* flag;                 // [tiles] 1 = queued and not yet popped
-    unsigned int* ctrl;        // [0] head (tickets claimed), [1] tail (tickets issued), [2] pending (queued + in flight), [3] tile visits
+    unsigned int* ctrl;        // four counters, each on its own 128-byte line (SFF_Q_*): head (tickets claimed), tail (tickets issued),
+                               // pending (queued + in flight), tile visits -- idle consumers poll `pending` and must not slow the tickets down
     unsigned int cap;
 };
 
 __device__ __forceinline__ void sff_push(const SffQueue& q, int tile) {
     if (atomicExch(&q.flag[tile], 1) != 0) return;             // already queued: whoever pops it reads our data
-    atomicAdd(&q.ctrl[2], 1u);
-    const unsigned int t = atomicAdd(&q.ctrl[1], 1u);
+    atomicAdd(&q.ctrl[SFF_Q_PENDING], 1u);
+    const unsigned int t = atomicAdd(&q.ctrl[SFF_Q_TAIL], 1u);
     volatile int* slot = q.ring + (t % q.cap);
     while (*slot != -1) __nanosleep(32);                        // the ticket one lap behind has been claimed, not yet taken
     *slot = tile;
@@ -126,20 +128,22 @@ sff_relax_queue_kernel(const uint8_t* __restrict__ maps, float* dist, SffQueue q
             // word); nothing queued and nothing in flight means no push can follow -- done
             int tile = -1;
             volatile unsigned int* ctrl = q.ctrl;
-            const unsigned int h = atomicAdd(&q.ctrl[0], 1u);
+            const unsigned int h = atomicAdd(&q.ctrl[SFF_Q_HEAD], 1u);
             volatile int* slot = q.ring + (h % q.cap);
-            for (;;) {
+            unsigned int ns = 32, miss = 0;
+            for (;;) {                                             // back off, and look at `pending` only every 8th miss
                 tile = *slot;
                 if (tile != -1) break;
-                if (ctrl[2] == 0u) break;
-                __nanosleep(64);
+                if ((++miss & 7u) == 0u && ctrl[SFF_Q_PENDING] == 0u) break;
+                __nanosleep(ns);
+                if (ns < 512) ns <<= 1;
             }
             if (tile != -1) {
                 *slot = -1;
                 __threadfence();
                 atomicExch(&q.flag[tile], 0);                      // from here on an improved neighbour re-queues this tile
                 __threadfence();
-                atomicAdd(&q.ctrl[3], 1u);
+                atomicAdd(&q.ctrl[SFF_Q_VISITS], 1u);
             }
             s_tile = tile;
             rim_changed[0] = rim_changed[1] = rim_changed[2] = rim_changed[3] = 0;
@@ -222,7 +226,7 @@ sff_relax_queue_kernel(const uint8_t* __restrict__ maps, float* dist, SffQueue q
             }
         }
         __syncthreads();
-        if (threadIdx.x == 0) { __threadfence(); atomicSub(&q.ctrl[2], 1u); }
+        if (threadIdx.x == 0) { __threadfence(); atomicSub(&q.ctrl[SFF_Q_PENDING], 1u); }
     }
 }
 
@@ -250,20 +254,22 @@ sff_bfs_warp_kernel(const uint8_t* __restrict__ maps, float* dist, SffQueue q, i
         int tile = -1;
         if (lane == 0) {
             volatile unsigned int* ctrl = q.ctrl;
-            const unsigned int h = atomicAdd(&q.ctrl[0], 1u);
+            const unsigned int h = atomicAdd(&q.ctrl[SFF_Q_HEAD], 1u);
             volatile int* slot = q.ring + (h % q.cap);
-            for (;;) {
+            unsigned int ns = 32, miss = 0;
+            for (;;) {                                             // back off, and look at `pending` only every 8th miss
                 tile = *slot;
                 if (tile != -1) break;
-                if (ctrl[2] == 0u) break;
-                __nanosleep(64);
+                if ((++miss & 7u) == 0u && ctrl[SFF_Q_PENDING] == 0u) break;
+                __nanosleep(ns);
+                if (ns < 512) ns <<= 1;
             }
             if (tile != -1) {
                 *slot = -1;
                 __threadfence();
                 atomicExch(&q.flag[tile], 0);                      // from here on an improved neighbour re-queues this tile
                 __threadfence();
-                atomicAdd(&q.ctrl[3], 1u);
+                atomicAdd(&q.ctrl[SFF_Q_VISITS], 1u);
             }
         }
         tile = __shfl_sync(FULL, tile, 0);
@@ -298,19 +304,20 @@ sff_bfs_warp_kernel(const uint8_t* __restrict__ maps, float* dist, SffQueue q, i
             }
         }
         uint32_t pass = 0, exw = 0;                        // passable cells / exit cells of this lane's row
-        {
-            uint8_t mv[T];
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            uint8_t mv[T / 2];
             const int c = c0 + lane;
 #pragma unroll
-            for (int rr = 0; rr < T; ++rr) {
-                const int r = r0 + rr;
+            for (int rr = 0; rr < T / 2; ++rr) {
+                const int r = r0 + half * (T / 2) + rr;
                 mv[rr] = (r < H && c < W) ? map[(size_t)r * W + c] : (uint8_t)2;
             }
 #pragma unroll
-            for (int rr = 0; rr < T; ++rr) {
+            for (int rr = 0; rr < T / 2; ++rr) {
                 const uint32_t wv = __ballot_sync(FULL, mv[rr] == 0 || mv[rr] == 3);
                 const uint32_t we = __ballot_sync(FULL, mv[rr] == 3);
-                if (lane == rr) { pass = wv; exw = we; }
+                if (lane == half * (T / 2) + rr) { pass = wv; exw = we; }
             }
         }
         __syncwarp();
@@ -327,9 +334,25 @@ sff_bfs_warp_kernel(const uint8_t* __restrict__ maps, float* dist, SffQueue q, i
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) base = min(base, __shfl_xor_sync(FULL, base, o));
         base = has_exit ? 0 : (base < BIG ? base + 1 : BIG);            // first level at which anything appears
-        uint32_t V = 0, F = 0;
-        uint32_t pl[8] = {0, 0, 0, 0, 0, 0, 0, 0}, ph[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-        int relmax = 0;
+        uint32_t V = 0, F = 0, flushed = 0;
+        uint32_t pl[8] = {0, 0, 0, 0, 0, 0, 0, 0};         // eight planes = 256 levels per epoch; a longer run rebases (flush)
+        // cells visited since the last flush: level = base + the number spelled by the planes; shared memory then holds the new
+        // value where it improves on the loaded one, -1 elsewhere
+        auto flush = [&]() {
+            const uint32_t todo = V & ~flushed;
+#pragma unroll
+            for (int j = 0; j < T; ++j)
+                if ((todo >> j) & 1u) {
+                    uint32_t v = 0;
+#pragma unroll
+                    for (int b2 = 0; b2 < 8; ++b2) v |= ((pl[b2] >> j) & 1u) << b2;
+                    const int nv = base + (int)v, o = s[lane + 1][j + 1];
+                    s[lane + 1][j + 1] = nv < o ? nv : -1;
+                }
+            flushed = V;
+#pragma unroll
+            for (int b2 = 0; b2 < 8; ++b2) pl[b2] = 0u;
+        };
         int L = base;
         while (L < BIG) {                                  // warp-uniform
             const int hv = L - 1;                          // halo value that injects at this level
@@ -377,46 +400,20 @@ sff_bfs_warp_kernel(const uint8_t* __restrict__ maps, float* dist, SffQueue q, i
                 F = 0u;
                 continue;
             }
+            if (L - base >= 256) { flush(); base = L; }    // warp-uniform
             V |= nf;
             const int rel = L - base;
-            relmax = rel;
 #pragma unroll
             for (int b2 = 0; b2 < 8; ++b2)
                 if ((rel >> b2) & 1) pl[b2] |= nf;
-            if (rel >> 8) {
-#pragma unroll
-                for (int b2 = 0; b2 < 16; ++b2)
-                    if ((rel >> (8 + b2)) & 1) ph[b2] |= nf;
-            }
             F = nf;
             ++L;
         }
-        // levels of this lane's row from the bit planes
-        int d[T];
+        flush();
 #pragma unroll
-        for (int j = 0; j < T; ++j) {
-            uint32_t v = 0;
-#pragma unroll
-            for (int b2 = 0; b2 < 8; ++b2) v |= ((pl[b2] >> j) & 1u) << b2;
-            d[j] = (int)v;
-        }
-        if (relmax >> 8) {
-#pragma unroll
-            for (int j = 0; j < T; ++j) {
-                uint32_t v = 0;
-#pragma unroll
-                for (int b2 = 0; b2 < 16; ++b2) v |= ((ph[b2] >> j) & 1u) << (8 + b2);
-                d[j] |= (int)v;
-            }
-        }
-#pragma unroll
-        for (int j = 0; j < T; ++j) d[j] = ((V >> j) & 1u) ? base + d[j] : BIG;
-        // improved cells go back through shared memory so that the fold is coalesced
-#pragma unroll
-        for (int j = 0; j < T; ++j) {
-            const int o = s[lane + 1][j + 1];
-            s[lane + 1][j + 1] = d[j] < o ? d[j] : -1;
-        }
+        for (int j = 0; j < T; ++j)
+            if (!((V >> j) & 1u)) s[lane + 1][j + 1] = -1;  // never reached in this visit: nothing to fold
+        // (the improved cells went back through shared memory so that the fold is coalesced)
         __syncwarp();
         // fire-and-forget minima (no round trip per row); a rim cell improved against what this visit loaded wakes the
         // neighbour even if somebody else got there first (a superset of the necessary wake-ups)
@@ -445,7 +442,7 @@ sff_bfs_warp_kernel(const uint8_t* __restrict__ maps, float* dist, SffQueue q, i
             }
         }
         __syncwarp();
-        if (lane == 0) { __threadfence(); atomicSub(&q.ctrl[2], 1u); }
+        if (lane == 0) { __threadfence(); atomicSub(&q.ctrl[SFF_Q_PENDING], 1u); }
     }
 }
 
