@@ -82,3 +82,55 @@ def test_geodesic_work_queue_is_order_independent(cuda_device, mode):
     for rep in range(12):
         got = generate_sff(dm, mode, np.float32).cpu().numpy()
         assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), rep
+
+
+def _serpentine(h, w, gap_every=2, thick=1):
+    """Walls on every other row with the gap alternating between the left and the right end: the only path is a serpentine,
+    so in-tile path lengths run into the hundreds (the warp kernel's bit planes rebase after 256 levels) and the two sides of
+    a tile can be thousands of steps apart (level jumps)."""
+    m = np.zeros((h, w), np.uint8)
+    m[0, :] = 2; m[-1, :] = 2; m[:, 0] = 2; m[:, -1] = 2
+    left = True
+    for r in range(2, h - 2, gap_every):
+        m[r:r + thick, 1:w - 1] = 2
+        if left:
+            m[r:r + thick, 1] = 0
+        else:
+            m[r:r + thick, w - 2] = 0
+        left = not left
+    m[0, 1] = 3
+    m[1, 1] = 0
+    return m
+
+
+@pytest.mark.parametrize("mode", ["bfs4", "bfs8", "dijkstra8"])
+def test_geodesic_serpentine_mazes(cuda_device, mode):
+    """Long in-tile paths, huge halo spreads, ragged edge tiles, exits in tile corners: BFS levels bit for bit."""
+    from ffm_b200.sff import generate_sff
+    for shape, every in (((64, 64), 2), ((97, 131), 2), ((130, 70), 3)):
+        m = _serpentine(shape[0], shape[1], gap_every=every)
+        got = generate_sff(m, mode, np.float32)
+        want = c_oracle.geodesic(m, mode)
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), (mode, shape)
+        assert np.nanmax(np.where(np.isfinite(want), want, 0)) > 1000          # the path really is long
+    # a spiral-free but dense case: random 45 % obstacles, many exits (most cells unreachable pockets)
+    rng = np.random.RandomState(3)
+    m = (rng.rand(150, 190) < 0.45).astype(np.uint8) * 2
+    m[0, :] = 2; m[-1, :] = 2; m[:, 0] = 2; m[:, -1] = 2
+    for k in range(6):
+        m[0, 10 + 30 * k] = 3
+        m[1, 10 + 30 * k] = 0
+    got = generate_sff(m, mode, np.float32)
+    assert np.array_equal(got.view(np.uint32), c_oracle.geodesic(m, mode).view(np.uint32))
+
+
+def test_geodesic_unit_cost_kernels_agree(cuda_device, monkeypatch):
+    """The warp-per-tile kernel (default for BFS-4 / BFS-8) and the CTA-per-tile kernel (FFM_SFF_KERNEL=tile) give the same field."""
+    from ffm_b200.sff import generate_sff
+    maps = np.stack([assets.obstacle_map_c5(300, 260, index=70 + i, fill=0.35, n_exits=4) for i in range(6)])
+    for mode in ("bfs4", "bfs8"):
+        monkeypatch.delenv("FFM_SFF_KERNEL", raising=False)
+        a = generate_sff(maps, mode, np.float32)
+        monkeypatch.setenv("FFM_SFF_KERNEL", "tile")
+        b = generate_sff(maps, mode, np.float32)
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), mode
