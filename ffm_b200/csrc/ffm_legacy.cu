@@ -755,12 +755,6 @@ __global__ void __launch_bounds__(256) leg_dff_update_kernel(const float* in, fl
     dff_decay_diffuse<NBR>(in + off, out + off, H, W, c0, c1, thr, threadIdx.x, make_stencil_geom(H, W, threadIdx.x, 256));
 }
 
-// fills the rows of every EMPTY slot with the default value (what an unseen key reads as)
-__global__ void leg_fill_default_kernel(const unsigned long long* keys, double* rows, uint32_t cap, int width, double value, bool all) {
-    for (size_t x = (size_t)blockIdx.x * blockDim.x + threadIdx.x; x < (size_t)cap * width; x += (size_t)gridDim.x * blockDim.x)
-        if (all || keys[x / width] == LEG_EMPTY) rows[x] = value;
-}
-
 }  // namespace ffm
 
 // ---------------------------------------------------------------------------------------------------------------------------
