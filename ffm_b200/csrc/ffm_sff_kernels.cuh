@@ -238,6 +238,7 @@ sff_relax_queue_kernel(const uint8_t* __restrict__ maps, float* dist, SffQueue q
 // over.  That is Dijkstra with unit weights from many sources at different offsets -- the fixpoint the sweeps of
 // sff_relax_queue_kernel converge to, reached with ~10x fewer instructions per tile visit.  Queue protocol, fold with
 // atomicMin and neighbour wake-up are the same as there; eight warps of a CTA are eight independent consumers.
+// (capping the registers at 64 for four CTAs per SM measured slower: BFS-4 3.6 ms instead of 3.0 ms per 64 maps)
 template <bool DIAG>
 __global__ void __launch_bounds__(256)
 sff_bfs_warp_kernel(const uint8_t* __restrict__ maps, float* dist, SffQueue q, int H, int W, int tiles_x, int tiles_y) {
