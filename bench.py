@@ -822,7 +822,7 @@ def run_legacy_workload(ctx, name, wl):
         return None
     value = sums[0] / (ms[0] * 1e-3)
     return {
-        "metric": "ped_steps_per_sec", "value": value, "unit": UNIT, "n_gpus": ctx.world, "steps": args.steps, "warmup": min(args.warmup, 2),
+        "metric": "pedestrian_steps_per_sec", "value": value, "unit": UNIT, "n_gpus": ctx.world, "steps": args.steps, "warmup": min(args.warmup, 2),
         "ms_per_step": ms[0] / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": wl["desc"], "episodes_per_step_per_gpu": E, "parallelism": f"replicas only: {ctx.world} independent learner(s), no collective",
                    "reference": "critic_training/run_20251206_153157/summary.txt: 11 000 episodes in 03:25:36 = 0.89 episodes/s (hardware unknown)"},

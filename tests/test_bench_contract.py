@@ -53,10 +53,11 @@ def test_gpu_arm_line(cuda_device):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("workload,metric", [("c2traj", "pedestrian_steps_per_sec"), ("sff", "sff_cells_per_sec"), ("c4", "pedestrian_steps_per_sec"),
-                                             ("c4train", "training_episodes_per_sec"), ("c5train", "training_episodes_per_sec")])
+                                             ("c4train", "training_episodes_per_sec"), ("c5train", "training_episodes_per_sec"),
+                                             ("legacy", "pedestrian_steps_per_sec")])
 def test_gpu_arm_secondary_workloads(cuda_device, workload, metric):
     """Each secondary workload of the default run, stand-alone and shortened."""
-    extra = {"c2traj": ["--episodes", "32"], "c4": ["--episodes", "512"], "sff": [], "c4train": [], "c5train": []}[workload]
+    extra = {"c2traj": ["--episodes", "32"], "c4": ["--episodes", "512"], "sff": [], "c4train": [], "c5train": [], "legacy": []}[workload]
     d = _run(["--workload", workload, "--steps", "1", "--warmup", "3", "--no-cpu"] + extra)
     assert BASE_KEYS | {"clocks", "gpu_launches", "roofline"} <= set(d) and d["metric"] == metric and d["value"] > 0
     assert d["e2e"]["value"] > 0 and d["e2e"]["d2h_bytes_per_step"] > 0 and d["e2e"]["h2d_bytes_per_step"] > 0
@@ -66,5 +67,8 @@ def test_gpu_arm_secondary_workloads(cuda_device, workload, metric):
         assert d["config"]["syncs_timed"] == 16 and d["sync_ms_blocking"] > 0
     if workload == "c5train":
         assert d["config"]["pretrain_patterns"] == 11328 and d["tables"]["Q_rows_after_training"] > d["tables"]["Q_rows_after_pretrain"] > 1000
+    if workload == "legacy":
+        assert d["episodes_per_sec"] > 10 and d["actor_only"]["value"] > 0 and d["frozen_batch"]["value"] > 1e8
+        assert d["tables"]["V_states"] > 100 and d["tables"]["actor_H_rows"] > 10
     if workload == "c4train":
         assert d["value"] > 1000 and all(v["in_band_2N-1..2N+14"] >= 0.9 for v in d["acceptance"].values()), d["acceptance"]
