@@ -15,6 +15,10 @@
 //                             (fl32(d + w) is monotone in d), so the result is bit-identical to a
 //                             float32 Dijkstra (which is what the CPU checker of the test-suite runs).
 //                             North-star item 2 (the reference has no obstacle-aware generator).
+//                             Runs the Dijkstra mode (float costs).
+//  * sff_bfs_warp_kernel      the unit-cost modes (BFS-4 / BFS-8) on the same queue, one WARP per tile visit: rows in
+//                             lanes, cell sets as 32-bit words, the tile solved level by level from its halo and exits
+//                             with shifts and shuffles, levels recorded in bit planes (see the kernel)
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -71,7 +75,7 @@ __global__ void sff_norm_min_kernel(const uint8_t* __restrict__ maps, const int3
 
 // ---- geodesic fields: asynchronous tile relaxation driven by a device-side work queue ---------------------------------
 // Scratch of one ffm_sff_generate call: a ring of tile ids (capacity 2 x tiles), a "queued" flag per tile (so a tile is
-// in the ring at most once) and three counters.  No host round trip: the persistent CTAs of sff_relax_queue_kernel pop
+// in the ring at most once) and four counters.  No host round trip: the persistent CTAs of sff_relax_queue_kernel pop
 // tiles until the ring is empty and nothing is in flight.
 constexpr int SFF_Q_HEAD = 0, SFF_Q_TAIL = 32, SFF_Q_PENDING = 64, SFF_Q_VISITS = 96, SFF_Q_WORDS = 128;
 struct SffQueue {
