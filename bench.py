@@ -242,6 +242,32 @@ def cpu_numpy_port_unified(wl, budget_s, seed=1234, cores=None):
                        f"{sum(r[2] for r in res)} CA steps")
 
 
+def cpu_numpy_port_legacy(m, sff, pos, params, cap, budget_s, seed):
+    """cpu_baseline of the legacy workload: the NumPy restatement of model/ffm_ac_core.py (oracle/legacy_numpy.py) running whole
+    sequential-exact learning episodes on ONE host core -- the reference's own shape: one Python process, one shared V dict."""
+    from oracle import legacy_numpy
+
+    class Src:
+        def __init__(self, s): self.rs = np.random.RandomState(s)
+        def move(self, t, i, cdf=None): return self.rs.random_sample()
+        def winner(self, t, c, k): return self.rs.random_sample()
+
+    V, ped, eps, steps = {}, 0, 0, 0
+    t0 = time.perf_counter()
+    while time.perf_counter() - t0 < budget_s and eps < len(pos):
+        o = legacy_numpy.AcOracle(m, sff, pos[eps], params, Src(seed + eps), v_table=V)
+        while o.positions.shape[0] > 0 and o.t < cap:
+            ped += o.positions.shape[0]
+            o.step()
+        steps += o.t
+        V = o.V
+        eps += 1
+    wall = time.perf_counter() - t0
+    return dict(value=ped / wall, unit=UNIT, cores=1, kind="port", episodes_per_sec=eps / wall,
+                sample=f"{eps} whole learning episodes of the NumPy port of model/ffm_ac_core.py (oracle/legacy_numpy.py) on one core, "
+                       f"shared V dict: {ped} ped-steps, {steps} CA steps in {wall:.1f} s")
+
+
 def cpu_numpy_port(wl, budget_s, seed=1234, cores=None):
     import multiprocessing as mp
     cores = cores or os.cpu_count() or 1
@@ -821,7 +847,14 @@ def run_legacy_workload(ctx, name, wl):
     if ctx.rank != 0:
         return None
     value = sums[0] / (ms[0] * 1e-3)
+    cpu = None
+    if ctx.world == 1 and not args.no_cpu:
+        try:
+            cpu = cpu_numpy_port_legacy(m, sff64, pos, LEGACY_PARAMS, cap, min(args.cpu_budget, 8.0), args.seed & 0x7FFFFFFF)
+        except Exception as ex:   # the baseline is reporting, never the product
+            cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": f"failed: {ex!r}"}
     return {
+        "cpu_baseline": cpu,
         "metric": "pedestrian_steps_per_sec", "value": value, "unit": UNIT, "n_gpus": ctx.world, "steps": args.steps, "warmup": min(args.warmup, 2),
         "ms_per_step": ms[0] / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": wl["desc"], "episodes_per_step_per_gpu": E, "parallelism": f"replicas only: {ctx.world} independent learner(s), no collective",
