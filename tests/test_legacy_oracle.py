@@ -50,3 +50,15 @@ def test_actor_only_oracle_reproduces_reference(name):
     assert np.array_equal(np.array([V[int(k)] for k in vk]), g["v_vals"])
     assert np.array_equal(np.array([Ht[int(k)] for k in hk]).reshape(len(hk), -1), g["h_vals"])
     assert np.array_equal(o.dff, g["final_dff"])
+
+
+def test_product_key_helpers_match_the_checker():
+    """ffm_b200.legacy.state_to_key / key_to_state (what the drop-ins use to rebuild the reference's pickled keys) against the
+    checker's, on the keys of a reference fixture."""
+    from ffm_b200 import legacy as product
+    g = load_legacy("legacy_ac_moore_f64")
+    nby = (g["map"].shape[1] + g["params"]["block_size"] - 1) // g["params"]["block_size"]
+    for k in g["v_keys"][:500]:
+        st = legacy_numpy.key_to_state(int(k), nby)
+        assert product.key_to_state(k, nby) == st and product.state_to_key(st, nby) == int(k)
+        assert st[0][4] == 1 and len(st[0]) == 13            # the centre cell of a state is the pedestrian itself
